@@ -1,0 +1,316 @@
+"""MCTS over the GPU arena, behind the reference's MCTS surface (MCTS.py:10-240).
+
+`BatchedMCTS` drives `n_games` independent searches in lock step: every round is one
+arena `select` (all games descend to a leaf), ONE batched leaf evaluation, one
+`expand_backup`.  `MCTS` is the single-game drop-in with the reference's constructor and
+methods (`getActionProb`, `expand_tree`, dict views `Qsa Nsa Ns Ps Es Vs`).
+
+Leaf evaluation:
+  * a B200 wrapper (has `forward_states`) is called on the device-resident leaf batch;
+  * any other NeuralNet (e.g. the tests' table-driven fake net) is called per leaf on the host
+    exactly as MCTS.py:169-173 does -- that is how tree statistics are compared bit for bit
+    against the reference under identical priors and values.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .arena import DeviceArena, action_size
+
+EPS = 1e-8  # MCTS.py:6
+
+
+def arg(args, name, default=None):
+    """args may be main.py's dotdict (raises KeyError from __getattr__), a dict or a namespace."""
+    try:
+        return getattr(args, name)
+    except (AttributeError, KeyError):
+        try:
+            return args[name]
+        except (KeyError, TypeError, IndexError):
+            return default
+
+
+def game_kind(game):
+    k = getattr(game, "azg_kind", None)
+    if k:
+        return k
+    name = type(game).__name__.lower()
+    for kind in ("connect4", "tictactoe", "frozenlake"):
+        if kind in name:
+            return kind
+    raise ValueError(f"cannot infer game kind from {type(game).__name__}; set game.azg_kind")
+
+
+# ------------------------------------------------------------------------------------- state <-> board
+def pack_states(kind, boards):
+    """boards [B,n,n] (reference canonical arrays) -> int64 [B,2] holding the uint64 {mine, theirs}."""
+    b = np.asarray(boards)
+    B, n = b.shape[0], b.shape[1]
+    flat = b.reshape(B, n * n)
+    out = np.zeros((B, 2), dtype=np.uint64)
+    if kind == "frozenlake":
+        out[:, 0] = np.argmax(flat, axis=1).astype(np.uint64)  # FrozenLakeGame.py:197-202
+    else:
+        w = (np.uint64(1) << np.arange(n * n, dtype=np.uint64))
+        out[:, 0] = ((flat > 0).astype(np.uint64) * w).sum(axis=1, dtype=np.uint64)
+        out[:, 1] = ((flat < 0).astype(np.uint64) * w).sum(axis=1, dtype=np.uint64)
+    return out.view(np.int64)
+
+
+def unpack_state(kind, n, state):
+    """one packed state -> the reference's board array (int64 cells; FrozenLake: float64 one-hot)."""
+    mine, theirs = (int(x) & 0xFFFFFFFFFFFFFFFF for x in state)
+    if kind == "frozenlake":
+        b = np.zeros((n, n))
+        b[mine // n, mine % n] = 1
+        return b
+    bits = np.arange(n * n, dtype=np.uint64)
+    m = ((np.uint64(mine) >> bits) & np.uint64(1)).astype(np.int64)
+    t = ((np.uint64(theirs) >> bits) & np.uint64(1)).astype(np.int64)
+    return (m - t).reshape(n, n)
+
+
+def typed_value(d, tag):
+    """(float64 payload, AZG_TAG_*) -> the Python/NumPy object the reference would hold."""
+    if tag == _lib.TAG_F32:
+        return np.float32(d)
+    if tag == _lib.TAG_PYFLOAT:
+        return float(d)
+    if tag == _lib.TAG_PYINT:
+        return int(d)
+    return 0
+
+
+class BatchedMCTS:
+    def __init__(self, game, nnet, args, n_games=1, arena=None, capacity=None, max_depth=None):
+        self.game, self.nnet, self.args = game, nnet, args
+        self.kind = game_kind(game)
+        self.n = game.getBoardSize()[0]
+        self.A = game.getActionSize()
+        assert self.A == action_size(self.kind, self.n)
+        self.G = n_games
+        self.use_gnn = bool(arg(args, "use_gnn", False))
+        sims = int(arg(args, "numMCTSSims")) + (int(arg(args, "expand_by", 5)) if self.use_gnn else 0)
+        if arena is None:
+            fl_map = b"".join(np.asarray(game.desc).reshape(-1).tolist()) if self.kind == "frozenlake" else None
+            arena = DeviceArena(self.kind, self.n, n_games, sims, float(arg(args, "cpuct")), capacity=capacity,
+                                max_depth=max_depth, fl_map=fl_map)
+        self.arena = arena
+        self.device_eval = hasattr(nnet, "forward_states")
+        self.standard_predictions = [dict() for _ in range(n_games)]
+        self.gnn_predictions = [dict() for _ in range(n_games)]
+        self.leaf_evals = 0
+
+    # ------------------------------------------------------------------ roots
+    def reset(self, game_ids=None):
+        self.arena.reset(game_ids)
+
+    def set_root_boards(self, boards):
+        self.arena.set_roots(pack_states(self.kind, np.stack([np.asarray(b) for b in boards])))
+
+    def root_boards(self):
+        roots = self.arena.to_host(self.arena.get_roots())
+        return [unpack_state(self.kind, self.n, r) for r in roots]
+
+    # ------------------------------------------------------------------ leaf evaluation
+    def _evaluate_device(self, leaf_states):
+        mask = (_lib.EVAL_STD | _lib.EVAL_GNN) if self.use_gnn else _lib.EVAL_STD
+        out = self.nnet.forward_states(leaf_states, mask)
+        return (out["pi_gnn"], out["v_gnn"]) if self.use_gnn else (out["pi"], out["v"])
+
+    def _evaluate_host(self, leaf_states, leaf_mask):
+        ar = self.arena
+        states, mask = ar.to_host(leaf_states), ar.to_host(leaf_mask)
+        pi = np.zeros((self.G, self.A), dtype=np.float32)
+        v = np.zeros(self.G, dtype=np.float32)
+        for g in np.flatnonzero(mask):
+            board = unpack_state(self.kind, self.n, states[g])
+            s = self.game.stringRepresentation(board)
+            std = self.nnet.predict(board)  # MCTS.py:169-170
+            self.standard_predictions[g][s] = std
+            use = std
+            if self.use_gnn:  # MCTS.py:172-176
+                use = self.nnet.predict_with_gnn(board)
+                self.gnn_predictions[g][s] = use
+            pi[g] = np.asarray(use[0], dtype=np.float32)
+            v[g] = np.float32(np.asarray(use[1]).reshape(-1)[0])
+            self.leaf_evals += 1
+        return ar.to_device(pi, torch.float32), ar.to_device(v, torch.float32), int(mask.sum())
+
+    def search(self, n_sims):
+        """n_sims MCTS.search calls per game (MCTS.py:33-34), in lock step."""
+        ar = self.arena
+        ar.begin(n_sims)
+        if self.device_eval:
+            for _ in range(n_sims):  # every round retires >= 1 simulation per game that has budget
+                leaf_states, _mask = ar.select()
+                pi, v = self._evaluate_device(leaf_states)
+                ar.expand_backup(pi, v)
+                self.leaf_evals += self.G
+        else:
+            while True:
+                leaf_states, leaf_mask = ar.select()
+                pi, v, pending = self._evaluate_host(leaf_states, leaf_mask)
+                if pending == 0:
+                    break
+                ar.expand_backup(pi, v)
+        ar.check_status()
+
+    # ------------------------------------------------------------------ MCTS.getActionProb (MCTS.py:29-58)
+    def root_stats(self):
+        N, Q, qtag = self.arena.root_stats()
+        h = self.arena.to_host
+        return h(N), h(Q), h(qtag)
+
+    def probs_from_counts(self, counts, temp, board_fn):
+        counts = [int(c) for c in counts]
+        if temp == 0:
+            bestAs = np.array(np.argwhere(counts == np.max(counts))).flatten()
+            bestA = np.random.choice(bestAs)  # consumes the global NumPy RNG like MCTS.py:41
+            probs = [0] * len(counts)
+            probs[bestA] = 1
+            return probs
+        cs = [(x + EPS) ** (1. / temp) for x in counts]
+        counts_sum = float(sum(cs))
+        if counts_sum <= 0:
+            valids = self.game.getValidMoves(board_fn(), 1)
+            vs = np.sum(valids)
+            return valids / vs if vs > 0 else np.ones(len(cs)) / len(cs)
+        return [x / counts_sum for x in cs]
+
+    def getActionProbs(self, temp=1, temps=None):
+        for d in self.standard_predictions + self.gnn_predictions:
+            d.clear()  # MCTS.py:30-31
+        self.search(int(arg(self.args, "numMCTSSims")))
+        N, _, _ = self.root_stats()
+        boards = None
+        out = []
+        for g in range(self.G):
+            def board_fn(g=g):
+                nonlocal boards
+                boards = boards or self.root_boards()
+                return boards[g]
+            out.append(self.probs_from_counts(N[g], temps[g] if temps is not None else temp, board_fn))
+        return out
+
+    # ------------------------------------------------------------------ MCTS.expand_tree (MCTS.py:60-149)
+    def _root_std_values(self):
+        if self.device_eval:
+            out = self.nnet.forward_states(self.arena.get_roots(), _lib.EVAL_STD)
+            v = self.arena.to_host(out["v"])
+            return [np.float32(x) for x in v]
+        vals = []
+        for g, board in enumerate(self.root_boards()):
+            s = self.game.stringRepresentation(board)
+            if s not in self.standard_predictions[g]:  # MCTS.py:108-111
+                self.standard_predictions[g][s] = self.nnet.predict(board)
+            vals.append(self.standard_predictions[g][s][1])
+        return vals
+
+    def expand_tree(self, expand_by=5):
+        A = self.A
+        N0, _, _ = self.root_stats()
+        if (N0.sum(axis=1) == 0).any():  # MCTS.py:83-92: no counts yet -> run the standard simulations first
+            if not (N0.sum(axis=1) == 0).all():
+                raise RuntimeError("expand_tree: some games have root visits and some do not; call getActionProbs first")
+            self.search(int(arg(self.args, "numMCTSSims")))
+            N0, _, _ = self.root_stats()
+        v0 = self._root_std_values()
+        self.search(expand_by)
+        N1, Q1, T1 = self.root_stats()
+        results = []
+        for g in range(self.G):
+            initial_policy = np.zeros(A)
+            for a in range(A):
+                if N0[g, a] > 0:
+                    initial_policy[a] = int(N0[g, a])
+            isum = np.sum(initial_policy)
+            if isum > 0:
+                initial_policy = initial_policy / isum
+            else:
+                valids = self.game.getValidMoves(self.root_boards()[g], 1)
+                initial_policy = valids / np.sum(valids)
+            expanded_policy = np.zeros(A)
+            for a in range(A):
+                if N1[g, a] > 0:
+                    expanded_policy[a] = int(N1[g, a])
+            esum = np.sum(expanded_policy)
+            expanded_policy = expanded_policy / esum if esum > 0 else initial_policy
+            expanded_value, valid_count = 0, 0  # MCTS.py:132-143, same promotion rules
+            for a in range(A):
+                if T1[g, a] != _lib.TAG_NONE and N1[g, a] > 0:
+                    expanded_value += typed_value(Q1[g, a], T1[g, a]) * int(N1[g, a])
+                    valid_count += int(N1[g, a])
+            expanded_value = expanded_value / valid_count if valid_count > 0 else v0[g]
+            results.append((initial_policy, v0[g], expanded_policy, expanded_value))
+        return results
+
+    # ------------------------------------------------------------------ moves
+    def advance(self, actions):
+        """Play actions[g] in game g (Coach.py:63-66); returns getGameEnded of the new position for the
+        player to move, with the reference's value types (0 = still running).  action -1 = leave."""
+        ended, tag = self.arena.advance(np.asarray(actions, dtype=np.int32))
+        e, t = self.arena.to_host(ended), self.arena.to_host(tag)
+        return [typed_value(e[g], t[g]) for g in range(self.G)]
+
+    # ------------------------------------------------------------------ dict views (MCTS.py:15-21)
+    def tables(self, g=0):
+        ex = self.arena.export(g)
+        Qsa, Nsa, Ns, Ps, Es, Vs = {}, {}, {}, {}, {}, {}
+        vdtype = np.int8 if self.kind == "frozenlake" else np.int64
+        for i in range(ex["count"]):
+            board = unpack_state(self.kind, self.n, ex["keys"][i])
+            s = self.game.stringRepresentation(board)
+            Es[s] = typed_value(ex["es"][i], ex["es_tag"][i])
+            if ex["valids"][i] != 0:
+                Vs[s] = np.array([(int(ex["valids"][i]) >> a) & 1 for a in range(self.A)], dtype=vdtype)
+            if ex["ns"][i] >= 0:
+                Ps[s] = ex["P"][i].astype(np.float32) if ex["ptag"][i] else ex["P"][i].copy()
+                Ns[s] = int(ex["ns"][i])
+            for a in range(self.A):
+                if ex["qtag"][i, a] != _lib.TAG_NONE:
+                    Qsa[(s, a)] = typed_value(ex["Q"][i, a], ex["qtag"][i, a])
+                    Nsa[(s, a)] = int(ex["N"][i, a])
+        return dict(Qsa=Qsa, Nsa=Nsa, Ns=Ns, Ps=Ps, Es=Es, Vs=Vs)
+
+
+class MCTS:
+    """Drop-in for the reference class: `MCTS(game, nnet, args)` (MCTS.py:10-27), one game."""
+
+    def __init__(self, game, nnet, args, arena=None, capacity=None, max_depth=None):
+        self.game, self.nnet, self.args = game, nnet, args
+        if capacity is None:  # the table persists for as long as the object lives (Coach.py:128-142 reuses it)
+            n = game.getBoardSize()[0]
+            capacity = max(4096, 4 * (int(arg(args, "numMCTSSims")) + 5) * (n * n + 1))
+        self._b = BatchedMCTS(game, nnet, args, n_games=1, arena=arena, capacity=capacity, max_depth=max_depth)
+        self.expanded, self.expanded_nodes = False, {}
+
+    standard_predictions = property(lambda self: self._b.standard_predictions[0])
+    gnn_predictions = property(lambda self: self._b.gnn_predictions[0])
+
+    def getActionProb(self, canonicalBoard, temp=1):
+        self._b.set_root_boards([canonicalBoard])
+        return self._b.getActionProbs(temp)[0]
+
+    def expand_tree(self, canonicalBoard, expand_by=5):
+        self._b.set_root_boards([canonicalBoard])
+        self.expanded = True
+        res = self._b.expand_tree(expand_by)[0]
+        self.expanded_nodes = {self.game.stringRepresentation(np.asarray(canonicalBoard)): res}
+        self.expanded = False
+        return self.expanded_nodes
+
+    def search(self, canonicalBoard):
+        self._b.set_root_boards([canonicalBoard])
+        self._b.search(1)
+
+    def _view(self, name):
+        return self._b.tables(0)[name]
+
+    Qsa = property(lambda self: self._view("Qsa"))
+    Nsa = property(lambda self: self._view("Nsa"))
+    Ns = property(lambda self: self._view("Ns"))
+    Ps = property(lambda self: self._view("Ps"))
+    Es = property(lambda self: self._view("Es"))
+    Vs = property(lambda self: self._view("Vs"))

@@ -1,0 +1,277 @@
+"""NeuralNet wrappers (Net.py:1-62 surface) whose compute runs in libazgnn_b200.so.
+
+    B200Connect4NNetWrapper / B200Connect4GNNWrapper    <- connect4/Connect4Net.py:62-147, Connect4GNN.py:11-221
+    B200TicTacToeNNetWrapper / B200TicTacToeGNNWrapper  <- tictactoe/TicTacToeNet.py:50-105, TicTacToeGNN.py:10-181
+    B200FrozenLakeNet                                   <- frozenlake/FrozenLakeNet.py:36-251
+
+Same constructor `(game, args)`, same methods (`predict`, `predict_with_gnn`, `train`,
+`save_checkpoint`, `load_checkpoint`), same attributes (`nnet`, `gnn`, `device`, `board_x/y`,
+`action_size`, `args`), same checkpoint format.  Added: `predict_batch` / `forward_states` --
+the batched entry points the arena uses (one launch sequence per leaf batch instead of one
+`predict` per leaf, MCTS.py:169-173).
+
+Parameters are ordinary torch CUDA tensors inside `modules.*` (so `state_dict`, Adam and
+checkpoints are untouched); kernels read them in place through raw pointers.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, modules
+from ._lib import ptr, stream
+from .mcts import arg, game_kind, pack_states
+
+_CELL = {torch.int8: _lib.CELL_I8, torch.int64: _lib.CELL_I64, torch.float32: _lib.CELL_F32,
+         torch.float64: _lib.CELL_F64}
+
+
+def _device():
+    _lib.require_device()
+    return torch.device(f"cuda:{torch.cuda.current_device()}")
+
+
+class _Base:
+    kind = None
+
+    def _common(self, game, args):
+        self.board_x, self.board_y = game.getBoardSize()
+        assert self.board_x == self.board_y, "square boards only (Connect4Game.py:123-137)"
+        self.n = self.board_x
+        self.action_size = game.getActionSize()
+        self.args = args
+        self.game = game
+        self.device = _device()
+        self.lib = _lib.lib()
+        self._ws = None
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ---- host boards -> device states -----------------------------------------------------
+    def states_from_boards(self, boards):
+        """boards: numpy / torch array [B,n,n] of cells (any of int8, int64, float32, float64), host
+        (pinned or pageable) or device.  Returns int64 [B,2] device states (packing runs on the GPU)."""
+        if self.kind == "frozenlake":
+            b = np.asarray(boards)
+            return torch.as_tensor(pack_states(self.kind, b)).to(self.device)
+        t = boards if torch.is_tensor(boards) else torch.from_numpy(np.ascontiguousarray(boards))
+        if t.dtype not in _CELL:
+            t = t.to(torch.int64)
+        t = t.to(self.device, non_blocking=True).contiguous()
+        B = t.shape[0]
+        states = torch.empty(B, 2, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.azg_pack_boards(ptr(t), _CELL[t.dtype], self.n, B, ptr(states), stream()))
+        return states
+
+    def predict_batch(self, boards, eval_mask=None):
+        """Batched predict (+predict_with_gnn): returns host numpy arrays."""
+        out = self.forward_states(self.states_from_boards(boards), eval_mask)
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
+    def predict(self, board):
+        out = self.forward_states(self.states_from_boards(np.asarray(board)[None]), _lib.EVAL_STD)
+        return out["pi"].cpu().numpy()[0], out["v"].cpu().numpy()[0]
+
+    def predict_with_gnn(self, board):
+        out = self.forward_states(self.states_from_boards(np.asarray(board)[None]), _lib.EVAL_GNN)
+        return out["pi_gnn"].cpu().numpy()[0], out["v_gnn"].cpu().numpy()[0]
+
+    # ---- checkpoints (Connect4Net.py:136-147, Connect4GNN.py:199-221) -----------------------
+    def save_checkpoint(self, folder, filename):
+        if not os.path.exists(folder):
+            os.makedirs(folder)
+        d = {"state_dict": self.nnet.state_dict()}
+        if getattr(self, "gnn", None) is not None:
+            d["gnn"] = self.gnn.state_dict()
+        torch.save(d, os.path.join(folder, filename))
+
+    def load_checkpoint(self, folder, filename):
+        ck = torch.load(os.path.join(folder, filename), map_location=self.device)
+        self.nnet.load_state_dict(ck["state_dict"])
+        if getattr(self, "gnn", None) is not None:
+            if "gnn" in ck:
+                self.gnn.load_state_dict(ck["gnn"])
+            else:
+                print(f"GNN state not found in {os.path.join(folder, filename)}, initializing new GNN")
+        self.weights_changed()
+
+    def weights_changed(self):
+        """Call after any in-place parameter update (optimizer step, load): re-tiled copies are stale."""
+        self._packed_ok = False
+
+
+class _TwoPlayer(_Base):
+    has_gnn = False
+
+    def _outputs(self, B, eval_mask):
+        A, dev = self.action_size, self.device
+        o = {}
+        if eval_mask & _lib.EVAL_STD:
+            o["pi"] = torch.empty(B, A, dtype=torch.float32, device=dev)
+            o["v"] = torch.empty(B, dtype=torch.float32, device=dev)
+        if eval_mask & _lib.EVAL_GNN:
+            o["pi_gnn"] = torch.empty(B, A, dtype=torch.float32, device=dev)
+            o["v_gnn"] = torch.empty(B, dtype=torch.float32, device=dev)
+        return o
+
+    def _default_mask(self):
+        return (_lib.EVAL_STD | _lib.EVAL_GNN) if self.has_gnn else _lib.EVAL_STD
+
+    def _init_gnn(self, args, feature_dim):
+        self.feature_dim = feature_dim
+        self.gnn = modules.PolicyValueGNN(feature_dim, arg(args, "gnn_layers", 2) or 2).to(self.device)
+
+
+# ---------------------------------------------------------------------------------------- Connect4
+class B200Connect4NNetWrapper(_TwoPlayer):
+    kind = "connect4"
+
+    def __init__(self, game, args):
+        self._common(game, args)
+        dropout = arg(args, "dropout", 0.3)
+        self.nnet = modules.Connect4Trunk(self.n, self.action_size, 0.3 if dropout is None else dropout).to(self.device)
+        self.gnn = None
+        self.precision = _lib.PRECISIONS[arg(args, "b200_precision", "fp32") or "fp32"]
+        self._packed, self._packed_ok = None, False
+
+    def _params(self, need_packed):
+        n, g = self.nnet, self.gnn
+        p = _lib.C4Params(ptr(n.conv1.weight), ptr(n.conv1.bias), ptr(n.conv2.weight), ptr(n.conv2.bias),
+                          ptr(n.fc_policy.weight), ptr(n.fc_policy.bias), ptr(n.fc_value.weight), ptr(n.fc_value.bias))
+        if g is not None:
+            ot = g.output_transform
+            p.ot0_w, p.ot0_b, p.ot2_w, p.ot2_b = ptr(ot[0].weight), ptr(ot[0].bias), ptr(ot[2].weight), ptr(ot[2].bias)
+            if need_packed:
+                p.ot_packed = ptr(self._ensure_packed())
+        return p
+
+    def _ensure_packed(self):
+        if not self._packed_ok:
+            nbytes = self.lib.azg_c4_packed_bytes(self.n, self.precision)
+            if self._packed is None or self._packed.numel() != nbytes:
+                self._packed = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            ot = self.gnn.output_transform
+            _lib.check(self.lib.azg_c4_pack_gnn(ptr(ot[0].weight), ptr(ot[2].weight), self.n, self.precision,
+                                                ptr(self._packed), nbytes, stream()))
+            self._packed_ok = True
+        return self._packed
+
+    def forward_states(self, states, eval_mask=None, precision=None):
+        """states: int64 [B,2] on the device.  Returns device tensors pi/v (+pi_gnn/v_gnn)."""
+        eval_mask = self._default_mask() if eval_mask is None else eval_mask
+        if (eval_mask & _lib.EVAL_GNN) and self.gnn is None:
+            raise RuntimeError("predict_with_gnn needs the GNN wrapper")
+        prec = self.precision if precision is None else precision
+        B = int(states.shape[0])
+        o = self._outputs(B, eval_mask)
+        p = self._params(bool(eval_mask & _lib.EVAL_GNN) and prec != _lib.PREC_FP32)
+        nbytes = self.lib.azg_c4_workspace_bytes(self.n, B, eval_mask, prec)
+        ws = self._workspace(nbytes)
+        _lib.check(self.lib.azg_c4_forward(C.byref(p), self.n, ptr(states), B, eval_mask, prec, ptr(o.get("pi")),
+                                           ptr(o.get("v")), ptr(o.get("pi_gnn")), ptr(o.get("v_gnn")), ptr(ws),
+                                           ws.numel(), stream()))
+        return o
+
+    def train(self, examples, gnn_examples=None):
+        from .training import train_two_player
+        train_two_player(self, examples, gnn_examples)
+
+
+class B200Connect4GNNWrapper(B200Connect4NNetWrapper):
+    has_gnn = True
+
+    def __init__(self, game, args):
+        super().__init__(game, args)
+        self._init_gnn(args, 64 * self.n * self.n)  # Connect4GNN.py:21
+
+
+# ---------------------------------------------------------------------------------------- TicTacToe
+class B200TicTacToeNNetWrapper(_TwoPlayer):
+    kind = "tictactoe"
+
+    def __init__(self, game, args):
+        self._common(game, args)
+        self.nnet = modules.TicTacToeTrunk(self.n, self.action_size).to(self.device)
+        self.gnn = None
+
+    def _params(self):
+        n, g = self.nnet, self.gnn
+        p = _lib.TTTParams(ptr(n.conv1.weight), ptr(n.conv1.bias), ptr(n.conv2.weight), ptr(n.conv2.bias),
+                           ptr(n.conv3.weight), ptr(n.conv3.bias), ptr(n.fc1.weight), ptr(n.fc1.bias),
+                           ptr(n.fc_policy.weight), ptr(n.fc_policy.bias), ptr(n.fc2.weight), ptr(n.fc2.bias),
+                           ptr(n.fc_value.weight), ptr(n.fc_value.bias))
+        if g is not None:
+            ot = g.output_transform
+            p.ot0_w, p.ot0_b, p.ot2_w, p.ot2_b = ptr(ot[0].weight), ptr(ot[0].bias), ptr(ot[2].weight), ptr(ot[2].bias)
+        return p
+
+    def forward_states(self, states, eval_mask=None):
+        eval_mask = self._default_mask() if eval_mask is None else eval_mask
+        if (eval_mask & _lib.EVAL_GNN) and self.gnn is None:
+            raise RuntimeError("predict_with_gnn needs the GNN wrapper")
+        B = int(states.shape[0])
+        o = self._outputs(B, eval_mask)
+        p = self._params()
+        ws = self._workspace(self.lib.azg_ttt_workspace_bytes(self.n, B, eval_mask))
+        _lib.check(self.lib.azg_ttt_forward(C.byref(p), self.n, ptr(states), B, eval_mask, ptr(o.get("pi")), ptr(o.get("v")),
+                                            ptr(o.get("pi_gnn")), ptr(o.get("v_gnn")), ptr(ws), ws.numel(), stream()))
+        return o
+
+    def train(self, examples, gnn_examples=None):
+        from .training import train_two_player
+        train_two_player(self, examples, gnn_examples)
+
+
+class B200TicTacToeGNNWrapper(B200TicTacToeNNetWrapper):
+    has_gnn = True
+
+    def __init__(self, game, args):
+        super().__init__(game, args)
+        self._init_gnn(args, 128 * (self.n - 2) * (self.n - 2))  # TicTacToeGNN.py:15
+
+
+# ---------------------------------------------------------------------------------------- FrozenLake
+class B200FrozenLakeNet(_Base):
+    kind = "frozenlake"
+
+    def __init__(self, game, args):
+        self._common(game, args)
+        self.board_size = game.getBoardSize()
+        self.embedding_dim = arg(args, "embedding_dim", 64) or 64
+        self.layers = arg(args, "gnn_layers", 2)
+        self.layers = 2 if self.layers is None else self.layers
+        self.nnet = modules.FrozenLakeGraphNet(self.board_size, self.action_size, self.embedding_dim,
+                                               self.layers).to(self.device)
+        self.gnn = None
+
+    def forward_states(self, states, eval_mask=None):
+        n = self.nnet
+        L = self.layers
+        gw = (C.c_void_p * max(L, 1))(*[n.gnn_layers[l].W.weight.data_ptr() for l in range(L)])
+        gb = (C.c_void_p * max(L, 1))(*[n.gnn_layers[l].W.bias.data_ptr() for l in range(L)])
+        fe = n.feature_extractor
+        p = _lib.FLParams(ptr(fe[0].weight), ptr(fe[0].bias), ptr(fe[2].weight), ptr(fe[2].bias),
+                          C.cast(gw, C.POINTER(C.c_void_p)), C.cast(gb, C.POINTER(C.c_void_p)),
+                          ptr(n.policy_head.weight), ptr(n.policy_head.bias), ptr(n.value_head.weight),
+                          ptr(n.value_head.bias))
+        B = int(states.shape[0])
+        pi = torch.empty(B, 4, dtype=torch.float32, device=self.device)
+        v = torch.empty(B, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.azg_fl_forward(C.byref(p), self.n, self.embedding_dim, L, ptr(states), B, ptr(pi), ptr(v),
+                                           stream()))
+        return {"pi": pi, "v": v}
+
+    def predict(self, board, neighbor_states=None):
+        out = self.forward_states(self.states_from_boards(np.asarray(board)[None]))
+        return out["pi"].cpu().numpy()[0], out["v"].cpu().numpy()[0:1]  # v has shape (1,), FrozenLakeNet.py:226
+
+    def predict_with_gnn(self, board):
+        raise NotImplementedError("FrozenLake has no separate GNN wrapper (register.py:69-70)")
+
+    def train(self, examples):
+        from .training import train_frozenlake
+        train_frozenlake(self, examples)

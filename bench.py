@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- Connect4 GNN leaf evaluations/s (BASELINE.json metric, configs[1]).
+
+One *step* = one pass of the hot path over one batch of 65,536 synthetic Connect4 positions
+(7x7, the reference's only constructible geometry -- SURVEY.md section 8d): board encode ->
+conv trunk -> std heads + output_transform -> GNN heads, i.e. what MCTS.py:169-173 does per
+leaf (`predict` + `predict_with_gnn`) for the whole batch.
+
+  value      device-resident throughput (states already in HBM), CUDA events, max over ranks
+  e2e        same metric through the reference-facing API (`predict_batch`) with pinned HOST
+             boards in, host pi/v out -- H2D and D2H inside the timed region
+  roofline   dominant kernel (the two F x F output_transform contractions), timed live with
+             CUDA events on the launching stream (library phase hooks)
+  cpu_baseline  the oracle's restatement of the reference path (per-position B=1 torch calls,
+             all host threads) on a bounded sample, rank 0 only
+
+`--impl reference` times that CPU path alone (rank 0; other ranks exit).  N > 1: one process
+per GPU (torchrun), positions sharded, no data-path collective ("scaling": "weak").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BOARD = 7
+BATCH = 65536
+MFLOP_PER_LEAF = 41.29  # 20,642,720 MAC
+GEMM_FLOP_PER_LEAF = 2 * 2 * 3136 * 3136  # the two output_transform contractions
+
+
+class Args(dict):
+    __getattr__ = dict.__getitem__
+
+
+def reference_args():
+    return Args(lr=1e-3, dropout=0.3, epochs=20, batch_size=64, gnn_layers=2, use_gnn=True, numMCTSSims=10,
+                cpuct=1.0, expand_by=5, tempThreshold=15)
+
+
+def synthetic_boards(count, seed):
+    import numpy as np
+    return np.random.default_rng(seed).integers(-1, 2, size=(count, N_BOARD, N_BOARD)).astype(np.int8)
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+def cpu_leaf_evals(sample, threads=None):
+    """Oracle restatement of the reference leaf evaluation, driven as MCTS.py:169-173 drives it:
+    one `predict` + one `predict_with_gnn` per position (B=1), torch CPU with all host threads."""
+    import numpy as np
+    import torch
+    from oracle import nets as onets
+    from azgnn_b200 import modules
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    nnet = modules.Connect4Trunk(N_BOARD, N_BOARD + 1)
+    gnn = modules.PolicyValueGNN(64 * N_BOARD * N_BOARD, 2)
+    p, q = dict(nnet.state_dict()), dict(gnn.state_dict())
+    boards = synthetic_boards(sample + 8, 1).astype(np.int64)
+
+    def leaf(b):
+        bt = onets.boards_to_tensor(b[None])
+        with torch.no_grad():
+            onets.c4_predict(p, bt, N_BOARD)
+            onets.c4_predict_with_gnn(p, q, bt, N_BOARD)
+    for b in boards[:8]:
+        leaf(b)
+    t0 = time.perf_counter()
+    for b in boards[8:]:
+        leaf(b)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt, torch.get_num_threads()
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    sample = 256
+    for _ in range(args.warmup):
+        cpu_leaf_evals(32)
+    rates, t_total, cores = [], 0.0, 1
+    for _ in range(args.steps):
+        r, dt, cores = cpu_leaf_evals(sample)
+        rates.append(r)
+        t_total += dt
+    value = sample * args.steps / t_total
+    line = {"impl": "reference", "metric": "connect4_gnn_leaf_evals_per_s", "value": value, "unit": "leaf_evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "connect4_7x7_gnn_leaf_eval_per_position_b1", "positions_per_step": sample,
+                       "board": "7x7", "use_gnn": True},
+            "cpu_baseline": {"value": value, "unit": "leaf_evals/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} positions per step, predict + predict_with_gnn per position (B=1), "
+                                       "oracle/nets.py on torch CPU"},
+            "e2e": {"value": value, "unit": "leaf_evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        import statistics
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from azgnn_b200 import _lib
+    from azgnn_b200.nets import B200Connect4GNNWrapper
+    from azgnn_b200.games import Connect4Game
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    a = reference_args()
+    a["b200_precision"] = args.precision
+    torch.manual_seed(0)
+    net = B200Connect4GNNWrapper(Connect4Game(N_BOARD), a)
+    mask = _lib.EVAL_STD | _lib.EVAL_GNN
+    B = args.batch
+    n_rot = 4  # rotate distinct input batches; the ~GBs of per-step intermediates sweep the 126 MB L2 anyway
+    host_boards = [torch.from_numpy(synthetic_boards(B, 100 + rank * 16 + i)).pin_memory() for i in range(n_rot)]
+    dev_states = [net.states_from_boards(hb) for hb in host_boards]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        return net.forward_states(dev_states[i % n_rot], mask)
+
+    out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in step_device(0).items()}
+
+    def step_e2e(i):
+        states = net.states_from_boards(host_boards[i % n_rot])  # H2D + pack on the device
+        o = net.forward_states(states, mask)
+        for k, v in o.items():
+            out_host[k].copy_(v, non_blocking=True)  # D2H
+        torch.cuda.current_stream().synchronize()  # the caller reads pi/v on the host
+
+    for i in range(max(args.warmup, 3)):
+        step_device(i)
+    barrier()
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, phase timing on ----
+    lib.azg_timing_enable(1)
+    launches0 = lib.azg_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            step_device(i)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.azg_launch_count() - launches0
+    phase = {}
+    for pid, name in ((0, "trunk"), (1, "gemm"), (2, "heads")):
+        tot, cnt = C.c_double(), C.c_int()
+        _lib.check(lib.azg_timing_read(pid, C.byref(tot), C.byref(cnt)))
+        phase[name] = (tot.value, cnt.value)
+    lib.azg_timing_enable(0)
+
+    # ---- end-to-end through the host-facing API ----
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_src = "measured" if peaks else "fallback"
+        bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0) if peaks else 1400.0
+        total = B * args.steps * world
+        value = total / (ms / 1e3)
+        gemm_ms, gemm_cnt = phase["gemm"]
+        gemm_tflops = (GEMM_FLOP_PER_LEAF * B * gemm_cnt) / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        # fp32 FFMA path: the relevant ceiling is the CUDA-core FFMA rate, reported as a note; the
+        # roofline entry always uses the measured bf16 tensor peak (the path's real ceiling).
+        roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
+                "frac": (gemm_tflops / bf16_peak) if gemm_tflops else None, "traffic": None,
+                "peak_source": peak_src + " (bf16_tflops_sustained)",
+                "kernel": "output_transform F x F contractions (2 launches per step)",
+                "kernel_ms_per_step": gemm_ms / max(gemm_cnt, 1),
+                "phase_ms_per_step": {k: v[0] / args.steps for k, v in phase.items()}}
+        cpu_rate, cpu_dt, cores = cpu_leaf_evals(args.cpu_sample)
+        line = {"metric": "connect4_gnn_leaf_evals_per_s", "value": value, "unit": "leaf_evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "bf16x3": "f32 (3xbf16 split, f32 accumulate)", "bf16": "bf16 (f32 accumulate)"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": "connect4_7x7_gnn_leaf_eval_batch_65536", "positions_per_step_per_gpu": B,
+                           "board": "7x7 (reference geometry; 6x7 is not constructible, SURVEY 8d)", "use_gnn": True,
+                           "eval": "predict + predict_with_gnn (shared trunk)", "weights": "random-init seed 0",
+                           "precision": args.precision,
+                           "l2": "4 rotating input batches; per-step intermediates (>2 GB) exceed the 126 MB L2"},
+                "tflops_algorithmic": value * MFLOP_PER_LEAF * 1e6 / 1e12,
+                "roofline": roof,
+                "cpu_baseline": {"value": cpu_rate, "unit": "leaf_evals/s", "cores": cores, "kind": "port",
+                                 "sample": f"{args.cpu_sample} positions, predict + predict_with_gnn per position "
+                                           f"(B=1) as MCTS.py:169-173, {cpu_dt:.1f} s"},
+                "e2e": {"value": total / (ms_e2e / 1e3), "unit": "leaf_evals/s",
+                        "h2d_bytes_per_step": int(B * N_BOARD * N_BOARD),
+                        "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_host.values())),
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "clocks": clocks.summary()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--cpu-sample", type=int, default=4096)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun, one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

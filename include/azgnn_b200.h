@@ -1,0 +1,205 @@
+/* azgnn_b200.h -- C ABI of libazgnn_b200.so (sm_100a only).
+ *
+ * The reference (andrpac/alphazero-gnn) is pure Python and has no FFI; its seam for this
+ * hot path is the duck-typed NeuralNet / MCTS surface.  Every entry
+ * point below names the reference call it replaces.  Conventions:
+ *   - plain C: pointers + sizes, no C++/torch types; all data pointers are DEVICE pointers
+ *     to caller-owned memory unless a parameter says "host";
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = AZG_OK; otherwise azg_last_error() describes the failure
+ *     (the Python wrappers raise RuntimeError -- no silent fallbacks, cf. MCTS.py:195-200);
+ *   - the library keeps no global mutable state except the thread-local error string;
+ *     an arena handle is thread-compatible (one user at a time).
+ *
+ * Position format ("state"): two uint64 per position, {mine, theirs}, canonical form
+ * (player to move = +1, Connect4Game.py:185-187).  Bit x*n + y is cell board[x][y] of the
+ * reference's n x n int64 array (Connect4: x = column, y = row from the bottom,
+ * Connect4Game.py:18-22; TicTacToe: action a = x*n + y, TicTacToeGame.py:153).
+ * FrozenLake: mine = agent cell index r*n + c, theirs = 0 (FrozenLakeGame.py:197-202).
+ */
+#ifndef AZGNN_B200_H
+#define AZGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZG_ABI_VERSION 1
+
+#define AZG_OK 0
+#define AZG_ERR_INVALID 1   /* bad argument */
+#define AZG_ERR_CUDA 2      /* CUDA runtime error (message in azg_last_error) */
+#define AZG_ERR_DEVICE 3    /* not an sm_100 device / no device */
+#define AZG_ERR_CAPACITY 4  /* arena node table full */
+
+#define AZG_GAME_CONNECT4 0
+#define AZG_GAME_TICTACTOE 1
+#define AZG_GAME_FROZENLAKE 2
+
+/* which predictions to produce (MCTS.py:169-178 evaluates both when use_gnn) */
+#define AZG_EVAL_STD 1 /* NeuralNet.predict            */
+#define AZG_EVAL_GNN 2 /* NeuralNet.predict_with_gnn   */
+
+/* arithmetic of the dense F x F contractions (output_transform, gnn_utils.py:99-103) */
+#define AZG_PREC_FP32 0   /* fp32 FFMA on CUDA cores                                  */
+#define AZG_PREC_BF16X3 1 /* tcgen05 kind::f16, 3-term bf16 split, fp32 accumulate    */
+#define AZG_PREC_BF16 2   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate        */
+
+/* value type tags (NumPy>=2 / NEP 50 semantics of MCTS.py:228-233) */
+#define AZG_TAG_NONE (-1) /* edge not in Qsa            */
+#define AZG_TAG_F32 0     /* numpy.float32              */
+#define AZG_TAG_PYFLOAT 1 /* Python float (binary64)    */
+#define AZG_TAG_PYINT 2   /* Python int                 */
+
+typedef void* azg_stream; /* cudaStream_t */
+
+const char* azg_last_error(void);
+int azg_abi_version(void);
+/* host out-params; fails with AZG_ERR_DEVICE when the current device is not compute 10.x */
+int azg_device_info(int* cc_major, int* cc_minor, int* sm_count);
+
+/* measurement hooks (bench.py): number of kernels this library has launched so far, and optional
+ * CUDA-event timing of the phases of a forward call on the launching stream.  phase: 0 trunk
+ * (encode + convolutions), 1 dense F x F contractions, 2 heads, 3 arena kernels. */
+unsigned long long azg_launch_count(void);
+int azg_timing_enable(int on); /* also clears the records */
+int azg_timing_read(int phase, double* total_ms, int* records);
+
+/* ---------------------------------------------------------------- K1: encode ------------ */
+/* cells [B, n*n] with values {-1,0,1} -> states [B,2].  cell_dtype selects the element type of
+ * `cells` (the reference keeps boards as int64, Connect4Game.py:129-132; FrozenLake as float64
+ * one-hot, FrozenLakeGame.py:76-78, for which the state is the arg-max cell).  Replaces the
+ * per-call numpy->tensor hop torch.FloatTensor(board.astype(np.float64)) (Connect4GNN.py:71-72). */
+#define AZG_CELL_I8 0
+#define AZG_CELL_I64 1
+#define AZG_CELL_F32 2
+#define AZG_CELL_F64 3
+int azg_pack_boards(const void* cells, int cell_dtype, int n, int64_t B, uint64_t* states, azg_stream stream);
+/* states [B,2] -> fp32 planes [B, n*n] in {-1,0,1}: the network input of
+ * Connect4Net.forward (Connect4Net.py:42) / TicTacToeNet.forward (TicTacToeNet.py:30). */
+int azg_encode_planes(const uint64_t* states, int n, int64_t B, float* planes, azg_stream stream);
+/* FrozenLake graph build of FrozenLakeNet.predict (FrozenLakeNet.py:197-213): node 0 = the
+ * state, nodes 1..k = successors of the valid actions; writes one-hot node features
+ * [B,5,n*n] (unused nodes zero) and the node count [B] (3..5). */
+int azg_fl_encode_graph(const uint64_t* states, int n, int64_t B, float* nodes, int32_t* counts,
+                        azg_stream stream);
+
+/* ---------------------------------------------------------------- K2: forward ----------- */
+/* Connect4 (connect4/Connect4Net.py:18-60, connect4/Connect4GNN.py:31-120).  fp32 tensors in
+ * the reference's own layouts (Conv2d [Cout,Cin,3,3], Linear [out,in]). */
+typedef struct azg_c4_params {
+  const float *conv1_w, *conv1_b;         /* [32,1,3,3], [32]   */
+  const float *conv2_w, *conv2_b;         /* [64,32,3,3], [64]  */
+  const float *fc_policy_w, *fc_policy_b; /* [n+1, 64 n^2], [n+1] */
+  const float *fc_value_w, *fc_value_b;   /* [1, 64 n^2], [1]   */
+  const float *ot0_w, *ot0_b;             /* gnn.output_transform.0: [F,F], [F] (may be NULL without AZG_EVAL_GNN) */
+  const float *ot2_w, *ot2_b;             /* gnn.output_transform.2: [F,F], [F] */
+  const void* ot_packed;                  /* azg_c4_pack_gnn output for AZG_PREC_BF16X3/BF16, else NULL */
+} azg_c4_params;
+
+size_t azg_c4_workspace_bytes(int n, int64_t B, int eval_mask, int prec);
+/* Batched Connect4GNNWrapper.predict (+ predict_with_gnn): every row has the reference's B=1
+ * semantics (each GNNLayer is the identity at B=1, gnn_utils.py:35-36).  Outputs: pi [B,n+1]
+ * (= exp(log_softmax)), v [B] (= tanh).  Output pointers for a prediction not in eval_mask
+ * may be NULL. */
+int azg_c4_forward(const azg_c4_params* p, int n, const uint64_t* states, int64_t B, int eval_mask,
+                   int prec, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn,
+                   void* workspace, size_t workspace_bytes, azg_stream stream);
+/* Re-tile output_transform weights into the tcgen05 operand images (call after every
+ * optimizer step / load_checkpoint). */
+size_t azg_c4_packed_bytes(int n, int prec);
+int azg_c4_pack_gnn(const float* ot0_w, const float* ot2_w, int n, int prec, void* packed,
+                    size_t packed_bytes, azg_stream stream);
+
+/* TicTacToe (tictactoe/TicTacToeNet.py:16-48, tictactoe/TicTacToeGNN.py:25-87) */
+typedef struct azg_ttt_params {
+  const float *conv1_w, *conv1_b, *conv2_w, *conv2_b, *conv3_w, *conv3_b; /* 1->32->64->128 */
+  const float *fc1_w, *fc1_b, *fc_policy_w, *fc_policy_b;                 /* F->512->n^2+1 */
+  const float *fc2_w, *fc2_b, *fc_value_w, *fc_value_b;                   /* F->512->1     */
+  const float *ot0_w, *ot0_b, *ot2_w, *ot2_b;                             /* F->F->F       */
+} azg_ttt_params;
+size_t azg_ttt_workspace_bytes(int n, int64_t B, int eval_mask);
+int azg_ttt_forward(const azg_ttt_params* p, int n, const uint64_t* states, int64_t B, int eval_mask,
+                    float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* workspace,
+                    size_t workspace_bytes, azg_stream stream);
+
+/* FrozenLake (frozenlake/FrozenLakeNet.py:178-230 predict, :297-334 EnhancedNNet.forward) */
+typedef struct azg_fl_params {
+  const float *fe0_w, *fe0_b; /* feature_extractor.0: [128, n^2] */
+  const float *fe2_w, *fe2_b; /* feature_extractor.2: [E, 128]   */
+  const float* const* gnn_w;  /* host array of `layers` device pointers, each [E,E] */
+  const float* const* gnn_b;  /* host array of `layers` device pointers, each [E]   */
+  const float *policy_w, *policy_b; /* [4,E] */
+  const float *value_w, *value_b;   /* [1,E] */
+} azg_fl_params;
+int azg_fl_forward(const azg_fl_params* p, int n, int embedding_dim, int layers, const uint64_t* states,
+                   int64_t B, float* pi, float* v, azg_stream stream);
+
+/* generic dense layer on device tensors: C[M,N] = act(A[M,K] . W[N,K]^T + bias), fp32 FFMA.
+ * (torch.nn.functional.linear as used throughout the reference nets.) relu: 0/1. */
+int azg_linear_f32(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,
+                   int relu, azg_stream stream);
+
+/* ---------------------------------------------------------------- K4: search arena ------ */
+/* A GPU-resident set of n_games independent transposition tables, one per game, holding what
+ * MCTS.__init__ keeps in Qsa/Nsa/Ns/Ps/Es/Vs (MCTS.py:15-21).  Simulations within one game are
+ * strictly sequential (bit-exact statistics); games advance in lock step. */
+typedef struct azg_arena azg_arena;
+
+/* bytes of device memory the caller must provide to azg_arena_create */
+size_t azg_arena_bytes(int game, int n, int n_games, int capacity_nodes, int max_depth);
+/* fl_map: host pointer to n*n map characters ('S','F','H','G') for AZG_GAME_FROZENLAKE, else NULL.
+ * max_depth: a search call entered at depth >= max_depth returns Python-int 0 (cycle policy for
+ * single-player games; never reached in two-player games when > n*n+1). */
+int azg_arena_create(azg_arena** out, int game, int n, int n_games, int capacity_nodes, int max_depth,
+                     double cpuct, void* device_mem, size_t device_bytes, const uint8_t* fl_map,
+                     azg_stream stream);
+int azg_arena_destroy(azg_arena* a);
+int azg_arena_action_size(const azg_arena* a);
+/* new MCTS object for the listed games (Coach.py:96): clear their tables.  game_ids: device
+ * int32 [count], or NULL = all games. */
+int azg_arena_reset(azg_arena* a, const int32_t* game_ids, int count, azg_stream stream);
+/* canonical root positions of every game, states [n_games,2] */
+int azg_arena_set_roots(azg_arena* a, const uint64_t* states, azg_stream stream);
+int azg_arena_get_roots(azg_arena* a, uint64_t* states, azg_stream stream);
+/* grant every game `n_sims` more MCTS.search calls from its root (MCTS.py:33-34) */
+int azg_arena_begin(azg_arena* a, int n_sims, azg_stream stream);
+/* MCTS.search descend phase (MCTS.py:151-226) for every game with simulations left: runs
+ * searches until one reaches an unexpanded non-terminal leaf (searches that end on a terminal
+ * state are backed up immediately, MCTS.py:154-157).  Writes leaf_states [n_games,2] and
+ * leaf_mask [n_games] (1 = this game waits for a prediction of leaf_states[g]). */
+int azg_arena_select(azg_arena* a, uint64_t* leaf_states, int32_t* leaf_mask, azg_stream stream);
+/* MCTS.search leaf + backup phase (MCTS.py:162-193, 228-240) for games with leaf_mask set:
+ * pi [n_games,A] fp32 and v [n_games] fp32 are the predictions for leaf_states. */
+int azg_arena_expand_backup(azg_arena* a, const float* pi, const float* v, azg_stream stream);
+/* root edge statistics for getActionProb / expand_tree (MCTS.py:36-37, 79-81, 121-143):
+ * N [n_games,A] int32, Q [n_games,A] float64, qtag [n_games,A] int8 (AZG_TAG_*). */
+int azg_arena_root_stats(azg_arena* a, int32_t* N, double* Q, int8_t* qtag, azg_stream stream);
+/* play actions[g] (Coach.py:63-66): root <- canonical(next(root, a)); ended [n_games] float64 =
+ * getGameEnded of the new root for the player to move (0 = running); ended_tag as AZG_TAG_*.
+ * actions[g] < 0 leaves game g untouched. */
+int azg_arena_advance(azg_arena* a, const int32_t* actions, double* ended, int8_t* ended_tag,
+                      azg_stream stream);
+/* sticky per-game error flags (0 = fine, AZG_ERR_CAPACITY ...), int32 [n_games] */
+int azg_arena_status(azg_arena* a, int32_t* status, azg_stream stream);
+/* test read-back of one game's table (the reference's public dicts): returns the node count via
+ * host pointer n_nodes (synchronises `stream`).  Arrays are sized for capacity_nodes rows:
+ * keys [cap,2] u64, es [cap] f64 (0 = not ended), es_tag [cap] i8, ns [cap] i32 (-1 = not in Ns/Ps),
+ * valids [cap] u32 bit mask (Vs), ptag [cap] i8 (dtype of Ps[s]: 0 float64, 1 float32), P [cap,A] f64, Q [cap,A] f64, qtag [cap,A] i8, N [cap,A] i32. */
+int azg_arena_export(azg_arena* a, int game_index, int* n_nodes, uint64_t* keys, double* es, int8_t* es_tag,
+                     int32_t* ns, uint32_t* valids, int8_t* ptag, double* P, double* Q, int8_t* qtag, int32_t* N,
+                     azg_stream stream);
+
+/* rules as the arena applies them, exposed for parity tests against
+ * Connect4Game.py:143-187 / TicTacToeGame.py:145-183 / FrozenLakeGame.py:88-187.
+ * valids [B] u32 masks, ended [B] f64 (+tags), next [B,A,2] canonical successor states. */
+int azg_rules_eval(int game, int n, const uint8_t* fl_map_host, const uint64_t* states, int64_t B,
+                   uint32_t* valids, double* ended, int8_t* ended_tag, uint64_t* next, azg_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZGNN_B200_H */

@@ -1,0 +1,150 @@
+"""K1/K2 parity on the GPU: CUDA forward of the three games' networks vs the torch-fp32 oracle
+(oracle/nets.py) and vs the committed golden outputs of the reference itself.
+
+Tolerances (north_star): 1e-5 absolute on pi and v for the fp32 path; the tcgen05 paths state
+their own below."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets as onets
+from oracle import rules as orules
+
+from azgnn_b200 import _lib
+from azgnn_b200.mcts import pack_states
+from azgnn_b200.nets import (B200Connect4GNNWrapper, B200FrozenLakeNet, B200TicTacToeGNNWrapper)
+from helpers import dotdict, golden
+
+pytestmark = pytest.mark.gpu
+TOL = dict(rtol=0, atol=1e-5)
+
+
+def _args(**kw):
+    return dotdict(dict(dict(lr=1e-3, dropout=0.3, epochs=1, batch_size=64, gnn_layers=2, use_gnn=True), **kw))
+
+
+def _wrapper(kind, n, **kw):
+    game = (orules.Connect4Rules if kind == "c4" else orules.TicTacToeRules)(n)
+    torch.manual_seed(0)  # same construction order as the reference -> the golden weights
+    return (B200Connect4GNNWrapper if kind == "c4" else B200TicTacToeGNNWrapper)(game, _args(**kw))
+
+
+def _cpu_sd(m):
+    return {k: v.detach().cpu() for k, v in m.state_dict().items()}
+
+
+@pytest.mark.parametrize("kind,n", [("c4", 5), ("c4", 7), ("ttt", 3), ("ttt", 4)])
+def test_golden_outputs_of_the_reference(kind, n):
+    g = golden(f"nets_{kind}_{n}")
+    w = _wrapper(kind, n)
+    out = w.predict_batch(g["boards"])
+    np.testing.assert_allclose(out["pi"], g["pi"], **TOL)
+    np.testing.assert_allclose(out["v"], g["v"], **TOL)
+    np.testing.assert_allclose(out["pi_gnn"], g["gnn_pi"], **TOL)
+    np.testing.assert_allclose(out["v_gnn"], g["gnn_v"], **TOL)
+    # reference-facing single-position calls return the reference's types
+    pi, v = w.predict(g["boards"][0])
+    assert pi.dtype == np.float32 and pi.shape == (w.action_size,) and isinstance(v, np.float32)
+    np.testing.assert_allclose(pi, g["pi"][0], **TOL)
+    gpi, gv = w.predict_with_gnn(g["boards"][0])
+    np.testing.assert_allclose(gpi, g["gnn_pi"][0], **TOL)
+    assert abs(float(gv) - float(g["gnn_v"][0])) <= 1e-5
+
+
+@pytest.mark.parametrize("kind,n,B", [("c4", 7, 1), ("c4", 7, 333), ("c4", 7, 4096), ("c4", 4, 130), ("c4", 8, 257),
+                                      ("ttt", 3, 1000), ("ttt", 4, 1000), ("ttt", 5, 129)])
+def test_forward_matches_oracle(kind, n, B):
+    w = _wrapper(kind, n)
+    rng = np.random.default_rng(B + n)
+    boards = rng.integers(-1, 2, size=(B, n, n)).astype(np.int64)
+    out = w.predict_batch(boards)
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    bt = onets.boards_to_tensor(boards)
+    with torch.no_grad():
+        if kind == "c4":
+            pi, v = onets.c4_predict(p, bt, n)
+            gpi, gv = onets.c4_predict_with_gnn(p, q, bt, n)
+        else:
+            pi, v = onets.ttt_predict(p, bt, n)
+            gpi, gv = onets.ttt_predict_with_gnn(p, q, bt, n)
+    np.testing.assert_allclose(out["pi"], pi.numpy(), **TOL)
+    np.testing.assert_allclose(out["v"], v.numpy(), **TOL)
+    np.testing.assert_allclose(out["pi_gnn"], gpi.numpy(), **TOL)
+    np.testing.assert_allclose(out["v_gnn"], gv.numpy(), **TOL)
+    assert np.allclose(out["pi"].sum(1), 1, atol=1e-5)
+
+
+def test_input_dtypes_and_empty_batch():
+    w = _wrapper("c4", 7)
+    rng = np.random.default_rng(1)
+    boards = rng.integers(-1, 2, size=(64, 7, 7))
+    ref = w.predict_batch(boards.astype(np.int64))
+    for dt in (np.int8, np.float32, np.float64):
+        out = w.predict_batch(boards.astype(dt))
+        assert np.array_equal(out["pi_gnn"], ref["pi_gnn"])
+    pinned = torch.from_numpy(boards.astype(np.int8)).pin_memory()
+    assert np.array_equal(w.predict_batch(pinned)["v_gnn"], ref["v_gnn"])
+    empty = w.predict_batch(np.zeros((0, 7, 7), dtype=np.int64))
+    assert empty["pi"].shape == (0, 8)
+
+
+def test_encode_planes_and_pack_round_trip():
+    """K1: states -> planes equals the reference's float tensor of the board (Connect4GNN.py:71-72)."""
+    lib = _lib.lib()
+    rng = np.random.default_rng(3)
+    for n in (3, 4, 7, 8):
+        B = 1000
+        boards = rng.integers(-1, 2, size=(B, n, n)).astype(np.int64)
+        dev = torch.device("cuda")
+        cells = torch.from_numpy(boards).to(dev)
+        states = torch.empty(B, 2, dtype=torch.int64, device=dev)
+        _lib.check(lib.azg_pack_boards(_lib.ptr(cells), _lib.CELL_I64, n, B, _lib.ptr(states), _lib.stream()))
+        assert np.array_equal(states.cpu().numpy(), pack_states("connect4", boards))
+        planes = torch.empty(B, n * n, dtype=torch.float32, device=dev)
+        _lib.check(lib.azg_encode_planes(_lib.ptr(states), n, B, _lib.ptr(planes), _lib.stream()))
+        assert np.array_equal(planes.cpu().numpy().reshape(B, n, n), boards.astype(np.float32))
+
+
+@pytest.mark.parametrize("n,layers", [(4, 2), (4, 3), (8, 2), (8, 3)])
+def test_frozenlake_forward(n, layers):
+    g = golden(f"nets_fl_{n}_L{layers}")
+    game = orules.FrozenLakeRules(n)
+    torch.manual_seed(0)
+    w = B200FrozenLakeNet(game, dotdict(dict(lr=1e-3, embedding_dim=128, gnn_layers=layers)))
+    cells = g["cells"]
+    states = np.zeros((len(cells), 2), dtype=np.int64)
+    states[:, 0] = cells
+    out = w.forward_states(torch.from_numpy(states).cuda())
+    np.testing.assert_allclose(out["pi"].cpu().numpy(), g["pi"], **TOL)
+    np.testing.assert_allclose(out["v"].cpu().numpy(), g["v"][:, 0], **TOL)
+    b = np.zeros((n, n)); b[0, 0] = 1
+    pi, v = w.predict(b)
+    assert v.shape == (1,) and v.dtype == np.float32  # FrozenLakeNet.py:226
+    # K1 graph build (FrozenLakeNet.py:197-213)
+    lib = _lib.lib()
+    st = torch.from_numpy(states).cuda()
+    nodes = torch.empty(len(cells), 5, n * n, dtype=torch.float32, device="cuda")
+    counts = torch.empty(len(cells), dtype=torch.int32, device="cuda")
+    _lib.check(lib.azg_fl_encode_graph(_lib.ptr(st), n, len(cells), _lib.ptr(nodes), _lib.ptr(counts), _lib.stream()))
+    for i, cell in enumerate(cells):
+        want = onets.fl_node_cells(int(cell), n)
+        assert int(counts[i]) == len(want)
+        got = nodes[i].cpu().numpy()
+        for j, c in enumerate(want):
+            assert got[j].argmax() == c and got[j].sum() == 1
+        assert got[len(want):].sum() == 0
+
+
+def test_checkpoint_round_trip(tmp_path):
+    w = _wrapper("c4", 5)
+    w.save_checkpoint(str(tmp_path), "best_gnn.pth.tar")
+    ck = torch.load(str(tmp_path / "best_gnn.pth.tar"), map_location="cpu")
+    assert set(ck.keys()) == {"state_dict", "gnn"}  # Connect4GNN.py:205-208
+    assert "conv1.weight" in ck["state_dict"] and "output_transform.0.weight" in ck["gnn"]
+    b = np.random.default_rng(0).integers(-1, 2, size=(8, 5, 5))
+    before = w.predict_batch(b)
+    torch.manual_seed(123)
+    w2 = B200Connect4GNNWrapper(orules.Connect4Rules(5), _args())
+    w2.load_checkpoint(str(tmp_path), "best_gnn.pth.tar")
+    after = w2.predict_batch(b)
+    assert np.array_equal(before["pi_gnn"], after["pi_gnn"])
