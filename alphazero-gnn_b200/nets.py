@@ -64,6 +64,8 @@ class _Base:
         t = t.to(self.device, non_blocking=True).contiguous()
         B = t.shape[0]
         states = torch.empty(B, 2, dtype=torch.int64, device=self.device)
+        if B == 0:
+            return states
         _lib.check(self.lib.azg_pack_boards(ptr(t), _CELL[t.dtype], self.n, B, ptr(states), stream()))
         return states
 
@@ -168,6 +170,8 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         prec = self.precision if precision is None else precision
         B = int(states.shape[0])
         o = self._outputs(B, eval_mask)
+        if B == 0:
+            return o
         p = self._params(bool(eval_mask & _lib.EVAL_GNN) and prec != _lib.PREC_FP32)
         nbytes = self.lib.azg_c4_workspace_bytes(self.n, B, eval_mask, prec)
         ws = self._workspace(nbytes)
@@ -215,6 +219,8 @@ class B200TicTacToeNNetWrapper(_TwoPlayer):
             raise RuntimeError("predict_with_gnn needs the GNN wrapper")
         B = int(states.shape[0])
         o = self._outputs(B, eval_mask)
+        if B == 0:
+            return o
         p = self._params()
         ws = self._workspace(self.lib.azg_ttt_workspace_bytes(self.n, B, eval_mask))
         _lib.check(self.lib.azg_ttt_forward(C.byref(p), self.n, ptr(states), B, eval_mask, ptr(o.get("pi")), ptr(o.get("v")),

@@ -114,6 +114,12 @@ size_t azg_c4_packed_bytes(int n, int prec);
 int azg_c4_pack_gnn(const float* ot0_w, const float* ot2_w, int n, int prec, void* packed,
                     size_t packed_bytes, azg_stream stream);
 
+/* One dense layer on the tcgen05 path, for parity tests of the GEMM in isolation:
+ * C[M,F] = act(A[M,F] . W[F,F]^T + bias), fp32 in/out, prec = AZG_PREC_BF16X3 | AZG_PREC_BF16.
+ * scratch: >= 2*(ceil(M/128)*128 + F)*F*2 + 1024 bytes (x3) or half of that (bf16). */
+int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int F, int prec,
+                  int relu, void* scratch, size_t scratch_bytes, azg_stream stream);
+
 /* TicTacToe (tictactoe/TicTacToeNet.py:16-48, tictactoe/TicTacToeGNN.py:25-87) */
 typedef struct azg_ttt_params {
   const float *conv1_w, *conv1_b, *conv2_w, *conv2_b, *conv3_w, *conv3_b; /* 1->32->64->128 */
