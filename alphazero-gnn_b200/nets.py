@@ -138,9 +138,9 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         self.nnet = modules.Connect4Trunk(self.n, self.action_size, 0.3 if dropout is None else dropout).to(self.device)
         self.gnn = None
         self.precision = _lib.PRECISIONS[arg(args, "b200_precision", "fp32") or "fp32"]
-        self._packed, self._packed_ok = None, False
+        self._packed, self._packed_ok = {}, False
 
-    def _params(self, need_packed):
+    def _params(self, prec, need_packed):
         n, g = self.nnet, self.gnn
         p = _lib.C4Params(ptr(n.conv1.weight), ptr(n.conv1.bias), ptr(n.conv2.weight), ptr(n.conv2.bias),
                           ptr(n.fc_policy.weight), ptr(n.fc_policy.bias), ptr(n.fc_value.weight), ptr(n.fc_value.bias))
@@ -148,19 +148,23 @@ class B200Connect4NNetWrapper(_TwoPlayer):
             ot = g.output_transform
             p.ot0_w, p.ot0_b, p.ot2_w, p.ot2_b = ptr(ot[0].weight), ptr(ot[0].bias), ptr(ot[2].weight), ptr(ot[2].bias)
             if need_packed:
-                p.ot_packed = ptr(self._ensure_packed())
+                p.ot_packed = ptr(self._ensure_packed(prec))
         return p
 
-    def _ensure_packed(self):
+    def _ensure_packed(self, prec):
+        """tcgen05 operand images of output_transform's weights, one blob per precision, rebuilt
+        lazily after weights_changed()."""
         if not self._packed_ok:
-            nbytes = self.lib.azg_c4_packed_bytes(self.n, self.precision)
-            if self._packed is None or self._packed.numel() != nbytes:
-                self._packed = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            ot = self.gnn.output_transform
-            _lib.check(self.lib.azg_c4_pack_gnn(ptr(ot[0].weight), ptr(ot[2].weight), self.n, self.precision,
-                                                ptr(self._packed), nbytes, stream()))
+            self._packed = {}
             self._packed_ok = True
-        return self._packed
+        if prec not in self._packed:
+            nbytes = self.lib.azg_c4_packed_bytes(self.n, prec)
+            blob = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            ot = self.gnn.output_transform
+            _lib.check(self.lib.azg_c4_pack_gnn(ptr(ot[0].weight), ptr(ot[2].weight), self.n, prec, ptr(blob), nbytes,
+                                                stream()))
+            self._packed[prec] = blob
+        return self._packed[prec]
 
     def forward_states(self, states, eval_mask=None, precision=None):
         """states: int64 [B,2] on the device.  Returns device tensors pi/v (+pi_gnn/v_gnn)."""
@@ -172,7 +176,7 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         o = self._outputs(B, eval_mask)
         if B == 0:
             return o
-        p = self._params(bool(eval_mask & _lib.EVAL_GNN) and prec != _lib.PREC_FP32)
+        p = self._params(prec, bool(eval_mask & _lib.EVAL_GNN) and prec != _lib.PREC_FP32)
         nbytes = self.lib.azg_c4_workspace_bytes(self.n, B, eval_mask, prec)
         ws = self._workspace(nbytes)
         _lib.check(self.lib.azg_c4_forward(C.byref(p), self.n, ptr(states), B, eval_mask, prec, ptr(o.get("pi")),

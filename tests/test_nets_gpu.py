@@ -148,3 +148,63 @@ def test_checkpoint_round_trip(tmp_path):
     w2.load_checkpoint(str(tmp_path), "best_gnn.pth.tar")
     after = w2.predict_batch(b)
     assert np.array_equal(before["pi_gnn"], after["pi_gnn"])
+
+
+# ------------------------------------------------------------------------------------ tcgen05 path
+def _tc_linear(A, W, b, prec, relu):
+    lib = _lib.lib()
+    M, F = A.shape
+    Mp = (M + 127) // 128 * 128
+    nbytes = (2 if prec == _lib.PREC_BF16X3 else 1) * (Mp + F) * F * 2 + 2048
+    scratch = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    C = torch.full((M, F), float("nan"), device="cuda")
+    _lib.check(lib.azg_tc_linear(_lib.ptr(A), _lib.ptr(W), _lib.ptr(b), _lib.ptr(C), M, F, prec, relu, _lib.ptr(scratch),
+                                 scratch.numel(), _lib.stream()))
+    return C
+
+
+@pytest.mark.parametrize("M,F", [(1, 1024), (128, 1024), (200, 3136), (1000, 1600), (4096, 3136)])
+@pytest.mark.parametrize("relu", [0, 1])
+def test_tc_linear(M, F, relu):
+    """The tensor-core dense layer vs a float64 reference.  bf16x3 (3-term split, fp32 accumulate)
+    keeps ~16 mantissa bits per operand: |err| <= 1e-4 at K = 3136 with O(1) outputs; plain bf16 is
+    compared against the same product of bf16-rounded operands (fp32 accumulation error only)."""
+    g = torch.Generator().manual_seed(M + F)
+    A = (torch.randn(M, F, generator=g) * 0.5).cuda()
+    W = ((torch.rand(F, F, generator=g) * 2 - 1) / F ** 0.5).cuda()
+    b = (torch.randn(F, generator=g) * 0.1).cuda()
+    ref = A.double() @ W.double().t() + b.double()
+    refb = A.bfloat16().double() @ W.bfloat16().double().t() + b.double()
+    if relu:
+        ref, refb = ref.clamp(min=0), refb.clamp(min=0)
+    c3 = _tc_linear(A, W, b, _lib.PREC_BF16X3, relu)
+    assert (c3.double() - ref).abs().max().item() <= 1e-4
+    c1 = _tc_linear(A, W, b, _lib.PREC_BF16, relu)
+    assert (c1.double() - refb).abs().max().item() <= 5e-5
+
+
+@pytest.mark.parametrize("n,B", [(7, 1), (7, 777), (7, 4096), (4, 300), (5, 300), (6, 300), (8, 300)])
+def test_forward_tensor_core_precisions(n, B):
+    """Connect4 GNN head on tcgen05: bf16x3 stays inside the fp32 contract (1e-5 on pi and v);
+    plain bf16 is the throughput mode with a stated tolerance of 5e-3 (random-init weights)."""
+    w = _wrapper("c4", n)
+    rng = np.random.default_rng(B + n)
+    boards = rng.integers(-1, 2, size=(B, n, n)).astype(np.int64)
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    with torch.no_grad():
+        gpi, gv = onets.c4_predict_with_gnn(p, q, onets.boards_to_tensor(boards), n)
+    states = w.states_from_boards(boards)
+    o3 = w.forward_states(states, _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
+    np.testing.assert_allclose(o3["pi_gnn"].cpu().numpy(), gpi.numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(o3["v_gnn"].cpu().numpy(), gv.numpy(), rtol=0, atol=1e-5)
+    o1 = w.forward_states(states, _lib.EVAL_GNN, precision=_lib.PREC_BF16)
+    e_pi = np.abs(o1["pi_gnn"].cpu().numpy() - gpi.numpy()).max()
+    e_v = np.abs(o1["v_gnn"].cpu().numpy() - gv.numpy()).max()
+    print(f"bf16 n={n} B={B}: max |dpi| = {e_pi:.2e}, max |dv| = {e_v:.2e}")
+    assert e_pi <= 5e-3 and e_v <= 5e-3
+    # re-tiling follows weight updates
+    with torch.no_grad():
+        w.gnn.output_transform[2].bias.add_(0.25)
+    w.weights_changed()
+    o3b = w.forward_states(states, _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
+    assert not np.allclose(o3b["v_gnn"].cpu().numpy(), o3["v_gnn"].cpu().numpy())
