@@ -467,7 +467,7 @@ int azg_c4_pack_gnn(const float* ot0_w, const float* ot2_w, int n, int prec, voi
   AZG_REQUIRE(ot0_w && ot2_w && packed, "azg_c4_pack_gnn: null pointer");
   AZG_REQUIRE(BN != 0 && (prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16), "azg_c4_pack_gnn: unsupported n=%d prec=%d", n, prec);
   AZG_REQUIRE(packed_bytes >= azg_c4_packed_bytes(n, prec), "azg_c4_pack_gnn: buffer too small");
-  AZG_REQUIRE(((uintptr_t)packed & 1023) == 0, "azg_c4_pack_gnn: buffer must be 1024-byte aligned");
+  AZG_REQUIRE(((uintptr_t)packed & 15) == 0, "azg_c4_pack_gnn: buffer must be 16-byte aligned (bulk-copy source)");
   const bool x3 = prec == AZG_PREC_BF16X3;
   uint8_t* w = (uint8_t*)packed;
   const size_t wb = image_bytes(F);

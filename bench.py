@@ -273,10 +273,10 @@ def run_gpu_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-sample", type=int, default=4096)
     args = ap.parse_args()
