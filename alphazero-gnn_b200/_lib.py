@@ -31,6 +31,17 @@ class TTTParams(C.Structure):
                                    "ot0_w", "ot0_b", "ot2_w", "ot2_b")]
 
 
+_GNN_LAYER_FIELDS = ("att0_w", "att0_b", "att2_w", "att2_b", "upd0_w", "upd0_b", "upd2_w", "upd2_b", "gate_w", "gate_b")
+
+
+class GNNLayerParams(C.Structure):
+    _fields_ = [(k, _vp) for k in _GNN_LAYER_FIELDS]
+
+
+class GNNLayerGrads(C.Structure):
+    _fields_ = [(k, _vp) for k in _GNN_LAYER_FIELDS]
+
+
 class FLParams(C.Structure):
     _fields_ = [("fe0_w", _vp), ("fe0_b", _vp), ("fe2_w", _vp), ("fe2_b", _vp), ("gnn_w", C.POINTER(_vp)),
                 ("gnn_b", C.POINTER(_vp)), ("policy_w", _vp), ("policy_b", _vp), ("value_w", _vp), ("value_b", _vp)]
@@ -56,6 +67,16 @@ SIGNATURES = {
     "azg_ttt_forward": (_i, [C.POINTER(TTTParams), _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "azg_fl_forward": (_i, [C.POINTER(FLParams), _i, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "azg_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
+    "azg_gemm_f32": (_i, [_i, _i, _i64, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, C.c_float, _vp]),
+    "azg_mul_f32": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "azg_linear_backward": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "azg_conv3x3_relu_forward": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "azg_conv3x3_relu_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "azg_policy_value_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "azg_gnn_layer_saved_floats": (_sz, [_i, _i]),
+    "azg_gnn_layer_scratch_floats": (_sz, [_i, _i]),
+    "azg_gnn_layer_forward": (_i, [C.POINTER(GNNLayerParams), _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "azg_gnn_layer_backward": (_i, [C.POINTER(GNNLayerParams), _vp, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(GNNLayerGrads), _vp, _vp]),
     "azg_arena_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "azg_arena_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _d, _vp, _sz, C.c_char_p, _vp]),
     "azg_arena_destroy": (_i, [_vp]),

@@ -422,6 +422,13 @@ int azg_fl_encode_graph(const uint64_t* states, int n, int64_t B, float* nodes, 
   return AZG_OK;
 }
 
+int azg_conv3x3_relu_forward(const float* in, const float* w, const float* b, float* out, int64_t B, int Cin, int Cout,
+                             int H, int W, int pad, azg_stream stream) {
+  AZG_REQUIRE(in && w && b && out, "azg_conv3x3_relu_forward: null pointer");
+  if (B <= 0) return AZG_OK;
+  return launch_conv(in, w, b, out, B, Cin, Cout, H, W, pad, (cudaStream_t)stream);
+}
+
 int azg_linear_f32(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K, int relu,
                    azg_stream stream) {
   AZG_REQUIRE(A && W && C, "azg_linear_f32: null pointer");

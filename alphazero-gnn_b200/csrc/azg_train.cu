@@ -1,0 +1,475 @@
+// azg_train.cu -- K3: forward/backward pieces of the training step (fp32, CUDA cores).
+//
+//   Connect4GNNWrapper.train / TicTacToeGNNWrapper.train   connect4/Connect4GNN.py:122-197
+//   GNNLayer.forward at B > 1 (row 0 = target, rows 1.. = path states)   gnn_utils.py:34-74
+//   losses  -sum(pi*logp)/B + sum((v_t - v)^2)/B                          Connect4GNN.py:150-152
+//
+// The batch is 64 rows: every contraction here is either a skinny GEMM against a big weight
+// matrix or a rank-1 update of one, i.e. bound by streaming the 39-79 MB weight / gradient
+// tensors once (SURVEY section 8d "K3: HBM bound").  One generic tiled SGEMM with arbitrary
+// transposes and leading dimensions serves all of them; the rest are small fused element-wise
+// kernels.  torch.autograd.Function wrappers (training.py) only route tensors.
+#include "azg_common.cuh"
+
+namespace {
+
+inline int grid_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------ generic SGEMM
+// C[M,N] = op(A)[M,K] . op(B)[K,N] + beta * C     (row-major, leading dimensions lda/ldb/ldc)
+//   TA = 0: A is [M,K] (A[m*lda + k]);  TA = 1: A is [K,M] (A[k*lda + m])
+//   TB = 0: B is [K,N] (B[k*ldb + n]);  TB = 1: B is [N,K] (B[n*ldb + k])
+constexpr int GT = 64, GK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_generic_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda,
+                                                           const float* __restrict__ B, int64_t ldb, float* __restrict__ C,
+                                                           int64_t ldc, float beta) {
+  __shared__ float As[GK][GT + 4];
+  __shared__ float Bs[GK][GT + 4];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.y * GT;
+  const int n0 = blockIdx.x * GT;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m, k;
+      if (TA) { m = tid & 63; k = (tid >> 6) + 4 * i; } else { k = tid & 15; m = (tid >> 4) + 16 * i; }
+      const int64_t gm = m0 + m;
+      const int gk = k0 + k;
+      float v = 0.0f;
+      if (gm < M && gk < K) v = TA ? A[(int64_t)gk * lda + gm] : A[gm * lda + gk];
+      As[k][m] = v;
+      int n, kb;
+      if (TB) { kb = tid & 15; n = (tid >> 4) + 16 * i; } else { n = tid & 63; kb = (tid >> 6) + 4 * i; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      float w = 0.0f;
+      if (gn < N && gkb < K) w = TB ? B[(int64_t)gn * ldb + gkb] : B[(int64_t)gkb * ldb + gn];
+      Bs[kb][n] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = As[kk][ty * 4 + i];
+        b[i] = Bs[kk][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float* c = C + m * ldc + n;
+      *c = (beta == 0.0f) ? acc[i][j] : acc[i][j] + beta * (*c);
+    }
+  }
+}
+
+int gemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+         int64_t ldc, float beta, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return AZG_OK;
+  dim3 grid((N + GT - 1) / GT, (unsigned)((M + GT - 1) / GT));
+  AZG_REQUIRE(grid.y <= 65535, "gemm: M too large");
+  if (ta && tb) gemm_generic_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+  else if (ta) gemm_generic_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+  else if (tb) gemm_generic_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+  else gemm_generic_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+// ------------------------------------------------------------------------------ element-wise
+__global__ void mul_kernel(const float* a, const float* b, float* o, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] * b[i];
+}
+__global__ void relu_bwd_kernel(const float* dy, const float* y, float* dx, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = y[i] > 0.0f ? dy[i] : 0.0f;
+}
+__global__ void add_bias_act_kernel(float* x, const float* bias, int64_t rows, int cols, int relu) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  float v = x[i] + (bias ? bias[i % cols] : 0.0f);
+  x[i] = relu ? fmaxf(v, 0.0f) : v;
+}
+// out[c] = sum over rows of x[r, c] (bias gradients); one thread per column, fixed order
+__global__ void col_sum_kernel(const float* x, int64_t rows, int cols, int64_t ld, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.0f;
+  for (int64_t r = 0; r < rows; ++r) s += x[r * ld + c];
+  out[c] = s;
+}
+__global__ void axpy_kernel(float* y, const float* x, int64_t n) {  // y += x
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+
+// ------------------------------------------------------------------------------ conv backward
+// g = dout * (out > 0);  dw[co,ci,kx,ky] = sum_{b,ox,oy} g * in[b,ci,ox+kx-p,oy+ky-p];  db[co] = sum g
+__global__ void conv_bwd_weight_kernel(const float* __restrict__ in, const float* __restrict__ out,
+                                       const float* __restrict__ dout, float* __restrict__ dw, float* __restrict__ db,
+                                       int64_t B, int Cin, int Cout, int H, int W, int pad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  const int total = Cout * Cin * 9;
+  if (idx < total) {
+    const int co = idx / (Cin * 9), r = idx % (Cin * 9), ci = r / 9, kx = (r % 9) / 3, ky = r % 3;
+    float s = 0.0f;
+    for (int64_t b = 0; b < B; ++b)
+      for (int ox = 0; ox < Ho; ++ox) {
+        const int x = ox + kx - pad;
+        if (x < 0 || x >= H) continue;
+        for (int oy = 0; oy < Wo; ++oy) {
+          const int y = oy + ky - pad;
+          if (y < 0 || y >= W) continue;
+          const int64_t o = ((b * Cout + co) * Ho + ox) * Wo + oy;
+          if (out[o] > 0.0f) s = fmaf(dout[o], in[((b * Cin + ci) * H + x) * W + y], s);
+        }
+      }
+    dw[idx] = s;
+  } else if (idx < total + Cout) {
+    const int co = idx - total;
+    float s = 0.0f;
+    for (int64_t b = 0; b < B; ++b)
+      for (int p = 0; p < Ho * Wo; ++p) {
+        const int64_t o = (b * Cout + co) * Ho * Wo + p;
+        if (out[o] > 0.0f) s += dout[o];
+      }
+    db[co] = s;
+  }
+}
+
+// din[b,ci,x,y] = sum_{co,kx,ky} g[b,co,x-kx+p,y-ky+p] * w[co,ci,kx,ky]
+__global__ void conv_bwd_data_kernel(const float* __restrict__ w, const float* __restrict__ out,
+                                     const float* __restrict__ dout, float* __restrict__ din, int64_t B, int Cin, int Cout,
+                                     int H, int W, int pad) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Cin * H * W) return;
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  const int y = (int)(idx % W), x = (int)((idx / W) % H), ci = (int)((idx / ((int64_t)W * H)) % Cin);
+  const int64_t b = idx / ((int64_t)W * H * Cin);
+  float s = 0.0f;
+  for (int co = 0; co < Cout; ++co)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ox = x - kx + pad;
+      if (ox < 0 || ox >= Ho) continue;
+      for (int ky = 0; ky < 3; ++ky) {
+        const int oy = y - ky + pad;
+        if (oy < 0 || oy >= Wo) continue;
+        const int64_t o = ((b * Cout + co) * Ho + ox) * Wo + oy;
+        if (out[o] > 0.0f) s = fmaf(dout[o], w[((size_t)co * Cin + ci) * 9 + kx * 3 + ky], s);
+      }
+    }
+  din[idx] = s;
+}
+
+// ------------------------------------------------------------------------------ loss
+// one CTA; rows strided over threads; deterministic block reduction of the scalar loss
+__global__ void __launch_bounds__(256) policy_value_loss_kernel(const float* __restrict__ logits, const float* __restrict__ vraw,
+                                                                const float* __restrict__ tpi, const float* __restrict__ tv,
+                                                                int B, int A, float inv_norm, float* __restrict__ loss,
+                                                                float* __restrict__ logp, float* __restrict__ v,
+                                                                float* __restrict__ dlogits, float* __restrict__ dvraw) {
+  __shared__ float red[256];
+  float part = 0.0f;
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    const float* lg = logits + (size_t)r * A;
+    float m = -INFINITY;
+    for (int a = 0; a < A; ++a) m = fmaxf(m, lg[a]);
+    float s = 0.0f;
+    for (int a = 0; a < A; ++a) s += expf(lg[a] - m);
+    const float lse = logf(s);
+    float tsum = 0.0f, lpi = 0.0f;
+    for (int a = 0; a < A; ++a) {
+      const float lp = (lg[a] - m) - lse;
+      logp[(size_t)r * A + a] = lp;
+      tsum += tpi[(size_t)r * A + a];
+      lpi += tpi[(size_t)r * A + a] * lp;
+    }
+    for (int a = 0; a < A; ++a)  // d(-sum pi*logp / norm)/dlogit = (softmax * sum(pi) - pi) / norm
+      dlogits[(size_t)r * A + a] = (expf(logp[(size_t)r * A + a]) * tsum - tpi[(size_t)r * A + a]) * inv_norm;
+    const float vv = tanhf(vraw[r]);
+    v[r] = vv;
+    const float diff = tv[r] - vv;
+    dvraw[r] = -2.0f * diff * (1.0f - vv * vv) * inv_norm;
+    part += (-lpi + diff * diff) * inv_norm;
+  }
+  red[threadIdx.x] = part;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = red[0];
+}
+
+// ------------------------------------------------------------------------------ GNN layer pieces
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// h[i,:] = relu(S[i,:] + t0 + b0);  s[i] = sigmoid(h[i,:] . w2 + b2)     (one warp per path row)
+__global__ void att_scores_kernel(float* __restrict__ S, const float* __restrict__ t0, const float* __restrict__ b0,
+                                  const float* __restrict__ w2, const float* __restrict__ b2, int P, float* __restrict__ s) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= P) return;
+  float acc = 0.0f;
+  for (int j = lane; j < 128; j += 32) {
+    const float h = fmaxf(S[(size_t)row * 128 + j] + t0[j] + b0[j], 0.0f);
+    S[(size_t)row * 128 + j] = h;
+    acc = fmaf(h, w2[j], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s[row] = sigmoidf_(acc + b2[0]);
+}
+
+// alpha = s / sum(s) when the sum is positive (gnn_utils.py:58-59); single thread, fixed order
+__global__ void att_normalise_kernel(const float* s, int P, float* alpha, float* tot) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float t = 0.0f;
+  for (int i = 0; i < P; ++i) t += s[i];
+  tot[0] = t;
+  for (int i = 0; i < P; ++i) alpha[i] = t > 0.0f ? s[i] / t : s[i];
+}
+
+// gate = sigmoid(gpre) (in place);  out0 = f0 + gate * upd
+__global__ void gate_out_kernel(float* gate, const float* upd, const float* f0, float* out0, int F) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F) return;
+  const float g = sigmoidf_(gate[i]);
+  gate[i] = g;
+  out0[i] = f0[i] + g * upd[i];
+}
+
+__global__ void gate_bwd_kernel(const float* dout0, const float* gate, const float* upd, float* dgpre, float* dupd, int F) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F) return;
+  const float g = gate[i];
+  dgpre[i] = dout0[i] * upd[i] * g * (1.0f - g);
+  dupd[i] = dout0[i] * g;
+}
+
+// d_alpha -> d_z (pre-sigmoid attention logits); single thread
+__global__ void att_bwd_kernel(const float* dalpha, const float* s, const float* tot, int P, float* dz) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float t = tot[0];
+  float dot = 0.0f;
+  for (int i = 0; i < P; ++i) dot += dalpha[i] * s[i];
+  for (int i = 0; i < P; ++i) {
+    const float ds = t > 0.0f ? dalpha[i] / t - dot / (t * t) : dalpha[i];
+    dz[i] = ds * s[i] * (1.0f - s[i]);
+  }
+}
+
+// dhpre[i,j] = dz[i] * w2[j] * (h[i,j] > 0)
+__global__ void att_hidden_bwd_kernel(const float* dz, const float* w2, const float* h, int P, float* dhpre) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * 128) return;
+  dhpre[i] = h[i] > 0.0f ? dz[i / 128] * w2[i % 128] : 0.0f;
+}
+
+struct Bump {
+  float* p;
+  float* take(size_t n) {
+    float* r = p;
+    p += (n + 63) / 64 * 64;
+    return r;
+  }
+};
+
+// layout of the `saved` buffer of a layer forward (floats)
+struct LayerSaved {
+  float *t0, *h, *s, *alpha, *tot, *agg, *cat2, *gate, *u1, *upd;
+  static size_t carve(LayerSaved* L, float* base, int P, int F) {
+    Bump b{base};
+    float* t0 = b.take(128); float* h = b.take((size_t)P * 128); float* s = b.take(P); float* al = b.take(P);
+    float* tot = b.take(1); float* agg = b.take(F); float* cat2 = b.take(2 * (size_t)F); float* gate = b.take(F);
+    float* u1 = b.take(F); float* upd = b.take(F);
+    if (L) { L->t0 = t0; L->h = h; L->s = s; L->alpha = al; L->tot = tot; L->agg = agg; L->cat2 = cat2; L->gate = gate; L->u1 = u1; L->upd = upd; }
+    return (size_t)(b.p - base);
+  }
+};
+
+int linear_fwd(const float* X, const float* W, int64_t ldw, const float* bias, float* Y, int64_t M, int N, int K, int relu,
+               cudaStream_t st) {
+  int rc = gemm(false, true, M, N, K, X, K, W, ldw, Y, N, 0.0f, st);
+  if (rc) return rc;
+  add_bias_act_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(Y, bias, M, N, relu);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int azg_gemm_f32(int transA, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                 float* C, int64_t ldc, float beta, azg_stream stream) {
+  AZG_REQUIRE(A && B && C && K > 0, "azg_gemm_f32: bad argument");
+  return gemm(transA != 0, transB != 0, M, N, K, A, lda, B, ldb, C, ldc, beta, (cudaStream_t)stream);
+}
+
+int azg_mul_f32(const float* a, const float* b, float* out, int64_t n, azg_stream stream) {
+  AZG_REQUIRE(a && b && out, "azg_mul_f32: null pointer");
+  if (n <= 0) return AZG_OK;
+  mul_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+// Y = act(X W^T + b) backward: dX = g W, dW = g^T X, db = column sums of g, g = dY * (Y > 0) if relu.
+// Any of dX / dW / db may be NULL.  scratch: M*N floats when relu, else unused.
+int azg_linear_backward(const float* dY, const float* X, const float* W, const float* Y, int64_t M, int N, int K, int relu,
+                        float* dX, float* dW, float* db, float* scratch, azg_stream stream) {
+  AZG_REQUIRE(dY && X && W, "azg_linear_backward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* g = dY;
+  if (relu) {
+    AZG_REQUIRE(Y && scratch, "azg_linear_backward: relu needs Y and scratch");
+    relu_bwd_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(dY, Y, scratch, M * N);
+    AZG_LAUNCH_CHECK();
+    g = scratch;
+  }
+  int rc;
+  if (dX && (rc = gemm(false, false, M, K, N, g, N, W, K, dX, K, 0.0f, st))) return rc;
+  if (dW && (rc = gemm(true, false, N, K, (int)M, g, N, X, K, dW, K, 0.0f, st))) return rc;
+  if (db) {
+    col_sum_kernel<<<grid_for(N, 128), 128, 0, st>>>(g, M, N, N, db);
+    AZG_LAUNCH_CHECK();
+  }
+  return AZG_OK;
+}
+
+// conv3x3 + ReLU backward (Connect4Net.py:45-46 / TicTacToeNet.py:33-35).  din may be NULL (first layer).
+int azg_conv3x3_relu_backward(const float* in, const float* w, const float* out, const float* dout, float* din, float* dw,
+                              float* db, int64_t B, int Cin, int Cout, int H, int W, int pad, azg_stream stream) {
+  AZG_REQUIRE(in && w && out && dout && dw && db, "azg_conv3x3_relu_backward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  conv_bwd_weight_kernel<<<grid_for(Cout * Cin * 9 + Cout, 128), 128, 0, st>>>(in, out, dout, dw, db, B, Cin, Cout, H, W, pad);
+  AZG_LAUNCH_CHECK();
+  if (din) {
+    conv_bwd_data_kernel<<<grid_for(B * Cin * H * W, 128), 128, 0, st>>>(w, out, dout, din, B, Cin, Cout, H, W, pad);
+    AZG_LAUNCH_CHECK();
+  }
+  return AZG_OK;
+}
+
+// loss = (-sum(target_pi * log_softmax(logits)) + sum((target_v - tanh(vraw))^2)) / norm, with its gradients.
+// Outputs: loss[1], logp[B,A], v[B], dlogits[B,A], dvraw[B] (all device).  norm = the GLOBAL batch size
+// (the reference divides by size()[0]; data-parallel ranks pass the global B).
+int azg_policy_value_loss(const float* logits, const float* vraw, const float* target_pi, const float* target_v, int B,
+                          int A, float norm, float* loss, float* logp, float* v, float* dlogits, float* dvraw,
+                          azg_stream stream) {
+  AZG_REQUIRE(logits && vraw && target_pi && target_v && loss && logp && v && dlogits && dvraw && norm > 0,
+              "azg_policy_value_loss: bad argument");
+  policy_value_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, vraw, target_pi, target_v, B, A, 1.0f / norm, loss,
+                                                                logp, v, dlogits, dvraw);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+// ---- GNNLayer (gnn_utils.py:5-74) at B = P + 1 > 1 -----------------------------------------------
+size_t azg_gnn_layer_saved_floats(int P, int F) { return LayerSaved::carve(nullptr, nullptr, P, F); }
+size_t azg_gnn_layer_scratch_floats(int P, int F) { return 8 * (size_t)F + 2 * (size_t)P * 128 + 4 * (size_t)P + 1024; }
+
+// f0 [F] = target row, path [P,F] = rows 1..; writes out0 [F] (the updated target row) and `saved`.
+int azg_gnn_layer_forward(const azg_gnn_layer_params* p, const float* f0, const float* path, int P, int F, float* out0,
+                          float* saved, azg_stream stream) {
+  AZG_REQUIRE(p && f0 && path && out0 && saved && P >= 1, "azg_gnn_layer_forward: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  LayerSaved L;
+  LayerSaved::carve(&L, saved, P, F);
+  int rc;
+  const int64_t F2 = 2 * (int64_t)F;
+  // attention logits: W[:, :F] f0 (once) + W[:, F:] f_i
+  if ((rc = gemm(false, true, 1, 128, F, f0, F, p->att0_w, F2, L.t0, 128, 0.0f, st))) return rc;
+  if ((rc = gemm(false, true, P, 128, F, path, F, p->att0_w + F, F2, L.h, 128, 0.0f, st))) return rc;
+  att_scores_kernel<<<grid_for((int64_t)P * 32, 256), 256, 0, st>>>(L.h, L.t0, p->att0_b, p->att2_w, p->att2_b, P, L.s);
+  AZG_LAUNCH_CHECK();
+  att_normalise_kernel<<<1, 32, 0, st>>>(L.s, P, L.alpha, L.tot);
+  AZG_LAUNCH_CHECK();
+  if ((rc = gemm(false, false, 1, F, P, L.alpha, P, path, F, L.agg, F, 0.0f, st))) return rc;  // sum_i alpha_i f_i
+  AZG_CUDA_CHECK(cudaMemcpyAsync(L.cat2, f0, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
+  AZG_CUDA_CHECK(cudaMemcpyAsync(L.cat2 + F, L.agg, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
+  if ((rc = linear_fwd(L.cat2, p->gate_w, F2, p->gate_b, L.gate, 1, F, (int)F2, 0, st))) return rc;
+  if ((rc = linear_fwd(L.cat2, p->upd0_w, F2, p->upd0_b, L.u1, 1, F, (int)F2, 1, st))) return rc;
+  if ((rc = linear_fwd(L.u1, p->upd2_w, F, p->upd2_b, L.upd, 1, F, F, 0, st))) return rc;
+  gate_out_kernel<<<grid_for(F, 256), 256, 0, st>>>(L.gate, L.upd, f0, out0, F);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+// d_out0 [F] -> parameter gradients (overwritten) and d_f0 [F] (gradient w.r.t. the input target row).
+// Gradients w.r.t. the path rows are not produced: nothing trainable lies upstream of them in the GNN
+// step (Connect4GNN.py:195-197 steps only the GNN optimizer).
+int azg_gnn_layer_backward(const azg_gnn_layer_params* p, const float* f0, const float* path, int P, int F,
+                           const float* saved, const float* d_out0, float* d_f0, const azg_gnn_layer_grads* g,
+                           float* scratch, azg_stream stream) {
+  AZG_REQUIRE(p && f0 && path && saved && d_out0 && d_f0 && g && scratch, "azg_gnn_layer_backward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  LayerSaved L;
+  LayerSaved::carve(&L, const_cast<float*>(saved), P, F);
+  Bump b{scratch};
+  float* dgpre = b.take(F); float* dupd = b.take(F); float* du1 = b.take(F); float* dcat2 = b.take(2 * (size_t)F);
+  float* dalpha = b.take(P); float* dz = b.take(P); float* dhpre = b.take((size_t)P * 128); float* dhsum = b.take(128);
+  const int64_t F2 = 2 * (int64_t)F;
+  int rc;
+  gate_bwd_kernel<<<grid_for(F, 256), 256, 0, st>>>(d_out0, L.gate, L.upd, dgpre, dupd, F);
+  AZG_LAUNCH_CHECK();
+  // gate = sigmoid(Wg cat2 + bg)
+  if ((rc = gemm(true, false, F, (int)F2, 1, dgpre, F, L.cat2, F2, g->gate_w, F2, 0.0f, st))) return rc;
+  AZG_CUDA_CHECK(cudaMemcpyAsync(g->gate_b, dgpre, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
+  if ((rc = gemm(false, false, 1, (int)F2, F, dgpre, F, p->gate_w, F2, dcat2, F2, 0.0f, st))) return rc;
+  // upd = W2 relu(W0 cat2 + b0) + b2
+  if ((rc = gemm(true, false, F, F, 1, dupd, F, L.u1, F, g->upd2_w, F, 0.0f, st))) return rc;
+  AZG_CUDA_CHECK(cudaMemcpyAsync(g->upd2_b, dupd, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
+  if ((rc = gemm(false, false, 1, F, F, dupd, F, p->upd2_w, F, du1, F, 0.0f, st))) return rc;
+  relu_bwd_kernel<<<grid_for(F, 256), 256, 0, st>>>(du1, L.u1, du1, F);
+  AZG_LAUNCH_CHECK();
+  if ((rc = gemm(true, false, F, (int)F2, 1, du1, F, L.cat2, F2, g->upd0_w, F2, 0.0f, st))) return rc;
+  AZG_CUDA_CHECK(cudaMemcpyAsync(g->upd0_b, du1, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
+  if ((rc = gemm(false, false, 1, (int)F2, F, du1, F, p->upd0_w, F2, dcat2, F2, 1.0f, st))) return rc;
+  // cat2 = [f0, agg];  out0 = f0 + ...
+  AZG_CUDA_CHECK(cudaMemcpyAsync(d_f0, d_out0, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
+  axpy_kernel<<<grid_for(F, 256), 256, 0, st>>>(d_f0, dcat2, F);
+  AZG_LAUNCH_CHECK();
+  // agg = sum_i alpha_i f_i  ->  d_alpha_i = d_agg . f_i
+  if ((rc = gemm(false, true, 1, P, F, dcat2 + F, F, path, F, dalpha, P, 0.0f, st))) return rc;
+  att_bwd_kernel<<<1, 32, 0, st>>>(dalpha, L.s, L.tot, P, dz);
+  AZG_LAUNCH_CHECK();
+  // z_i = w2 . h_i + b2
+  if ((rc = gemm(false, false, 1, 128, P, dz, P, L.h, 128, g->att2_w, 128, 0.0f, st))) return rc;
+  col_sum_kernel<<<1, 32, 0, st>>>(dz, P, 1, 1, g->att2_b);
+  AZG_LAUNCH_CHECK();
+  att_hidden_bwd_kernel<<<grid_for((int64_t)P * 128, 256), 256, 0, st>>>(dz, p->att2_w, L.h, P, dhpre);
+  AZG_LAUNCH_CHECK();
+  // hpre_i = W[:, :F] f0 + W[:, F:] f_i + b
+  col_sum_kernel<<<1, 128, 0, st>>>(dhpre, P, 128, 128, dhsum);
+  AZG_LAUNCH_CHECK();
+  AZG_CUDA_CHECK(cudaMemcpyAsync(g->att0_b, dhsum, sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
+  if ((rc = gemm(true, false, 128, F, 1, dhsum, 128, f0, F, g->att0_w, F2, 0.0f, st))) return rc;
+  if ((rc = gemm(true, false, 128, F, P, dhpre, 128, path, F, g->att0_w + F, F2, 0.0f, st))) return rc;
+  return gemm(false, false, 1, F, 128, dhsum, 128, p->att0_w, F2, d_f0, F, 1.0f, st);
+}
+
+}  // extern "C"

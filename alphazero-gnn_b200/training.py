@@ -1,0 +1,379 @@
+"""Training step of the two-player wrappers on the CUDA library (K3) + the data-parallel
+gradient exchange (K5).
+
+    train_two_player   <- Connect4GNNWrapper.train (connect4/Connect4GNN.py:122-197),
+                          TicTacToeGNNWrapper.train (tictactoe/TicTacToeGNN.py:89-160),
+                          Connect4NNetWrapper.train (connect4/Connect4Net.py:76-108)
+
+Every floating-point operation of forward and backward runs in libazgnn_b200.so; the
+`torch.autograd.Function` classes below only route tensors between those kernels, and the
+optimizer is torch's Adam exactly as in the reference (re-created per `train` call, lr from
+args).  Reference behaviours kept: minibatches are drawn with replacement through the global
+NumPy RNG (`np.random.randint`), one std step + one GNN step per "epoch", dropout is live on
+the flattened Connect4 features in both steps, and the GNN step only ever updates GNN
+parameters (its trunk/head weight gradients are discarded by the next zero_grad in the
+reference, so they are not computed here -- SURVEY.md section 8e).
+
+Multi-GPU (one process per GPU, torch.distributed initialised by the caller): rows of the
+minibatch are sharded in contiguous chunks; losses are normalised by the GLOBAL batch size;
+parameter gradients are summed with one NCCL all-reduce per optimizer.  GNNLayer couples every
+row to row 0 (gnn_utils.py:38-74), so the trunk features are all-gathered and the (cheap,
+weight-bandwidth bound) layers run replicated, while output_transform + heads + loss shard by
+rows; only the rank that owns row 0 contributes layer gradients.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import ptr, stream
+from .mcts import arg
+
+
+def _lib_check(rc):
+    _lib.check(rc)
+
+
+class _ConvRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, pad):
+        x, w, b = x.contiguous(), w.contiguous(), b.contiguous()
+        B, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        out = torch.empty(B, Cout, H + 2 * pad - 2, W + 2 * pad - 2, dtype=torch.float32, device=x.device)
+        _lib_check(_lib.lib().azg_conv3x3_relu_forward(ptr(x), ptr(w), ptr(b), ptr(out), B, Cin, Cout, H, W, pad, stream()))
+        ctx.save_for_backward(x, w, out)
+        ctx.pad = pad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, out = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        din = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw, db = torch.empty_like(w), torch.empty(Cout, dtype=torch.float32, device=x.device)
+        _lib_check(_lib.lib().azg_conv3x3_relu_backward(ptr(x), ptr(w), ptr(out), ptr(dout), ptr(din), ptr(dw), ptr(db), B,
+                                                        Cin, Cout, H, W, ctx.pad, stream()))
+        return din, dw, db, None
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        x, w, b = x.contiguous(), w.contiguous(), b.contiguous()
+        M, K = x.shape
+        N = w.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        _lib_check(_lib.lib().azg_linear_f32(ptr(x), ptr(w), ptr(b), ptr(y), M, N, K, int(relu), stream()))
+        ctx.save_for_backward(x, w, y)
+        ctx.relu = int(relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = w.shape[0]
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        dx = torch.empty_like(x) if need_x else None
+        dw = torch.empty_like(w) if need_w else None
+        db = torch.empty(N, dtype=torch.float32, device=x.device) if need_b else None
+        scratch = torch.empty(M * N, dtype=torch.float32, device=x.device) if ctx.relu else None
+        _lib_check(_lib.lib().azg_linear_backward(ptr(dy), ptr(x), ptr(w), ptr(y), M, N, K, ctx.relu, ptr(dx), ptr(dw),
+                                                  ptr(db), ptr(scratch), stream()))
+        return dx, dw, db, None
+
+
+class _Mul(torch.autograd.Function):
+    """x * mask (dropout with a pre-scaled keep mask); gradient flows to x only."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        x, mask = x.contiguous(), mask.contiguous()
+        out = torch.empty_like(x)
+        _lib_check(_lib.lib().azg_mul_f32(ptr(x), ptr(mask), ptr(out), x.numel(), stream()))
+        ctx.save_for_backward(mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        _lib_check(_lib.lib().azg_mul_f32(ptr(dy), ptr(mask), ptr(dx), dy.numel(), stream()))
+        return dx, None
+
+
+class _PVLoss(torch.autograd.Function):
+    """-sum(pi*log_softmax(logits))/norm + sum((v_t - tanh(vraw))^2)/norm, Connect4GNN.py:150-152."""
+
+    @staticmethod
+    def forward(ctx, logits, vraw, target_pi, target_v, norm):
+        logits, vraw = logits.contiguous(), vraw.contiguous().view(-1)
+        B, A = logits.shape
+        dev = logits.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        logp = torch.empty(B, A, dtype=torch.float32, device=dev)
+        v = torch.empty(B, dtype=torch.float32, device=dev)
+        dlogits = torch.empty(B, A, dtype=torch.float32, device=dev)
+        dvraw = torch.empty(B, dtype=torch.float32, device=dev)
+        _lib_check(_lib.lib().azg_policy_value_loss(ptr(logits), ptr(vraw), ptr(target_pi.contiguous()),
+                                                    ptr(target_v.contiguous()), B, A, float(norm), ptr(loss), ptr(logp),
+                                                    ptr(v), ptr(dlogits), ptr(dvraw), stream()))
+        ctx.save_for_backward(dlogits, dvraw)
+        ctx.vshape = None
+        ctx.mark_non_differentiable(logp, v)
+        return loss, logp, v
+
+    @staticmethod
+    def backward(ctx, gloss, _glogp, _gv):
+        dlogits, dvraw = ctx.saved_tensors
+        g = gloss.reshape(())
+        return dlogits * g, (dvraw * g).view(-1, 1), None, None, None
+
+
+def _layer_params(layer):
+    return [layer.attention[0].weight, layer.attention[0].bias, layer.attention[2].weight, layer.attention[2].bias,
+            layer.update_net[0].weight, layer.update_net[0].bias, layer.update_net[2].weight, layer.update_net[2].bias,
+            layer.gate[0].weight, layer.gate[0].bias]
+
+
+class _GNNLayer(torch.autograd.Function):
+    """GNNLayer.forward at B > 1 (gnn_utils.py:38-74): returns the updated target row."""
+
+    @staticmethod
+    def forward(ctx, f0, path, *params):
+        f0, path = f0.contiguous(), path.contiguous()
+        P, F = path.shape
+        lib = _lib.lib()
+        saved = torch.empty(lib.azg_gnn_layer_saved_floats(P, F), dtype=torch.float32, device=f0.device)
+        out0 = torch.empty(F, dtype=torch.float32, device=f0.device)
+        cp = _lib.GNNLayerParams(*[ptr(p.contiguous()) for p in params])
+        _lib_check(lib.azg_gnn_layer_forward(C.byref(cp), ptr(f0), ptr(path), P, F, ptr(out0), ptr(saved), stream()))
+        ctx.save_for_backward(f0, path, saved, *params)
+        return out0
+
+    @staticmethod
+    def backward(ctx, d_out0):
+        f0, path, saved, *params = ctx.saved_tensors
+        P, F = path.shape
+        lib = _lib.lib()
+        d_out0 = d_out0.contiguous()
+        grads = [torch.empty_like(p) for p in params]
+        d_f0 = torch.empty_like(f0)
+        scratch = torch.empty(lib.azg_gnn_layer_scratch_floats(P, F), dtype=torch.float32, device=f0.device)
+        cp = _lib.GNNLayerParams(*[ptr(p) for p in params])
+        cg = _lib.GNNLayerGrads(*[ptr(g) for g in grads])
+        _lib_check(lib.azg_gnn_layer_backward(C.byref(cp), ptr(f0), ptr(path), P, F, ptr(saved), ptr(d_out0), ptr(d_f0),
+                                              C.byref(cg), ptr(scratch), stream()))
+        return (d_f0, None, *grads)
+
+
+class CudaOps:
+    """The compute vocabulary of the training step, bound to libazgnn_b200.so."""
+
+    @staticmethod
+    def conv_relu(x, conv):
+        return _ConvRelu.apply(x, conv.weight, conv.bias, int(conv.padding[0]))
+
+    @staticmethod
+    def linear(x, lin, relu=False):
+        return _Linear.apply(x, lin.weight, lin.bias, relu)
+
+    @staticmethod
+    def dropout(x, p):
+        if p <= 0:
+            return x
+        keep = (torch.rand_like(x) >= p).to(torch.float32) / (1.0 - p)  # F.dropout scaling
+        return _Mul.apply(x, keep)
+
+    @staticmethod
+    def pv_loss(logits, vraw, target_pi, target_v, norm):
+        return _PVLoss.apply(logits, vraw, target_pi, target_v, norm)
+
+    @staticmethod
+    def gnn_layer(f0, path, layer):
+        return _GNNLayer.apply(f0, path, *_layer_params(layer))
+
+
+# ----------------------------------------------------------------------------------------- network graphs
+def trunk_features(ops, w, boards, training):
+    """extract_features: Connect4GNN.py:31-46 (dropout live in training) / TicTacToeGNN.py:25-34."""
+    n = w.nnet
+    s = boards.view(-1, 1, w.board_x, w.board_y)
+    s = ops.conv_relu(s, n.conv1)
+    s = ops.conv_relu(s, n.conv2)
+    if w.kind == "tictactoe":
+        s = ops.conv_relu(s, n.conv3)
+    s = s.reshape(s.shape[0], -1)
+    if w.kind == "connect4" and training:
+        s = ops.dropout(s, float(n.dropout))
+    return s
+
+
+def head_logits(ops, w, feats):
+    """apply_policy_value_heads up to the pre-activation outputs (Connect4GNN.py:48-57, TicTacToeGNN.py:36-45)."""
+    n = w.nnet
+    if w.kind == "connect4":
+        return ops.linear(feats, n.fc_policy), ops.linear(feats, n.fc_value)
+    return ops.linear(ops.linear(feats, n.fc1, relu=True), n.fc_policy), ops.linear(ops.linear(feats, n.fc2, relu=True), n.fc_value)
+
+
+def gnn_enhance(ops, gnn, feats):
+    """PolicyValueGNN.forward (gnn_utils.py:107-117) on a [B,F] batch: row 0 is the target."""
+    x = feats
+    if feats.shape[0] > 1:
+        f0, path = feats[0], feats[1:]
+        for layer in gnn.layers:
+            f0 = ops.gnn_layer(f0, path, layer)
+        x = torch.cat([f0.unsqueeze(0), path], dim=0)
+    ot = gnn.output_transform
+    return ops.linear(ops.linear(x, ot[0], relu=True), ot[2])
+
+
+# ----------------------------------------------------------------------------------------- data parallel
+def _world():
+    return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+
+def shard_rows(B, rank, world):
+    """contiguous row range of rank `rank`; row 0 always lives on rank 0"""
+    per = (B + world - 1) // world
+    lo = min(rank * per, B)
+    return lo, min(lo + per, B)
+
+
+def allreduce_grads(params):
+    """one summed all-reduce over a flat bucket of all parameter gradients (NCCL over NVLink on GPUs)"""
+    rank, world = _world()
+    if world == 1:
+        return
+    params = [p for p in params]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
+        p.grad.copy_(g)
+
+
+def std_step(ops, w, boards, target_pi, target_v):
+    """Loss of the standard-network step on this rank's rows (global normalisation)."""
+    rank, world = _world()
+    B = boards.shape[0]
+    lo, hi = shard_rows(B, rank, world)
+    if hi <= lo:
+        return None
+    feats = trunk_features(ops, w, boards[lo:hi], training=True)
+    logits, vraw = head_logits(ops, w, feats)
+    loss, _, _ = ops.pv_loss(logits, vraw, target_pi[lo:hi], target_v[lo:hi], B)
+    return loss
+
+
+def gnn_step(ops, w, boards, target_pi, target_v):
+    """Loss of the GNN step on this rank's rows; gradients reach GNN parameters only."""
+    rank, world = _world()
+    B = boards.shape[0]
+    lo, hi = shard_rows(B, rank, world)
+    with torch.no_grad():  # trunk/head weight gradients of this step are never consumed
+        mine = trunk_features(ops, w, boards[lo:hi], training=True) if hi > lo else boards.new_zeros(0, w.feature_dim)
+        if world > 1:
+            per = (B + world - 1) // world
+            pad = torch.zeros(per, w.feature_dim, dtype=mine.dtype, device=mine.device)
+            pad[:mine.shape[0]] = mine
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)
+            feats = torch.cat(parts, dim=0)[:B]
+        else:
+            feats = mine
+    gnn = w.gnn
+    x = feats
+    if B > 1:
+        f0, path = feats[0], feats[1:]
+        for layer in gnn.layers:
+            f0 = ops.gnn_layer(f0, path, layer)
+        x = torch.cat([f0.unsqueeze(0), path], dim=0)
+    if hi <= lo:
+        return None
+    ot = gnn.output_transform
+    enh = ops.linear(ops.linear(x[lo:hi], ot[0], relu=True), ot[2])
+    heads = _FrozenHeads(w)
+    logits, vraw = head_logits(ops, heads, enh)
+    loss, _, _ = ops.pv_loss(logits, vraw, target_pi[lo:hi], target_v[lo:hi], B)
+    return loss
+
+
+class _FrozenHeads:
+    """view of a wrapper whose head parameters are detached: the GNN step needs d(loss)/d(enhanced)
+    through the heads but no head-weight gradients"""
+
+    def __init__(self, w):
+        self.kind = w.kind
+
+        class _L:
+            def __init__(self, lin):
+                self.weight, self.bias = lin.weight.detach(), lin.bias.detach()
+        n = w.nnet
+        names = ["fc_policy", "fc_value"] + (["fc1", "fc2"] if w.kind == "tictactoe" else [])
+        self.nnet = type("N", (), {k: _L(getattr(n, k)) for k in names})()
+
+
+def _sample(examples, batch_size):
+    """np.random.randint minibatch with replacement (Connect4GNN.py:141,160); rank 0's draw is
+    broadcast so every rank works on the same minibatch."""
+    idx = np.random.randint(0, len(examples), min(len(examples), batch_size))
+    rank, world = _world()
+    if world > 1:
+        t = torch.as_tensor(idx, dtype=torch.int64)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = t.to(dev)
+        dist.broadcast(t, src=0)
+        idx = t.cpu().numpy()
+    return idx
+
+
+def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
+    lr = float(arg(w.args, "lr"))
+    epochs, batch_size = int(arg(w.args, "epochs")), int(arg(w.args, "batch_size"))
+    dev = w.device
+    nnet_params = list(w.nnet.parameters())
+    nnet_opt = torch.optim.Adam(nnet_params, lr=lr)
+    gnn_params = list(w.gnn.parameters()) if getattr(w, "gnn", None) is not None else []
+    gnn_opt = torch.optim.Adam(gnn_params, lr=lr) if gnn_params else None
+    for _ in range(epochs):
+        if examples:
+            idx = _sample(examples, batch_size)
+            boards, pis, vs = list(zip(*[examples[i] for i in idx]))
+            boards = torch.FloatTensor(np.array(boards)).to(dev)
+            target_pis = torch.FloatTensor(np.array(pis)).to(dev)
+            target_vs = torch.FloatTensor(np.array(vs).astype(np.float64)).to(dev)
+            nnet_opt.zero_grad()
+            loss = std_step(ops, w, boards, target_pis, target_vs)
+            if loss is not None:
+                loss.backward()
+            allreduce_grads(nnet_params)
+            nnet_opt.step()
+        if gnn_opt is not None and gnn_examples and len(gnn_examples) > 0:
+            idx = _sample(gnn_examples, batch_size)
+            batch = [gnn_examples[i] for i in idx]
+            boards = torch.FloatTensor(np.array([b[0] for b in batch])).to(dev)
+            expanded_pis = torch.FloatTensor(np.array([b[4] for b in batch])).to(dev)
+            expanded_vs = torch.FloatTensor(np.array([b[5] for b in batch]).astype(np.float64)).to(dev)
+            gnn_opt.zero_grad()
+            loss = gnn_step(ops, w, boards, expanded_pis, expanded_vs)
+            if loss is not None:
+                loss.backward()
+            allreduce_grads(gnn_params)
+            gnn_opt.step()
+    w.weights_changed()
+
+
+def train_frozenlake(w, examples):
+    raise NotImplementedError("FrozenLake training (frozenlake/FrozenLakeNet.py:76-176) is listed under 'next' in "
+                              "SURVEY.md section 8f and is not part of this round's hot path")

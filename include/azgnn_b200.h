@@ -149,6 +149,47 @@ int azg_fl_forward(const azg_fl_params* p, int n, int embedding_dim, int layers,
 int azg_linear_f32(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,
                    int relu, azg_stream stream);
 
+/* ---------------------------------------------------------------- K3: training pieces ---- */
+/* fp32 building blocks of Connect4GNNWrapper.train / TicTacToeGNNWrapper.train
+ * (connect4/Connect4GNN.py:122-197); torch.autograd.Function wrappers route tensors between them,
+ * the optimizer step stays in torch. */
+/* C[M,N] = op(A) . op(B) + beta*C, row-major with leading dimensions; transX = 1: stored transposed */
+int azg_gemm_f32(int transA, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+                 int64_t ldb, float* C, int64_t ldc, float beta, azg_stream stream);
+int azg_mul_f32(const float* a, const float* b, float* out, int64_t n, azg_stream stream); /* dropout mask */
+/* backward of Y = act(X W^T + b): dX [M,K], dW [N,K], db [N] (each may be NULL); relu: Y and an
+ * M*N-float scratch are required */
+int azg_linear_backward(const float* dY, const float* X, const float* W, const float* Y, int64_t M, int N, int K,
+                        int relu, float* dX, float* dW, float* db, float* scratch, azg_stream stream);
+/* backward of out = relu(conv3x3(in, w) + b) (Connect4Net.py:45-46); din may be NULL */
+int azg_conv3x3_relu_forward(const float* in, const float* w, const float* b, float* out, int64_t B, int Cin, int Cout,
+                             int H, int W, int pad, azg_stream stream);
+int azg_conv3x3_relu_backward(const float* in, const float* w, const float* out, const float* dout, float* din,
+                              float* dw, float* db, int64_t B, int Cin, int Cout, int H, int W, int pad,
+                              azg_stream stream);
+/* loss = (-sum(target_pi*log_softmax(logits)) + sum((target_v - tanh(vraw))^2)) / norm and its gradients
+ * (Connect4GNN.py:150-152, 187-193); norm = the global batch size.  All outputs on the device. */
+int azg_policy_value_loss(const float* logits, const float* vraw, const float* target_pi, const float* target_v,
+                          int B, int A, float norm, float* loss, float* logp, float* v, float* dlogits,
+                          float* dvraw, azg_stream stream);
+/* GNNLayer.forward / backward at B = P + 1 > 1 (gnn_utils.py:34-74): row 0 (f0) is the target, rows
+ * 1.. (path) are attended over; only the target row changes. */
+typedef struct azg_gnn_layer_params {
+  const float *att0_w, *att0_b, *att2_w, *att2_b; /* attention: Linear(2F,128), Linear(128,1)   */
+  const float *upd0_w, *upd0_b, *upd2_w, *upd2_b; /* update_net: Linear(2F,F), Linear(F,F)      */
+  const float *gate_w, *gate_b;                   /* gate: Linear(2F,F)                         */
+} azg_gnn_layer_params;
+typedef struct azg_gnn_layer_grads {
+  float *att0_w, *att0_b, *att2_w, *att2_b, *upd0_w, *upd0_b, *upd2_w, *upd2_b, *gate_w, *gate_b;
+} azg_gnn_layer_grads;
+size_t azg_gnn_layer_saved_floats(int P, int F);
+size_t azg_gnn_layer_scratch_floats(int P, int F);
+int azg_gnn_layer_forward(const azg_gnn_layer_params* p, const float* f0, const float* path, int P, int F,
+                          float* out0, float* saved, azg_stream stream);
+int azg_gnn_layer_backward(const azg_gnn_layer_params* p, const float* f0, const float* path, int P, int F,
+                           const float* saved, const float* d_out0, float* d_f0, const azg_gnn_layer_grads* g,
+                           float* scratch, azg_stream stream);
+
 /* ---------------------------------------------------------------- K4: search arena ------ */
 /* A GPU-resident set of n_games independent transposition tables, one per game, holding what
  * MCTS.__init__ keeps in Qsa/Nsa/Ns/Ps/Es/Vs (MCTS.py:15-21).  Simulations within one game are

@@ -1,0 +1,116 @@
+"""K3 parity on the GPU: forward/backward of the training step in libazgnn_b200.so vs the
+reference's autograd (golden gradient summaries) and vs the oracle graph on random batches.
+Tolerances: losses/outputs 1e-5; gradients rtol 1e-3 / atol 2e-6 (fp32, different summation order)."""
+import numpy as np
+import pytest
+import torch
+
+from azgnn_b200 import games, training
+from azgnn_b200.nets import B200Connect4GNNWrapper, B200TicTacToeGNNWrapper
+from helpers import dotdict, golden, sample_index
+from train_helpers import OracleOps
+
+pytestmark = pytest.mark.gpu
+
+
+def _wrapper(kind, n, dropout=0.0, **kw):
+    game = games.Connect4Game(n) if kind == "c4" else games.TicTacToeGame(n)
+    args = dotdict(dict(dict(lr=1e-3, dropout=dropout, epochs=2, batch_size=64, gnn_layers=2, use_gnn=True), **kw))
+    torch.manual_seed(0)
+    return (B200Connect4GNNWrapper if kind == "c4" else B200TicTacToeGNNWrapper)(game, args)
+
+
+def _zero(w):
+    for p in list(w.nnet.parameters()) + list(w.gnn.parameters()):
+        p.grad = None
+
+
+@pytest.mark.parametrize("kind,n", [("c4", 5), ("c4", 7), ("ttt", 3), ("ttt", 4)])
+def test_gradients_match_reference_golden(kind, n):
+    g = golden(f"nets_{kind}_{n}")
+    w = _wrapper(kind, n)
+    dev = w.device
+    boards = torch.FloatTensor(g["train_boards"].astype(np.float64)).to(dev)
+    tpi, tv = torch.tensor(g["train_pi"]).to(dev), torch.tensor(g["train_v"]).to(dev)
+    _zero(w)
+    loss = training.std_step(training.CudaOps, w, boards, tpi, tv)
+    assert abs(loss.item() - float(g["std_loss"])) < 1e-5
+    loss.backward()
+    named = dict(w.nnet.named_parameters())
+    for name, row, samp in zip(g["std_grad_names"], g["std_grad_rows"], g["std_grad_samples"]):
+        gr = named[str(name)].grad.double().flatten().cpu()
+        np.testing.assert_allclose(gr[sample_index(gr.numel(), 64)].numpy(), samp, rtol=1e-3, atol=2e-6)
+        assert abs(gr.norm().item() - row[2]) <= 1e-3 * max(1e-3, row[2])
+    _zero(w)
+    loss = training.gnn_step(training.CudaOps, w, boards, tpi, tv)
+    assert abs(loss.item() - float(g["gnn_loss"])) < 1e-5
+    loss.backward()
+    named = dict(w.gnn.named_parameters())
+    for name, row, samp in zip(g["gnn_grad_names"], g["gnn_grad_rows"], g["gnn_grad_samples"]):
+        gr = named[str(name)].grad.double().flatten().cpu()
+        np.testing.assert_allclose(gr[sample_index(gr.numel(), 64)].numpy(), samp, rtol=1e-3, atol=2e-6)
+        assert abs(gr.norm().item() - row[2]) <= 1e-3 * max(1e-3, row[2])
+    assert all(p.grad is None for p in w.nnet.parameters())  # the GNN step leaves the trunk alone
+
+
+@pytest.mark.parametrize("kind,n,B", [("c4", 5, 2), ("c4", 5, 33), ("c4", 6, 64), ("ttt", 3, 17), ("ttt", 5, 64)])
+def test_gradients_match_oracle_graph(kind, n, B):
+    w = _wrapper(kind, n)
+    dev = w.device
+    rng = np.random.default_rng(B * n)
+    A = w.action_size
+    boards = torch.FloatTensor(rng.integers(-1, 2, size=(B, n, n)).astype(np.float64)).to(dev)
+    tpi = torch.FloatTensor(rng.dirichlet(np.ones(A), size=B)).to(dev)
+    tv = torch.FloatTensor(rng.uniform(-1, 1, B)).to(dev)
+    for step, params in ((training.std_step, lambda: w.nnet), (training.gnn_step, lambda: w.gnn)):
+        _zero(w)
+        l_cuda = step(training.CudaOps, w, boards, tpi, tv)
+        l_cuda.backward()
+        got = {k: p.grad.clone() for k, p in params().named_parameters()}
+        _zero(w)
+        l_ref = step(OracleOps, w, boards, tpi, tv)  # same graph on torch's own CUDA ops
+        l_ref.backward()
+        assert abs(l_cuda.item() - l_ref.item()) < 1e-5
+        for k, p in params().named_parameters():
+            ref = p.grad
+            err = (got[k] - ref).abs().max().item()
+            scale = ref.abs().max().item()
+            assert err <= 1e-3 * scale + 2e-6, (k, err, scale)
+
+
+def test_gnn_layers_are_identity_at_batch_one():
+    w = _wrapper("c4", 5)
+    b = torch.zeros(1, 5, 5, device=w.device)
+    feats = training.trunk_features(training.CudaOps, w, b, training=False)
+    enh = training.gnn_enhance(training.CudaOps, w.gnn, feats)
+    ref = training.gnn_enhance(OracleOps, w.gnn, feats)
+    assert torch.allclose(enh, ref, atol=1e-5)
+
+
+def test_train_runs_and_learns():
+    """Wrapper.train with the reference's example formats: repeated minibatches reduce the losses."""
+    w = _wrapper("c4", 5, dropout=0.3, epochs=30, batch_size=16)
+    rng = np.random.default_rng(0)
+    A = w.action_size
+    boards = rng.integers(-1, 2, size=(16, 5, 5)).astype(np.int64)
+    pis = rng.dirichlet(np.ones(A), size=16)
+    vs = rng.choice([-1, 1], size=16)
+    examples = [(boards[i], list(pis[i]), int(vs[i])) for i in range(16)]
+    gnn_examples = [(boards[i], 1, pis[i], np.float32(0.1), pis[i], np.float32(vs[i] * 0.5), int(vs[i])) for i in range(16)]
+    bt = torch.FloatTensor(boards.astype(np.float64)).to(w.device)
+    tpi, tv = torch.FloatTensor(pis).to(w.device), torch.FloatTensor(vs.astype(np.float64)).to(w.device)
+
+    def losses():
+        w.nnet.dropout, keep = 0.0, w.nnet.dropout
+        with torch.no_grad():
+            a = training.std_step(training.CudaOps, w, bt, tpi, tv).item()
+            b = training.gnn_step(training.CudaOps, w, bt, tpi, tv * 0.5).item()
+        w.nnet.dropout = keep
+        return a, b
+    before = losses()
+    out0 = w.predict_batch(boards)
+    np.random.seed(0)
+    w.train(examples, gnn_examples)
+    after = losses()
+    assert after[0] < before[0] and after[1] < before[1], (before, after)
+    assert not np.allclose(out0["pi_gnn"], w.predict_batch(boards)["pi_gnn"])
