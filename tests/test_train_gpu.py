@@ -11,6 +11,9 @@ from helpers import dotdict, golden, sample_index
 from train_helpers import OracleOps
 
 pytestmark = pytest.mark.gpu
+# the comparison graph runs on torch's CUDA ops: keep them in true fp32 (cuDNN convs default to TF32)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def _wrapper(kind, n, dropout=0.0, **kw):
