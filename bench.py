@@ -79,6 +79,51 @@ def cpu_leaf_evals(sample, threads=None):
     return sample / dt, dt, torch.get_num_threads()
 
 
+def cpu_selfplay(episodes):
+    """Oracle restatement of Coach.executeEpisode with the reference's connect4/config.yaml search
+    settings (10 sims + 5 expand_by, cpuct 1.0, tempThreshold 15): moves/s on the host cores."""
+    import numpy as np
+    import torch
+    from oracle import nets as onets
+    from oracle.mcts import OracleMCTS
+    from oracle.selfplay import execute_episode
+    from azgnn_b200 import modules
+    from azgnn_b200.games import Connect4Game
+    torch.manual_seed(0)
+    nnet = modules.Connect4Trunk(N_BOARD, N_BOARD + 1)
+    gnn = modules.PolicyValueGNN(64 * N_BOARD * N_BOARD, 2)
+    net = onets.OracleConnect4Net(nnet.state_dict(), gnn.state_dict(), N_BOARD)
+    game, a = Connect4Game(N_BOARD), reference_args()
+    np.random.seed(0)
+    moves, t0 = 0, time.perf_counter()
+    for _ in range(episodes):
+        m, _r = execute_episode(game, OracleMCTS(game, net, a), a)
+        moves += m
+    dt = time.perf_counter() - t0
+    return moves / dt, moves, dt
+
+
+def gpu_selfplay(net, a, games, moves, seed):
+    """Lock-step self-play of `games` concurrent episodes on this GPU: moves/s over `moves` move-steps
+    (each = getActionProb's 10 searches + expand_tree's 5 for every live game, then one move)."""
+    import torch
+    from azgnn_b200.games import Connect4Game
+    from azgnn_b200.selfplay import BatchedSelfPlay
+    sp = BatchedSelfPlay(Connect4Game(N_BOARD), net, a, games, seed=seed, collect_examples=False)
+    for _ in range(2):
+        sp.step_all()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0, l0 = sp.moves_played, sp.mcts.leaf_evals
+    e0.record()
+    for _ in range(moves):
+        sp.step_all()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return (sp.moves_played - m0) / (ms / 1e3), (sp.mcts.leaf_evals - l0) / (ms / 1e3), ms
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -219,10 +264,18 @@ def run_gpu_arm(args, rank, local_rank, world):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    sp_moves, sp_leaves, sp_ms = (0.0, 0.0, 0.0)
+    if args.selfplay_games > 0:
+        barrier()
+        sp_moves, sp_leaves, sp_ms = gpu_selfplay(net, a, args.selfplay_games, args.selfplay_moves, seed=rank)
+        barrier()
+    t = torch.tensor([ms, ms_e2e, sp_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([sp_moves * sp_ms, sp_leaves * sp_ms], dtype=torch.float64, device=dev)  # counts
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, ms_e2e, sp_ms = t.tolist()
+    sp_moves, sp_leaves = [(x / sp_ms if sp_ms > 0 else 0.0) for x in tot.tolist()]
     if rank == 0:
         peaks = {}
         try:
@@ -244,6 +297,17 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "kernel_ms_per_step": gemm_ms / max(gemm_cnt, 1),
                 "phase_ms_per_step": {k: v[0] / args.steps for k, v in phase.items()}}
         cpu_rate, cpu_dt, cores = cpu_leaf_evals(args.cpu_sample)
+        selfplay = None
+        if args.selfplay_games > 0:
+            cpu_mps, cpu_moves, cpu_sp_dt = cpu_selfplay(args.cpu_selfplay_episodes)
+            selfplay = {"metric": "connect4_selfplay_moves_per_s", "value": sp_moves, "unit": "moves/s",
+                        "leaf_evals_per_s_in_search": sp_leaves, "games_per_gpu": args.selfplay_games,
+                        "move_steps_timed": args.selfplay_moves, "ms_per_move_step": sp_ms / max(args.selfplay_moves, 1),
+                        "config": "connect4/config.yaml search settings: numMCTSSims 10, expand_by 5, cpuct 1.0, "
+                                  "tempThreshold 15, use_gnn (std+GNN evaluated per leaf)",
+                        "cpu_baseline": {"value": cpu_mps, "unit": "moves/s", "cores": cores, "kind": "port",
+                                         "sample": f"{args.cpu_selfplay_episodes} sequential episodes ({cpu_moves} moves, "
+                                                   f"{cpu_sp_dt:.1f} s), oracle MCTS + per-leaf B=1 torch CPU calls"}}
         line = {"metric": "connect4_gnn_leaf_evals_per_s", "value": value, "unit": "leaf_evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -263,6 +327,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                         "h2d_bytes_per_step": int(B * N_BOARD * N_BOARD),
                         "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_host.values())),
                         "ms_per_step": ms_e2e / args.steps},
+                "selfplay": selfplay,
                 "gpu_launches": int(launches),
                 "clocks": clocks.summary()}
         print(json.dumps(line))
@@ -279,6 +344,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--selfplay-games", type=int, default=4096, help="concurrent self-play games per GPU (0 = skip)")
+    ap.add_argument("--selfplay-moves", type=int, default=6)
+    ap.add_argument("--cpu-selfplay-episodes", type=int, default=2)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -174,3 +174,21 @@ def to_numpy_sd(sd):
 def boards_to_tensor(boards):
     """torch.FloatTensor(board.astype(np.float64)) -- Connect4GNN.py:71."""
     return torch.FloatTensor(np.asarray(boards).astype(np.float64))
+
+
+class OracleConnect4Net:
+    """NeuralNet-shaped view of the functional Connect4 oracle (predict / predict_with_gnn at B=1,
+    returning the reference's types: np.float32 vector and np.float32 scalar, Connect4GNN.py:80-84)."""
+
+    def __init__(self, nnet_sd, gnn_sd, n):
+        self.p, self.g, self.n = dict(nnet_sd), dict(gnn_sd), n
+
+    def predict(self, board):
+        with torch.no_grad():
+            pi, v = c4_predict(self.p, boards_to_tensor(np.asarray(board)[None]), self.n)
+        return pi.numpy()[0], v.numpy()[0]
+
+    def predict_with_gnn(self, board):
+        with torch.no_grad():
+            pi, v = c4_predict_with_gnn(self.p, self.g, boards_to_tensor(np.asarray(board)[None]), self.n)
+        return pi.numpy()[0], v.numpy()[0]
