@@ -61,7 +61,7 @@ SIGNATURES = {
     "azg_c4_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "azg_c4_forward": (_i, [C.POINTER(C4Params), _i, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "azg_c4_packed_bytes": (_sz, [_i, _i]),
-    "azg_c4_pack_gnn": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "azg_c4_pack": (_i, [C.POINTER(C4Params), _i, _i, _vp, _sz, _vp]),
     "azg_tc_linear": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _sz, _vp]),
     "azg_ttt_workspace_bytes": (_sz, [_i, _i64, _i]),
     "azg_ttt_forward": (_i, [C.POINTER(TTTParams), _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -8,7 +8,7 @@
 //     chunks XOR-swizzled by the row index = the SWIZZLE_128B K-major canonical layout), so a
 //     pipeline stage is filled by two plain bulk-async copies (cp.async.bulk -> UBLKCP) that
 //     complete on an mbarrier; no tensor maps, no in-kernel shuffling.  Weights are re-tiled
-//     once per optimizer step (azg_c4_pack_gnn); activations are written as images by the
+//     once per optimizer step (azg_c4_pack); activations are written as images by the
 //     producer (the f32->image kernel for X, the GEMM epilogue for H).
 //   * One persistent CTA per SM, warp-specialised: warp 0 = bulk-copy producer, warp 1 = MMA
 //     issuer (a single thread issues tcgen05.mma, M=128 x N=BN x K=16 per instruction),
@@ -137,7 +137,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 // ---- epilogue output modes -----------------------------------------------------------------
-enum { OUT_F32 = 0, OUT_IMG = 1, OUT_IMG_HILO = 2 };
+enum { OUT_F32 = 0, OUT_IMG = 1, OUT_IMG_HILO = 2, OUT_FEAT = 3, OUT_FEAT_HILO = 4 };
 
 struct GemmArgs {
   const uint8_t* a_hi;  // activation images, tiles [128 x 64], (mt * KB + kb) * 16384
@@ -153,6 +153,8 @@ struct GemmArgs {
   int x3;               // 0: bf16, 1: 3-term split
   int relu;
   int out_mode;
+  int feat_nn;          // OUT_FEAT*: rows are (board b, cell p) pairs, m = b*feat_nn + p; the 64 columns (conv2
+                        // channels) become k-block p of row b of the feature image  [K' = p*64 + co]
 };
 
 template <int BN>
@@ -280,7 +282,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
           float x = __uint_as_float(rr[j]) + __ldg(g.bias + n0 + j);
           v[j] = g.relu ? fmaxf(x, 0.0f) : x;
         }
-        if (g.out_mode == OUT_F32) {
+        if (g.out_mode >= OUT_FEAT) {
+          if (row < g.M) {
+            const int64_t bidx = row / g.feat_nn;
+            const int p = (int)(row - bidx * g.feat_nn);
+            const size_t tile = ((size_t)(bidx >> 7) * g.feat_nn + p) * A_STAGE_BYTES;
+            const int rb = (int)(bidx & 127);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x0 = v[c * 8 + 2 * e], x1 = v[c * 8 + 2 * e + 1];
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              const size_t off = tile + image_offset(rb, c0 + c * 8);
+              *reinterpret_cast<uint4*>(g.out_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              if (g.out_mode == OUT_FEAT_HILO) *reinterpret_cast<uint4*>(g.out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        } else if (g.out_mode == OUT_F32) {
           if (row < g.M) {
             float4* dst = reinterpret_cast<float4*>(g.out_f32 + row * (int64_t)(g.n_tiles * BN) + n0);
 #pragma unroll
@@ -392,6 +417,7 @@ int run_gemm(int BN, const GemmArgs& g, cudaStream_t st) {
     case 224: return launch_gemm<224>(g, st);
     case 256: return launch_gemm<256>(g, st);
     case 160: return launch_gemm<160>(g, st);
+    case 64: return launch_gemm<64>(g, st);
   }
   azg_set_error("tcgen05 GEMM: no tile width for this feature size");
   return AZG_ERR_INVALID;
@@ -404,78 +430,354 @@ int to_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R, 
   return AZG_OK;
 }
 
+
+// ---- Connect4 trunk on the tensor cores ------------------------------------------------------
+// conv2 (32 -> 64 channels, 3x3, pad 1) as an implicit GEMM:  rows m = (board b, cell p),
+// K = (tap, cin) = 9*32 = 288 (padded to 320 = 5 k-blocks), N = 64 output channels.  This kernel
+// evaluates conv1 + ReLU on the fly from the packed position (K1 encode fused in) and writes the
+// im2col operand directly as tile images (hi/lo bf16), 1280 B per row.
+constexpr int C2_K = 320, C2_KB = C2_K / BK;
+
+__device__ __forceinline__ void split_store(const float* x, uint8_t* hi, uint8_t* lo, size_t off) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * e]), h1 = __float2bfloat16_rn(x[2 * e + 1]);
+    h[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * e] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * e + 1] - __bfloat162float(h1));
+    l[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(256) c4_im2col_kernel(const uint64_t* __restrict__ states, int n, int64_t B,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        uint8_t* __restrict__ a_hi, uint8_t* __restrict__ a_lo) {
+  __shared__ float planes[100];            // (n+2)^2 board with a zero border
+  __shared__ __align__(16) float a1s[100 * 32];  // relu(conv1) per padded cell, 32 channels each, zero border
+  __shared__ float w1s[32 * 9], b1s[32];
+  const int np = n + 2, nn = n * n;
+  for (int i = threadIdx.x; i < 100 * 32; i += blockDim.x) a1s[i] = 0.0f;
+  for (int i = threadIdx.x; i < 32 * 9; i += blockDim.x) w1s[i] = w1[i];
+  if (threadIdx.x < 32) b1s[threadIdx.x] = b1[threadIdx.x];
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    const uint64_t mine = states[2 * b], theirs = states[2 * b + 1];
+    for (int i = threadIdx.x; i < np * np; i += blockDim.x) {
+      const int x = i / np - 1, y = i % np - 1;
+      float v = 0.0f;
+      if (x >= 0 && x < n && y >= 0 && y < n) {
+        const int c = x * n + y;
+        v = (float)((int)((mine >> c) & 1ull) - (int)((theirs >> c) & 1ull));
+      }
+      planes[i] = v;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 32 * nn; o += blockDim.x) {  // conv1 + ReLU, Connect4Net.py:45
+      const int ci = o & 31, pc = o >> 5, x = pc / n, y = pc % n;
+      float acc = b1s[ci];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) acc = fmaf(planes[(x + kx) * np + y + ky], w1s[ci * 9 + kx * 3 + ky], acc);
+      a1s[((x + 1) * np + y + 1) * 32 + ci] = fmaxf(acc, 0.0f);
+    }
+    __syncthreads();
+    for (int task = threadIdx.x; task < nn * (C2_K / 8); task += blockDim.x) {
+      const int pc = task / (C2_K / 8), c = task % (C2_K / 8);
+      float x8[8];
+      if (c < 36) {
+        const int tap = c >> 2, ci0 = (c & 3) * 8, kx = tap / 3, ky = tap % 3, x = pc / n, y = pc % n;
+        const float4* src = reinterpret_cast<const float4*>(a1s + ((x + kx) * np + y + ky) * 32 + ci0);
+        const float4 u = src[0], w = src[1];
+        x8[0] = u.x; x8[1] = u.y; x8[2] = u.z; x8[3] = u.w; x8[4] = w.x; x8[5] = w.y; x8[6] = w.z; x8[7] = w.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x8[e] = 0.0f;
+      }
+      const int64_t m = b * nn + pc;
+      const size_t off = ((size_t)(m >> 7) * C2_KB + (c >> 3)) * A_STAGE_BYTES + image_offset((int)(m & 127), (c & 7) * 8);
+      split_store(x8, a_hi, a_lo, off);
+    }
+  }
+}
+
+// conv2 weights [64,32,3,3] -> [64 x 320] image, k = tap*32 + cin (zero padded)
+__global__ void conv2_weight_image_kernel(const float* __restrict__ w2, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * (C2_K / 8)) return;
+  const int co = idx / (C2_K / 8), c = idx % (C2_K / 8);
+  float x8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = c * 8 + e, tap = k >> 5, ci = k & 31;
+    x8[e] = (k < 288) ? w2[(co * 32 + ci) * 9 + tap] : 0.0f;
+  }
+  const size_t off = (size_t)(c >> 3) * (64 * 128) + image_offset(co, (c & 7) * 8);
+  split_store(x8, hi, lo, off);
+}
+
+// Linear weight [N, F] whose input index is the reference's flatten order k = co*nn + p
+// (Connect4Net.py:49) -> image over the feature image's order k' = p*64 + co
+__global__ void __launch_bounds__(256) permuted_weight_image_kernel(const float* __restrict__ w, int N, int F, int nn, int R,
+                                                                    uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+  const int chunks = F / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * chunks) return;
+  const int row = (int)(idx / chunks), c = (int)(idx % chunks);
+  float x8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int kp = c * 8 + e, pc = kp >> 6, co = kp & 63;
+    x8[e] = w[(size_t)row * F + co * nn + pc];
+  }
+  const int KB = F / BK;
+  const size_t off = ((size_t)(row / R) * KB + (c >> 3)) * ((size_t)R * 128) + image_offset(row % R, (c & 7) * 8);
+  split_store(x8, hi, lo, off);
+}
+
+// head weights (policy rows then the value row) permuted to the feature image's order, fp32
+__global__ void permute_heads_kernel(const float* __restrict__ wp, const float* __restrict__ wv, int A, int F, int nn,
+                                     float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)(A + 1) * F) return;
+  const int row = (int)(idx / F), kp = (int)(idx % F), pc = kp >> 6, co = kp & 63;
+  const float* src = row < A ? wp + (size_t)row * F : wv;
+  out[idx] = src[co * nn + pc];
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4 u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __uint_as_float(w[e] << 16);
+    f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+
+// standard heads (predict, Connect4Net.py:55-60) straight from the feature image: one warp per position
+template <int MAXA>
+__global__ void __launch_bounds__(256) heads_image_kernel(const uint8_t* __restrict__ f_hi, const uint8_t* __restrict__ f_lo,
+                                                          int KB, const float* __restrict__ wperm,
+                                                          const float* __restrict__ bp, const float* __restrict__ bv, int A,
+                                                          int64_t B, float* __restrict__ pi, float* __restrict__ v) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = KB * BK;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < B; row += (int64_t)gridDim.x * 8) {
+    const size_t tile0 = (size_t)(row >> 7) * KB * A_STAGE_BYTES;
+    const int r = (int)(row & 127);
+    float acc[MAXA + 1];
+#pragma unroll
+    for (int a = 0; a <= MAXA; ++a) acc[a] = 0.0f;
+    for (int q = lane; q < KB * 8; q += 32) {
+      const int kb = q >> 3, j = q & 7;
+      const size_t off = tile0 + (size_t)kb * A_STAGE_BYTES + image_offset(r, j * 8);
+      float f[8], l[8];
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(f_hi + off), f);
+      if (f_lo) {
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(f_lo + off), l);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += l[e];
+      }
+      const int kp = kb * BK + j * 8;
+#pragma unroll
+      for (int a = 0; a <= MAXA; ++a) {
+        if (a <= A) {  // rows 0..A-1 policy, row A value
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wperm + (size_t)a * F + kp));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wperm + (size_t)a * F + kp + 4));
+          acc[a] = fmaf(f[0], w0.x, fmaf(f[1], w0.y, fmaf(f[2], w0.z, fmaf(f[3], w0.w, acc[a]))));
+          acc[a] = fmaf(f[4], w1.x, fmaf(f[5], w1.y, fmaf(f[6], w1.z, fmaf(f[7], w1.w, acc[a]))));
+        }
+      }
+    }
+    float logit[MAXA + 1];
+#pragma unroll
+    for (int a = 0; a <= MAXA; ++a) logit[a] = warp_sum(acc[a]);
+    float m = -INFINITY;
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < A) { logit[a] += __ldg(bp + a); m = fmaxf(m, logit[a]); }
+    float sum = 0.0f;
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < A) sum += expf(logit[a] - m);
+    const float lse = logf(sum);
+    float vraw = 0.0f;
+#pragma unroll
+    for (int a = 0; a <= MAXA; ++a) {
+      if (a < A && lane == a) pi[row * A + a] = expf((logit[a] - m) - lse);
+      if (a == A) vraw = logit[a];
+    }
+    if (lane == 0) v[row] = tanhf(vraw + __ldg(bv));
+  }
+}
+
+int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R, uint8_t* hi, uint8_t* lo, cudaStream_t st) {
+  return to_image(src, rows, rows_padded, K, R, hi, lo, st);
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
-// packed weight blob: [W0_hi | W0_lo | W2_hi | W2_lo] images (lo parts only for BF16X3)
-static size_t image_bytes(int F) { return (size_t)F * F * 2; }
+// Packed weight blob of the tensor-core Connect4 path (azg_c4_pack), sections 1024-B aligned:
+//   W0 (output_transform.0, input order permuted to the feature image) hi [lo]
+//   W2 (output_transform.2) hi [lo] | conv2 [64 x 320] hi [lo] | head weights permuted, fp32
+namespace {
+struct PackLayout {
+  size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, total;
+  bool x3, gnn;
+};
 
-size_t azg_tc_scratch_bytes(int n, int64_t B, int prec) {
-  const size_t F = 64 * (size_t)n * n;
-  const size_t Mp = (size_t)azg_ceil_div(B, tc::BM) * tc::BM;
-  const size_t per = Mp * F * 2;  // one bf16 image of [Mp, F]
-  const int parts = (prec == AZG_PREC_BF16X3) ? 2 : 1;
-  return 2 * parts * per + 1024;  // X image(s) + H image(s)
+size_t up1k(size_t v) { return (v + 1023) / 1024 * 1024; }
+
+PackLayout pack_layout(int n, int prec, bool gnn) {
+  PackLayout L{};
+  const size_t F = 64 * (size_t)n * n, wimg = F * F * 2, cimg = 64 * (size_t)tc::C2_K * 2;
+  L.x3 = prec == AZG_PREC_BF16X3;
+  L.gnn = gnn;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = up1k(off + bytes); return o; };
+  if (gnn) {
+    L.w0_hi = take(wimg);
+    L.w0_lo = L.x3 ? take(wimg) : 0;
+    L.w2_hi = take(wimg);
+    L.w2_lo = L.x3 ? take(wimg) : 0;
+  }
+  L.c2_hi = take(cimg);
+  L.c2_lo = L.x3 ? take(cimg) : 0;
+  L.heads = take((size_t)(n + 2) * F * 4);
+  L.total = off;
+  return L;
 }
 
-int azg_tc_output_transform(const void* packed, int n, int prec, const float* feat, const float* b0, const float* b2,
-                            float* enh, int64_t B, void* scratch, size_t scratch_bytes, cudaStream_t st) {
-  const int F = 64 * n * n, BN = tc::pick_bn(F);
-  AZG_REQUIRE(BN != 0, "tcgen05 path: unsupported board size %d", n);
-  AZG_REQUIRE(scratch && scratch_bytes >= azg_tc_scratch_bytes(n, B, prec), "tcgen05 path: scratch too small");
+struct ScratchLayout {
+  size_t a2_hi, a2_lo, f_hi, f_lo, h_hi, h_lo, total;
+};
+
+ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
+  ScratchLayout S{};
   const bool x3 = prec == AZG_PREC_BF16X3;
-  const int64_t m_tiles = azg_ceil_div(B, tc::BM), Mp = m_tiles * tc::BM;
-  const size_t per = (size_t)Mp * F * 2;
-  uint8_t* base = (uint8_t*)(((uintptr_t)scratch + 1023) & ~(uintptr_t)1023);
-  uint8_t* x_hi = base;
-  uint8_t* x_lo = x3 ? x_hi + per : nullptr;
-  uint8_t* h_hi = base + (x3 ? 2 : 1) * per;
-  uint8_t* h_lo = x3 ? h_hi + per : nullptr;
+  const size_t nn = (size_t)n * n, F = 64 * nn;
+  const size_t M2p = (size_t)azg_ceil_div(B * (int64_t)nn, tc::BM) * tc::BM, Mp = (size_t)azg_ceil_div(B, tc::BM) * tc::BM;
+  const size_t a2 = M2p * tc::C2_K * 2, fimg = Mp * F * 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = up1k(off + bytes); return o; };
+  S.a2_hi = take(a2);
+  S.a2_lo = x3 ? take(a2) : 0;
+  S.f_hi = take(fimg);
+  S.f_lo = x3 ? take(fimg) : 0;
+  if (gnn) {
+    S.h_hi = take(fimg);
+    S.h_lo = x3 ? take(fimg) : 0;
+  }
+  S.total = off + 1024;
+  return S;
+}
+}  // namespace
+
+size_t azg_tc_scratch_bytes(int n, int64_t B, int prec) { return scratch_layout(n, B, prec, true).total; }
+
+// Whole Connect4 leaf evaluation on the tensor-core path: im2col(encode+conv1) -> conv2 GEMM ->
+// [std heads] -> [output_transform GEMMs -> enh fp32 for the GNN heads].
+int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int prec, const uint64_t* states, int64_t B,
+                      int eval_mask, float* pi_std, float* v_std, float* enh, void* scratch, size_t scratch_bytes,
+                      cudaStream_t st) {
+  const int nn = n * n, F = 64 * nn, A = n + 1, BN = tc::pick_bn(F);
+  AZG_REQUIRE(BN != 0, "tcgen05 path: unsupported board size %d", n);
+  const bool x3 = prec == AZG_PREC_BF16X3, gnn = (eval_mask & AZG_EVAL_GNN) != 0;
+  const PackLayout L = pack_layout(n, prec, true);
+  const ScratchLayout S = scratch_layout(n, B, prec, true);
+  AZG_REQUIRE(scratch && scratch_bytes >= S.total, "tcgen05 path: scratch %zu < %zu", scratch_bytes, S.total);
+  uint8_t* sc = (uint8_t*)(((uintptr_t)scratch + 1023) & ~(uintptr_t)1023);
   const uint8_t* w = (const uint8_t*)packed;
-  const size_t wb = image_bytes(F);
-  const uint8_t *w0_hi = w, *w0_lo = x3 ? w + wb : nullptr;
-  const uint8_t *w2_hi = w + (x3 ? 2 : 1) * wb, *w2_lo = x3 ? w2_hi + wb : nullptr;
+  uint8_t *a2_hi = sc + S.a2_hi, *a2_lo = x3 ? sc + S.a2_lo : nullptr;
+  uint8_t *f_hi = sc + S.f_hi, *f_lo = x3 ? sc + S.f_lo : nullptr;
+  uint8_t *h_hi = sc + S.h_hi, *h_lo = x3 ? sc + S.h_lo : nullptr;
   int rc;
-  if ((rc = tc::to_image(feat, B, Mp, F, tc::BM, x_hi, x_lo, st))) return rc;
+  azg_phase_begin(AZG_PHASE_TRUNK, st);
+  {
+    const int grid = (int)(B < 148 * 8 ? B : 148 * 8);
+    tc::c4_im2col_kernel<<<grid, 256, 0, st>>>(states, n, B, p->conv1_w, p->conv1_b, a2_hi, a2_lo);
+    AZG_LAUNCH_CHECK();
+  }
   tc::GemmArgs g{};
+  g.M = B * (int64_t)nn;
+  g.m_tiles = (int)azg_ceil_div(g.M, tc::BM);
+  g.n_tiles = 1;
+  g.KB = tc::C2_KB;
+  g.x3 = x3;
+  g.a_hi = a2_hi; g.a_lo = a2_lo; g.w_hi = w + L.c2_hi; g.w_lo = x3 ? w + L.c2_lo : nullptr;
+  g.bias = p->conv2_b; g.relu = 1; g.out_mode = x3 ? tc::OUT_FEAT_HILO : tc::OUT_FEAT; g.feat_nn = nn;
+  g.out_hi = f_hi; g.out_lo = f_lo;
+  if ((rc = tc::run_gemm(64, g, st))) return rc;
+  azg_phase_end(AZG_PHASE_TRUNK, st);
+  if (eval_mask & AZG_EVAL_STD) {
+    AZG_REQUIRE(pi_std && v_std && A <= 9, "tcgen05 path: bad std outputs");
+    azg_phase_begin(AZG_PHASE_HEADS, st);
+    const int grid = (int)(azg_ceil_div(B, 8) < 148 * 8 ? azg_ceil_div(B, 8) : 148 * 8);
+    tc::heads_image_kernel<9><<<grid, 256, 0, st>>>(f_hi, f_lo, nn, (const float*)(w + L.heads), p->fc_policy_b,
+                                                    p->fc_value_b, A, B, pi_std, v_std);
+    AZG_LAUNCH_CHECK();
+    azg_phase_end(AZG_PHASE_HEADS, st);
+  }
+  if (!gnn) return AZG_OK;
+  azg_phase_begin(AZG_PHASE_GEMM, st);
+  g = tc::GemmArgs{};
   g.M = B;
-  g.m_tiles = (int)m_tiles;
+  g.m_tiles = (int)azg_ceil_div(B, tc::BM);
   g.n_tiles = F / BN;
   g.KB = F / tc::BK;
   g.x3 = x3;
-  // H = relu(X W0^T + b0), written as the next GEMM's operand image
-  g.a_hi = x_hi; g.a_lo = x_lo; g.w_hi = w0_hi; g.w_lo = w0_lo; g.bias = b0; g.relu = 1;
-  g.out_mode = x3 ? tc::OUT_IMG_HILO : tc::OUT_IMG; g.out_hi = h_hi; g.out_lo = h_lo; g.out_f32 = nullptr;
+  g.a_hi = f_hi; g.a_lo = f_lo; g.w_hi = w + L.w0_hi; g.w_lo = x3 ? w + L.w0_lo : nullptr; g.bias = p->ot0_b; g.relu = 1;
+  g.out_mode = x3 ? tc::OUT_IMG_HILO : tc::OUT_IMG; g.out_hi = h_hi; g.out_lo = h_lo;
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
-  // E = H W2^T + b2, fp32 row-major for the heads
-  g.a_hi = h_hi; g.a_lo = h_lo; g.w_hi = w2_hi; g.w_lo = w2_lo; g.bias = b2; g.relu = 0;
+  g.a_hi = h_hi; g.a_lo = h_lo; g.w_hi = w + L.w2_hi; g.w_lo = x3 ? w + L.w2_lo : nullptr; g.bias = p->ot2_b; g.relu = 0;
   g.out_mode = tc::OUT_F32; g.out_f32 = enh; g.out_hi = g.out_lo = nullptr;
-  return tc::run_gemm(BN, g, st);
+  rc = tc::run_gemm(BN, g, st);
+  azg_phase_end(AZG_PHASE_GEMM, st);
+  return rc;
 }
 
 extern "C" {
 
 size_t azg_c4_packed_bytes(int n, int prec) {
   const int F = 64 * n * n;
-  if (tc::pick_bn(F) == 0 || prec == AZG_PREC_FP32) return 0;
-  return (prec == AZG_PREC_BF16X3 ? 4 : 2) * image_bytes(F) + 1024;
+  if (n < 4 || n > 8 || tc::pick_bn(F) == 0 || prec == AZG_PREC_FP32) return 0;
+  return pack_layout(n, prec, true).total + 1024;
 }
 
-int azg_c4_pack_gnn(const float* ot0_w, const float* ot2_w, int n, int prec, void* packed, size_t packed_bytes,
-                    azg_stream stream) {
-  const int F = 64 * n * n, BN = tc::pick_bn(F);
-  AZG_REQUIRE(ot0_w && ot2_w && packed, "azg_c4_pack_gnn: null pointer");
-  AZG_REQUIRE(BN != 0 && (prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16), "azg_c4_pack_gnn: unsupported n=%d prec=%d", n, prec);
-  AZG_REQUIRE(packed_bytes >= azg_c4_packed_bytes(n, prec), "azg_c4_pack_gnn: buffer too small");
-  AZG_REQUIRE(((uintptr_t)packed & 15) == 0, "azg_c4_pack_gnn: buffer must be 16-byte aligned (bulk-copy source)");
-  const bool x3 = prec == AZG_PREC_BF16X3;
+int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t packed_bytes, azg_stream stream) {
+  const int nn = n * n, F = 64 * nn, A = n + 1, BN = tc::pick_bn(F);
+  AZG_REQUIRE(p && packed && p->conv2_w && p->fc_policy_w && p->fc_value_w, "azg_c4_pack: null pointer");
+  AZG_REQUIRE(n >= 4 && n <= 8 && BN != 0 && (prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16), "azg_c4_pack: unsupported n=%d prec=%d", n, prec);
+  AZG_REQUIRE(packed_bytes >= azg_c4_packed_bytes(n, prec), "azg_c4_pack: buffer too small");
+  AZG_REQUIRE(((uintptr_t)packed & 15) == 0, "azg_c4_pack: buffer must be 16-byte aligned (bulk-copy source)");
+  const PackLayout L = pack_layout(n, prec, true);
+  const bool x3 = L.x3;
   uint8_t* w = (uint8_t*)packed;
-  const size_t wb = image_bytes(F);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  if ((rc = tc::to_image(ot0_w, F, F, F, BN, w, x3 ? w + wb : nullptr, st))) return rc;
-  uint8_t* w2 = w + (x3 ? 2 : 1) * wb;
-  return tc::to_image(ot2_w, F, F, F, BN, w2, x3 ? w2 + wb : nullptr, st);
+  if (p->ot0_w && p->ot2_w) {
+    const int64_t cnt = (int64_t)F * (F / 8);
+    tc::permuted_weight_image_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(p->ot0_w, F, F, nn, BN, w + L.w0_hi,
+                                                                                   x3 ? w + L.w0_lo : nullptr);
+    AZG_LAUNCH_CHECK();
+    int rc = tc::make_image(p->ot2_w, F, F, F, BN, w + L.w2_hi, x3 ? w + L.w2_lo : nullptr, st);
+    if (rc) return rc;
+  }
+  tc::conv2_weight_image_kernel<<<(64 * (tc::C2_K / 8) + 127) / 128, 128, 0, st>>>(p->conv2_w, w + L.c2_hi, x3 ? w + L.c2_lo : nullptr);
+  AZG_LAUNCH_CHECK();
+  const int64_t hn = (int64_t)(A + 1) * F;
+  tc::permute_heads_kernel<<<(unsigned)((hn + 255) / 256), 256, 0, st>>>(p->fc_policy_w, p->fc_value_w, A, F, nn, (float*)(w + L.heads));
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
 }
 
 // Stand-alone dense layer on the tensor-core path, for parity tests of the GEMM itself:
@@ -487,7 +789,7 @@ int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, i
   AZG_REQUIRE(BN != 0 && F % 64 == 0 && (prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16), "azg_tc_linear: unsupported F=%d prec=%d", F, prec);
   const bool x3 = prec == AZG_PREC_BF16X3;
   const int64_t m_tiles = azg_ceil_div(M, tc::BM), Mp = m_tiles * tc::BM;
-  const size_t a_img = (size_t)Mp * F * 2, w_img = image_bytes(F);
+  const size_t a_img = (size_t)Mp * F * 2, w_img = (size_t)F * F * 2;
   const size_t need = (x3 ? 2 : 1) * (a_img + w_img) + 1024;
   AZG_REQUIRE(scratch_bytes >= need, "azg_tc_linear: scratch %zu < %zu", scratch_bytes, need);
   uint8_t* base = (uint8_t*)(((uintptr_t)scratch + 1023) & ~(uintptr_t)1023);

@@ -382,8 +382,9 @@ struct Carver {
 }  // namespace
 
 // tcgen05 path (azg_gemm_tc.cu)
-int azg_tc_output_transform(const void* packed, int n, int prec, const float* feat, const float* b0, const float* b2,
-                            float* enh, int64_t B, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int prec, const uint64_t* states, int64_t B,
+                      int eval_mask, float* pi_std, float* v_std, float* enh, void* scratch, size_t scratch_bytes,
+                      cudaStream_t st);
 size_t azg_tc_scratch_bytes(int n, int64_t B, int prec);
 
 extern "C" {
@@ -440,20 +441,18 @@ int azg_linear_f32(const float* A, const float* W, const float* bias, float* C, 
 static size_t c4_carve(Carver& c, int n, int64_t B, int eval_mask, int prec, float** planes, float** c1, float** feat,
                        float** hid, float** enh, void** scratch, size_t* scratch_bytes) {
   const size_t nn = (size_t)n * n, F = 64 * nn;
-  *planes = c.take(B * nn);
-  *c1 = c.take(B * 32 * nn);
-  *feat = c.take(B * F);
-  *hid = *enh = nullptr;
+  *planes = *c1 = *feat = *hid = *enh = nullptr;
   *scratch = nullptr;
   *scratch_bytes = 0;
-  if (eval_mask & AZG_EVAL_GNN) {
-    *enh = c.take(B * F);
-    if (prec == AZG_PREC_FP32) {
-      *hid = c.take(B * F);
-    } else {
-      *scratch_bytes = azg_tc_scratch_bytes(n, B, prec);
-      *scratch = c.take((*scratch_bytes + 3) / 4);
-    }
+  if (eval_mask & AZG_EVAL_GNN) *enh = c.take(B * F);
+  if (prec == AZG_PREC_FP32) {
+    *planes = c.take(B * nn);
+    *c1 = c.take(B * 32 * nn);
+    *feat = c.take(B * F);
+    if (eval_mask & AZG_EVAL_GNN) *hid = c.take(B * F);
+  } else {  // tensor-core path: operand images live in the scratch area
+    *scratch_bytes = azg_tc_scratch_bytes(n, B, prec);
+    *scratch = c.take((*scratch_bytes + 3) / 4);
   }
   return (c.off + 255) / 256 * 256;
 }
@@ -483,32 +482,34 @@ int azg_c4_forward(const azg_c4_params* p, int n, const uint64_t* states, int64_
   AZG_REQUIRE(need <= workspace_bytes, "azg_c4_forward: workspace %zu < %zu bytes", workspace_bytes, need);
   const int nn = n * n, F = 64 * nn, A = n + 1;
   int rc;
-  azg_phase_begin(AZG_PHASE_TRUNK, st);
-  if ((rc = azg_encode_planes(states, n, B, planes, stream))) return rc;
-  if ((rc = launch_conv(planes, p->conv1_w, p->conv1_b, c1, B, 1, 32, n, n, 1, st))) return rc;
-  if ((rc = launch_conv(c1, p->conv2_w, p->conv2_b, feat, B, 32, 64, n, n, 1, st))) return rc;
-  azg_phase_end(AZG_PHASE_TRUNK, st);
-  if (eval_mask & AZG_EVAL_STD) {
-    AZG_REQUIRE(pi_std && v_std, "azg_c4_forward: null std outputs");
-    azg_phase_begin(AZG_PHASE_HEADS, st);
-    if ((rc = launch_heads(feat, F, p->fc_policy_w, p->fc_policy_b, A, feat, F, p->fc_value_w, p->fc_value_b, B, pi_std,
-                           v_std, st)))
-      return rc;
-    azg_phase_end(AZG_PHASE_HEADS, st);
-  }
-  if (eval_mask & AZG_EVAL_GNN) {
-    AZG_REQUIRE(pi_gnn && v_gnn && p->ot0_b && p->ot2_b, "azg_c4_forward: null gnn outputs/params");
-    azg_phase_begin(AZG_PHASE_GEMM, st);
-    if (prec == AZG_PREC_FP32) {
+  if (eval_mask & AZG_EVAL_STD) AZG_REQUIRE(pi_std && v_std, "azg_c4_forward: null std outputs");
+  if (eval_mask & AZG_EVAL_GNN) AZG_REQUIRE(pi_gnn && v_gnn && p->ot0_b && p->ot2_b, "azg_c4_forward: null gnn outputs/params");
+  if (prec == AZG_PREC_FP32) {
+    azg_phase_begin(AZG_PHASE_TRUNK, st);
+    if ((rc = azg_encode_planes(states, n, B, planes, stream))) return rc;
+    if ((rc = launch_conv(planes, p->conv1_w, p->conv1_b, c1, B, 1, 32, n, n, 1, st))) return rc;
+    if ((rc = launch_conv(c1, p->conv2_w, p->conv2_b, feat, B, 32, 64, n, n, 1, st))) return rc;
+    azg_phase_end(AZG_PHASE_TRUNK, st);
+    if (eval_mask & AZG_EVAL_STD) {
+      azg_phase_begin(AZG_PHASE_HEADS, st);
+      if ((rc = launch_heads(feat, F, p->fc_policy_w, p->fc_policy_b, A, feat, F, p->fc_value_w, p->fc_value_b, B, pi_std,
+                             v_std, st)))
+        return rc;
+      azg_phase_end(AZG_PHASE_HEADS, st);
+    }
+    if (eval_mask & AZG_EVAL_GNN) {
       AZG_REQUIRE(p->ot0_w && p->ot2_w, "azg_c4_forward: null output_transform weights");
+      azg_phase_begin(AZG_PHASE_GEMM, st);
       if ((rc = launch_linear(feat, p->ot0_w, p->ot0_b, hid, B, F, F, 1, st))) return rc;
       if ((rc = launch_linear(hid, p->ot2_w, p->ot2_b, enh, B, F, F, 0, st))) return rc;
-    } else {
-      AZG_REQUIRE(p->ot_packed, "azg_c4_forward: prec %d needs ot_packed (azg_c4_pack_gnn)", prec);
-      if ((rc = azg_tc_output_transform(p->ot_packed, n, prec, feat, p->ot0_b, p->ot2_b, enh, B, scratch, scratch_bytes, st)))
-        return rc;
+      azg_phase_end(AZG_PHASE_GEMM, st);
     }
-    azg_phase_end(AZG_PHASE_GEMM, st);
+  } else {
+    AZG_REQUIRE(p->ot_packed, "azg_c4_forward: prec %d needs ot_packed (azg_c4_pack)", prec);
+    if ((rc = azg_tc_c4_forward(p->ot_packed, p, n, prec, states, B, eval_mask, pi_std, v_std, enh, scratch, scratch_bytes, st)))
+      return rc;
+  }
+  if (eval_mask & AZG_EVAL_GNN) {
     azg_phase_begin(AZG_PHASE_HEADS, st);
     if ((rc = launch_heads(enh, F, p->fc_policy_w, p->fc_policy_b, A, enh, F, p->fc_value_w, p->fc_value_b, B, pi_gnn,
                            v_gnn, st)))

@@ -147,22 +147,20 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         if g is not None:
             ot = g.output_transform
             p.ot0_w, p.ot0_b, p.ot2_w, p.ot2_b = ptr(ot[0].weight), ptr(ot[0].bias), ptr(ot[2].weight), ptr(ot[2].bias)
-            if need_packed:
-                p.ot_packed = ptr(self._ensure_packed(prec))
+        if need_packed:
+            p.ot_packed = ptr(self._ensure_packed(prec, p))
         return p
 
-    def _ensure_packed(self, prec):
-        """tcgen05 operand images of output_transform's weights, one blob per precision, rebuilt
-        lazily after weights_changed()."""
+    def _ensure_packed(self, prec, params):
+        """tcgen05 operand images of the weights (conv2, output_transform, permuted heads), one blob
+        per precision, rebuilt lazily after weights_changed()."""
         if not self._packed_ok:
             self._packed = {}
             self._packed_ok = True
         if prec not in self._packed:
             nbytes = self.lib.azg_c4_packed_bytes(self.n, prec)
             blob = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            ot = self.gnn.output_transform
-            _lib.check(self.lib.azg_c4_pack_gnn(ptr(ot[0].weight), ptr(ot[2].weight), self.n, prec, ptr(blob), nbytes,
-                                                stream()))
+            _lib.check(self.lib.azg_c4_pack(C.byref(params), self.n, prec, ptr(blob), nbytes, stream()))
             self._packed[prec] = blob
         return self._packed[prec]
 
@@ -176,7 +174,7 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         o = self._outputs(B, eval_mask)
         if B == 0:
             return o
-        p = self._params(prec, bool(eval_mask & _lib.EVAL_GNN) and prec != _lib.PREC_FP32)
+        p = self._params(prec, prec != _lib.PREC_FP32)
         nbytes = self.lib.azg_c4_workspace_bytes(self.n, B, eval_mask, prec)
         ws = self._workspace(nbytes)
         _lib.check(self.lib.azg_c4_forward(C.byref(p), self.n, ptr(states), B, eval_mask, prec, ptr(o.get("pi")),

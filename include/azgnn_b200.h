@@ -97,7 +97,7 @@ typedef struct azg_c4_params {
   const float *fc_value_w, *fc_value_b;   /* [1, 64 n^2], [1]   */
   const float *ot0_w, *ot0_b;             /* gnn.output_transform.0: [F,F], [F] (may be NULL without AZG_EVAL_GNN) */
   const float *ot2_w, *ot2_b;             /* gnn.output_transform.2: [F,F], [F] */
-  const void* ot_packed;                  /* azg_c4_pack_gnn output for AZG_PREC_BF16X3/BF16, else NULL */
+  const void* ot_packed;                  /* azg_c4_pack output for AZG_PREC_BF16X3/BF16, else NULL */
 } azg_c4_params;
 
 size_t azg_c4_workspace_bytes(int n, int64_t B, int eval_mask, int prec);
@@ -108,11 +108,11 @@ size_t azg_c4_workspace_bytes(int n, int64_t B, int eval_mask, int prec);
 int azg_c4_forward(const azg_c4_params* p, int n, const uint64_t* states, int64_t B, int eval_mask,
                    int prec, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn,
                    void* workspace, size_t workspace_bytes, azg_stream stream);
-/* Re-tile output_transform weights into the tcgen05 operand images (call after every
- * optimizer step / load_checkpoint). */
+/* Build the tcgen05 operand images of the weights (conv2, output_transform, permuted heads) for
+ * AZG_PREC_BF16X3 / AZG_PREC_BF16; the result goes into azg_c4_params.ot_packed.  Call again after
+ * every optimizer step / load_checkpoint.  packed: device memory, 16-byte aligned. */
 size_t azg_c4_packed_bytes(int n, int prec);
-int azg_c4_pack_gnn(const float* ot0_w, const float* ot2_w, int n, int prec, void* packed,
-                    size_t packed_bytes, azg_stream stream);
+int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t packed_bytes, azg_stream stream);
 
 /* One dense layer on the tcgen05 path, for parity tests of the GEMM in isolation:
  * C[M,F] = act(A[M,F] . W[F,F]^T + bias), fp32 in/out, prec = AZG_PREC_BF16X3 | AZG_PREC_BF16.

@@ -193,11 +193,20 @@ def test_forward_tensor_core_precisions(n, B):
     p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
     with torch.no_grad():
         gpi, gv = onets.c4_predict_with_gnn(p, q, onets.boards_to_tensor(boards), n)
+    with torch.no_grad():
+        spi, sv = onets.c4_predict(p, onets.boards_to_tensor(boards), n)
     states = w.states_from_boards(boards)
-    o3 = w.forward_states(states, _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
+    both = _lib.EVAL_STD | _lib.EVAL_GNN
+    o3 = w.forward_states(states, both, precision=_lib.PREC_BF16X3)
     np.testing.assert_allclose(o3["pi_gnn"].cpu().numpy(), gpi.numpy(), rtol=0, atol=1e-5)
     np.testing.assert_allclose(o3["v_gnn"].cpu().numpy(), gv.numpy(), rtol=0, atol=1e-5)
-    o1 = w.forward_states(states, _lib.EVAL_GNN, precision=_lib.PREC_BF16)
+    # the trunk runs on the tensor cores too (conv2 as an implicit GEMM): std heads see the same features
+    np.testing.assert_allclose(o3["pi"].cpu().numpy(), spi.numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(o3["v"].cpu().numpy(), sv.numpy(), rtol=0, atol=1e-5)
+    only_std = w.forward_states(states, _lib.EVAL_STD, precision=_lib.PREC_BF16X3)
+    assert torch.equal(only_std["pi"], o3["pi"])
+    o1 = w.forward_states(states, both, precision=_lib.PREC_BF16)
+    assert np.abs(o1["pi"].cpu().numpy() - spi.numpy()).max() <= 5e-3 and np.abs(o1["v"].cpu().numpy() - sv.numpy()).max() <= 5e-3
     e_pi = np.abs(o1["pi_gnn"].cpu().numpy() - gpi.numpy()).max()
     e_v = np.abs(o1["v_gnn"].cpu().numpy() - gv.numpy()).max()
     print(f"bf16 n={n} B={B}: max |dpi| = {e_pi:.2e}, max |dv| = {e_v:.2e}")
