@@ -1,0 +1,145 @@
+"""Coach with the reference's surface (`Coach(game, nnet, args)`, `executeEpisode()`, `learn()`;
+Coach.py:16-176) on top of the arena.
+
+* `executeEpisode()` is the reference loop for ONE game (Coach.py:27-79): same call order, same
+  use of the process-global NumPy RNG (`np.random.choice` for the temp-0 tie-break inside
+  `getActionProb` and for the move sample), so with the same seed and the same network outputs it
+  plays the same moves and returns the same example tuples as the reference.
+* `learn()` keeps the reference's iteration structure (self-play -> history window -> train ->
+  pit new vs previous -> accept/reject -> checkpoints, Coach.py:87-176) but collects the
+  `numEps` episodes with `BatchedSelfPlay` (`n_parallel_games` concurrent games, default
+  min(numEps, 4096)) and pits with the arena-backed MCTS.  Example pickling and `--load_model`
+  resume stay in the reference's own Coach (out of scope).
+"""
+import logging
+import os
+from collections import deque
+from random import shuffle
+
+import numpy as np
+
+from .mcts import MCTS, arg
+from .selfplay import BatchedSelfPlay
+
+log = logging.getLogger(__name__)
+
+
+class Coach:
+    def __init__(self, game, nnet, args, arena_factory=None):
+        self.game, self.nnet, self.args = game, nnet, args
+        self._arena_factory = arena_factory  # tests inject the host check arena
+        self.pnet = None
+        self.mcts = self._new_mcts(self.nnet)
+        self.trainExamplesHistory = []
+        self.curPlayer = 1
+
+    def _new_mcts(self, nnet):
+        arena = self._arena_factory() if self._arena_factory else None
+        return MCTS(self.game, nnet, self.args, arena=arena)
+
+    def _use_gnn(self):
+        return bool(arg(self.args, "use_gnn", False))
+
+    # ------------------------------------------------------------------ Coach.py:27-79
+    def executeEpisode(self):
+        trainExamples, gnnExamples = [], []
+        board = self.game.getInitBoard()
+        self.curPlayer = 1
+        episodeStep = 0
+        while True:
+            episodeStep += 1
+            canonicalBoard = self.game.getCanonicalForm(board, self.curPlayer)
+            temp = int(episodeStep < arg(self.args, "tempThreshold"))
+            pi = self.mcts.getActionProb(canonicalBoard, temp=temp)
+            sym = self.game.getSymmetries(canonicalBoard, pi)
+            for b, p in sym:
+                trainExamples.append([b, self.curPlayer, p, None])
+            if self._use_gnn():
+                expanded = self.mcts.expand_tree(canonicalBoard, expand_by=arg(self.args, "expand_by", 5))
+                for s, (ip, iv, ep, ev) in expanded.items():
+                    for b, _ in sym:
+                        if self.game.stringRepresentation(b) == s:
+                            gnnExamples.append([b, self.curPlayer, ip, iv, ep, ev, None])
+                            break
+            action = np.random.choice(len(pi), p=pi)
+            board, self.curPlayer = self.game.getNextState(board, self.curPlayer, action)
+            r = self.game.getGameEnded(board, self.curPlayer)
+            if r != 0:
+                std = [(x[0], x[2], r * ((-1) ** (x[1] != self.curPlayer))) for x in trainExamples]
+                if self._use_gnn() and gnnExamples:
+                    gnn = [(x[0], x[1], x[2], x[3], x[4], x[5], r * ((-1) ** (x[1] != self.curPlayer))) for x in gnnExamples]
+                    return std, gnn
+                return std, []
+
+    # ------------------------------------------------------------------ pit (Arena.py:106-152, two-player)
+    def _pit(self, pmcts, nmcts, n_games):
+        """new vs previous, alternating the first move; returns (prev wins, new wins, draws)"""
+        def play(first, second):
+            players = {1: first, -1: second}
+            board, cur = self.game.getInitBoard(), 1
+            while self.game.getGameEnded(board, cur) == 0:
+                canon = self.game.getCanonicalForm(board, cur)
+                action = int(np.argmax(players[cur].getActionProb(canon, temp=0)))
+                valids = self.game.getValidMoves(canon, 1)
+                assert valids[action] > 0
+                board, cur = self.game.getNextState(board, cur, action)
+            return cur * self.game.getGameEnded(board, cur)  # result from player 1's point of view
+        pw = nw = dr = 0
+        half = n_games // 2
+        for i in range(2 * half):
+            prev_first = i < half
+            res = play(pmcts, nmcts) if prev_first else play(nmcts, pmcts)
+            if abs(res) != 1:
+                dr += 1
+            elif (res == 1) == prev_first:
+                pw += 1
+            else:
+                nw += 1
+        return pw, nw, dr
+
+    def getCheckpointFile(self, iteration):
+        return f"checkpoint_{iteration}" + ("_gnn" if self._use_gnn() else "") + ".pth.tar"
+
+    # ------------------------------------------------------------------ Coach.py:87-176
+    def learn(self):
+        a = self.args
+        for i in range(1, arg(a, "numIters") + 1):
+            log.info(f"Starting Iter #{i} ...")
+            it_std = deque([], maxlen=arg(a, "maxlenOfQueue"))
+            it_gnn = deque([], maxlen=arg(a, "maxlenOfQueue"))
+            n_eps = arg(a, "numEps")
+            games = int(arg(a, "n_parallel_games", min(n_eps, 4096)) or min(n_eps, 4096))
+            sp = BatchedSelfPlay(self.game, self.nnet, a, games, seed=i,
+                                 arena=self._arena_factory(games) if self._arena_factory else None)
+            for std, gnn in sp.play(n_eps):
+                it_std += std
+                it_gnn += gnn
+            self.trainExamplesHistory.append((it_std, it_gnn))
+            if len(self.trainExamplesHistory) > arg(a, "numItersForTrainExamplesHistory"):
+                self.trainExamplesHistory.pop(0)
+            trainExamples, gnnExamples = [], []
+            for std, gnn in self.trainExamplesHistory:
+                trainExamples.extend(std)
+                gnnExamples.extend(gnn)
+            shuffle(trainExamples)
+            shuffle(gnnExamples)
+            folder = arg(a, "checkpoint", arg(a, "checkpoint_path", "./checkpoints/"))
+            self.nnet.save_checkpoint(folder=folder, filename="temp.pth.tar")
+            if self.pnet is None:
+                self.pnet = self.nnet.__class__(self.game, a)
+            self.pnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
+            pmcts = self._new_mcts(self.pnet)
+            if self._use_gnn() and gnnExamples:
+                self.nnet.train(trainExamples, gnnExamples)
+            else:
+                self.nnet.train(trainExamples)
+            nmcts = self._new_mcts(self.nnet)
+            pwins, nwins, draws = self._pit(pmcts, nmcts, arg(a, "arenaCompare"))
+            log.info("NEW/PREV WINS : %d / %d ; DRAWS : %d" % (nwins, pwins, draws))
+            accept = i == 1 or ((pwins + nwins > 0) and float(nwins) / (pwins + nwins) >= arg(a, "updateThreshold"))
+            if not accept:
+                self.nnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
+            else:
+                best = "best_gnn.pth.tar" if self._use_gnn() else "best.pth.tar"
+                self.nnet.save_checkpoint(folder=folder, filename=self.getCheckpointFile(i))
+                self.nnet.save_checkpoint(folder=folder, filename=best)
