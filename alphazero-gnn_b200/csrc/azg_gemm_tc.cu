@@ -137,7 +137,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 // ---- epilogue output modes -----------------------------------------------------------------
-enum { OUT_F32 = 0, OUT_IMG = 1, OUT_IMG_HILO = 2, OUT_FEAT = 3, OUT_FEAT_HILO = 4 };
+enum { OUT_F32 = 0, OUT_IMG = 1, OUT_IMG_HILO = 2, OUT_FEAT = 3, OUT_FEAT_HILO = 4, OUT_HEADS = 5 };
+constexpr int HEAD_ROWS = 10;    // <= 9 policy logits + 1 value (Connect4 n <= 8)
+constexpr int HEAD_STRIDE = 16;  // floats per (row, n-tile) record of partial head sums
 
 struct GemmArgs {
   const uint8_t* a_hi;  // activation images, tiles [128 x 64], (mt * KB + kb) * 16384
@@ -153,6 +155,9 @@ struct GemmArgs {
   int x3;               // 0: bf16, 1: 3-term split
   int relu;
   int out_mode;
+  const float* head_w;  // OUT_HEADS: [head_rows, N] fp32 (policy rows then the value row), reference order
+  float* head_part;     // OUT_HEADS: [M, n_tiles, HEAD_STRIDE] partial sums, reduced in fixed order by heads_finalize
+  int head_rows;
   int feat_nn;          // OUT_FEAT*: rows are (board b, cell p) pairs, m = b*feat_nn + p; the 64 columns (conv2
                         // channels) become k-block p of row b of the feature image  [K' = p*64 + co]
 };
@@ -270,6 +275,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      float hacc[HEAD_ROWS];
+#pragma unroll
+      for (int a = 0; a < HEAD_ROWS; ++a) hacc[a] = 0.0f;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t rr[32];
@@ -282,7 +290,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
           float x = __uint_as_float(rr[j]) + __ldg(g.bias + n0 + j);
           v[j] = g.relu ? fmaxf(x, 0.0f) : x;
         }
-        if (g.out_mode >= OUT_FEAT) {
+        if (g.out_mode == OUT_HEADS) {
+          // policy/value heads fused into the epilogue (Connect4GNN.py:48-57): this tile's share of
+          // logits[a] = sum_n E[row, n] * Wh[a, n]; the head weights are warp-uniform loads
+          const int N = g.n_tiles * BN;
+#pragma unroll
+          for (int a = 0; a < HEAD_ROWS; ++a) {
+            if (a < g.head_rows) {
+              const float4* wr = reinterpret_cast<const float4*>(g.head_w + (size_t)a * N + n0);
+              float s = hacc[a];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w4 = __ldg(wr + j);
+                s = fmaf(v[4 * j], w4.x, fmaf(v[4 * j + 1], w4.y, fmaf(v[4 * j + 2], w4.z, fmaf(v[4 * j + 3], w4.w, s))));
+              }
+              hacc[a] = s;
+            }
+          }
+        } else if (g.out_mode >= OUT_FEAT) {
           if (row < g.M) {
             const int64_t bidx = row / g.feat_nn;
             const int p = (int)(row - bidx * g.feat_nn);
@@ -337,6 +362,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);  // 128 arrivals release the accumulator
+      if (g.out_mode == OUT_HEADS && row < g.M) {
+        float* dst = g.head_part + ((size_t)row * g.n_tiles + nt) * HEAD_STRIDE;
+#pragma unroll
+        for (int a = 0; a < HEAD_ROWS; ++a)
+          if (a < g.head_rows) dst[a] = hacc[a];
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -620,6 +651,46 @@ __global__ void __launch_bounds__(256) heads_image_kernel(const uint8_t* __restr
   }
 }
 
+// logits = fixed-order sum of the per-tile partial head sums + bias; then exp(log_softmax) and tanh
+__global__ void heads_finalize_kernel(const float* __restrict__ part, int n_tiles, int A, const float* __restrict__ bp,
+                                      const float* __restrict__ bv, int64_t B, float* __restrict__ pi, float* __restrict__ v) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B) return;
+  float logit[HEAD_ROWS];
+#pragma unroll
+  for (int a = 0; a < HEAD_ROWS; ++a) logit[a] = 0.0f;
+  const float* p = part + (size_t)row * n_tiles * HEAD_STRIDE;
+  for (int t = 0; t < n_tiles; ++t)
+#pragma unroll
+    for (int a = 0; a < HEAD_ROWS; ++a)
+      if (a <= A) logit[a] += p[t * HEAD_STRIDE + a];
+  float m = -INFINITY;
+#pragma unroll
+  for (int a = 0; a < HEAD_ROWS; ++a)
+    if (a < A) { logit[a] += __ldg(bp + a); m = fmaxf(m, logit[a]); }
+  float sum = 0.0f;
+#pragma unroll
+  for (int a = 0; a < HEAD_ROWS; ++a)
+    if (a < A) sum += expf(logit[a] - m);
+  const float lse = logf(sum);
+  float vraw = 0.0f;
+#pragma unroll
+  for (int a = 0; a < HEAD_ROWS; ++a) {
+    if (a < A) pi[row * A + a] = expf((logit[a] - m) - lse);
+    if (a == A) vraw = logit[a];
+  }
+  v[row] = tanhf(vraw + __ldg(bv));
+}
+
+// [policy rows ; value row] in the reference's input order, fp32 (for the fused-heads epilogue)
+__global__ void concat_heads_kernel(const float* __restrict__ wp, const float* __restrict__ wv, int A, int F,
+                                    float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)(A + 1) * F) return;
+  const int row = (int)(idx / F), k = (int)(idx % F);
+  out[idx] = row < A ? wp[(size_t)row * F + k] : wv[k];
+}
+
 int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R, uint8_t* hi, uint8_t* lo, cudaStream_t st) {
   return to_image(src, rows, rows_padded, K, R, hi, lo, st);
 }
@@ -632,7 +703,7 @@ int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R
 //   W2 (output_transform.2) hi [lo] | conv2 [64 x 320] hi [lo] | head weights permuted, fp32
 namespace {
 struct PackLayout {
-  size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, total;
+  size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, heads_cat, total;
   bool x3, gnn;
 };
 
@@ -653,13 +724,14 @@ PackLayout pack_layout(int n, int prec, bool gnn) {
   }
   L.c2_hi = take(cimg);
   L.c2_lo = L.x3 ? take(cimg) : 0;
-  L.heads = take((size_t)(n + 2) * F * 4);
+  L.heads = take((size_t)(n + 2) * F * 4);      // permuted to the feature image order (std heads)
+  L.heads_cat = take((size_t)(n + 2) * F * 4);  // reference order (GNN heads fused into the GEMM-2 epilogue)
   L.total = off;
   return L;
 }
 
 struct ScratchLayout {
-  size_t a2_hi, a2_lo, f_hi, f_lo, h_hi, h_lo, total;
+  size_t a2_hi, a2_lo, f_hi, f_lo, h_hi, h_lo, part, total;
 };
 
 ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
@@ -677,6 +749,7 @@ ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
   if (gnn) {
     S.h_hi = take(fimg);
     S.h_lo = x3 ? take(fimg) : 0;
+    S.part = take(Mp * 16 * tc::HEAD_STRIDE * sizeof(float));  // <= 16 n-tiles
   }
   S.total = off + 1024;
   return S;
@@ -688,8 +761,8 @@ size_t azg_tc_scratch_bytes(int n, int64_t B, int prec) { return scratch_layout(
 // Whole Connect4 leaf evaluation on the tensor-core path: im2col(encode+conv1) -> conv2 GEMM ->
 // [std heads] -> [output_transform GEMMs -> enh fp32 for the GNN heads].
 int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int prec, const uint64_t* states, int64_t B,
-                      int eval_mask, float* pi_std, float* v_std, float* enh, void* scratch, size_t scratch_bytes,
-                      cudaStream_t st) {
+                      int eval_mask, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* scratch,
+                      size_t scratch_bytes, cudaStream_t st) {
   const int nn = n * n, F = 64 * nn, A = n + 1, BN = tc::pick_bn(F);
   AZG_REQUIRE(BN != 0, "tcgen05 path: unsupported board size %d", n);
   const bool x3 = prec == AZG_PREC_BF16X3, gnn = (eval_mask & AZG_EVAL_GNN) != 0;
@@ -740,10 +813,17 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   g.out_mode = x3 ? tc::OUT_IMG_HILO : tc::OUT_IMG; g.out_hi = h_hi; g.out_lo = h_lo;
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
   g.a_hi = h_hi; g.a_lo = h_lo; g.w_hi = w + L.w2_hi; g.w_lo = x3 ? w + L.w2_lo : nullptr; g.bias = p->ot2_b; g.relu = 0;
-  g.out_mode = tc::OUT_F32; g.out_f32 = enh; g.out_hi = g.out_lo = nullptr;
-  rc = tc::run_gemm(BN, g, st);
+  g.out_mode = tc::OUT_HEADS; g.out_hi = g.out_lo = nullptr; g.out_f32 = nullptr;
+  g.head_w = (const float*)(w + L.heads_cat); g.head_rows = A + 1; g.head_part = (float*)(sc + S.part);
+  AZG_REQUIRE(g.n_tiles <= 16 && A + 1 <= tc::HEAD_ROWS, "tcgen05 path: head fusion limits exceeded");
+  if ((rc = tc::run_gemm(BN, g, st))) return rc;
   azg_phase_end(AZG_PHASE_GEMM, st);
-  return rc;
+  azg_phase_begin(AZG_PHASE_HEADS, st);
+  tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles, A, p->fc_policy_b,
+                                                                        p->fc_value_b, B, pi_gnn, v_gnn);
+  AZG_LAUNCH_CHECK();
+  azg_phase_end(AZG_PHASE_HEADS, st);
+  return AZG_OK;
 }
 
 extern "C" {
@@ -776,6 +856,8 @@ int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t pa
   AZG_LAUNCH_CHECK();
   const int64_t hn = (int64_t)(A + 1) * F;
   tc::permute_heads_kernel<<<(unsigned)((hn + 255) / 256), 256, 0, st>>>(p->fc_policy_w, p->fc_value_w, A, F, nn, (float*)(w + L.heads));
+  AZG_LAUNCH_CHECK();
+  tc::concat_heads_kernel<<<(unsigned)((hn + 255) / 256), 256, 0, st>>>(p->fc_policy_w, p->fc_value_w, A, F, (float*)(w + L.heads_cat));
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }

@@ -383,8 +383,8 @@ struct Carver {
 
 // tcgen05 path (azg_gemm_tc.cu)
 int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int prec, const uint64_t* states, int64_t B,
-                      int eval_mask, float* pi_std, float* v_std, float* enh, void* scratch, size_t scratch_bytes,
-                      cudaStream_t st);
+                      int eval_mask, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* scratch,
+                      size_t scratch_bytes, cudaStream_t st);
 size_t azg_tc_scratch_bytes(int n, int64_t B, int prec);
 
 extern "C" {
@@ -444,8 +444,8 @@ static size_t c4_carve(Carver& c, int n, int64_t B, int eval_mask, int prec, flo
   *planes = *c1 = *feat = *hid = *enh = nullptr;
   *scratch = nullptr;
   *scratch_bytes = 0;
-  if (eval_mask & AZG_EVAL_GNN) *enh = c.take(B * F);
   if (prec == AZG_PREC_FP32) {
+    if (eval_mask & AZG_EVAL_GNN) *enh = c.take(B * F);
     *planes = c.take(B * nn);
     *c1 = c.take(B * 32 * nn);
     *feat = c.take(B * F);
@@ -504,17 +504,18 @@ int azg_c4_forward(const azg_c4_params* p, int n, const uint64_t* states, int64_
       if ((rc = launch_linear(hid, p->ot2_w, p->ot2_b, enh, B, F, F, 0, st))) return rc;
       azg_phase_end(AZG_PHASE_GEMM, st);
     }
+    if (eval_mask & AZG_EVAL_GNN) {
+      azg_phase_begin(AZG_PHASE_HEADS, st);
+      if ((rc = launch_heads(enh, F, p->fc_policy_w, p->fc_policy_b, A, enh, F, p->fc_value_w, p->fc_value_b, B, pi_gnn,
+                             v_gnn, st)))
+        return rc;
+      azg_phase_end(AZG_PHASE_HEADS, st);
+    }
   } else {
     AZG_REQUIRE(p->ot_packed, "azg_c4_forward: prec %d needs ot_packed (azg_c4_pack)", prec);
-    if ((rc = azg_tc_c4_forward(p->ot_packed, p, n, prec, states, B, eval_mask, pi_std, v_std, enh, scratch, scratch_bytes, st)))
+    if ((rc = azg_tc_c4_forward(p->ot_packed, p, n, prec, states, B, eval_mask, pi_std, v_std, pi_gnn, v_gnn, scratch,
+                                scratch_bytes, st)))
       return rc;
-  }
-  if (eval_mask & AZG_EVAL_GNN) {
-    azg_phase_begin(AZG_PHASE_HEADS, st);
-    if ((rc = launch_heads(enh, F, p->fc_policy_w, p->fc_policy_b, A, enh, F, p->fc_value_w, p->fc_value_b, B, pi_gnn,
-                           v_gnn, st)))
-      return rc;
-    azg_phase_end(AZG_PHASE_HEADS, st);
   }
   return AZG_OK;
 }

@@ -57,8 +57,7 @@ def cpu_leaf_evals(sample, threads=None):
     import torch
     from oracle import nets as onets
     from azgnn_b200 import modules
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use all host cores
     torch.manual_seed(0)
     nnet = modules.Connect4Trunk(N_BOARD, N_BOARD + 1)
     gnn = modules.PolicyValueGNN(64 * N_BOARD * N_BOARD, 2)
@@ -89,6 +88,7 @@ def cpu_selfplay(episodes):
     from oracle.selfplay import execute_episode
     from azgnn_b200 import modules
     from azgnn_b200.games import Connect4Game
+    torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     nnet = modules.Connect4Trunk(N_BOARD, N_BOARD + 1)
     gnn = modules.PolicyValueGNN(64 * N_BOARD * N_BOARD, 2)
@@ -296,18 +296,20 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "kernel": "output_transform F x F contractions (2 launches per step)",
                 "kernel_ms_per_step": gemm_ms / max(gemm_cnt, 1),
                 "phase_ms_per_step": {k: v[0] / args.steps for k, v in phase.items()}}
-        cpu_rate, cpu_dt, cores = cpu_leaf_evals(args.cpu_sample)
+        # CPU baselines are timed at N=1 only (rank 0); multi-GPU lines carry null
+        cpu_rate, cpu_dt, cores = cpu_leaf_evals(args.cpu_sample) if world == 1 else (None, 0.0, 0)
         selfplay = None
         if args.selfplay_games > 0:
-            cpu_mps, cpu_moves, cpu_sp_dt = cpu_selfplay(args.cpu_selfplay_episodes)
+            cpu_mps, cpu_moves, cpu_sp_dt = cpu_selfplay(args.cpu_selfplay_episodes) if world == 1 else (None, 0, 0.0)
             selfplay = {"metric": "connect4_selfplay_moves_per_s", "value": sp_moves, "unit": "moves/s",
                         "leaf_evals_per_s_in_search": sp_leaves, "games_per_gpu": args.selfplay_games,
                         "move_steps_timed": args.selfplay_moves, "ms_per_move_step": sp_ms / max(args.selfplay_moves, 1),
                         "config": "connect4/config.yaml search settings: numMCTSSims 10, expand_by 5, cpuct 1.0, "
                                   "tempThreshold 15, use_gnn (std+GNN evaluated per leaf)",
-                        "cpu_baseline": {"value": cpu_mps, "unit": "moves/s", "cores": cores, "kind": "port",
-                                         "sample": f"{args.cpu_selfplay_episodes} sequential episodes ({cpu_moves} moves, "
-                                                   f"{cpu_sp_dt:.1f} s), oracle MCTS + per-leaf B=1 torch CPU calls"}}
+                        "cpu_baseline": None if cpu_mps is None else
+                        {"value": cpu_mps, "unit": "moves/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.cpu_selfplay_episodes} sequential episodes ({cpu_moves} moves, "
+                                   f"{cpu_sp_dt:.1f} s), oracle MCTS + per-leaf B=1 torch CPU calls"}}
         line = {"metric": "connect4_gnn_leaf_evals_per_s", "value": value, "unit": "leaf_evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -320,9 +322,10 @@ def run_gpu_arm(args, rank, local_rank, world):
                            "l2": "4 rotating input batches; per-step intermediates (>2 GB) exceed the 126 MB L2"},
                 "tflops_algorithmic": value * MFLOP_PER_LEAF * 1e6 / 1e12,
                 "roofline": roof,
-                "cpu_baseline": {"value": cpu_rate, "unit": "leaf_evals/s", "cores": cores, "kind": "port",
-                                 "sample": f"{args.cpu_sample} positions, predict + predict_with_gnn per position "
-                                           f"(B=1) as MCTS.py:169-173, {cpu_dt:.1f} s"},
+                "cpu_baseline": None if cpu_rate is None else
+                {"value": cpu_rate, "unit": "leaf_evals/s", "cores": cores, "kind": "port",
+                 "sample": f"{args.cpu_sample} positions, predict + predict_with_gnn per position "
+                           f"(B=1) as MCTS.py:169-173, {cpu_dt:.1f} s"},
                 "e2e": {"value": total / (ms_e2e / 1e3), "unit": "leaf_evals/s",
                         "h2d_bytes_per_step": int(B * N_BOARD * N_BOARD),
                         "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_host.values())),
