@@ -54,3 +54,56 @@ def test_rules(tag):
 
 def test_capacity_overflow():
     cases.case_capacity_overflow(make_arena)
+
+
+# ------------------------------------------------------------------ arena + CUDA networks end to end
+class _AsReference:
+    """feeds the oracle MCTS the CUDA network's own single-position predictions"""
+
+    def __init__(self, net):
+        self.net = net
+
+    def predict(self, b):
+        return self.net.predict(b)
+
+    def predict_with_gnn(self, b):
+        return self.net.predict_with_gnn(b)
+
+
+@pytest.mark.parametrize("kind,n,prec", [("connect4", 7, "fp32"), ("connect4", 7, "bf16x3"), ("connect4", 5, "bf16"),
+                                         ("tictactoe", 4, "fp32"), ("frozenlake", 4, "fp32")])
+def test_search_with_device_networks_matches_oracle_search(kind, n, prec):
+    """Lock-step search of several games whose leaves are evaluated in ONE batched CUDA pass per round
+    gives the visit counts and Q values of the sequential oracle search that calls the same network
+    per leaf (MCTS.py:169-173)."""
+    from azgnn_b200 import games
+    from azgnn_b200.mcts import BatchedMCTS
+    from azgnn_b200.nets import B200Connect4GNNWrapper, B200FrozenLakeNet, B200TicTacToeGNNWrapper
+    from oracle.mcts import OracleMCTS
+    from helpers import dotdict
+    use_gnn = kind != "frozenlake"
+    args = dotdict(dict(lr=1e-3, dropout=0.3, gnn_layers=2, embedding_dim=128, numMCTSSims=20, cpuct=1.0 if use_gnn else 2.0,
+                        use_gnn=use_gnn, expand_by=5, b200_precision=prec))
+    game = {"connect4": games.Connect4Game, "tictactoe": games.TicTacToeGame, "frozenlake": games.FrozenLakeGame}[kind](n)
+    torch.manual_seed(0)
+    net = {"connect4": B200Connect4GNNWrapper, "tictactoe": B200TicTacToeGNNWrapper, "frozenlake": B200FrozenLakeNet}[kind](game, args)
+    # a few distinct root positions: play 0..3 fixed moves from the start
+    roots, b, player = [], game.getInitBoard(), 1
+    for step in range(4):
+        roots.append(game.getCanonicalForm(b, player))
+        a = int(np.flatnonzero(game.getValidMoves(b, player))[step % 2])
+        b, player = game.getNextState(b, player, a)
+    cap = 4 * n * n if kind == "frozenlake" else None
+    bm = BatchedMCTS(game, net, args, n_games=len(roots), max_depth=cap)
+    bm.set_root_boards(roots)
+    probs = bm.getActionProbs(temp=1)
+    for g, root in enumerate(roots):
+        om = OracleMCTS(game, _AsReference(net), args, max_depth=cap)
+        want = om.getActionProb(root, temp=1)
+        assert np.array_equal(np.asarray(probs[g]), np.asarray(want)), (g, probs[g], want)
+        t = bm.tables(g)
+        s = game.stringRepresentation(root)
+        for a in range(game.getActionSize()):
+            if (s, a) in om.Nsa:
+                assert t["Nsa"][(s, a)] == om.Nsa[(s, a)]
+                assert float(np.asarray(t["Qsa"][(s, a)]).reshape(-1)[0]) == float(np.asarray(om.Qsa[(s, a)]).reshape(-1)[0])
