@@ -22,6 +22,7 @@
 #include "azg_common.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace tc {
 
@@ -691,6 +692,278 @@ __global__ void concat_heads_kernel(const float* __restrict__ wp, const float* _
   out[idx] = row < A ? wp[(size_t)row * F + k] : wv[k];
 }
 
+// ---- fused trunk: encode + conv1 + im2col in shared memory -> tcgen05 conv2 --------------------
+// One persistent CTA per SM, 12 warps.  A tile is G = 128 / n^2 whole boards (G*n^2 <= 128 GEMM rows).
+//   warps 0-3   builders: relu(conv1) of the tile's boards into smem (bf16 hi/lo, zero border, 80-byte
+//               cell stride = conflict-free 16-byte gathers), then per k-block copy the 3x3 patches
+//               into the SWIZZLE_128B operand stage (pure 16-byte smem->smem moves), fence.proxy.async,
+//               arrive on the stage's mbarrier
+//   warp 4      MMA issuer (one thread): M=128 x N=64 x K=16, conv2 weight images resident in smem
+//   warp 5      TMEM allocation, barrier init, one-time bulk copy of the conv2 weight images
+//   warps 8-11  epilogue: TMEM -> +bias, ReLU -> feature image (the A operand of GEMM-1)
+// The im2col matrix never exists in HBM (the split version moved 2 x 4.1 GB per 65,536 positions).
+constexpr int TR_THREADS = 384;
+constexpr int TR_CELL_STRIDE = 80;   // bytes per padded cell: 32 channels x bf16 + 16 B pad
+constexpr int TR_MAX_CELLS = 288;    // max over n of G * (n+2)^2
+constexpr int TR_W_BYTES = C2_KB * 64 * 128;  // conv2 weight image [64 x 320] bf16 = 40 KB
+
+template <bool X3>
+struct TrunkSmem {
+  static constexpr int STAGES = X3 ? 3 : 4;
+  static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * A_STAGE_BYTES;
+  static constexpr int W_OFF = 0;
+  static constexpr int A1_OFF = (X3 ? 2 : 1) * TR_W_BYTES;
+  static constexpr int A1_BYTES = ((TR_MAX_CELLS * TR_CELL_STRIDE + 1023) / 1024) * 1024;
+  static constexpr int STAGE_OFF = A1_OFF + (X3 ? 2 : 1) * A1_BYTES;
+  static constexpr int MISC_OFF = STAGE_OFF + STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = MISC_OFF + 2048 + 1024;
+};
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+struct TrunkArgs {
+  const uint64_t* states;
+  const float *w1, *b1, *b2;   // conv1 weights/bias, conv2 bias
+  const uint8_t *w_hi, *w_lo;  // conv2 weight images
+  uint8_t *f_hi, *f_lo;        // feature image out
+  int64_t B;
+  int n;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t) {
+  using S = TrunkSmem<X3>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_s = smem + S::W_OFF;
+  uint8_t* a1hi = smem + S::A1_OFF;
+  uint8_t* a1lo = a1hi + S::A1_BYTES;
+  uint8_t* stages = smem + S::STAGE_OFF;
+  uint64_t* full = (uint64_t*)(smem + S::MISC_OFF);
+  uint64_t* empty = full + S::STAGES;
+  uint64_t* tfull = empty + S::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
+  float* w1s = (float*)(smem + S::MISC_OFF + 256);  // [32*9] + [32]
+  float* b1s = w1s + 288;
+  uint64_t* st_s = (uint64_t*)(b1s + 32);           // [8 boards][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = t.n, nn = n * n, np = n + 2, cells = np * np;
+  const int G = 128 / nn;  // boards per tile
+  const int64_t tiles = (t.B + G - 1) / G;
+  constexpr int BN = 64;
+  constexpr uint32_t TMEM_COLS = 128;
+
+  // one-time setup
+  for (int i = threadIdx.x; i < (X3 ? 2 : 1) * S::A1_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(a1hi)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < S::STAGES * S::STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 288; i += blockDim.x) w1s[i] = t.w1[i];
+  if (threadIdx.x < 32) b1s[threadIdx.x] = t.b1[threadIdx.x];
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+  fence_async_smem();  // the zero-filled stages are read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (lane == 0) {  // conv2 weight images -> smem, once
+      mbar_expect_tx(wbar, (X3 ? 2 : 1) * TR_W_BYTES);
+      bulk_g2s(w_s, t.w_hi, TR_W_BYTES, wbar);
+      if (X3) bulk_g2s(w_s + TR_W_BYTES, t.w_lo, TR_W_BYTES, wbar);
+    }
+  } else if (warp < 4) {
+    // ======================= builders =======================
+    const int r = threadIdx.x;  // tile row
+    const int bl = r / nn, pc = r - bl * nn, x = pc / n, y = pc - x * n;
+    const bool row_valid = bl < G;
+    const int cell0 = bl * cells + x * np + y;  // padded cell of tap (0,0); tap (kx,ky) adds kx*np + ky
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t b0 = tile * G;
+      named_bar(1, 128);  // every builder is done reading the previous tile's conv1 output
+      if (r < G) {
+        const int64_t b = b0 + r;
+        st_s[2 * r] = b < t.B ? t.states[2 * b] : 0ull;
+        st_s[2 * r + 1] = b < t.B ? t.states[2 * b + 1] : 0ull;
+      }
+      named_bar(2, 128);
+      // relu(conv1): lanes = channels, each warp walks cells (Connect4Net.py:45)
+      {
+        float w9[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w9[k] = w1s[lane * 9 + k];
+        const float bias = b1s[lane];
+        for (int c = warp; c < G * nn; c += 4) {
+          const int cb = c / nn, cp = c - cb * nn, cx = cp / n, cy = cp - cx * n;
+          const uint64_t mine = st_s[2 * cb], theirs = st_s[2 * cb + 1];
+          float acc = bias;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int ix = cx + kx - 1, iy = cy + ky - 1;
+              if (ix >= 0 && ix < n && iy >= 0 && iy < n) {
+                const int bit = ix * n + iy;
+                const float v = (float)((int)((mine >> bit) & 1ull) - (int)((theirs >> bit) & 1ull));
+                acc = fmaf(v, w9[kx * 3 + ky], acc);
+              }
+            }
+          acc = fmaxf(acc, 0.0f);
+          const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+          const size_t off = (size_t)(cb * cells + (cx + 1) * np + cy + 1) * TR_CELL_STRIDE + lane * 2;
+          *reinterpret_cast<__nv_bfloat16*>(a1hi + off) = h;
+          if (X3) *reinterpret_cast<__nv_bfloat16*>(a1lo + off) = __float2bfloat16_rn(acc - __bfloat162float(h));
+        }
+      }
+      named_bar(1, 128);  // conv1 output complete
+      for (int kb = 0; kb < C2_KB; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = stages + stage * S::STAGE_BYTES;
+        if (row_valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = kb * 8 + j;  // 16-byte chunk of the K = (tap, cin) axis
+            uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
+            if (c < 36) {
+              const int tap = c >> 2, kx = tap / 3, ky = tap - kx * 3;
+              const size_t src = (size_t)(cell0 + kx * np + ky) * TR_CELL_STRIDE + (c & 3) * 16;
+              vh = *reinterpret_cast<const uint4*>(a1hi + src);
+              if (X3) vl = *reinterpret_cast<const uint4*>(a1lo + src);
+            }
+            const uint32_t dst = image_offset(r, j * 8);
+            *reinterpret_cast<uint4*>(sa + dst) = vh;
+            if (X3) *reinterpret_cast<uint4*>(sa + A_STAGE_BYTES + dst) = vl;
+          }
+        }
+        fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&full[stage]);
+        if (++stage == S::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      mbar_wait(wbar, 0);
+      const uint32_t w_addr = smem_u32(w_s);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < C2_KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stages + stage * S::STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_STAGE_BYTES);
+          const uint64_t b_hi = make_smem_desc(w_addr + kb * (64 * 128));
+          const uint64_t b_lo = make_smem_desc(w_addr + TR_W_BYTES + kb * (64 * 128));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+          if (X3) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ======================= epilogue =======================
+    const int q = warp & 3, r = q * 32 + lane;
+    const int bl = r / nn, pc = r - bl * nn;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t b = tile * G + bl;
+      const bool valid = bl < G && b < t.B;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const size_t tbase = ((size_t)(b >> 7) * nn + pc) * A_STAGE_BYTES;
+      const int rb = (int)(b & 127);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + (uint32_t)c0, rr);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float x8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x8[e] = fmaxf(__uint_as_float(rr[c * 8 + e]) + __ldg(t.b2 + c0 + c * 8 + e), 0.0f);
+            split_store(x8, t.f_hi, X3 ? t.f_lo : nullptr, tbase + image_offset(rb, c0 + c * 8));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <bool X3>
+int launch_trunk(const TrunkArgs& t, cudaStream_t st) {
+  static bool configured = false;
+  int dev = 0, sms = 0;
+  AZG_CUDA_CHECK(cudaGetDevice(&dev));
+  AZG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!configured) {
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(c4_trunk_tc_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrunkSmem<X3>::TOTAL));
+    configured = true;
+  }
+  const int G = 128 / (t.n * t.n);
+  const int64_t tiles = (t.B + G - 1) / G;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  c4_trunk_tc_kernel<X3><<<grid, TR_THREADS, TrunkSmem<X3>::TOTAL, st>>>(t);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
 int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R, uint8_t* hi, uint8_t* lo, cudaStream_t st) {
   return to_image(src, rows, rows_padded, K, R, hi, lo, st);
 }
@@ -756,6 +1029,15 @@ ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
 }
 }  // namespace
 
+static int azg_trunk_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("AZG_TRUNK");
+    mode = (e && strcmp(e, "split") == 0) ? 1 : 0;
+  }
+  return mode;
+}
+
 size_t azg_tc_scratch_bytes(int n, int64_t B, int prec) { return scratch_layout(n, B, prec, true).total; }
 
 // Whole Connect4 leaf evaluation on the tensor-core path: im2col(encode+conv1) -> conv2 GEMM ->
@@ -776,21 +1058,26 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   uint8_t *h_hi = sc + S.h_hi, *h_lo = x3 ? sc + S.h_lo : nullptr;
   int rc;
   azg_phase_begin(AZG_PHASE_TRUNK, st);
-  {
+  tc::GemmArgs g{};
+  if (azg_trunk_mode() == 0) {  // fused: encode + conv1 + im2col in smem -> tcgen05 conv2
+    tc::TrunkArgs t{};
+    t.states = states; t.w1 = p->conv1_w; t.b1 = p->conv1_b; t.b2 = p->conv2_b;
+    t.w_hi = w + L.c2_hi; t.w_lo = x3 ? w + L.c2_lo : nullptr; t.f_hi = f_hi; t.f_lo = f_lo; t.B = B; t.n = n;
+    if ((rc = x3 ? tc::launch_trunk<true>(t, st) : tc::launch_trunk<false>(t, st))) return rc;
+  } else {  // split: im2col image through HBM, conv2 on the generic GEMM kernel (kept for A/B measurements)
     const int grid = (int)(B < 148 * 8 ? B : 148 * 8);
     tc::c4_im2col_kernel<<<grid, 256, 0, st>>>(states, n, B, p->conv1_w, p->conv1_b, a2_hi, a2_lo);
     AZG_LAUNCH_CHECK();
+    g.M = B * (int64_t)nn;
+    g.m_tiles = (int)azg_ceil_div(g.M, tc::BM);
+    g.n_tiles = 1;
+    g.KB = tc::C2_KB;
+    g.x3 = x3;
+    g.a_hi = a2_hi; g.a_lo = a2_lo; g.w_hi = w + L.c2_hi; g.w_lo = x3 ? w + L.c2_lo : nullptr;
+    g.bias = p->conv2_b; g.relu = 1; g.out_mode = x3 ? tc::OUT_FEAT_HILO : tc::OUT_FEAT; g.feat_nn = nn;
+    g.out_hi = f_hi; g.out_lo = f_lo;
+    if ((rc = tc::run_gemm(64, g, st))) return rc;
   }
-  tc::GemmArgs g{};
-  g.M = B * (int64_t)nn;
-  g.m_tiles = (int)azg_ceil_div(g.M, tc::BM);
-  g.n_tiles = 1;
-  g.KB = tc::C2_KB;
-  g.x3 = x3;
-  g.a_hi = a2_hi; g.a_lo = a2_lo; g.w_hi = w + L.c2_hi; g.w_lo = x3 ? w + L.c2_lo : nullptr;
-  g.bias = p->conv2_b; g.relu = 1; g.out_mode = x3 ? tc::OUT_FEAT_HILO : tc::OUT_FEAT; g.feat_nn = nn;
-  g.out_hi = f_hi; g.out_lo = f_lo;
-  if ((rc = tc::run_gemm(64, g, st))) return rc;
   azg_phase_end(AZG_PHASE_TRUNK, st);
   if (eval_mask & AZG_EVAL_STD) {
     AZG_REQUIRE(pi_std && v_std && A <= 9, "tcgen05 path: bad std outputs");
