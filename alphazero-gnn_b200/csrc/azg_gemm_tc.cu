@@ -450,6 +450,7 @@ int run_gemm(int BN, const GemmArgs& g, cudaStream_t st) {
     case 256: return launch_gemm<256>(g, st);
     case 160: return launch_gemm<160>(g, st);
     case 64: return launch_gemm<64>(g, st);
+    case 32: return launch_gemm<32>(g, st);
   }
   azg_set_error("tcgen05 GEMM: no tile width for this feature size");
   return AZG_ERR_INVALID;
@@ -683,18 +684,36 @@ __global__ void heads_finalize_kernel(const float* __restrict__ part, int n_tile
   v[row] = tanhf(vraw + __ldg(bv));
 }
 
-// [policy rows ; value row] in the reference's input order, fp32 (for the fused-heads epilogue)
-__global__ void concat_heads_kernel(const float* __restrict__ wp, const float* __restrict__ wv, int A, int F,
-                                    float* __restrict__ out) {
+// [policy rows ; value row ; zero rows up to 32] in the reference's input order, fp32 (fused-heads
+// epilogue of GEMM-2 and source of the std-heads weight image)
+__global__ void concat_heads_kernel(const float* __restrict__ wp, const float* __restrict__ wv, const float* __restrict__ bp,
+                                    const float* __restrict__ bv, int A, int F, float* __restrict__ out,
+                                    float* __restrict__ bias32) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)(A + 1) * F) return;
+  if (idx < 32) bias32[idx] = idx < A ? bp[idx] : (idx == A ? bv[0] : 0.0f);
+  if (idx >= (int64_t)32 * F) return;
   const int row = (int)(idx / F), k = (int)(idx % F);
-  out[idx] = row < A ? wp[(size_t)row * F + k] : wv[k];
+  out[idx] = row < A ? wp[(size_t)row * F + k] : (row == A ? wv[k] : 0.0f);
+}
+
+// std heads from the [B,32] logits block produced by the skinny tensor-core GEMM (bias already added)
+__global__ void heads32_finalize_kernel(const float* __restrict__ lg, int A, int64_t B, float* __restrict__ pi,
+                                        float* __restrict__ v) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B) return;
+  const float* x = lg + row * 32;
+  float m = -INFINITY;
+  for (int a = 0; a < A; ++a) m = fmaxf(m, x[a]);
+  float sum = 0.0f;
+  for (int a = 0; a < A; ++a) sum += expf(x[a] - m);
+  const float lse = logf(sum);
+  for (int a = 0; a < A; ++a) pi[row * A + a] = expf((x[a] - m) - lse);
+  v[row] = tanhf(x[A]);
 }
 
 // ---- fused trunk: encode + conv1 + im2col in shared memory -> tcgen05 conv2 --------------------
 // One persistent CTA per SM, 12 warps.  A tile is G = 128 / n^2 whole boards (G*n^2 <= 128 GEMM rows).
-//   warps 0-3   builders: relu(conv1) of the tile's boards into smem (bf16 hi/lo, zero border, 80-byte
+//   warps 0-3   builders (+ warps 6-7 for the conv1 part): relu(conv1) of the tile's boards into smem (bf16 hi/lo, zero border, 80-byte
 //               cell stride = conflict-free 16-byte gathers), then per k-block copy the 3x3 patches
 //               into the SWIZZLE_128B operand stage (pure 16-byte smem->smem moves), fence.proxy.async,
 //               arrive on the stage's mbarrier
@@ -716,7 +735,7 @@ struct TrunkSmem {
   static constexpr int A1_BYTES = ((TR_MAX_CELLS * TR_CELL_STRIDE + 1023) / 1024) * 1024;
   static constexpr int STAGE_OFF = A1_OFF + (X3 ? 2 : 1) * A1_BYTES;
   static constexpr int MISC_OFF = STAGE_OFF + STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = MISC_OFF + 2048 + 1024;
+  static constexpr int TOTAL = MISC_OFF + 3072 + 1024;
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -748,7 +767,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
   float* w1s = (float*)(smem + S::MISC_OFF + 256);  // [32*9] + [32]
   float* b1s = w1s + 288;
-  uint64_t* st_s = (uint64_t*)(b1s + 32);           // [8 boards][2]
+  float* planes_s = b1s + 32;                       // [G boards][(n+2)^2] cells in {-1,0,1}, zero border
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = t.n, nn = n * n, np = n + 2, cells = np * np;
@@ -761,6 +780,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   for (int i = threadIdx.x; i < (X3 ? 2 : 1) * S::A1_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(a1hi)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < S::STAGES * S::STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < 288; i += blockDim.x) w1s[i] = t.w1[i];
+  for (int i = threadIdx.x; i < TR_MAX_CELLS; i += blockDim.x) planes_s[i] = 0.0f;
   if (threadIdx.x < 32) b1s[threadIdx.x] = t.b1[threadIdx.x];
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
@@ -787,52 +807,51 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
       bulk_g2s(w_s, t.w_hi, TR_W_BYTES, wbar);
       if (X3) bulk_g2s(w_s + TR_W_BYTES, t.w_lo, TR_W_BYTES, wbar);
     }
-  } else if (warp < 4) {
-    // ======================= builders =======================
-    const int r = threadIdx.x;  // tile row
+  } else if (warp < 4 || warp == 6 || warp == 7) {
+    // ============ builders (warps 0-3) + conv1 helpers (warps 6-7) ============
+    const bool builder = warp < 4;
+    const int r = threadIdx.x;  // tile row (builders)
     const int bl = r / nn, pc = r - bl * nn, x = pc / n, y = pc - x * n;
-    const bool row_valid = bl < G;
+    const bool row_valid = builder && bl < G;
     const int cell0 = bl * cells + x * np + y;  // padded cell of tap (0,0); tap (kx,ky) adds kx*np + ky
+    const int cw = builder ? warp : warp - 2;   // conv1 worker index 0..5
+    float w9[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w9[k] = w1s[lane * 9 + k];
+    const float bias = b1s[lane];
     int stage = 0;
     uint32_t phase = 0;
+    // the packed positions of the next tile are fetched one tile ahead (global latency off the critical path)
+    uint64_t nm = 0, nt = 0;
+    if (row_valid) {
+      const int64_t b = (int64_t)blockIdx.x * G + bl;
+      if (b < t.B) { nm = t.states[2 * b]; nt = t.states[2 * b + 1]; }
+    }
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int64_t b0 = tile * G;
-      named_bar(1, 128);  // every builder is done reading the previous tile's conv1 output
-      if (r < G) {
-        const int64_t b = b0 + r;
-        st_s[2 * r] = b < t.B ? t.states[2 * b] : 0ull;
-        st_s[2 * r + 1] = b < t.B ? t.states[2 * b + 1] : 0ull;
+      if (row_valid) {  // K1 encode: this row's cell of the packed position -> {-1,0,1} in the padded plane
+        planes_s[cell0 + np + 1] = (float)((int)((nm >> pc) & 1ull) - (int)((nt >> pc) & 1ull));
+        const int64_t b = (tile + gridDim.x) * G + bl;
+        nm = nt = 0;
+        if (b < t.B) { nm = t.states[2 * b]; nt = t.states[2 * b + 1]; }
       }
-      named_bar(2, 128);
-      // relu(conv1): lanes = channels, each warp walks cells (Connect4Net.py:45)
-      {
-        float w9[9];
+      named_bar(1, 192);  // planes ready; every builder is done reading the previous tile's conv1 output
+      // relu(conv1): lanes = channels, six warps walk the cells (Connect4Net.py:45)
+      for (int c = cw; c < G * nn; c += 6) {
+        const int cb = c / nn, cp = c - cb * nn, cx = cp / n, cy = cp - cx * n;
+        const float* pl = planes_s + cb * cells + cx * np + cy;
+        float acc = bias;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) w9[k] = w1s[lane * 9 + k];
-        const float bias = b1s[lane];
-        for (int c = warp; c < G * nn; c += 4) {
-          const int cb = c / nn, cp = c - cb * nn, cx = cp / n, cy = cp - cx * n;
-          const uint64_t mine = st_s[2 * cb], theirs = st_s[2 * cb + 1];
-          float acc = bias;
+        for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const int ix = cx + kx - 1, iy = cy + ky - 1;
-              if (ix >= 0 && ix < n && iy >= 0 && iy < n) {
-                const int bit = ix * n + iy;
-                const float v = (float)((int)((mine >> bit) & 1ull) - (int)((theirs >> bit) & 1ull));
-                acc = fmaf(v, w9[kx * 3 + ky], acc);
-              }
-            }
-          acc = fmaxf(acc, 0.0f);
-          const __nv_bfloat16 h = __float2bfloat16_rn(acc);
-          const size_t off = (size_t)(cb * cells + (cx + 1) * np + cy + 1) * TR_CELL_STRIDE + lane * 2;
-          *reinterpret_cast<__nv_bfloat16*>(a1hi + off) = h;
-          if (X3) *reinterpret_cast<__nv_bfloat16*>(a1lo + off) = __float2bfloat16_rn(acc - __bfloat162float(h));
-        }
+          for (int ky = 0; ky < 3; ++ky) acc = fmaf(pl[kx * np + ky], w9[kx * 3 + ky], acc);
+        acc = fmaxf(acc, 0.0f);
+        const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+        const size_t off = (size_t)(cb * cells + (cx + 1) * np + cy + 1) * TR_CELL_STRIDE + lane * 2;
+        *reinterpret_cast<__nv_bfloat16*>(a1hi + off) = h;
+        if (X3) *reinterpret_cast<__nv_bfloat16*>(a1lo + off) = __float2bfloat16_rn(acc - __bfloat162float(h));
       }
-      named_bar(1, 128);  // conv1 output complete
+      named_bar(2, 192);  // conv1 output complete
+      if (!builder) continue;
       for (int kb = 0; kb < C2_KB; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = stages + stage * S::STAGE_BYTES;
@@ -976,7 +995,7 @@ int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R
 //   W2 (output_transform.2) hi [lo] | conv2 [64 x 320] hi [lo] | head weights permuted, fp32
 namespace {
 struct PackLayout {
-  size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, heads_cat, total;
+  size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, heads_cat, hd_hi, hd_lo, bias32, total;
   bool x3, gnn;
 };
 
@@ -998,13 +1017,16 @@ PackLayout pack_layout(int n, int prec, bool gnn) {
   L.c2_hi = take(cimg);
   L.c2_lo = L.x3 ? take(cimg) : 0;
   L.heads = take((size_t)(n + 2) * F * 4);      // permuted to the feature image order (std heads)
-  L.heads_cat = take((size_t)(n + 2) * F * 4);  // reference order (GNN heads fused into the GEMM-2 epilogue)
+  L.heads_cat = take((size_t)32 * F * 4);       // reference order, zero-padded to 32 rows (GEMM-2 epilogue)
+  L.hd_hi = take((size_t)32 * F * 2);           // std heads as a [32 x F] weight image (feature-image order)
+  L.hd_lo = L.x3 ? take((size_t)32 * F * 2) : 0;
+  L.bias32 = take(32 * 4);
   L.total = off;
   return L;
 }
 
 struct ScratchLayout {
-  size_t a2_hi, a2_lo, f_hi, f_lo, h_hi, h_lo, part, total;
+  size_t a2_hi, a2_lo, f_hi, f_lo, h_hi, h_lo, part, lg32, total;
 };
 
 ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
@@ -1019,6 +1041,7 @@ ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
   S.a2_lo = x3 ? take(a2) : 0;
   S.f_hi = take(fimg);
   S.f_lo = x3 ? take(fimg) : 0;
+  S.lg32 = take(Mp * 32 * sizeof(float));
   if (gnn) {
     S.h_hi = take(fimg);
     S.h_lo = x3 ? take(fimg) : 0;
@@ -1082,10 +1105,20 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   if (eval_mask & AZG_EVAL_STD) {
     AZG_REQUIRE(pi_std && v_std && A <= 9, "tcgen05 path: bad std outputs");
     azg_phase_begin(AZG_PHASE_HEADS, st);
-    const int grid = (int)(azg_ceil_div(B, 8) < 148 * 8 ? azg_ceil_div(B, 8) : 148 * 8);
-    tc::heads_image_kernel<9><<<grid, 256, 0, st>>>(f_hi, f_lo, nn, (const float*)(w + L.heads), p->fc_policy_b,
-                                                    p->fc_value_b, A, B, pi_std, v_std);
-    AZG_LAUNCH_CHECK();
+    if (azg_trunk_mode() == 0) {  // predict's heads (Connect4Net.py:55-60) as a skinny tcgen05 GEMM: [B,F] x [F,32]
+      tc::GemmArgs h{};
+      h.M = B; h.m_tiles = (int)azg_ceil_div(B, tc::BM); h.n_tiles = 1; h.KB = F / tc::BK; h.x3 = x3;
+      h.a_hi = f_hi; h.a_lo = f_lo; h.w_hi = w + L.hd_hi; h.w_lo = x3 ? w + L.hd_lo : nullptr;
+      h.bias = (const float*)(w + L.bias32); h.relu = 0; h.out_mode = tc::OUT_F32; h.out_f32 = (float*)(sc + S.lg32);
+      if ((rc = tc::run_gemm(32, h, st))) return rc;
+      tc::heads32_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const float*)(sc + S.lg32), A, B, pi_std, v_std);
+      AZG_LAUNCH_CHECK();
+    } else {
+      const int grid = (int)(azg_ceil_div(B, 8) < 148 * 8 ? azg_ceil_div(B, 8) : 148 * 8);
+      tc::heads_image_kernel<9><<<grid, 256, 0, st>>>(f_hi, f_lo, nn, (const float*)(w + L.heads), p->fc_policy_b,
+                                                      p->fc_value_b, A, B, pi_std, v_std);
+      AZG_LAUNCH_CHECK();
+    }
     azg_phase_end(AZG_PHASE_HEADS, st);
   }
   if (!gnn) return AZG_OK;
@@ -1144,8 +1177,15 @@ int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t pa
   const int64_t hn = (int64_t)(A + 1) * F;
   tc::permute_heads_kernel<<<(unsigned)((hn + 255) / 256), 256, 0, st>>>(p->fc_policy_w, p->fc_value_w, A, F, nn, (float*)(w + L.heads));
   AZG_LAUNCH_CHECK();
-  tc::concat_heads_kernel<<<(unsigned)((hn + 255) / 256), 256, 0, st>>>(p->fc_policy_w, p->fc_value_w, A, F, (float*)(w + L.heads_cat));
+  tc::concat_heads_kernel<<<(unsigned)(((int64_t)32 * F + 255) / 256), 256, 0, st>>>(
+      p->fc_policy_w, p->fc_value_w, p->fc_policy_b, p->fc_value_b, A, F, (float*)(w + L.heads_cat), (float*)(w + L.bias32));
   AZG_LAUNCH_CHECK();
+  {
+    const int64_t cnt = (int64_t)32 * (F / 8);
+    tc::permuted_weight_image_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((const float*)(w + L.heads_cat), 32, F, nn, 32,
+                                                                                   w + L.hd_hi, x3 ? w + L.hd_lo : nullptr);
+    AZG_LAUNCH_CHECK();
+  }
   return AZG_OK;
 }
 
