@@ -174,7 +174,7 @@ struct Smem {
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B wants 1024-B alignment
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B wants 1024-B alignment
   using S = Smem<BN>;
   uint64_t* full = (uint64_t*)(smem + S::BAR_OFFSET);
   uint64_t* empty = full + STAGES;
@@ -735,7 +735,7 @@ struct TrunkSmem {
   static constexpr int A1_BYTES = ((TR_MAX_CELLS * TR_CELL_STRIDE + 1023) / 1024) * 1024;
   static constexpr int STAGE_OFF = A1_OFF + (X3 ? 2 : 1) * A1_BYTES;
   static constexpr int MISC_OFF = STAGE_OFF + STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = MISC_OFF + 3072 + 1024;
+  static constexpr int TOTAL = MISC_OFF + 3072 + 1024;  // barriers, conv1 weights, planes, cell table + alignment slack
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -754,7 +754,7 @@ template <bool X3>
 __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t) {
   using S = TrunkSmem<X3>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS)
   uint8_t* w_s = smem + S::W_OFF;
   uint8_t* a1hi = smem + S::A1_OFF;
   uint8_t* a1lo = a1hi + S::A1_BYTES;
@@ -768,6 +768,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   float* w1s = (float*)(smem + S::MISC_OFF + 256);  // [32*9] + [32]
   float* b1s = w1s + 288;
   float* planes_s = b1s + 32;                       // [G boards][(n+2)^2] cells in {-1,0,1}, zero border
+  uint16_t* cell_tab = (uint16_t*)(planes_s + TR_MAX_CELLS);  // tile row -> padded cell index of its (0,0) tap
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = t.n, nn = n * n, np = n + 2, cells = np * np;
@@ -781,6 +782,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   for (int i = threadIdx.x; i < S::STAGES * S::STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < 288; i += blockDim.x) w1s[i] = t.w1[i];
   for (int i = threadIdx.x; i < TR_MAX_CELLS; i += blockDim.x) planes_s[i] = 0.0f;
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    const int ib = i / nn, ip = i - ib * nn, ix = ip / n;
+    cell_tab[i] = (uint16_t)(ib * cells + ix * np + (ip - ix * n));
+  }
   if (threadIdx.x < 32) b1s[threadIdx.x] = t.b1[threadIdx.x];
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
@@ -837,8 +842,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
       named_bar(1, 192);  // planes ready; every builder is done reading the previous tile's conv1 output
       // relu(conv1): lanes = channels, six warps walk the cells (Connect4Net.py:45)
       for (int c = cw; c < G * nn; c += 6) {
-        const int cb = c / nn, cp = c - cb * nn, cx = cp / n, cy = cp - cx * n;
-        const float* pl = planes_s + cb * cells + cx * np + cy;
+        const int ctap = cell_tab[c];
+        const float* pl = planes_s + ctap;
         float acc = bias;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
@@ -846,7 +851,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
           for (int ky = 0; ky < 3; ++ky) acc = fmaf(pl[kx * np + ky], w9[kx * 3 + ky], acc);
         acc = fmaxf(acc, 0.0f);
         const __nv_bfloat16 h = __float2bfloat16_rn(acc);
-        const size_t off = (size_t)(cb * cells + (cx + 1) * np + cy + 1) * TR_CELL_STRIDE + lane * 2;
+        const uint32_t off = (uint32_t)(ctap + np + 1) * TR_CELL_STRIDE + lane * 2;
         *reinterpret_cast<__nv_bfloat16*>(a1hi + off) = h;
         if (X3) *reinterpret_cast<__nv_bfloat16*>(a1lo + off) = __float2bfloat16_rn(acc - __bfloat162float(h));
       }
