@@ -252,6 +252,25 @@ def run_gpu_arm(args, rank, local_rank, world):
         phase[name] = (tot.value, cnt.value)
     lib.azg_timing_enable(0)
 
+    # ---- the other tensor-core precision, device-resident, short (reported under "also") ----
+    also = {}
+    for other in ("bf16", "bf16x3"):
+        if other == args.precision or args.precision == "fp32":
+            continue
+        oprec = _lib.PRECISIONS[other]
+        for i in range(3):
+            net.forward_states(dev_states[i % n_rot], mask, precision=oprec)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(5):
+            net.forward_states(dev_states[i % n_rot], mask, precision=oprec)
+        a1.record()
+        torch.cuda.synchronize()
+        also[other] = {"value": B * 5 / (a0.elapsed_time(a1) / 1e3), "unit": "leaf_evals/s per GPU", "ms_per_step": a0.elapsed_time(a1) / 5,
+                       "note": {"bf16": "single bf16 product, fp32 accumulate; stated tolerance 5e-3 on pi and v",
+                                "bf16x3": "3-term bf16 split, fp32 accumulate; pi and v within 1e-5 of the reference"}[other]}
+
     # ---- end-to-end through the host-facing API ----
     for i in range(3):
         step_e2e(i)
@@ -290,8 +309,17 @@ def run_gpu_arm(args, rank, local_rank, world):
         gemm_tflops = (GEMM_FLOP_PER_LEAF * B * gemm_cnt) / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         # fp32 FFMA path: the relevant ceiling is the CUDA-core FFMA rate, reported as a note; the
         # roofline entry always uses the measured bf16 tensor peak (the path's real ceiling).
+        terms = 3 if args.precision == "bf16x3" else 1
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this
+        # configuration (profiles/r01_gemm_bf16x3_v3.txt: GEMM-1 1.207+0.806 GB, GEMM-2 0.995+0.063 GB)
+        traffic = {"bf16x3": 1.535e9, "bf16": None, "fp32": None}[args.precision] if B == BATCH else None
         roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
-                "frac": (gemm_tflops / bf16_peak) if gemm_tflops else None, "traffic": None,
+                "frac": (gemm_tflops / bf16_peak) if gemm_tflops else None, "traffic": traffic,
+                "traffic_unit": "bytes per launch (average of the two launches)",
+                # GEMM-1 reads X images and writes H images, GEMM-2 reads H images and writes 59 MB of partial
+                # head sums; an image is B*F*2 bytes, hi+lo in bf16x3 (weights come from L2 after the first tile)
+                "algorithmic_bytes_per_launch": (3 * (B * 3136 * 2) * (2 if terms == 3 else 1) + B * 14 * 16 * 4) / 2,
+                "mma_terms": terms, "issued_tflops": gemm_tflops * terms if gemm_tflops else None,
                 "peak_source": peak_src + " (bf16_tflops_sustained)",
                 "kernel": "output_transform F x F contractions (2 launches per step)",
                 "kernel_ms_per_step": gemm_ms / max(gemm_cnt, 1),
@@ -331,6 +359,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                         "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_host.values())),
                         "ms_per_step": ms_e2e / args.steps},
                 "selfplay": selfplay,
+                "also": also,
                 "gpu_launches": int(launches),
                 "clocks": clocks.summary()}
         print(json.dumps(line))
