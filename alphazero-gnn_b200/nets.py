@@ -257,6 +257,17 @@ class B200FrozenLakeNet(_Base):
         self.gnn = None
 
     def forward_states(self, states, eval_mask=None):
+        """Only n^2 distinct inputs exist (the agent cell, FrozenLakeGame.py:197-202): the network is
+        evaluated once per cell per weight version and leaf batches are row gathers of that table."""
+        if not getattr(self, "_packed_ok", False) or getattr(self, "_table", None) is None:
+            cells = torch.zeros(self.n * self.n, 2, dtype=torch.int64, device=self.device)
+            cells[:, 0] = torch.arange(self.n * self.n, device=self.device)
+            self._table = self._forward_cells(cells)
+            self._packed_ok = True
+        idx = states[:, 0]
+        return {"pi": self._table["pi"].index_select(0, idx), "v": self._table["v"].index_select(0, idx)}
+
+    def _forward_cells(self, states):
         n = self.nnet
         L = self.layers
         gw = (C.c_void_p * max(L, 1))(*[n.gnn_layers[l].W.weight.data_ptr() for l in range(L)])

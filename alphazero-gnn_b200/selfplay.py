@@ -77,7 +77,7 @@ def sample_actions(probs, rng, u=None):
 
 
 class BatchedSelfPlay:
-    def __init__(self, game, nnet, args, n_games, seed=0, collect_examples=True, arena=None):
+    def __init__(self, game, nnet, args, n_games, seed=0, collect_examples=True, arena=None, max_episode_steps=None):
         self.game, self.nnet, self.args = game, nnet, args
         self.G = int(n_games)
         self.use_gnn = bool(arg(args, "use_gnn", False))
@@ -89,6 +89,9 @@ class BatchedSelfPlay:
         self.expand_by = int(arg(args, "expand_by", 5))
         self.two_player = bool(getattr(game, "is_two_player", True))
         self.init_state = pack_states(self.kind, np.asarray(game.getInitBoard())[None])[0]
+        # The reference has no step cap (Coach.py:34-79); single-player episodes can wander forever, so an
+        # optional cap ends an episode with result 0 (off by default = reference behaviour).
+        self.max_episode_steps = max_episode_steps
         self.moves_played = 0
         self.episodes_done = 0
         self._start_all()
@@ -150,7 +153,11 @@ class BatchedSelfPlay:
         self.moves_played += G
         if self.two_player:
             self.player = -self.player
-        done = [g for g in range(G) if ended[g] != 0]
+        if self.max_episode_steps is not None:
+            ended = [e if (e != 0 or self.step[g] < self.max_episode_steps) else 0.0 for g, e in enumerate(ended)]
+            done = [g for g in range(G) if ended[g] != 0 or self.step[g] >= self.max_episode_steps]
+        else:
+            done = [g for g in range(G) if ended[g] != 0]
         out = []
         for g in done:
             out.append(self._finish(g, ended[g]) if self.collect else ([], []))

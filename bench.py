@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-sample", type=int, default=4096)
-    ap.add_argument("--selfplay-games", type=int, default=4096, help="concurrent self-play games per GPU (0 = skip)")
+    ap.add_argument("--selfplay-games", type=int, default=16384, help="concurrent self-play games per GPU (0 = skip)")
     ap.add_argument("--selfplay-moves", type=int, default=6)
     ap.add_argument("--cpu-selfplay-episodes", type=int, default=2)
     args = ap.parse_args()

@@ -91,7 +91,10 @@ def test_search_with_device_networks_matches_oracle_search(kind, n, prec):
     roots, b, player = [], game.getInitBoard(), 1
     for step in range(4):
         roots.append(game.getCanonicalForm(b, player))
-        a = int(np.flatnonzero(game.getValidMoves(b, player))[step % 2])
+        if kind == "frozenlake":
+            a = [1, 1, 2, 2][step]  # right, right, down, down: stays on frozen cells of the 4x4 map
+        else:
+            a = int(np.flatnonzero(game.getValidMoves(b, player))[step % 2])
         b, player = game.getNextState(b, player, a)
     cap = 4 * n * n if kind == "frozenlake" else None
     bm = BatchedMCTS(game, net, args, n_games=len(roots), max_depth=cap)
@@ -107,3 +110,29 @@ def test_search_with_device_networks_matches_oracle_search(kind, n, prec):
             if (s, a) in om.Nsa:
                 assert t["Nsa"][(s, a)] == om.Nsa[(s, a)]
                 assert float(np.asarray(t["Qsa"][(s, a)]).reshape(-1)[0]) == float(np.asarray(om.Qsa[(s, a)]).reshape(-1)[0])
+
+
+@pytest.mark.parametrize("kind,n", [("connect4", 5), ("tictactoe", 3), ("frozenlake", 4)])
+def test_batched_selfplay_on_device(kind, n):
+    """Whole episodes with device-resident leaf evaluation: examples are well formed and every
+    concurrent game restarts with a fresh table when it ends (Coach.py:96)."""
+    from azgnn_b200 import games
+    from azgnn_b200.nets import B200Connect4GNNWrapper, B200FrozenLakeNet, B200TicTacToeGNNWrapper
+    from azgnn_b200.selfplay import BatchedSelfPlay
+    from helpers import dotdict
+    use_gnn = kind != "frozenlake"
+    args = dotdict(dict(lr=1e-3, dropout=0.3, gnn_layers=2, embedding_dim=128, numMCTSSims=6, cpuct=1.0, use_gnn=use_gnn,
+                        expand_by=2, tempThreshold=5))
+    game = {"connect4": games.Connect4Game, "tictactoe": games.TicTacToeGame, "frozenlake": games.FrozenLakeGame}[kind](n)
+    torch.manual_seed(0)
+    net = {"connect4": B200Connect4GNNWrapper, "tictactoe": B200TicTacToeGNNWrapper, "frozenlake": B200FrozenLakeNet}[kind](game, args)
+    sp = BatchedSelfPlay(game, net, args, n_games=32, seed=1, max_episode_steps=40 if kind == "frozenlake" else None)
+    eps = sp.play(40)
+    assert len(eps) == 40
+    A = game.getActionSize()
+    for std, gnn in eps:
+        assert len(std) > 0
+        for b, p, r in std:
+            assert np.asarray(b).shape == (n, n) and len(p) == A and abs(sum(p) - 1) < 1e-6
+        if use_gnn:
+            assert len(gnn) > 0
