@@ -106,6 +106,71 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+
+// ---- CTA-pair (cta_group::2) helpers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (an address in this CTA's shared window) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait_cluster(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N: N/2 rows per CTA]^T, issued by the leader CTA
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of the pair's MMAs arrives on the barrier at the same offset in both CTAs
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns of this warp's TMEM lane quarter
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -159,50 +224,66 @@ struct GemmArgs {
   const float* head_w;  // OUT_HEADS: [head_rows, N] fp32 (policy rows then the value row), reference order
   float* head_part;     // OUT_HEADS: [M, n_tiles, HEAD_STRIDE] partial sums, reduced in fixed order by heads_finalize
   int head_rows;
+  int pair_ok;          // the A image covers an even number of m-tiles: the CTA-pair kernel may be used
   int feat_nn;          // OUT_FEAT*: rows are (board b, cell p) pairs, m = b*feat_nn + p; the 64 columns (conv2
                         // channels) become k-block p of row b of the feature image  [K' = p*64 + co]
 };
 
-template <int BN>
+// TWO = CTA pair: cta_group::2 MMAs of 256 x BN (each CTA holds 128 rows of A and of the accumulator and
+// BN/2 rows of the weight tile), which halves the weight bytes each SM reads from shared memory per MMA.
+template <int BN, bool TWO>
 struct Smem {
-  static constexpr int W_STAGE_BYTES = BN * BK * 2;
+  static constexpr int NSTAGES = TWO ? 6 : STAGES;
+  static constexpr int W_STAGE_BYTES = (TWO ? BN / 2 : BN) * BK * 2;  // this CTA's share of a weight tile stage
+  static constexpr int W_TILE_BYTES = BN * BK * 2;                    // a whole weight tile stage in HBM
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + W_STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = NSTAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
 };
 
-template <int BN>
+template <int BN, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B wants 1024-B alignment
-  using S = Smem<BN>;
+  using S = Smem<BN, TWO>;
+  constexpr int NS = S::NSTAGES;
   uint64_t* full = (uint64_t*)(smem + S::BAR_OFFSET);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + NS;
+  uint64_t* pfull = empty + NS;  // TWO: "the peer CTA's stage has landed", arrived remotely by the peer
+  uint64_t* tfull = pfull + NS;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages of BN <= 256 fp32 columns
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+  const int unit = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // scheduling unit: CTA or CTA pair
+  const int n_units = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = TWO ? (g.m_tiles + 1) / 2 : g.m_tiles;             // a pair owns two consecutive m-tiles
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&pfull[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], TWO ? 256 : 128);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if (TWO) tmem_alloc2(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = g.m_tiles * g.n_tiles;
+  const int total_tiles = m_units * g.n_tiles;
   const int kb_total = g.x3 ? 3 * g.KB : g.KB;
 
   if (warp == 0) {
@@ -210,19 +291,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int mt = t / g.n_tiles, nt = t % g.n_tiles;
+      for (int t = unit; t < total_tiles; t += n_units) {
+        const int mt = (t / g.n_tiles) * (TWO ? 2 : 1) + (int)rank, nt = t % g.n_tiles;
         for (int kb = 0; kb < kb_total; ++kb) {
           // x3: [Xhi|Xhi|Xlo] against [Whi|Wlo|Whi]
           const int seg = g.x3 ? kb / g.KB : 0, kk = g.x3 ? kb % g.KB : kb;
           const uint8_t* a_src = (seg == 2 ? g.a_lo : g.a_hi) + ((size_t)mt * g.KB + kk) * A_STAGE_BYTES;
-          const uint8_t* w_src = (seg == 1 ? g.w_lo : g.w_hi) + ((size_t)nt * g.KB + kk) * S::W_STAGE_BYTES;
+          const uint8_t* w_src = (seg == 1 ? g.w_lo : g.w_hi) + ((size_t)nt * g.KB + kk) * S::W_TILE_BYTES +
+                                 (size_t)rank * S::W_STAGE_BYTES;  // pair: this CTA's half of the tile's rows
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], S::STAGE_BYTES);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           bulk_g2s(sa, a_src, A_STAGE_BYTES, &full[stage]);
           bulk_g2s(sa + A_STAGE_BYTES, w_src, S::W_STAGE_BYTES, &full[stage]);
-          if (++stage == STAGES) {
+          if (++stage == NS) {
             stage = 0;
             phase ^= 1;
           }
@@ -230,36 +312,57 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer: one thread =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+    // ================= MMA issuer: one thread (of the leader CTA when paired) =================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(TWO ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      for (int t = unit; t < total_tiles; t += n_units) {
+        if (TWO) mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues drained this accumulator
+        else mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&full[stage], phase);  // operands have landed
+          if (TWO) mbar_wait_cluster(&pfull[stage], phase);  // ... in the peer CTA as well
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa);
           const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // advance 32 bytes (2 x 16-byte units) per K=16 step
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) {
+          for (int k = 0; k < BK / 16; ++k) {  // advance 32 bytes (2 x 16-byte units) per K=16 step
+            if (TWO) umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          if (TWO) umma2_commit(&empty[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
+          else umma_commit(&empty[stage]);
+          if (++stage == NS) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (TWO) umma2_commit(&tfull[acc]);  // accumulator complete -> epilogue (of both CTAs)
+        else umma_commit(&tfull[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
+        }
+      }
+    } else if (TWO && lane == 0) {
+      // peer CTA: relay "my stage has landed" to the leader (a bulk copy can only signal its own CTA)
+      const uint32_t leader_pfull = map_to_cta(&pfull[0], 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = unit; t < total_tiles; t += n_units) {
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full[stage], phase);
+          mbar_arrive_cluster(leader_pfull + (uint32_t)stage * 8u);
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -270,8 +373,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
     int acc = 0;
     uint32_t acc_phase = 0;
     const int NKB = (g.n_tiles * BN) / BK;  // k-blocks of the output image
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = t / g.n_tiles, nt = t % g.n_tiles;
+    const uint32_t leader_tempty = TWO ? map_to_cta(&tempty[0], 0) : 0u;
+    for (int t = unit; t < total_tiles; t += n_units) {
+      const int mt = (t / g.n_tiles) * (TWO ? 2 : 1) + (int)rank, nt = t % g.n_tiles;
       const int64_t row = (int64_t)mt * BM + r_local;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -362,7 +466,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);  // 128 arrivals release the accumulator
+      if (TWO) mbar_arrive_cluster(leader_tempty + (uint32_t)acc * 8u);  // 2 x 128 arrivals on the leader's barrier
+      else mbar_arrive(&tempty[acc]);                                    // 128 arrivals release the accumulator
       if (g.out_mode == OUT_HEADS && row < g.M) {
         float* dst = g.head_part + ((size_t)row * g.n_tiles + nt) * HEAD_STRIDE;
 #pragma unroll
@@ -378,9 +483,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
 
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: leave together
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (TWO) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -427,21 +534,50 @@ inline int pick_bn(int F) {
   return 0;
 }
 
-template <int BN>
-int launch_gemm(const GemmArgs& g, cudaStream_t st) {
+static int gemm_pair_mode() {  // AZG_GEMM=1cta disables the CTA-pair kernels (A/B measurements)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("AZG_GEMM");
+    mode = (e && strcmp(e, "1cta") == 0) ? 0 : 1;
+  }
+  return mode;
+}
+
+template <int BN, bool TWO>
+int launch_gemm_impl(const GemmArgs& g, cudaStream_t st) {
   static bool configured = false;
   int dev = 0, sms = 0;
   AZG_CUDA_CHECK(cudaGetDevice(&dev));
   AZG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  using S = Smem<BN, TWO>;
   if (!configured) {
-    AZG_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  const int tiles = g.m_tiles * g.n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
-  gemm_bf16_tc_kernel<BN><<<grid, NUM_THREADS, Smem<BN>::TOTAL, st>>>(g);
+  const int units = (TWO ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles;
+  int grid = TWO ? 2 * (units < sms / 2 ? units : sms / 2) : (units < sms ? units : sms);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TWO ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AZG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, TWO>, g));
   AZG_LAUNCH_CHECK();
   return AZG_OK;
+}
+
+// the CTA-pair kernel needs BN/2 to be a multiple of 8 rows and an even number of padded m-tiles
+template <int BN>
+int launch_gemm(const GemmArgs& g, cudaStream_t st) {
+  if (gemm_pair_mode() && g.pair_ok && BN >= 128) return launch_gemm_impl<BN, true>(g, st);
+  return launch_gemm_impl<BN, false>(g, st);
 }
 
 int run_gemm(int BN, const GemmArgs& g, cudaStream_t st) {
@@ -1038,7 +1174,7 @@ ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
   ScratchLayout S{};
   const bool x3 = prec == AZG_PREC_BF16X3;
   const size_t nn = (size_t)n * n, F = 64 * nn;
-  const size_t M2p = (size_t)azg_ceil_div(B * (int64_t)nn, tc::BM) * tc::BM, Mp = (size_t)azg_ceil_div(B, tc::BM) * tc::BM;
+  const size_t M2p = (size_t)azg_ceil_div(B * (int64_t)nn, tc::BM) * tc::BM, Mp = (size_t)azg_ceil_div(B, 2 * tc::BM) * 2 * tc::BM;  // even number of m-tiles (CTA pairs)
   const size_t a2 = M2p * tc::C2_K * 2, fimg = Mp * F * 2;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = up1k(off + bytes); return o; };
@@ -1134,6 +1270,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   g.n_tiles = F / BN;
   g.KB = F / tc::BK;
   g.x3 = x3;
+  g.pair_ok = 1;
   g.a_hi = f_hi; g.a_lo = f_lo; g.w_hi = w + L.w0_hi; g.w_lo = x3 ? w + L.w0_lo : nullptr; g.bias = p->ot0_b; g.relu = 1;
   g.out_mode = x3 ? tc::OUT_IMG_HILO : tc::OUT_IMG; g.out_hi = h_hi; g.out_lo = h_lo;
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
@@ -1202,7 +1339,7 @@ int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, i
   AZG_REQUIRE(A && W && bias && C && scratch, "azg_tc_linear: null pointer");
   AZG_REQUIRE(BN != 0 && F % 64 == 0 && (prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16), "azg_tc_linear: unsupported F=%d prec=%d", F, prec);
   const bool x3 = prec == AZG_PREC_BF16X3;
-  const int64_t m_tiles = azg_ceil_div(M, tc::BM), Mp = m_tiles * tc::BM;
+  const int64_t m_tiles = azg_ceil_div(M, tc::BM), Mp = azg_ceil_div(M, 2 * tc::BM) * 2 * tc::BM;
   const size_t a_img = (size_t)Mp * F * 2, w_img = (size_t)F * F * 2;
   const size_t need = (x3 ? 2 : 1) * (a_img + w_img) + 1024;
   AZG_REQUIRE(scratch_bytes >= need, "azg_tc_linear: scratch %zu < %zu", scratch_bytes, need);
@@ -1215,7 +1352,7 @@ int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, i
   if ((rc = tc::to_image(A, M, Mp, F, tc::BM, a_hi, a_lo, st))) return rc;
   if ((rc = tc::to_image(W, F, F, F, BN, w_hi, w_lo, st))) return rc;
   tc::GemmArgs g{};
-  g.M = M; g.m_tiles = (int)m_tiles; g.n_tiles = F / BN; g.KB = F / tc::BK; g.x3 = x3;
+  g.M = M; g.m_tiles = (int)m_tiles; g.n_tiles = F / BN; g.KB = F / tc::BK; g.x3 = x3; g.pair_ok = 1;
   g.a_hi = a_hi; g.a_lo = a_lo; g.w_hi = w_hi; g.w_lo = w_lo; g.bias = bias; g.relu = relu;
   g.out_mode = tc::OUT_F32; g.out_f32 = C;
   return tc::run_gemm(BN, g, st);

@@ -116,7 +116,7 @@ int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t pa
 
 /* One dense layer on the tcgen05 path, for parity tests of the GEMM in isolation:
  * C[M,F] = act(A[M,F] . W[F,F]^T + bias), fp32 in/out, prec = AZG_PREC_BF16X3 | AZG_PREC_BF16.
- * scratch: >= 2*(ceil(M/128)*128 + F)*F*2 + 1024 bytes (x3) or half of that (bf16). */
+ * scratch: >= 2*(ceil(M/256)*256 + F)*F*2 + 1024 bytes (x3) or half of that (bf16). */
 int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int F, int prec,
                   int relu, void* scratch, size_t scratch_bytes, azg_stream stream);
 

@@ -15,7 +15,7 @@ def run(M, F, prec, relu, seed=0):
     b = torch.randn(F, generator=g) * 0.1
     Ad, Wd, bd = A.cuda(), W.cuda(), b.cuda()
     C = torch.full((M, F), float("nan"), device="cuda")
-    Mp = (M + 127) // 128 * 128
+    Mp = (M + 255) // 256 * 256
     nbytes = 2 * (Mp + F) * F * 2 + 1024 if prec == _lib.PREC_BF16X3 else (Mp + F) * F * 2 + 1024
     scratch = torch.zeros(nbytes + 1024, dtype=torch.uint8, device="cuda")
     _lib.check(lib.azg_tc_linear(_lib.ptr(Ad), _lib.ptr(Wd), _lib.ptr(bd), _lib.ptr(C), M, F, prec, relu,

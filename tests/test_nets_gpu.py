@@ -154,7 +154,7 @@ def test_checkpoint_round_trip(tmp_path):
 def _tc_linear(A, W, b, prec, relu):
     lib = _lib.lib()
     M, F = A.shape
-    Mp = (M + 127) // 128 * 128
+    Mp = (M + 255) // 256 * 256
     nbytes = (2 if prec == _lib.PREC_BF16X3 else 1) * (Mp + F) * F * 2 + 2048
     scratch = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
     C = torch.full((M, F), float("nan"), device="cuda")
