@@ -848,16 +848,16 @@ __global__ void heads32_finalize_kernel(const float* __restrict__ lg, int A, int
 }
 
 // ---- fused trunk: encode + conv1 + im2col in shared memory -> tcgen05 conv2 --------------------
-// One persistent CTA per SM, 12 warps.  A tile is G = 128 / n^2 whole boards (G*n^2 <= 128 GEMM rows).
-//   warps 0-3   builders (+ warps 6-7 for the conv1 part): relu(conv1) of the tile's boards into smem (bf16 hi/lo, zero border, 80-byte
+// One persistent CTA per SM, 16 warps.  A tile is G = 128 / n^2 whole boards (G*n^2 <= 128 GEMM rows).
+//   warps 0-7   builders: relu(conv1) of the tile's boards into smem (bf16 hi/lo, zero border, 80-byte
 //               cell stride = conflict-free 16-byte gathers), then per k-block copy the 3x3 patches
-//               into the SWIZZLE_128B operand stage (pure 16-byte smem->smem moves), fence.proxy.async,
-//               arrive on the stage's mbarrier
-//   warp 4      MMA issuer (one thread): M=128 x N=64 x K=16, conv2 weight images resident in smem
-//   warp 5      TMEM allocation, barrier init, one-time bulk copy of the conv2 weight images
-//   warps 8-11  epilogue: TMEM -> +bias, ReLU -> feature image (the A operand of GEMM-1)
+//               into the SWIZZLE_128B operand stage (pure 16-byte smem->smem moves, two threads per
+//               row), fence.proxy.async, arrive on the stage's mbarrier
+//   warp 8      MMA issuer (one thread): M=128 x N=64 x K=16, conv2 weight images resident in smem
+//   warp 9      TMEM allocation, barrier init, one-time bulk copy of the conv2 weight images
+//   warps 12-15 epilogue: TMEM -> +bias, ReLU -> feature image (the A operand of GEMM-1)
 // The im2col matrix never exists in HBM (the split version moved 2 x 4.1 GB per 65,536 positions).
-constexpr int TR_THREADS = 384;
+constexpr int TR_THREADS = 512;
 constexpr int TR_CELL_STRIDE = 80;   // bytes per padded cell: 32 channels x bf16 + 16 B pad
 constexpr int TR_MAX_CELLS = 288;    // max over n of G * (n+2)^2
 constexpr int TR_W_BYTES = C2_KB * 64 * 128;  // conv2 weight image [64 x 320] bf16 = 40 KB
@@ -923,9 +923,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
     cell_tab[i] = (uint16_t)(ib * cells + ix * np + (ip - ix * n));
   }
   if (threadIdx.x < 32) b1s[threadIdx.x] = t.b1[threadIdx.x];
-  if (warp == 5 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
-      mbar_init(&full[s], 128);
+      mbar_init(&full[s], 256);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -935,27 +935,26 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
   fence_async_smem();  // the zero-filled stages are read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {  // conv2 weight images -> smem, once
       mbar_expect_tx(wbar, (X3 ? 2 : 1) * TR_W_BYTES);
       bulk_g2s(w_s, t.w_hi, TR_W_BYTES, wbar);
       if (X3) bulk_g2s(w_s + TR_W_BYTES, t.w_lo, TR_W_BYTES, wbar);
     }
-  } else if (warp < 4 || warp == 6 || warp == 7) {
-    // ============ builders (warps 0-3) + conv1 helpers (warps 6-7) ============
-    const bool builder = warp < 4;
-    const int r = threadIdx.x;  // tile row (builders)
+  } else if (warp < 8) {
+    // ============ builders: 8 warps, two threads per tile row (each moves half of a row's chunks) ============
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;  // tile row, chunk half
     const int bl = r / nn, pc = r - bl * nn, x = pc / n, y = pc - x * n;
-    const bool row_valid = builder && bl < G;
+    const bool row_valid = bl < G;
     const int cell0 = bl * cells + x * np + y;  // padded cell of tap (0,0); tap (kx,ky) adds kx*np + ky
-    const int cw = builder ? warp : warp - 2;   // conv1 worker index 0..5
+    const int cw = warp;                        // conv1 worker index 0..7
     float w9[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) w9[k] = w1s[lane * 9 + k];
@@ -964,41 +963,53 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
     uint32_t phase = 0;
     // the packed positions of the next tile are fetched one tile ahead (global latency off the critical path)
     uint64_t nm = 0, nt = 0;
-    if (row_valid) {
+    if (row_valid && half == 0) {
       const int64_t b = (int64_t)blockIdx.x * G + bl;
       if (b < t.B) { nm = t.states[2 * b]; nt = t.states[2 * b + 1]; }
     }
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      if (row_valid) {  // K1 encode: this row's cell of the packed position -> {-1,0,1} in the padded plane
+      if (row_valid && half == 0) {  // K1 encode: this row's cell of the packed position -> {-1,0,1} in the padded plane
         planes_s[cell0 + np + 1] = (float)((int)((nm >> pc) & 1ull) - (int)((nt >> pc) & 1ull));
         const int64_t b = (tile + gridDim.x) * G + bl;
         nm = nt = 0;
         if (b < t.B) { nm = t.states[2 * b]; nt = t.states[2 * b + 1]; }
       }
-      named_bar(1, 192);  // planes ready; every builder is done reading the previous tile's conv1 output
+      named_bar(1, 256);  // planes ready; every builder is done reading the previous tile's conv1 output
       // relu(conv1): lanes = channels, six warps walk the cells (Connect4Net.py:45)
-      for (int c = cw; c < G * nn; c += 6) {
-        const int ctap = cell_tab[c];
+      for (int c = cw; c < G * nn; c += 16) {  // two cells per iteration (independent FMA chains)
+        const int c2 = c + 8;
+        const bool has2 = c2 < G * nn;
+        const int ctap = cell_tab[c], ctap2 = cell_tab[has2 ? c2 : c];
         const float* pl = planes_s + ctap;
-        float acc = bias;
+        const float* pl2 = planes_s + ctap2;
+        float acc = bias, acc2 = bias;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) acc = fmaf(pl[kx * np + ky], w9[kx * 3 + ky], acc);
+          for (int ky = 0; ky < 3; ++ky) {
+            acc = fmaf(pl[kx * np + ky], w9[kx * 3 + ky], acc);
+            acc2 = fmaf(pl2[kx * np + ky], w9[kx * 3 + ky], acc2);
+          }
         acc = fmaxf(acc, 0.0f);
-        const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+        acc2 = fmaxf(acc2, 0.0f);
+        const __nv_bfloat16 h = __float2bfloat16_rn(acc), h2 = __float2bfloat16_rn(acc2);
         const uint32_t off = (uint32_t)(ctap + np + 1) * TR_CELL_STRIDE + lane * 2;
+        const uint32_t off2 = (uint32_t)(ctap2 + np + 1) * TR_CELL_STRIDE + lane * 2;
         *reinterpret_cast<__nv_bfloat16*>(a1hi + off) = h;
         if (X3) *reinterpret_cast<__nv_bfloat16*>(a1lo + off) = __float2bfloat16_rn(acc - __bfloat162float(h));
+        if (has2) {
+          *reinterpret_cast<__nv_bfloat16*>(a1hi + off2) = h2;
+          if (X3) *reinterpret_cast<__nv_bfloat16*>(a1lo + off2) = __float2bfloat16_rn(acc2 - __bfloat162float(h2));
+        }
       }
-      named_bar(2, 192);  // conv1 output complete
-      if (!builder) continue;
+      named_bar(2, 256);  // conv1 output complete
       for (int kb = 0; kb < C2_KB; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = stages + stage * S::STAGE_BYTES;
         if (row_valid) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = half * 4 + jj;
             const int c = kb * 8 + j;  // 16-byte chunk of the K = (tap, cin) axis
             uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
             if (c < 36) {
@@ -1020,7 +1031,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
@@ -1060,7 +1071,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ======================= epilogue =======================
     const int q = warp & 3, r = q * 32 + lane;
     const int bl = r / nn, pc = r - bl * nn;
@@ -1100,7 +1111,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
