@@ -151,23 +151,56 @@ def run_reference_arm(args, rank):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region (NVML every 10 ms; nvidia-smi as a
+    fallback when the NVML binding is unavailable)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.index, self.sm, self.max_sm, self.reasons, self.stop = index, [], [], set(), threading.Event()
         self.th = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            phys = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
+            dev = int(phys[index]) if phys and phys[0].strip().isdigit() and index < len(phys) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.max_sm.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in self.BITS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                              str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        if len(f) >= 6 and f[0].replace(".", "").isdigit():
+            self.sm.append(float(f[0]))
+            self.max_sm.append(float(f[1]))
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+                if val.lower() == "active":
+                    self.reasons.add(name)
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.01 if self.nvml else 0.1)
 
     def __enter__(self):
         self.th.start()
@@ -179,12 +212,8 @@ class ClockSampler:
 
     def summary(self):
         import statistics
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower() == "active"})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.max_sm) if self.max_sm else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -311,8 +340,9 @@ def run_gpu_arm(args, rank, local_rank, world):
         # roofline entry always uses the measured bf16 tensor peak (the path's real ceiling).
         terms = 3 if args.precision == "bf16x3" else 1
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this
-        # configuration (profiles/r01_gemm_bf16x3_v3.txt: GEMM-1 1.207+0.806 GB, GEMM-2 0.995+0.063 GB)
-        traffic = {"bf16x3": 1.535e9, "bf16": None, "fp32": None}[args.precision] if B == BATCH else None
+        # configuration (profiles/r01_main_kernels_bf16x3_v4.txt: GEMM-1 2.590+0.811 GB, GEMM-2 1.986+0.063 GB;
+        # the single-CTA kernel moved 1.207+0.806 / 0.995+0.063 GB, profiles/r01_gemm_bf16x3_v3.txt)
+        traffic = {"bf16x3": 2.725e9, "bf16": None, "fp32": None}[args.precision] if B == BATCH else None
         roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
                 "frac": (gemm_tflops / bf16_peak) if gemm_tflops else None, "traffic": traffic,
                 "traffic_unit": "bytes per launch (average of the two launches)",
@@ -370,7 +400,7 @@ def run_gpu_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
