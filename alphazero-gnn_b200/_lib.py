@@ -60,6 +60,7 @@ SIGNATURES = {
     "azg_fl_encode_graph": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "azg_c4_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "azg_c4_forward": (_i, [C.POINTER(C4Params), _i, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "azg_c4_forward_dyn": (_i, [C.POINTER(C4Params), _i, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "azg_c4_packed_bytes": (_sz, [_i, _i]),
     "azg_c4_pack": (_i, [C.POINTER(C4Params), _i, _i, _vp, _sz, _vp]),
     "azg_tc_linear": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _sz, _vp]),
@@ -87,6 +88,8 @@ SIGNATURES = {
     "azg_arena_begin": (_i, [_vp, _i, _vp]),
     "azg_arena_select": (_i, [_vp, _vp, _vp, _vp]),
     "azg_arena_expand_backup": (_i, [_vp, _vp, _vp, _vp]),
+    "azg_arena_select_compact": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "azg_arena_expand_backup_compact": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "azg_arena_root_stats": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "azg_arena_advance": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "azg_arena_status": (_i, [_vp, _vp, _vp]),

@@ -53,6 +53,8 @@ class DeviceArena:
         dev = self.device
         self.leaf_states = torch.zeros(G, 2, dtype=torch.int64, device=dev)
         self.leaf_mask = torch.zeros(G, dtype=torch.int32, device=dev)
+        self.leaf_game = torch.zeros(G, dtype=torch.int32, device=dev)
+        self.leaf_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.root_N = torch.zeros(G, A, dtype=torch.int32, device=dev)
         self.root_Q = torch.zeros(G, A, dtype=torch.float64, device=dev)
         self.root_qtag = torch.zeros(G, A, dtype=torch.int8, device=dev)
@@ -110,6 +112,18 @@ class DeviceArena:
     def select(self):
         self._check(self.lib.azg_arena_select(self.handle, ptr(self.leaf_states), ptr(self.leaf_mask), self._stream()))
         return self.leaf_states, self.leaf_mask
+
+    def select_compact(self):
+        """select with the waiting leaves written densely: (leaf_states[:count], leaf_game[:count], count on the device)"""
+        self._check(self.lib.azg_arena_select_compact(self.handle, ptr(self.leaf_states), ptr(self.leaf_mask),
+                                                      ptr(self.leaf_game), ptr(self.leaf_count), self._stream()))
+        return self.leaf_states, self.leaf_game, self.leaf_count
+
+    def expand_backup_compact(self, pi, v):
+        assert pi.shape == (self.G, self.A) and pi.dtype == torch.float32 and pi.is_contiguous()
+        assert v.shape == (self.G,) and v.dtype == torch.float32 and v.is_contiguous()
+        self._check(self.lib.azg_arena_expand_backup_compact(self.handle, ptr(pi), ptr(v), ptr(self.leaf_game),
+                                                             ptr(self.leaf_count), self._stream()))
 
     def expand_backup(self, pi, v):
         assert pi.shape == (self.G, self.A) and pi.dtype == torch.float32 and pi.is_contiguous()

@@ -40,6 +40,22 @@ __global__ void __launch_bounds__(kThreads) arena_expand_backup_kernel(AzgArenaV
   if (g < a.G) azg_expand_backup_game(a, g, pi, v);
 }
 
+__global__ void __launch_bounds__(kThreads) arena_select_compact_kernel(AzgArenaView a, AzgState* leaf_states,
+                                                                        int32_t* leaf_mask, int32_t* leaf_game,
+                                                                        int32_t* leaf_count) {
+  int g, lane;
+  unsigned mask;
+  if (!group_of(a.G, g, lane, mask)) return;
+  azg_select_game<kLanes>(a, g, lane, mask, leaf_states, leaf_mask, leaf_game, leaf_count);
+}
+
+__global__ void __launch_bounds__(kThreads) arena_expand_backup_compact_kernel(AzgArenaView a, const float* pi,
+                                                                               const float* v, const int32_t* leaf_game,
+                                                                               const int32_t* leaf_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *leaf_count) azg_expand_backup_game(a, leaf_game[i], pi, v, i);
+}
+
 __global__ void arena_reset_kernel(AzgArenaView a, const int32_t* ids, int count) {
   // one CTA per listed game: clear its hash slots and per-game scalars
   const int g = ids ? ids[blockIdx.x] : blockIdx.x;
@@ -202,6 +218,27 @@ int azg_arena_select(azg_arena* a, uint64_t* leaf_states, int32_t* leaf_mask, az
   const int64_t threads = (int64_t)a->view.G * kLanes;
   arena_select_kernel<<<grid_for(threads, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
       a->view, (AzgState*)leaf_states, leaf_mask);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+int azg_arena_select_compact(azg_arena* a, uint64_t* leaf_states, int32_t* leaf_mask, int32_t* leaf_game,
+                             int32_t* leaf_count, azg_stream stream) {
+  AZG_REQUIRE(a && leaf_states && leaf_mask && leaf_game && leaf_count, "azg_arena_select_compact: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  AZG_CUDA_CHECK(cudaMemsetAsync(leaf_count, 0, sizeof(int32_t), st));
+  const int64_t threads = (int64_t)a->view.G * kLanes;
+  arena_select_compact_kernel<<<grid_for(threads, kThreads), kThreads, 0, st>>>(a->view, (AzgState*)leaf_states, leaf_mask,
+                                                                                 leaf_game, leaf_count);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+int azg_arena_expand_backup_compact(azg_arena* a, const float* pi, const float* v, const int32_t* leaf_game,
+                                    const int32_t* leaf_count, azg_stream stream) {
+  AZG_REQUIRE(a && pi && v && leaf_game && leaf_count, "azg_arena_expand_backup_compact: null pointer");
+  arena_expand_backup_compact_kernel<<<grid_for(a->view.G, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      a->view, pi, v, leaf_game, leaf_count);
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }

@@ -266,14 +266,17 @@ AZG_HD int azg_select_action(const AzgArenaView& a, size_t node, int lane, unsig
 
 // MCTS.search descend phase for game g; runs searches until one needs a prediction or the
 // simulation budget is spent.
+// leaf_game/leaf_count (optional): compacted output -- games that wait for a prediction claim consecutive
+// slots; leaf_states then holds their positions densely and leaf_game the owning game of each slot.
 template <int W>
 AZG_HD void azg_select_game(const AzgArenaView& a, int g, int lane, unsigned mask, AzgState* leaf_states,
-                            int32_t* leaf_mask) {
+                            int32_t* leaf_mask, int32_t* leaf_game = nullptr, int32_t* leaf_count = nullptr) {
   int sims = a.sims_left[g];
   int count = a.node_count[g];
   const bool waiting = a.pending[g] >= 0;
   int emit = waiting ? 1 : 0;
-  if (waiting && lane == 0) leaf_states[g] = a.key[(size_t)g * a.cap + a.pending[g]];
+  AzgState emit_state = a.root[g];
+  if (waiting) emit_state = a.key[(size_t)g * a.cap + a.pending[g]];
   bool failed = a.status[g] != 0;
   while (!waiting && !failed && sims > 0) {
     AzgState s = a.root[g];
@@ -315,8 +318,8 @@ AZG_HD void azg_select_game(const AzgArenaView& a, int g, int lane, unsigned mas
           a.valids[node] = azg_valids(a.rules, s);
           a.pending[g] = idx;
           a.path_len[g] = depth;
-          leaf_states[g] = s;
         }
+        emit_state = s;
         need_eval = true;
         break;
       }
@@ -342,11 +345,26 @@ AZG_HD void azg_select_game(const AzgArenaView& a, int g, int lane, unsigned mas
     a.sims_left[g] = sims;
     a.node_count[g] = count;
     leaf_mask[g] = emit;
+    if (leaf_count) {
+      if (emit) {
+#if defined(__CUDA_ARCH__)
+        const int slot = atomicAdd(leaf_count, 1);
+#else
+        const int slot = (*leaf_count)++;
+#endif
+        leaf_states[slot] = emit_state;
+        leaf_game[slot] = g;
+      }
+    } else if (emit) {
+      leaf_states[g] = emit_state;
+    }
   }
 }
 
 // MCTS.search leaf phase + backup for a game whose prediction arrived (lane 0 only)
-AZG_HD void azg_expand_backup_game(const AzgArenaView& a, int g, const float* pi, const float* vpred) {
+// `row` = row of pi / vpred that holds game g's prediction (g itself, or its compact slot)
+AZG_HD void azg_expand_backup_game(const AzgArenaView& a, int g, const float* pi, const float* vpred, int64_t row = -1) {
+  if (row < 0) row = g;
   const int idx = a.pending[g];
   if (idx < 0) return;
   const size_t node = (size_t)g * a.cap + idx;
@@ -356,7 +374,7 @@ AZG_HD void azg_expand_backup_game(const AzgArenaView& a, int g, const float* pi
   int ptag = 0;
   if (!a.p_f32) {
     for (int i = 0; i < A; ++i)  // Ps = pi * valids: float32 * int64 -> float64, MCTS.py:180
-      ps[i] = azg_dmul((double)pi[(size_t)g * A + i], (double)((valids >> i) & 1u));
+      ps[i] = azg_dmul((double)pi[(size_t)row * A + i], (double)((valids >> i) & 1u));
     const double tot = azg_np_sum(ps, A);
     if (tot > 0) {
       for (int i = 0; i < A; ++i) ps[i] = azg_ddiv(ps[i], tot);  // MCTS.py:182-183
@@ -367,7 +385,7 @@ AZG_HD void azg_expand_backup_game(const AzgArenaView& a, int g, const float* pi
   } else {
     float pf[AZG_MAX_A];
     for (int i = 0; i < A; ++i)  // float32 * int8 -> float32
-      pf[i] = azg_fmul(pi[(size_t)g * A + i], (float)((valids >> i) & 1u));
+      pf[i] = azg_fmul(pi[(size_t)row * A + i], (float)((valids >> i) & 1u));
     const float tot = azg_np_sum_f32(pf, A);
     if (tot > 0) {
       for (int i = 0; i < A; ++i) ps[i] = (double)azg_fdiv(pf[i], tot);
@@ -381,7 +399,7 @@ AZG_HD void azg_expand_backup_game(const AzgArenaView& a, int g, const float* pi
   for (int i = 0; i < A; ++i) a.P[node * A + i] = ps[i];
   a.ns[node] = 0;  // MCTS.py:188
   AzgVal v;
-  v.d = (double)vpred[g];  // numpy.float32 from the net, MCTS.py:190-193
+  v.d = (double)vpred[row];  // numpy.float32 from the net, MCTS.py:190-193
   v.tag = AZG_TAG_F32;
   azg_backup(a, g, a.path_len[g], v);
   a.pending[g] = -1;

@@ -224,6 +224,7 @@ struct GemmArgs {
   const float* head_w;  // OUT_HEADS: [head_rows, N] fp32 (policy rows then the value row), reference order
   float* head_part;     // OUT_HEADS: [M, n_tiles, HEAD_STRIDE] partial sums, reduced in fixed order by heads_finalize
   int head_rows;
+  const int32_t* dyn_rows;  // optional device scalar: number of valid rows this launch (<= M), read by the kernel
   int pair_ok;          // the A image covers an even number of m-tiles: the CTA-pair kernel may be used
   int feat_nn;          // OUT_FEAT*: rows are (board b, cell p) pairs, m = b*feat_nn + p; the 64 columns (conv2
                         // channels) become k-block p of row b of the feature image  [K' = p*64 + co]
@@ -257,6 +258,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages of BN <= 256 fp32 columns
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+  if (g.dyn_rows) {  // row count decided on the device (compacted leaf batches): no host round trip
+    const int64_t rows = (int64_t)(*g.dyn_rows) * (g.out_mode >= OUT_FEAT && g.out_mode != OUT_HEADS ? g.feat_nn : 1);
+    if (rows < g.M) g.M = rows;
+    g.m_tiles = (int)((g.M + BM - 1) / BM);
+  }
   const int unit = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // scheduling unit: CTA or CTA pair
   const int n_units = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int m_units = TWO ? (g.m_tiles + 1) / 2 : g.m_tiles;             // a pair owns two consecutive m-tiles
@@ -791,9 +797,10 @@ __global__ void __launch_bounds__(256) heads_image_kernel(const uint8_t* __restr
 
 // logits = fixed-order sum of the per-tile partial head sums + bias; then exp(log_softmax) and tanh
 __global__ void heads_finalize_kernel(const float* __restrict__ part, int n_tiles, int A, const float* __restrict__ bp,
-                                      const float* __restrict__ bv, int64_t B, float* __restrict__ pi, float* __restrict__ v) {
+                                      const float* __restrict__ bv, int64_t B, const int32_t* __restrict__ dyn_rows,
+                                      float* __restrict__ pi, float* __restrict__ v) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= B) return;
+  if (row >= B || (dyn_rows && row >= *dyn_rows)) return;
   float logit[HEAD_ROWS];
 #pragma unroll
   for (int a = 0; a < HEAD_ROWS; ++a) logit[a] = 0.0f;
@@ -833,10 +840,10 @@ __global__ void concat_heads_kernel(const float* __restrict__ wp, const float* _
 }
 
 // std heads from the [B,32] logits block produced by the skinny tensor-core GEMM (bias already added)
-__global__ void heads32_finalize_kernel(const float* __restrict__ lg, int A, int64_t B, float* __restrict__ pi,
-                                        float* __restrict__ v) {
+__global__ void heads32_finalize_kernel(const float* __restrict__ lg, int A, int64_t B, const int32_t* __restrict__ dyn_rows,
+                                        float* __restrict__ pi, float* __restrict__ v) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= B) return;
+  if (row >= B || (dyn_rows && row >= *dyn_rows)) return;
   const float* x = lg + row * 32;
   float m = -INFINITY;
   for (int a = 0; a < A; ++a) m = fmaxf(m, x[a]);
@@ -884,6 +891,7 @@ struct TrunkArgs {
   uint8_t *f_hi, *f_lo;        // feature image out
   int64_t B;
   int n;
+  const int32_t* dyn_rows;  // optional device scalar: number of positions this launch (<= B)
 };
 
 template <bool X3>
@@ -909,6 +917,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = t.n, nn = n * n, np = n + 2, cells = np * np;
   const int G = 128 / nn;  // boards per tile
+  if (t.dyn_rows && *t.dyn_rows < t.B) t.B = *t.dyn_rows;
   const int64_t tiles = (t.B + G - 1) / G;
   constexpr int BN = 64;
   constexpr uint32_t TMEM_COLS = 128;
@@ -1219,7 +1228,7 @@ size_t azg_tc_scratch_bytes(int n, int64_t B, int prec) { return scratch_layout(
 // [std heads] -> [output_transform GEMMs -> enh fp32 for the GNN heads].
 int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int prec, const uint64_t* states, int64_t B,
                       int eval_mask, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* scratch,
-                      size_t scratch_bytes, cudaStream_t st) {
+                      size_t scratch_bytes, const int32_t* dyn_rows, cudaStream_t st) {
   const int nn = n * n, F = 64 * nn, A = n + 1, BN = tc::pick_bn(F);
   AZG_REQUIRE(BN != 0, "tcgen05 path: unsupported board size %d", n);
   const bool x3 = prec == AZG_PREC_BF16X3, gnn = (eval_mask & AZG_EVAL_GNN) != 0;
@@ -1238,6 +1247,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     tc::TrunkArgs t{};
     t.states = states; t.w1 = p->conv1_w; t.b1 = p->conv1_b; t.b2 = p->conv2_b;
     t.w_hi = w + L.c2_hi; t.w_lo = x3 ? w + L.c2_lo : nullptr; t.f_hi = f_hi; t.f_lo = f_lo; t.B = B; t.n = n;
+    t.dyn_rows = dyn_rows;
     if ((rc = x3 ? tc::launch_trunk<true>(t, st) : tc::launch_trunk<false>(t, st))) return rc;
   } else {  // split: im2col image through HBM, conv2 on the generic GEMM kernel (kept for A/B measurements)
     const int grid = (int)(B < 148 * 8 ? B : 148 * 8);
@@ -1250,7 +1260,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     g.x3 = x3;
     g.a_hi = a2_hi; g.a_lo = a2_lo; g.w_hi = w + L.c2_hi; g.w_lo = x3 ? w + L.c2_lo : nullptr;
     g.bias = p->conv2_b; g.relu = 1; g.out_mode = x3 ? tc::OUT_FEAT_HILO : tc::OUT_FEAT; g.feat_nn = nn;
-    g.out_hi = f_hi; g.out_lo = f_lo;
+    g.out_hi = f_hi; g.out_lo = f_lo; g.dyn_rows = dyn_rows;
     if ((rc = tc::run_gemm(64, g, st))) return rc;
   }
   azg_phase_end(AZG_PHASE_TRUNK, st);
@@ -1262,8 +1272,9 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
       h.M = B; h.m_tiles = (int)azg_ceil_div(B, tc::BM); h.n_tiles = 1; h.KB = F / tc::BK; h.x3 = x3;
       h.a_hi = f_hi; h.a_lo = f_lo; h.w_hi = w + L.hd_hi; h.w_lo = x3 ? w + L.hd_lo : nullptr;
       h.bias = (const float*)(w + L.bias32); h.relu = 0; h.out_mode = tc::OUT_F32; h.out_f32 = (float*)(sc + S.lg32);
+      h.dyn_rows = dyn_rows;
       if ((rc = tc::run_gemm(32, h, st))) return rc;
-      tc::heads32_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const float*)(sc + S.lg32), A, B, pi_std, v_std);
+      tc::heads32_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const float*)(sc + S.lg32), A, B, dyn_rows, pi_std, v_std);
       AZG_LAUNCH_CHECK();
     } else {
       const int grid = (int)(azg_ceil_div(B, 8) < 148 * 8 ? azg_ceil_div(B, 8) : 148 * 8);
@@ -1282,6 +1293,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   g.KB = F / tc::BK;
   g.x3 = x3;
   g.pair_ok = 1;
+  g.dyn_rows = dyn_rows;
   g.a_hi = f_hi; g.a_lo = f_lo; g.w_hi = w + L.w0_hi; g.w_lo = x3 ? w + L.w0_lo : nullptr; g.bias = p->ot0_b; g.relu = 1;
   g.out_mode = x3 ? tc::OUT_IMG_HILO : tc::OUT_IMG; g.out_hi = h_hi; g.out_lo = h_lo;
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
@@ -1293,7 +1305,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   azg_phase_end(AZG_PHASE_GEMM, st);
   azg_phase_begin(AZG_PHASE_HEADS, st);
   tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles, A, p->fc_policy_b,
-                                                                        p->fc_value_b, B, pi_gnn, v_gnn);
+                                                                        p->fc_value_b, B, dyn_rows, pi_gnn, v_gnn);
   AZG_LAUNCH_CHECK();
   azg_phase_end(AZG_PHASE_HEADS, st);
   return AZG_OK;

@@ -384,7 +384,7 @@ struct Carver {
 // tcgen05 path (azg_gemm_tc.cu)
 int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int prec, const uint64_t* states, int64_t B,
                       int eval_mask, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* scratch,
-                      size_t scratch_bytes, cudaStream_t st);
+                      size_t scratch_bytes, const int32_t* dyn_rows, cudaStream_t st);
 size_t azg_tc_scratch_bytes(int n, int64_t B, int prec);
 
 extern "C" {
@@ -468,6 +468,13 @@ size_t azg_c4_workspace_bytes(int n, int64_t B, int eval_mask, int prec) {
 int azg_c4_forward(const azg_c4_params* p, int n, const uint64_t* states, int64_t B, int eval_mask, int prec,
                    float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* workspace, size_t workspace_bytes,
                    azg_stream stream) {
+  return azg_c4_forward_dyn(p, n, states, B, nullptr, eval_mask, prec, pi_std, v_std, pi_gnn, v_gnn, workspace,
+                            workspace_bytes, stream);
+}
+
+int azg_c4_forward_dyn(const azg_c4_params* p, int n, const uint64_t* states, int64_t B, const int32_t* dyn_rows,
+                       int eval_mask, int prec, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* workspace,
+                       size_t workspace_bytes, azg_stream stream) {
   AZG_REQUIRE(p && states && workspace, "azg_c4_forward: null pointer");
   AZG_REQUIRE(n >= 4 && n <= 8, "azg_c4_forward: board size %d unsupported (4..8)", n);
   AZG_REQUIRE((eval_mask & ~3) == 0 && eval_mask != 0, "azg_c4_forward: bad eval_mask %d", eval_mask);
@@ -514,7 +521,7 @@ int azg_c4_forward(const azg_c4_params* p, int n, const uint64_t* states, int64_
   } else {
     AZG_REQUIRE(p->ot_packed, "azg_c4_forward: prec %d needs ot_packed (azg_c4_pack)", prec);
     if ((rc = azg_tc_c4_forward(p->ot_packed, p, n, prec, states, B, eval_mask, pi_std, v_std, pi_gnn, v_gnn, scratch,
-                                scratch_bytes, st)))
+                                scratch_bytes, dyn_rows, st)))
       return rc;
   }
   return AZG_OK;

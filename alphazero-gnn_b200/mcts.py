@@ -98,9 +98,12 @@ class BatchedMCTS:
                                 max_depth=max_depth, fl_map=fl_map)
         self.arena = arena
         self.device_eval = hasattr(nnet, "forward_states")
+        # compacted leaf batches (only waiting games are evaluated; the count never leaves the device)
+        self.compact = self.device_eval and getattr(nnet, "supports_dynamic_count", False)
         self.standard_predictions = [dict() for _ in range(n_games)]
         self.gnn_predictions = [dict() for _ in range(n_games)]
-        self.leaf_evals = 0
+        self.leaf_evals = 0          # positions submitted for evaluation (host path: exact; device paths: see below)
+        self._leaf_total = None      # compact path: exact count accumulated on the device
 
     # ------------------------------------------------------------------ roots
     def reset(self, game_ids=None):
@@ -114,9 +117,10 @@ class BatchedMCTS:
         return [unpack_state(self.kind, self.n, r) for r in roots]
 
     # ------------------------------------------------------------------ leaf evaluation
-    def _evaluate_device(self, leaf_states):
+    def _evaluate_device(self, leaf_states, count=None):
         mask = (_lib.EVAL_STD | _lib.EVAL_GNN) if self.use_gnn else _lib.EVAL_STD
-        out = self.nnet.forward_states(leaf_states, mask)
+        out = self.nnet.forward_states(leaf_states, mask, count=count) if count is not None else \
+            self.nnet.forward_states(leaf_states, mask)
         return (out["pi_gnn"], out["v_gnn"]) if self.use_gnn else (out["pi"], out["v"])
 
     def _evaluate_host(self, leaf_states, leaf_mask):
@@ -142,8 +146,14 @@ class BatchedMCTS:
         """n_sims MCTS.search calls per game (MCTS.py:33-34), in lock step."""
         ar = self.arena
         ar.begin(n_sims)
-        if self.device_eval:
+        if self.compact:
             for _ in range(n_sims):  # every round retires >= 1 simulation per game that has budget
+                leaf_states, _game, count = ar.select_compact()
+                pi, v = self._evaluate_device(leaf_states, count)
+                ar.expand_backup_compact(pi, v)
+                self._leaf_total = count.to(torch.int64) if self._leaf_total is None else self._leaf_total + count
+        elif self.device_eval:
+            for _ in range(n_sims):
                 leaf_states, _mask = ar.select()
                 pi, v = self._evaluate_device(leaf_states)
                 ar.expand_backup(pi, v)
@@ -156,6 +166,10 @@ class BatchedMCTS:
                     break
                 ar.expand_backup(pi, v)
         ar.check_status()
+
+    def leaf_evaluations(self):
+        """number of leaf positions evaluated so far (synchronises when the count lives on the device)"""
+        return self.leaf_evals + (int(self._leaf_total.item()) if self._leaf_total is not None else 0)
 
     # ------------------------------------------------------------------ MCTS.getActionProb (MCTS.py:29-58)
     def root_stats(self):

@@ -131,6 +131,7 @@ class _TwoPlayer(_Base):
 # ---------------------------------------------------------------------------------------- Connect4
 class B200Connect4NNetWrapper(_TwoPlayer):
     kind = "connect4"
+    supports_dynamic_count = True  # forward_states(count=device scalar): see azg_c4_forward_dyn
 
     def __init__(self, game, args):
         self._common(game, args)
@@ -164,8 +165,10 @@ class B200Connect4NNetWrapper(_TwoPlayer):
             self._packed[prec] = blob
         return self._packed[prec]
 
-    def forward_states(self, states, eval_mask=None, precision=None):
-        """states: int64 [B,2] on the device.  Returns device tensors pi/v (+pi_gnn/v_gnn)."""
+    def forward_states(self, states, eval_mask=None, precision=None, count=None):
+        """states: int64 [B,2] on the device.  Returns device tensors pi/v (+pi_gnn/v_gnn).
+        count: optional device int32 scalar -- only the first `count` rows are live (compacted leaf batches,
+        read by the kernels on the device; rows beyond it are left untouched on the tensor-core path)."""
         eval_mask = self._default_mask() if eval_mask is None else eval_mask
         if (eval_mask & _lib.EVAL_GNN) and self.gnn is None:
             raise RuntimeError("predict_with_gnn needs the GNN wrapper")
@@ -177,9 +180,9 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         p = self._params(prec, prec != _lib.PREC_FP32)
         nbytes = self.lib.azg_c4_workspace_bytes(self.n, B, eval_mask, prec)
         ws = self._workspace(nbytes)
-        _lib.check(self.lib.azg_c4_forward(C.byref(p), self.n, ptr(states), B, eval_mask, prec, ptr(o.get("pi")),
-                                           ptr(o.get("v")), ptr(o.get("pi_gnn")), ptr(o.get("v_gnn")), ptr(ws),
-                                           ws.numel(), stream()))
+        _lib.check(self.lib.azg_c4_forward_dyn(C.byref(p), self.n, ptr(states), B, ptr(count), eval_mask, prec,
+                                               ptr(o.get("pi")), ptr(o.get("v")), ptr(o.get("pi_gnn")), ptr(o.get("v_gnn")),
+                                               ptr(ws), ws.numel(), stream()))
         return o
 
     def train(self, examples, gnn_examples=None):

@@ -114,14 +114,14 @@ def gpu_selfplay(net, a, games, moves, seed):
         sp.step_all()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    m0, l0 = sp.moves_played, sp.mcts.leaf_evals
+    m0, l0 = sp.moves_played, sp.mcts.leaf_evaluations()
     e0.record()
     for _ in range(moves):
         sp.step_all()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    return (sp.moves_played - m0) / (ms / 1e3), (sp.mcts.leaf_evals - l0) / (ms / 1e3), ms
+    return (sp.moves_played - m0) / (ms / 1e3), (sp.mcts.leaf_evaluations() - l0) / (ms / 1e3), ms
 
 
 def run_reference_arm(args, rank):

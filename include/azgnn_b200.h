@@ -108,6 +108,12 @@ size_t azg_c4_workspace_bytes(int n, int64_t B, int eval_mask, int prec);
 int azg_c4_forward(const azg_c4_params* p, int n, const uint64_t* states, int64_t B, int eval_mask,
                    int prec, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn,
                    void* workspace, size_t workspace_bytes, azg_stream stream);
+/* Same with the number of valid positions decided on the device: dyn_rows (device int32, may be NULL)
+ * holds how many of the B rows are live (the arena's compacted leaf count); rows beyond it are neither
+ * computed nor written on the tensor-core path (the fp32 path evaluates all B rows). */
+int azg_c4_forward_dyn(const azg_c4_params* p, int n, const uint64_t* states, int64_t B, const int32_t* dyn_rows,
+                       int eval_mask, int prec, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn,
+                       void* workspace, size_t workspace_bytes, azg_stream stream);
 /* Build the tcgen05 operand images of the weights (conv2, output_transform, permuted heads) for
  * AZG_PREC_BF16X3 / AZG_PREC_BF16; the result goes into azg_c4_params.ot_packed.  Call again after
  * every optimizer step / load_checkpoint.  packed: device memory, 16-byte aligned. */
@@ -222,6 +228,14 @@ int azg_arena_select(azg_arena* a, uint64_t* leaf_states, int32_t* leaf_mask, az
 /* MCTS.search leaf + backup phase (MCTS.py:162-193, 228-240) for games with leaf_mask set:
  * pi [n_games,A] fp32 and v [n_games] fp32 are the predictions for leaf_states. */
 int azg_arena_expand_backup(azg_arena* a, const float* pi, const float* v, azg_stream stream);
+/* Compacted variants (no host synchronisation): the leaves that wait for a prediction are written
+ * densely -- leaf_states [count,2], leaf_game [count] = owning game, leaf_count [1] on the device --
+ * so the networks only evaluate `count` positions (azg_c4_forward_dyn reads the count on the device).
+ * expand_backup_compact consumes pi [count,A] / v [count] in that order. */
+int azg_arena_select_compact(azg_arena* a, uint64_t* leaf_states, int32_t* leaf_mask, int32_t* leaf_game,
+                             int32_t* leaf_count, azg_stream stream);
+int azg_arena_expand_backup_compact(azg_arena* a, const float* pi, const float* v, const int32_t* leaf_game,
+                                    const int32_t* leaf_count, azg_stream stream);
 /* root edge statistics for getActionProb / expand_tree (MCTS.py:36-37, 79-81, 121-143):
  * N [n_games,A] int32, Q [n_games,A] float64, qtag [n_games,A] int8 (AZG_TAG_*). */
 int azg_arena_root_stats(azg_arena* a, int32_t* N, double* Q, int8_t* qtag, azg_stream stream);

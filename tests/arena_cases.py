@@ -85,10 +85,6 @@ def case_lockstep_games(make_arena, tag="c4_7", G=6, moves=6, sims=12):
     A = game.getActionSize()
     args = dotdict(dict(numMCTSSims=sims, cpuct=1.3, use_gnn=True, expand_by=3))
     nets = [FakeNet(A, salt=100 + g, spread=1.0 + g) for g in range(G)]
-
-    class PerGame:  # routes by call order: BatchedMCTS evaluates masked games in ascending g
-        def __init__(self):
-            self.g = 0
     arena = make_arena(name, n, G, sims + 3, 1.3, capacity=(sims + 3) * (moves + 1) * 2 + 64)
     oracles = [OracleMCTS(game, nets[g], args) for g in range(G)]
     rng = np.random.default_rng(5)
@@ -107,7 +103,6 @@ def case_lockstep_games(make_arena, tag="c4_7", G=6, moves=6, sims=12):
     router = Router()
     bm = BatchedMCTS(game, router, args, n_games=G, arena=arena)
     # patch the host evaluation loop to tell the router which game is being evaluated
-    orig = bm._evaluate_host
 
     def routed(leaf_states, leaf_mask):
         ar = bm.arena
@@ -218,3 +213,58 @@ def case_capacity_overflow(make_arena):
         assert "table full" in str(e)
     else:
         raise AssertionError("capacity overflow was not reported")
+
+
+def case_compact_lockstep(make_arena, tag="c4_7", G=7, moves=5, sims=14):
+    """The compacted device path (select_compact -> forward(count) -> expand_backup_compact): leaves are
+    packed densely in claim order, evaluated, and scattered back; every game must still equal its own
+    sequential oracle search."""
+    import torch
+    name, game, n = _mk_game(tag)
+    A = game.getActionSize()
+    args = dotdict(dict(numMCTSSims=sims, cpuct=1.1, use_gnn=False, expand_by=3))
+    net = FakeNet(A, salt=77, spread=3.0)
+
+    class DenseFake:
+        """stands in for a B200 wrapper: forward_states on arena tensors, honouring the device-side count"""
+        supports_dynamic_count = True
+
+        def __init__(self, arena):
+            self.arena = arena
+
+        def forward_states(self, states, mask, count=None):
+            ar = self.arena
+            st = ar.to_host(states)
+            k = int(ar.to_host(count)[0]) if count is not None else st.shape[0]
+            pi = np.full((st.shape[0], A), np.nan, dtype=np.float32)  # rows beyond the count must never be read
+            v = np.full(st.shape[0], np.nan, dtype=np.float32)
+            for i in range(k):
+                pi[i], v[i] = net.predict(unpack_state(name, n, st[i]))
+            return {"pi": ar.to_device(pi, torch.float32), "v": ar.to_device(v, torch.float32)}
+    arena = make_arena(name, n, G, sims, 1.1, capacity=sims * (moves + 2) + 64)
+    bm = BatchedMCTS(game, DenseFake(arena), args, n_games=G, arena=arena)
+    assert bm.compact
+    rng = np.random.default_rng(9)
+    boards, players = [game.getInitBoard() for _ in range(G)], [1] * G
+    for g in range(G):  # desynchronise the games: g random moves each
+        for _ in range(g):
+            a = int(rng.choice(np.flatnonzero(game.getValidMoves(boards[g], players[g]))))
+            boards[g], players[g] = game.getNextState(boards[g], players[g], a)
+    oracles = [OracleMCTS(game, FakeNet(A, salt=77, spread=3.0), args) for _ in range(G)]
+    bm.set_root_boards([game.getCanonicalForm(b, p) for b, p in zip(boards, players)])
+    for mv in range(moves):
+        pis = bm.getActionProbs(temp=1)
+        actions = []
+        for g in range(G):
+            canon = game.getCanonicalForm(boards[g], players[g])
+            if game.getGameEnded(boards[g], players[g]) != 0:
+                actions.append(-1)
+                continue
+            opi = oracles[g].getActionProb(canon, temp=1)
+            assert np.array_equal(np.asarray(opi), np.asarray(pis[g])), (mv, g)
+            assert_tables_equal(mcts_as_tables(_View(bm.tables(g)), n, A), mcts_as_tables(oracles[g], n, A))
+            a = int(rng.choice(A, p=np.asarray(opi)))
+            actions.append(a)
+            boards[g], players[g] = game.getNextState(boards[g], players[g], a)
+        bm.advance(actions)
+    assert bm.leaf_evaluations() > 0

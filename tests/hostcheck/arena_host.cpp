@@ -80,6 +80,18 @@ int azgh_arena_select(azgh_arena* a, uint64_t* leaf_states, int32_t* leaf_mask, 
   for (int g = 0; g < a->view.G; ++g) azg_select_game<1>(a->view, g, 0, 1u, (AzgState*)leaf_states, leaf_mask);
   return 0;
 }
+int azgh_arena_select_compact(azgh_arena* a, uint64_t* leaf_states, int32_t* leaf_mask, int32_t* leaf_game,
+                              int32_t* leaf_count, void*) {
+  *leaf_count = 0;
+  for (int g = 0; g < a->view.G; ++g)
+    azg_select_game<1>(a->view, g, 0, 1u, (AzgState*)leaf_states, leaf_mask, leaf_game, leaf_count);
+  return 0;
+}
+int azgh_arena_expand_backup_compact(azgh_arena* a, const float* pi, const float* v, const int32_t* leaf_game,
+                                     const int32_t* leaf_count, void*) {
+  for (int i = 0; i < *leaf_count; ++i) azg_expand_backup_game(a->view, leaf_game[i], pi, v, i);
+  return 0;
+}
 int azgh_arena_expand_backup(azgh_arena* a, const float* pi, const float* v, void*) {
   for (int g = 0; g < a->view.G; ++g) azg_expand_backup_game(a->view, g, pi, v);
   return 0;

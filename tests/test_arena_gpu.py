@@ -56,6 +56,11 @@ def test_capacity_overflow():
     cases.case_capacity_overflow(make_arena)
 
 
+@pytest.mark.parametrize("tag", ["c4_7", "ttt_3"])
+def test_compacted_leaf_batches(tag):
+    cases.case_compact_lockstep(make_arena, tag)
+
+
 # ------------------------------------------------------------------ arena + CUDA networks end to end
 class _AsReference:
     """feeds the oracle MCTS the CUDA network's own single-position predictions"""

@@ -60,6 +60,11 @@ def test_capacity_overflow():
     cases.case_capacity_overflow(make_arena)
 
 
+@pytest.mark.parametrize("tag", ["c4_7", "ttt_3"])
+def test_compacted_leaf_batches(tag):
+    cases.case_compact_lockstep(make_arena, tag)
+
+
 def test_np_sum_order_matches_numpy():
     """Ps renormalisation uses numpy.sum (MCTS.py:181); the kernel restates its pairwise order.
     Wide-exponent inputs make the result order dependent, so this pins the order."""
