@@ -290,7 +290,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = m_units * g.n_tiles;
-  const int kb_total = g.x3 ? 3 * g.KB : g.KB;
+  // CTA pair + bf16x3: one stage holds hi AND lo of both operands of a k-block (60 KB per CTA, 3 stages) and
+  // feeds all three products, so every operand byte crosses L2 -> smem once instead of 1.5 times.  Otherwise
+  // the split is walked as three K segments [Xhi|Xhi|Xlo] x [Whi|Wlo|Whi] with one product per stage.
+  const bool fused3 = TWO && g.x3;
+  const int NSR = fused3 ? 3 : NS;                                         // stages in use
+  const uint32_t stage_bytes = fused3 ? 2 * S::STAGE_BYTES : S::STAGE_BYTES;
+  const int kb_total = (g.x3 && !fused3) ? 3 * g.KB : g.KB;
 
   if (warp == 0) {
     // ================= producer: bulk copies of operand tile images =================
@@ -300,17 +306,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
       for (int t = unit; t < total_tiles; t += n_units) {
         const int mt = (t / g.n_tiles) * (TWO ? 2 : 1) + (int)rank, nt = t % g.n_tiles;
         for (int kb = 0; kb < kb_total; ++kb) {
-          // x3: [Xhi|Xhi|Xlo] against [Whi|Wlo|Whi]
-          const int seg = g.x3 ? kb / g.KB : 0, kk = g.x3 ? kb % g.KB : kb;
-          const uint8_t* a_src = (seg == 2 ? g.a_lo : g.a_hi) + ((size_t)mt * g.KB + kk) * A_STAGE_BYTES;
-          const uint8_t* w_src = (seg == 1 ? g.w_lo : g.w_hi) + ((size_t)nt * g.KB + kk) * S::W_TILE_BYTES +
-                                 (size_t)rank * S::W_STAGE_BYTES;  // pair: this CTA's half of the tile's rows
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], S::STAGE_BYTES);
-          uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          bulk_g2s(sa, a_src, A_STAGE_BYTES, &full[stage]);
-          bulk_g2s(sa + A_STAGE_BYTES, w_src, S::W_STAGE_BYTES, &full[stage]);
-          if (++stage == NS) {
+          mbar_expect_tx(&full[stage], stage_bytes);
+          uint8_t* sa = smem + stage * stage_bytes;
+          if (fused3) {  // [A_hi | W_hi half | A_lo | W_lo half]
+            const size_t ao = ((size_t)mt * g.KB + kb) * A_STAGE_BYTES;
+            const size_t wo = ((size_t)nt * g.KB + kb) * S::W_TILE_BYTES + (size_t)rank * S::W_STAGE_BYTES;
+            bulk_g2s(sa, g.a_hi + ao, A_STAGE_BYTES, &full[stage]);
+            bulk_g2s(sa + A_STAGE_BYTES, g.w_hi + wo, S::W_STAGE_BYTES, &full[stage]);
+            bulk_g2s(sa + S::STAGE_BYTES, g.a_lo + ao, A_STAGE_BYTES, &full[stage]);
+            bulk_g2s(sa + S::STAGE_BYTES + A_STAGE_BYTES, g.w_lo + wo, S::W_STAGE_BYTES, &full[stage]);
+          } else {
+            // x3: [Xhi|Xhi|Xlo] against [Whi|Wlo|Whi]
+            const int seg = g.x3 ? kb / g.KB : 0, kk = g.x3 ? kb % g.KB : kb;
+            const uint8_t* a_src = (seg == 2 ? g.a_lo : g.a_hi) + ((size_t)mt * g.KB + kk) * A_STAGE_BYTES;
+            const uint8_t* w_src = (seg == 1 ? g.w_lo : g.w_hi) + ((size_t)nt * g.KB + kk) * S::W_TILE_BYTES +
+                                   (size_t)rank * S::W_STAGE_BYTES;  // pair: this CTA's half of the tile's rows
+            bulk_g2s(sa, a_src, A_STAGE_BYTES, &full[stage]);
+            bulk_g2s(sa + A_STAGE_BYTES, w_src, S::W_STAGE_BYTES, &full[stage]);
+          }
+          if (++stage == NSR) {
             stage = 0;
             phase ^= 1;
           }
@@ -334,7 +349,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
           mbar_wait(&full[stage], phase);  // operands have landed
           if (TWO) mbar_wait_cluster(&pfull[stage], phase);  // ... in the peer CTA as well
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa);
           const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
 #pragma unroll
@@ -342,9 +357,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
             if (TWO) umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
             else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
+          if (TWO && fused3) {  // + Xhi Wlo^T + Xlo Whi^T from the same stage
+            const uint64_t adesc_lo = make_smem_desc(sa + S::STAGE_BYTES);
+            const uint64_t bdesc_lo = make_smem_desc(sa + S::STAGE_BYTES + A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma2_bf16(d_tmem, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1);
+          }
           if (TWO) umma2_commit(&empty[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
           else umma_commit(&empty[stage]);
-          if (++stage == NS) {
+          if (++stage == NSR) {
             stage = 0;
             phase ^= 1;
           }
@@ -365,7 +388,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&full[stage], phase);
           mbar_arrive_cluster(leader_pfull + (uint32_t)stage * 8u);
-          if (++stage == NS) {
+          if (++stage == NSR) {
             stage = 0;
             phase ^= 1;
           }
