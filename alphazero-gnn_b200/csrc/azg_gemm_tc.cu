@@ -290,13 +290,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = m_units * g.n_tiles;
-  // CTA pair + bf16x3: one stage holds hi AND lo of both operands of a k-block (60 KB per CTA, 3 stages) and
-  // feeds all three products, so every operand byte crosses L2 -> smem once instead of 1.5 times.  Otherwise
-  // the split is walked as three K segments [Xhi|Xhi|Xlo] x [Whi|Wlo|Whi] with one product per stage.
+  // CTA pair: a stage holds TWO operand pairs (60 KB per CTA, 3 stages) and feeds 8-12 MMAs per barrier
+  // round trip.  bf16x3: hi and lo of both operands of one k-block -> all three products, so every operand
+  // byte crosses L2 -> smem once instead of 1.5 times.  Plain bf16: two consecutive k-blocks.
+  // Single CTA: one pair per stage; the bf16x3 split is walked as three K segments [Xhi|Xhi|Xlo] x [Whi|Wlo|Whi].
   const bool fused3 = TWO && g.x3;
-  const int NSR = fused3 ? 3 : NS;                                         // stages in use
-  const uint32_t stage_bytes = fused3 ? 2 * S::STAGE_BYTES : S::STAGE_BYTES;
-  const int kb_total = (g.x3 && !fused3) ? 3 * g.KB : g.KB;
+  const bool dual = TWO && !g.x3;
+  const int NSR = TWO ? 3 : NS;                                            // stages in use
+  const uint32_t stage_bytes = TWO ? 2 * S::STAGE_BYTES : S::STAGE_BYTES;
+  const int kb_total = fused3 ? g.KB : dual ? (g.KB + 1) / 2 : (g.x3 ? 3 * g.KB : g.KB);
 
   if (warp == 0) {
     // ================= producer: bulk copies of operand tile images =================
@@ -307,8 +309,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
         const int mt = (t / g.n_tiles) * (TWO ? 2 : 1) + (int)rank, nt = t % g.n_tiles;
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], stage_bytes);
           uint8_t* sa = smem + stage * stage_bytes;
+          if (dual) {  // [A(k0) | W(k0) half | A(k0+1) | W(k0+1) half]; an odd K leaves the last second half unused
+            const int k0 = 2 * kb, parts = (k0 + 1 < g.KB) ? 2 : 1;
+            mbar_expect_tx(&full[stage], parts * S::STAGE_BYTES);
+            for (int pt = 0; pt < parts; ++pt) {
+              const size_t ao = ((size_t)mt * g.KB + k0 + pt) * A_STAGE_BYTES;
+              const size_t wo = ((size_t)nt * g.KB + k0 + pt) * S::W_TILE_BYTES + (size_t)rank * S::W_STAGE_BYTES;
+              bulk_g2s(sa + pt * S::STAGE_BYTES, g.a_hi + ao, A_STAGE_BYTES, &full[stage]);
+              bulk_g2s(sa + pt * S::STAGE_BYTES + A_STAGE_BYTES, g.w_hi + wo, S::W_STAGE_BYTES, &full[stage]);
+            }
+            if (++stage == NSR) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_expect_tx(&full[stage], stage_bytes);
           if (fused3) {  // [A_hi | W_hi half | A_lo | W_lo half]
             const size_t ao = ((size_t)mt * g.KB + kb) * A_STAGE_BYTES;
             const size_t wo = ((size_t)nt * g.KB + kb) * S::W_TILE_BYTES + (size_t)rank * S::W_STAGE_BYTES;
@@ -356,6 +373,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
           for (int k = 0; k < BK / 16; ++k) {  // advance 32 bytes (2 x 16-byte units) per K=16 step
             if (TWO) umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
             else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          if (TWO && dual && 2 * kb + 1 < g.KB) {  // second k-block of the stage
+            const uint64_t adesc1 = make_smem_desc(sa + S::STAGE_BYTES);
+            const uint64_t bdesc1 = make_smem_desc(sa + S::STAGE_BYTES + A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma2_bf16(d_tmem, adesc1 + (uint64_t)(2 * k), bdesc1 + (uint64_t)(2 * k), idesc, 1);
           }
           if (TWO && fused3) {  // + Xhi Wlo^T + Xlo Whi^T from the same stage
             const uint64_t adesc_lo = make_smem_desc(sa + S::STAGE_BYTES);
