@@ -340,9 +340,8 @@ def run_gpu_arm(args, rank, local_rank, world):
         # roofline entry always uses the measured bf16 tensor peak (the path's real ceiling).
         terms = 3 if args.precision == "bf16x3" else 1
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this
-        # configuration (profiles/r01_main_kernels_bf16x3_v4.txt: GEMM-1 2.590+0.811 GB, GEMM-2 1.986+0.063 GB;
-        # the single-CTA kernel moved 1.207+0.806 / 0.995+0.063 GB, profiles/r01_gemm_bf16x3_v3.txt)
-        traffic = {"bf16x3": 2.725e9, "bf16": None, "fp32": None}[args.precision] if B == BATCH else None
+        # configuration (profiles/r01_main_kernels_bf16x3_v5.txt: GEMM-1 2.245+0.806 GB, GEMM-2 1.944+0.060 GB)
+        traffic = {"bf16x3": 2.528e9, "bf16": None, "fp32": None}[args.precision] if B == BATCH else None
         roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
                 "frac": (gemm_tflops / bf16_peak) if gemm_tflops else None, "traffic": traffic,
                 "traffic_unit": "bytes per launch (average of the two launches)",
