@@ -288,6 +288,35 @@ __global__ void att_hidden_bwd_kernel(const float* dz, const float* w2, const fl
   dhpre[i] = h[i] > 0.0f ? dz[i / 128] * w2[i % 128] : 0.0f;
 }
 
+// FrozenLake graph layer (FrozenLakeNet.py:8-33, 55-74): all-ones adjacency normalised to c = d*d,
+// d = k^-1/2, so every valid node of graph b receives relu(c * sum_j sup[b,j,:]).
+// sup/out: [B, 5, E] (unused nodes hold zeros), counts: [B] nodes per graph.
+__global__ void graph_mean_relu_fwd_kernel(const float* __restrict__ sup, const int32_t* __restrict__ counts, int64_t B,
+                                           int E, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * E) return;
+  const int64_t b = idx / E;
+  const int e = (int)(idx % E), k = counts[b];
+  const float d = 1.0f / sqrtf((float)k), c = d * d;
+  float agg = 0.0f;
+  for (int j = 0; j < k; ++j) agg = fmaf(c, sup[(b * 5 + j) * E + e], agg);
+  agg = fmaxf(agg, 0.0f);
+  for (int j = 0; j < 5; ++j) out[(b * 5 + j) * E + e] = j < k ? agg : 0.0f;
+}
+
+__global__ void graph_mean_relu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                           const int32_t* __restrict__ counts, int64_t B, int E, float* __restrict__ dsup) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * E) return;
+  const int64_t b = idx / E;
+  const int e = (int)(idx % E), k = counts[b];
+  const float d = 1.0f / sqrtf((float)k), c = d * d;
+  float g = 0.0f;
+  for (int j = 0; j < k; ++j) g += dout[(b * 5 + j) * E + e];
+  g = out[(b * 5) * E + e] > 0.0f ? g * c : 0.0f;
+  for (int j = 0; j < 5; ++j) dsup[(b * 5 + j) * E + e] = j < k ? g : 0.0f;
+}
+
 struct Bump {
   float* p;
   float* take(size_t n) {
@@ -384,6 +413,23 @@ int azg_policy_value_loss(const float* logits, const float* vraw, const float* t
               "azg_policy_value_loss: bad argument");
   policy_value_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, vraw, target_pi, target_v, B, A, 1.0f / norm, loss,
                                                                 logp, v, dlogits, dvraw);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+int azg_graph_mean_relu_forward(const float* sup, const int32_t* counts, int64_t B, int E, float* out, azg_stream stream) {
+  AZG_REQUIRE(sup && counts && out, "azg_graph_mean_relu_forward: null pointer");
+  if (B <= 0) return AZG_OK;
+  graph_mean_relu_fwd_kernel<<<grid_for(B * E, 256), 256, 0, (cudaStream_t)stream>>>(sup, counts, B, E, out);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+int azg_graph_mean_relu_backward(const float* dout, const float* out, const int32_t* counts, int64_t B, int E, float* dsup,
+                                 azg_stream stream) {
+  AZG_REQUIRE(dout && out && counts && dsup, "azg_graph_mean_relu_backward: null pointer");
+  if (B <= 0) return AZG_OK;
+  graph_mean_relu_bwd_kernel<<<grid_for(B * E, 256), 256, 0, (cudaStream_t)stream>>>(dout, out, counts, B, E, dsup);
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }

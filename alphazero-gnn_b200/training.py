@@ -137,6 +137,28 @@ class _PVLoss(torch.autograd.Function):
         return dlogits * g, (dvraw * g).view(-1, 1), None, None, None
 
 
+class _GraphMeanRelu(torch.autograd.Function):
+    """relu(bmm(adj, support)) for FrozenLake's all-ones normalised adjacency (FrozenLakeNet.py:27-33)."""
+
+    @staticmethod
+    def forward(ctx, sup, counts):
+        sup = sup.contiguous()
+        B, _, E = sup.shape
+        out = torch.empty_like(sup)
+        _lib_check(_lib.lib().azg_graph_mean_relu_forward(ptr(sup), ptr(counts), B, E, ptr(out), stream()))
+        ctx.save_for_backward(out, counts)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        out, counts = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, _, E = out.shape
+        dsup = torch.empty_like(out)
+        _lib_check(_lib.lib().azg_graph_mean_relu_backward(ptr(dout), ptr(out), ptr(counts), B, E, ptr(dsup), stream()))
+        return dsup, None
+
+
 def _layer_params(layer):
     return [layer.attention[0].weight, layer.attention[0].bias, layer.attention[2].weight, layer.attention[2].bias,
             layer.update_net[0].weight, layer.update_net[0].bias, layer.update_net[2].weight, layer.update_net[2].bias,
@@ -199,6 +221,19 @@ class CudaOps:
     @staticmethod
     def gnn_layer(f0, path, layer):
         return _GNNLayer.apply(f0, path, *_layer_params(layer))
+
+    @staticmethod
+    def graph_mean_relu(sup, counts):
+        return _GraphMeanRelu.apply(sup, counts)
+
+    @staticmethod
+    def fl_graph(states, n):
+        """K1 graph build (FrozenLakeNet.py:197-213): one-hot node features [B,5,n*n] + node counts [B]"""
+        B = states.shape[0]
+        nodes = torch.empty(B, 5, n * n, dtype=torch.float32, device=states.device)
+        counts = torch.empty(B, dtype=torch.int32, device=states.device)
+        _lib_check(_lib.lib().azg_fl_encode_graph(ptr(states), n, B, ptr(nodes), ptr(counts), stream()))
+        return nodes, counts
 
 
 # ----------------------------------------------------------------------------------------- network graphs
@@ -374,6 +409,58 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
     w.weights_changed()
 
 
-def train_frozenlake(w, examples):
-    raise NotImplementedError("FrozenLake training (frozenlake/FrozenLakeNet.py:76-176) is listed under 'next' in "
-                              "SURVEY.md section 8f and is not part of this round's hot path")
+def fl_step(ops, w, states, target_pi, target_v):
+    """Loss of one FrozenLake minibatch (FrozenLakeNet.py:113-160) with all graphs of the batch evaluated
+    together: nodes [B,5,n^2] -> feature_extractor -> L x (Linear, aggregate) -> node 0 -> heads -> loss.
+    The reference's `log(out_pi.clamp(min=1e-8))` equals log_softmax unless a probability underflows 1e-8."""
+    net = w.nnet
+    n = w.n
+    nodes, counts = ops.fl_graph(states, n)
+    B = nodes.shape[0]
+    x = nodes.reshape(B * 5, n * n)
+    fe = net.feature_extractor
+    x = ops.linear(ops.linear(x, fe[0], relu=True), fe[2], relu=True)
+    for layer in net.gnn_layers:
+        sup = ops.linear(x, layer.W)
+        x = ops.graph_mean_relu(sup.reshape(B, 5, -1), counts).reshape(B * 5, -1)
+    cur = x.reshape(B, 5, -1)[:, 0, :]
+    logits, vraw = ops.linear(cur, net.policy_head), ops.linear(cur, net.value_head)
+    loss, _, _ = ops.pv_loss(logits, vraw, target_pi, target_v, B)
+    return loss
+
+
+def train_frozenlake(w, examples, ops=CudaOps):
+    """FrozenLakeNet.train (FrozenLakeNet.py:76-176): fresh Adam, `epochs` passes over shuffled minibatches,
+    NaN batches skipped, gradient norm clipped to 1.0.  Graph construction and forward/backward run in the
+    CUDA library for the whole minibatch at once instead of one Python iteration per board."""
+    from .mcts import pack_states
+    if not examples or len(examples) < 4:
+        print("Not enough examples for training, need at least 4")
+        return
+    print(f"Training on {len(examples)} examples")
+    lr, epochs, batch_size = float(arg(w.args, "lr")), int(arg(w.args, "epochs")), int(arg(w.args, "batch_size"))
+    params = list(w.nnet.parameters())
+    w.optimizer = torch.optim.Adam(params, lr=lr)
+    examples = [(x[0], x[1], x[2]) for x in examples if x[2] is not None]
+    for epoch in range(epochs):
+        np.random.shuffle(examples)
+        bs = min(len(examples), batch_size)
+        epoch_loss, num_batches = 0.0, 0
+        for i in range(0, len(examples), bs):
+            boards, pis, vs = list(zip(*examples[i:i + bs]))
+            if any(np.isnan(np.sum(x)) for x in boards) or any(np.isnan(np.sum(x)) for x in pis) or any(np.isnan(x) for x in vs):
+                print("NaN values detected in input data, skipping batch")
+                continue
+            states = torch.as_tensor(pack_states("frozenlake", np.array(boards))).to(w.device)
+            target_pis = torch.FloatTensor(np.array(pis)).to(w.device)
+            target_vs = torch.FloatTensor(np.array(vs).astype(np.float64)).to(w.device)
+            w.optimizer.zero_grad()
+            loss = fl_step(ops, w, states, target_pis, target_vs)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
+            w.optimizer.step()
+            epoch_loss += loss.item()
+            num_batches += 1
+        if num_batches > 0:
+            print(f"Epoch {epoch + 1}/{epochs} - Loss: {epoch_loss / num_batches:.4f}")
+    w.weights_changed()

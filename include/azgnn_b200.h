@@ -178,6 +178,13 @@ int azg_conv3x3_relu_backward(const float* in, const float* w, const float* out,
 int azg_policy_value_loss(const float* logits, const float* vraw, const float* target_pi, const float* target_v,
                           int B, int A, float norm, float* loss, float* logp, float* v, float* dlogits,
                           float* dvraw, azg_stream stream);
+/* FrozenLake graph layer aggregation relu(bmm(adj, support)) with the all-ones, symmetrically normalised
+ * adjacency of FrozenLakeNet.create_adjacency (FrozenLakeNet.py:8-33, 55-74) for a batch of graphs:
+ * sup/out/dout/dsup [B,5,E] (unused nodes zero), counts [B] int32 nodes per graph (3..5). */
+int azg_graph_mean_relu_forward(const float* sup, const int32_t* counts, int64_t B, int E, float* out,
+                                azg_stream stream);
+int azg_graph_mean_relu_backward(const float* dout, const float* out, const int32_t* counts, int64_t B, int E,
+                                 float* dsup, azg_stream stream);
 /* GNNLayer.forward / backward at B = P + 1 > 1 (gnn_utils.py:34-74): row 0 (f0) is the target, rows
  * 1.. (path) are attended over; only the target row changes. */
 typedef struct azg_gnn_layer_params {

@@ -199,6 +199,45 @@ def gen_nets_fl(n, layers):
          nnet_names=names, nnet_checksum=rows)
 
 
+def gen_fl_train(n, layers):
+    """One minibatch of FrozenLakeNet.train (FrozenLakeNet.py:105-166): per-board graph forward, the
+    clamped-log policy loss + MSE value loss, backward; gradient summaries before clipping."""
+    args = dotdict(dict(lr=1e-3, dropout=0.3, epochs=1, batch_size=32, embedding_dim=128, gnn_layers=layers))
+    game = FrozenLakeGame(n)
+    torch.manual_seed(0)
+    w = FrozenLakeNet(game, args)
+    rng = np.random.default_rng(21)
+    cells = [c for c in range(n * n) if game.desc[c // n][c % n] not in (b"G", b"H")]
+    pick = rng.choice(cells, size=12)
+    boards = np.zeros((12, n, n)); boards[np.arange(12), pick // n, pick % n] = 1
+    tpi = rng.dirichlet(np.ones(4), size=12); tv = rng.choice([-1.0, 1.0], size=12)
+    w.nnet.train()
+    batch_boards = torch.FloatTensor(boards); target_pis = torch.FloatTensor(tpi); target_vs = torch.FloatTensor(tv.astype(np.float64))
+    outs_pi, outs_v = [], []
+    for i in range(12):
+        single = batch_boards[i].unsqueeze(0)
+        board_np = single.squeeze(0).cpu().numpy()
+        neigh = [board_np]
+        valids = game.getValidMoves(board_np, 1)
+        for a in range(4):
+            if valids[a]:
+                nb, _ = game.getNextState(board_np, 1, a)
+                neigh.append(game.getCanonicalForm(nb, 1))
+        nt = torch.FloatTensor(np.array(neigh))
+        adj = w.create_adjacency(len(neigh))
+        pi, v = w.nnet(single, nt, adj.unsqueeze(0))
+        outs_pi.append(pi); outs_v.append(v)
+    out_pi, out_v = torch.cat(outs_pi, 0), torch.cat(outs_v, 0)
+    w.nnet.zero_grad()
+    pi_loss = -torch.mean(torch.sum(target_pis * torch.log(out_pi.clamp(min=1e-8)), dim=1))
+    v_loss = torch.nn.functional.mse_loss(out_v.view(-1), target_vs)
+    (pi_loss + v_loss).backward()
+    names, rows, samples = grads_summary(w.nnet.named_parameters())
+    save(f"train_fl_{n}_L{layers}", n=n, layers=layers, cells=pick, train_pi=tpi.astype(np.float32), train_v=tv.astype(np.float32),
+         loss=(pi_loss + v_loss).item(), out_pi=out_pi.detach().numpy(), out_v=out_v.detach().numpy(),
+         grad_names=names, grad_rows=rows, grad_samples=samples)
+
+
 # ------------------------------------------------------------------------------------ mcts
 QT_F32, QT_FLOAT, QT_INT, QT_ARR = 0, 1, 2, 3
 
@@ -350,6 +389,8 @@ def main():
         for n in (4, 8):
             for L in (2, 3):
                 gen_nets_fl(n, L)
+        gen_fl_train(4, 3)
+        gen_fl_train(8, 2)
     if "mcts" in which:
         base = dict(cpuct=1.0, tempThreshold=15, expand_by=5)
         gen_mcts_episode("c4_7_gnn", Connect4Game(7), dotdict(dict(base, numMCTSSims=10, use_gnn=True)), seed=11, salt=1)

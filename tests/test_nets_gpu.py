@@ -217,3 +217,26 @@ def test_forward_tensor_core_precisions(n, B):
     w.weights_changed()
     o3b = w.forward_states(states, _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
     assert not np.allclose(o3b["v_gnn"].cpu().numpy(), o3["v_gnn"].cpu().numpy())
+
+
+@pytest.mark.parametrize("scale", [0.3, 3.0])
+def test_bf16x3_margin_under_weight_scale(scale):
+    """The 3-term split keeps ~16 mantissa bits per operand whatever the weight magnitude; with every
+    weight matrix scaled (sharper or flatter policies than random init) pi and v still track the fp32
+    oracle to 1e-5 / 2e-5."""
+    w = _wrapper("c4", 7)
+    with torch.no_grad():
+        for p_ in list(w.nnet.parameters()) + list(w.gnn.output_transform.parameters()):
+            if p_.dim() > 1:
+                p_.mul_(scale ** 0.5)
+    w.weights_changed()
+    rng = np.random.default_rng(11)
+    boards = rng.integers(-1, 2, size=(512, 7, 7)).astype(np.int64)
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    with torch.no_grad():
+        gpi, gv = onets.c4_predict_with_gnn(p, q, onets.boards_to_tensor(boards), 7)
+    o3 = w.forward_states(w.states_from_boards(boards), _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
+    e_pi = np.abs(o3["pi_gnn"].cpu().numpy() - gpi.numpy()).max()
+    e_v = np.abs(o3["v_gnn"].cpu().numpy() - gv.numpy()).max()
+    print(f"scale {scale}: max |dpi| = {e_pi:.2e}, max |dv| = {e_v:.2e}, max pi = {gpi.max().item():.3f}")
+    assert e_pi <= 1e-5 and e_v <= 2e-5

@@ -120,3 +120,55 @@ def test_train_runs_and_learns():
     after = losses()
     assert after[0] < before[0] and after[1] < before[1], (before, after)
     assert not np.allclose(out0["pi_gnn"], w.predict_batch(boards)["pi_gnn"])
+
+
+# ------------------------------------------------------------------------------------ FrozenLake training
+@pytest.mark.parametrize("n,layers", [(4, 3), (8, 2)])
+def test_frozenlake_training_step(n, layers):
+    """One minibatch of FrozenLakeNet.train (FrozenLakeNet.py:105-166): loss, outputs and every parameter
+    gradient vs the reference's autograd (golden), and vs the oracle graph on the same GPU."""
+    from azgnn_b200.nets import B200FrozenLakeNet
+    g = golden(f"train_fl_{n}_L{layers}")
+    torch.manual_seed(0)
+    w = B200FrozenLakeNet(games.FrozenLakeGame(n), dotdict(dict(lr=1e-3, epochs=2, batch_size=32, embedding_dim=128, gnn_layers=layers)))
+    states = torch.zeros(len(g["cells"]), 2, dtype=torch.int64, device=w.device)
+    states[:, 0] = torch.as_tensor(g["cells"]).to(w.device)
+    tpi, tv = torch.tensor(g["train_pi"]).to(w.device), torch.tensor(g["train_v"]).to(w.device)
+    for p in w.nnet.parameters():
+        p.grad = None
+    loss = training.fl_step(training.CudaOps, w, states, tpi, tv)
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    named = dict(w.nnet.named_parameters())
+    for name, row, samp in zip(g["grad_names"], g["grad_rows"], g["grad_samples"]):
+        gr = named[str(name)].grad.double().flatten().cpu()
+        np.testing.assert_allclose(gr[sample_index(gr.numel(), 64)].numpy(), samp, rtol=1e-3, atol=2e-6)
+        assert abs(gr.norm().item() - row[2]) <= 1e-3 * max(1e-3, row[2])
+    got = {k: p.grad.clone() for k, p in w.nnet.named_parameters()}
+    for p in w.nnet.parameters():
+        p.grad = None
+    l2 = training.fl_step(OracleOps, w, states, tpi, tv)
+    l2.backward()
+    assert abs(l2.item() - loss.item()) < 1e-5
+    for k, p in w.nnet.named_parameters():
+        bad = (got[k] - p.grad).abs() > 1e-3 * p.grad.abs().max() + 2e-6
+        assert bad.reshape(bad.shape[0], -1).any(dim=1).sum().item() <= 2, k
+
+
+def test_frozenlake_train_runs():
+    from azgnn_b200.nets import B200FrozenLakeNet
+    game = games.FrozenLakeGame(4)
+    torch.manual_seed(0)
+    w = B200FrozenLakeNet(game, dotdict(dict(lr=1e-2, epochs=15, batch_size=8, embedding_dim=128, gnn_layers=2)))
+    rng = np.random.default_rng(0)
+    examples = []
+    for _ in range(16):
+        cell = int(rng.choice([0, 1, 2, 4, 6, 8, 9, 10, 13, 14]))
+        b = np.zeros((4, 4)); b[cell // 4, cell % 4] = 1
+        pi = np.zeros(4); pi[2] = 1.0
+        examples.append((b, list(pi), 1.0))
+    before = w.predict(examples[0][0])
+    np.random.seed(0)
+    w.train(examples)
+    after = w.predict(examples[0][0])
+    assert after[0][2] > before[0][2] and after[1][0] > before[1][0]  # learns "down" and a positive value

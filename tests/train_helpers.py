@@ -34,3 +34,24 @@ class OracleOps:
         p = {"L." + k: v for k, v in layer.named_parameters()}
         out = onets.gnn_layer(p, "L.", torch.cat([f0.unsqueeze(0), path], dim=0))
         return out[0]
+
+    @staticmethod
+    def graph_mean_relu(sup, counts):
+        out = torch.zeros_like(sup)
+        for b in range(sup.shape[0]):
+            k = int(counts[b])
+            adj = onets.fl_adjacency(k).to(sup.device)
+            out[b, :k] = F.relu(torch.mm(adj, sup[b, :k]))
+        return out
+
+    @staticmethod
+    def fl_graph(states, n):
+        B = states.shape[0]
+        nodes = torch.zeros(B, 5, n * n, device=states.device)
+        counts = torch.zeros(B, dtype=torch.int32, device=states.device)
+        for b in range(B):
+            cells = onets.fl_node_cells(int(states[b, 0]), n)
+            counts[b] = len(cells)
+            for j, c in enumerate(cells):
+                nodes[b, j, c] = 1.0
+        return nodes, counts
