@@ -76,6 +76,8 @@ SIGNATURES = {
     "azg_policy_value_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
     "azg_graph_mean_relu_forward": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "azg_graph_mean_relu_backward": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "azg_grid_aggregate_relu_forward": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
+    "azg_grid_aggregate_relu_backward": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "azg_gnn_layer_saved_floats": (_sz, [_i, _i]),
     "azg_gnn_layer_scratch_floats": (_sz, [_i, _i]),
     "azg_gnn_layer_forward": (_i, [C.POINTER(GNNLayerParams), _vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -317,6 +317,48 @@ __global__ void graph_mean_relu_bwd_kernel(const float* __restrict__ dout, const
   for (int j = 0; j < 5; ++j) dsup[(b * 5 + j) * E + e] = j < k ? g : 0.0f;
 }
 
+// ---- grid-graph layer of the roofline sweep (BASELINE configs[4]) -----------------
+// relu(bmm(adj, support)) of FrozenLakeNet.GNNLayer (FrozenLakeNet.py:8-33) with adj = D^-1/2 (A + I) D^-1/2
+// of the gh x gw 4-neighbour grid (normalisation as create_adjacency, FrozenLakeNet.py:68-72).  The adjacency
+// is never materialised: each node gathers its <= 5 neighbours with coefficients d_i * d_j.
+// One thread per (graph, node, 4 channels): 128-bit loads, neighbours of a CTA's graphs hit L1/L2.
+__device__ __forceinline__ float grid_deg_inv_sqrt(int x, int y, int gh, int gw) {
+  const int deg = 1 + (x > 0) + (x < gh - 1) + (y > 0) + (y < gw - 1);
+  return 1.0f / sqrtf((float)deg);
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) grid_aggregate_kernel(const float* __restrict__ in, const float* __restrict__ act,
+                                                             int64_t B, int gh, int gw, int H, float* __restrict__ out) {
+  // FWD: out = relu(adj * in).            BWD: out = adj^T * (in * (act > 0)) = adj * (...), adj symmetric
+  const int H4 = H >> 2, n = gh * gw;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * n * H4) return;
+  const int c4 = (int)(idx % H4);
+  const int64_t node_g = idx / H4;
+  const int node = (int)(node_g % n);
+  const int64_t b = node_g / n;
+  const int x = node / gw, y = node % gw;
+  const float di = grid_deg_inv_sqrt(x, y, gh, gw);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int dx[5] = {0, -1, 1, 0, 0}, dy[5] = {0, 0, 0, -1, 1};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int nx = x + dx[k], ny = y + dy[k];
+    if (nx < 0 || nx >= gh || ny < 0 || ny >= gw) continue;
+    const float coef = di * grid_deg_inv_sqrt(nx, ny, gh, gw);
+    const size_t off = ((size_t)(b * n + nx * gw + ny) * H4 + c4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(in + off);
+    if (BWD) {
+      const float4 a = *reinterpret_cast<const float4*>(act + off);
+      v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
+    }
+    acc.x = fmaf(coef, v.x, acc.x); acc.y = fmaf(coef, v.y, acc.y); acc.z = fmaf(coef, v.z, acc.z); acc.w = fmaf(coef, v.w, acc.w);
+  }
+  if (!BWD) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+  *reinterpret_cast<float4*>(out + (size_t)idx * 4) = acc;
+}
+
 struct Bump {
   float* p;
   float* take(size_t n) {
@@ -430,6 +472,25 @@ int azg_graph_mean_relu_backward(const float* dout, const float* out, const int3
   AZG_REQUIRE(dout && out && counts && dsup, "azg_graph_mean_relu_backward: null pointer");
   if (B <= 0) return AZG_OK;
   graph_mean_relu_bwd_kernel<<<grid_for(B * E, 256), 256, 0, (cudaStream_t)stream>>>(dout, out, counts, B, E, dsup);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+int azg_grid_aggregate_relu_forward(const float* sup, int64_t B, int gh, int gw, int H, float* out, azg_stream stream) {
+  AZG_REQUIRE(sup && out && gh >= 1 && gw >= 1 && H % 4 == 0, "azg_grid_aggregate_relu_forward: bad argument");
+  if (B <= 0) return AZG_OK;
+  const int64_t n = B * gh * gw * (H / 4);
+  grid_aggregate_kernel<false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(sup, nullptr, B, gh, gw, H, out);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+int azg_grid_aggregate_relu_backward(const float* dout, const float* out, int64_t B, int gh, int gw, int H, float* dsup,
+                                     azg_stream stream) {
+  AZG_REQUIRE(dout && out && dsup && H % 4 == 0, "azg_grid_aggregate_relu_backward: bad argument");
+  if (B <= 0) return AZG_OK;
+  const int64_t n = B * gh * gw * (H / 4);
+  grid_aggregate_kernel<true><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dout, out, B, gh, gw, H, dsup);
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }

@@ -185,6 +185,13 @@ int azg_graph_mean_relu_forward(const float* sup, const int32_t* counts, int64_t
                                 azg_stream stream);
 int azg_graph_mean_relu_backward(const float* dout, const float* out, const int32_t* counts, int64_t B, int E,
                                  float* dsup, azg_stream stream);
+/* Grid-graph layer of the roofline sweep (BASELINE configs[4]): relu(bmm(adj, sup)) with
+ * adj = D^-1/2 (A + I) D^-1/2 of the gh x gw 4-neighbour grid (operator: FrozenLakeNet.GNNLayer,
+ * FrozenLakeNet.py:8-33; normalisation: create_adjacency :68-72).  sup/out [B, gh*gw, H] fp32, H % 4 == 0.
+ * backward: dsup = adj * (dout * (out > 0)). */
+int azg_grid_aggregate_relu_forward(const float* sup, int64_t B, int gh, int gw, int H, float* out, azg_stream stream);
+int azg_grid_aggregate_relu_backward(const float* dout, const float* out, int64_t B, int gh, int gw, int H,
+                                     float* dsup, azg_stream stream);
 /* GNNLayer.forward / backward at B = P + 1 > 1 (gnn_utils.py:34-74): row 0 (f0) is the target, rows
  * 1.. (path) are attended over; only the target row changes. */
 typedef struct azg_gnn_layer_params {

@@ -192,3 +192,29 @@ class OracleConnect4Net:
         with torch.no_grad():
             pi, v = c4_predict_with_gnn(self.p, self.g, boards_to_tensor(np.asarray(board)[None]), self.n)
         return pi.numpy()[0], v.numpy()[0]
+
+
+# ----------------------------------------------------------------------------- grid-graph sweep
+def grid_adjacency(gh, gw):
+    """D^-1/2 (A + I) D^-1/2 of the gh x gw 4-neighbour grid, normalised as create_adjacency
+    (FrozenLakeNet.py:68-72)."""
+    n = gh * gw
+    adj = torch.zeros(n, n)
+    for x in range(gh):
+        for y in range(gw):
+            i = x * gw + y
+            adj[i, i] = 1.0
+            for dx, dy in ((-1, 0), (1, 0), (0, -1), (0, 1)):
+                nx, ny = x + dx, y + dy
+                if 0 <= nx < gh and 0 <= ny < gw:
+                    adj[i, nx * gw + ny] = 1.0
+    d = torch.pow(adj.sum(1).clamp(min=1e-8), -0.5)
+    return torch.mm(torch.mm(torch.diag(d), adj), torch.diag(d))
+
+
+def grid_gnn_forward(weights, biases, x, gh, gw):
+    """Stack of FrozenLakeNet.GNNLayer (FrozenLakeNet.py:16-33): relu(bmm(adj, W x + b))."""
+    adj = grid_adjacency(gh, gw).to(x.device).unsqueeze(0).expand(x.shape[0], -1, -1)
+    for w, b in zip(weights, biases):
+        x = F.relu(torch.bmm(adj, F.linear(x, w, b)))
+    return x
