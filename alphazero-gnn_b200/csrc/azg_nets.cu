@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(SG_T) sgemm_tn_kernel(const float* __restrict_
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Ws[SG_BK][SG_BN + 4];
   const int tid = threadIdx.x;
-  const int64_t m0 = (int64_t)blockIdx.y * SG_BM;
-  const int n0 = blockIdx.x * SG_BN;
+  const int64_t m0 = (int64_t)blockIdx.x * SG_BM;  // M on grid.x (2^31 limit), N on grid.y
+  const int n0 = blockIdx.y * SG_BN;
   // loader mapping: 128 rows x 16 k = 512 float4; thread loads rows (tid>>2) and (tid>>2)+64, k4 = (tid&3)*4
   const int lr = tid >> 2, lk = (tid & 3) * 4;
   float4 ra[2], rw[2];
@@ -352,8 +352,8 @@ int launch_conv(const float* in, const float* w, const float* b, float* out, int
 int launch_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K, int relu,
                   cudaStream_t st) {
   AZG_REQUIRE(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
-  AZG_REQUIRE(M <= (int64_t)65535 * SG_BM, "linear: M=%lld too large for one launch", (long long)M);
-  dim3 grid((N + SG_BN - 1) / SG_BN, (unsigned)((M + SG_BM - 1) / SG_BM));
+  AZG_REQUIRE(N <= 65535 * SG_BN, "linear: N=%d too large for one launch", N);
+  dim3 grid((unsigned)((M + SG_BM - 1) / SG_BM), (N + SG_BN - 1) / SG_BN);
   sgemm_tn_kernel<<<grid, SG_T, 0, st>>>(A, W, bias, C, M, N, K, relu);
   AZG_LAUNCH_CHECK();
   return AZG_OK;

@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(int64_t M, int N, int
   __shared__ float As[GK][GT + 4];
   __shared__ float Bs[GK][GT + 4];
   const int tid = threadIdx.x;
-  const int64_t m0 = (int64_t)blockIdx.y * GT;
-  const int n0 = blockIdx.x * GT;
+  const int64_t m0 = (int64_t)blockIdx.x * GT;  // M on grid.x (2^31 limit), N on grid.y
+  const int n0 = blockIdx.y * GT;
   const int tx = tid & 15, ty = tid >> 4;
   float acc[4][4] = {};
   for (int k0 = 0; k0 < K; k0 += GK) {
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(int64_t M, int N, int
 int gemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
          int64_t ldc, float beta, cudaStream_t st) {
   if (M <= 0 || N <= 0) return AZG_OK;
-  dim3 grid((N + GT - 1) / GT, (unsigned)((M + GT - 1) / GT));
-  AZG_REQUIRE(grid.y <= 65535, "gemm: M too large");
+  dim3 grid((unsigned)((M + GT - 1) / GT), (N + GT - 1) / GT);
+  AZG_REQUIRE(grid.y <= 65535, "gemm: N too large");
   if (ta && tb) gemm_generic_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
   else if (ta) gemm_generic_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
   else if (tb) gemm_generic_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
