@@ -24,7 +24,8 @@ constexpr int GT = 64, GK = 16;
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) gemm_generic_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda,
                                                            const float* __restrict__ B, int64_t ldb, float* __restrict__ C,
-                                                           int64_t ldc, float beta) {
+                                                           int64_t ldc, float beta, int kper, int64_t zstride_c) {
+  // split-K: blockIdx.z owns the contraction range [z*kper, min(K, (z+1)*kper)) and its own C slab
   __shared__ float As[GK][GT + 4];
   __shared__ float Bs[GK][GT + 4];
   const int tid = threadIdx.x;
@@ -32,7 +33,10 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(int64_t M, int N, int
   const int n0 = blockIdx.y * GT;
   const int tx = tid & 15, ty = tid >> 4;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  const int kbeg = blockIdx.z * kper;
+  if (K > kbeg + kper) K = kbeg + kper;
+  C += (size_t)blockIdx.z * zstride_c;
+  for (int k0 = kbeg; k0 < K; k0 += GK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int m, k;
@@ -79,17 +83,42 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(int64_t M, int N, int
   }
 }
 
-int gemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
-         int64_t ldc, float beta, cudaStream_t st) {
+int gemm_split(bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+               int64_t ldc, float beta, int splits, int64_t zstride_c, cudaStream_t st) {
   if (M <= 0 || N <= 0) return AZG_OK;
-  dim3 grid((unsigned)((M + GT - 1) / GT), (N + GT - 1) / GT);
-  AZG_REQUIRE(grid.y <= 65535, "gemm: N too large");
-  if (ta && tb) gemm_generic_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-  else if (ta) gemm_generic_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-  else if (tb) gemm_generic_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-  else gemm_generic_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+  const int kper = (int)(((int64_t)(K + splits - 1) / splits + GK - 1) / GK * GK);
+  dim3 grid((unsigned)((M + GT - 1) / GT), (N + GT - 1) / GT, splits);
+  AZG_REQUIRE(grid.y <= 65535 && splits <= 65535, "gemm: N too large");
+  if (ta && tb) gemm_generic_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, kper, zstride_c);
+  else if (ta) gemm_generic_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, kper, zstride_c);
+  else if (tb) gemm_generic_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, kper, zstride_c);
+  else gemm_generic_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, kper, zstride_c);
   AZG_LAUNCH_CHECK();
   return AZG_OK;
+}
+
+int gemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+         int64_t ldc, float beta, cudaStream_t st) {
+  return gemm_split(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta, 1, 0, st);
+}
+
+// out[i] = sum_s part[s*n + i] in fixed order (deterministic split-K reduction)
+__global__ void reduce_splits_kernel(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int z = 0; z < splits; ++z) s += part[(size_t)z * n + i];
+  out[i] = s;
+}
+
+// partial column sums: blockIdx.y owns rows [y*rper, (y+1)*rper)
+__global__ void col_sum_split_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t rper, float* __restrict__ part) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rper, r1 = r0 + rper < rows ? r0 + rper : rows;
+  float s = 0.0f;
+  for (int64_t r = r0; r < r1; ++r) s += x[r * cols + c];
+  part[(size_t)blockIdx.y * cols + c] = s;
 }
 
 // ------------------------------------------------------------------------------ element-wise
@@ -423,11 +452,35 @@ int azg_linear_backward(const float* dY, const float* X, const float* W, const f
   }
   int rc;
   if (dX && (rc = gemm(false, false, M, K, N, g, N, W, K, dX, K, 0.0f, st))) return rc;
-  if (dW && (rc = gemm(true, false, N, K, (int)M, g, N, X, K, dW, K, 0.0f, st))) return rc;
-  if (db) {
-    col_sum_kernel<<<grid_for(N, 128), 128, 0, st>>>(g, M, N, N, db);
+  // weight / bias gradients contract over the M rows: with a large batch (the grid-graph sweep) a single pass
+  // would leave the whole contraction to (N/64)*(K/64) CTAs, so it is split over row chunks and reduced in
+  // fixed order (deterministic)
+  const int splits = M >= 8192 ? (int)(M / 4096 < 512 ? M / 4096 : 512) : 1;
+  if (splits == 1) {
+    if (dW && (rc = gemm(true, false, N, K, (int)M, g, N, X, K, dW, K, 0.0f, st))) return rc;
+    if (db) {
+      col_sum_kernel<<<grid_for(N, 128), 128, 0, st>>>(g, M, N, N, db);
+      AZG_LAUNCH_CHECK();
+    }
+    return AZG_OK;
+  }
+  float* part = nullptr;
+  const size_t wn = (size_t)N * K;
+  AZG_CUDA_CHECK(cudaMallocAsync((void**)&part, sizeof(float) * (size_t)splits * (wn + N), st));
+  if (dW) {
+    if ((rc = gemm_split(true, false, N, K, (int)M, g, N, X, K, part, K, 0.0f, splits, (int64_t)wn, st))) return rc;
+    reduce_splits_kernel<<<grid_for((int64_t)wn, 256), 256, 0, st>>>(part, splits, (int64_t)wn, dW);
     AZG_LAUNCH_CHECK();
   }
+  if (db) {
+    float* bpart = part + (size_t)splits * wn;
+    const int64_t rper = (M + splits - 1) / splits;
+    col_sum_split_kernel<<<dim3(grid_for(N, 128), splits), 128, 0, st>>>(g, M, N, rper, bpart);
+    AZG_LAUNCH_CHECK();
+    reduce_splits_kernel<<<grid_for(N, 256), 256, 0, st>>>(bpart, splits, N, db);
+    AZG_LAUNCH_CHECK();
+  }
+  AZG_CUDA_CHECK(cudaFreeAsync(part, st));
   return AZG_OK;
 }
 
