@@ -360,91 +360,57 @@ template <bool BWD>
 __global__ void __launch_bounds__(256) grid_aggregate_kernel(const float* __restrict__ in, const float* __restrict__ act,
                                                              int64_t B, int gh, int gw, int H, float* __restrict__ out) {
   // FWD: out = relu(adj * in).            BWD: out = adj^T * (in * (act > 0)) = adj * (...), adj symmetric
+  // Thread layout: x = 4-channel group, y = node slot; a CTA walks whole graphs.  The <= 5 (neighbour,
+  // coefficient) pairs of every node are tabulated once per CTA in shared memory, so the streaming loop is
+  // index-math free: per output float4 at most five 128-bit loads (neighbours of a graph hit L1) and one store.
+  __shared__ int16_t nb_idx[256 * 5];
+  __shared__ float nb_coef[256 * 5];
   const int H4 = H >> 2, n = gh * gw;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * n * H4) return;
-  const int c4 = (int)(idx % H4);
-  const int64_t node_g = idx / H4;
-  const int node = (int)(node_g % n);
-  const int64_t b = node_g / n;
-  const int x = node / gw, y = node % gw;
-  const float di = grid_deg_inv_sqrt(x, y, gh, gw);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int dx[5] = {0, -1, 1, 0, 0}, dy[5] = {0, 0, 0, -1, 1};
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const int nx = x + dx[k], ny = y + dy[k];
-    if (nx < 0 || nx >= gh || ny < 0 || ny >= gw) continue;
-    const float coef = di * grid_deg_inv_sqrt(nx, ny, gh, gw);
-    const size_t off = ((size_t)(b * n + nx * gw + ny) * H4 + c4) * 4;
-    float4 v = *reinterpret_cast<const float4*>(in + off);
-    if (BWD) {
-      const float4 a = *reinterpret_cast<const float4*>(act + off);
-      v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
-    }
-    acc.x = fmaf(coef, v.x, acc.x); acc.y = fmaf(coef, v.y, acc.y); acc.z = fmaf(coef, v.z, acc.z); acc.w = fmaf(coef, v.w, acc.w);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < n * 5; i += blockDim.x * blockDim.y) {
+    const int node = i / 5, k = i % 5, x = node / gw, y = node % gw;
+    const int dx = (k == 1) ? -1 : (k == 2) ? 1 : 0, dy = (k == 3) ? -1 : (k == 4) ? 1 : 0;
+    const int nx = x + dx, ny = y + dy;
+    const bool ok = nx >= 0 && nx < gh && ny >= 0 && ny < gw;
+    nb_idx[i] = ok ? (int16_t)(nx * gw + ny) : (int16_t)-1;
+    nb_coef[i] = ok ? grid_deg_inv_sqrt(x, y, gh, gw) * grid_deg_inv_sqrt(nx, ny, gh, gw) : 0.0f;
   }
-  if (!BWD) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-  *reinterpret_cast<float4*>(out + (size_t)idx * 4) = acc;
-}
-
-// Shared-memory variant for graphs that fit on chip: a CTA stages a tile of whole graphs (<= 48 KB) with
-// coalesced 128-bit loads, neighbours are then read from shared memory, so every element crosses HBM once
-// in and once out (the gather version re-reads neighbours through L1/L2 and reaches ~0.4 of the HBM peak).
-template <bool BWD>
-__global__ void __launch_bounds__(256) grid_aggregate_smem_kernel(const float* __restrict__ in, const float* __restrict__ act,
-                                                                  int64_t B, int gh, int gw, int H, int G,
-                                                                  float* __restrict__ out) {
-  extern __shared__ float4 tile[];  // [G graphs][n nodes][H/4]
-  const int H4 = H >> 2, n = gh * gw, per_graph = n * H4;
-  const int64_t n_tiles = (B + G - 1) / G;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int64_t b0 = t * G;
-    const int g_here = (int)((B - b0) < G ? (B - b0) : G);
-    const int64_t base = b0 * per_graph;
-    const int count = g_here * per_graph;
-    __syncthreads();
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-      float4 v = reinterpret_cast<const float4*>(in)[base + i];
-      if (BWD) {
-        const float4 a = reinterpret_cast<const float4*>(act)[base + i];
-        v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
-      }
-      tile[i] = v;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-      const int c4 = i % H4, node_l = i / H4, node = node_l % n, gl = node_l / n;
-      const int x = node / gw, y = node % gw;
-      const float di = grid_deg_inv_sqrt(x, y, gh, gw);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int dx[5] = {0, -1, 1, 0, 0}, dy[5] = {0, 0, 0, -1, 1};
+  __syncthreads();
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  const float4* act4 = reinterpret_cast<const float4*>(act);
+  float4* out4 = reinterpret_cast<float4*>(out);
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const int64_t g0 = b * n;
+    for (int node = threadIdx.y; node < n; node += blockDim.y) {
+      for (int c4 = threadIdx.x; c4 < H4; c4 += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int nx = x + dx[k], ny = y + dy[k];
-        if (nx < 0 || nx >= gh || ny < 0 || ny >= gw) continue;
-        const float coef = di * grid_deg_inv_sqrt(nx, ny, gh, gw);
-        const float4 v = tile[(gl * n + nx * gw + ny) * H4 + c4];
-        acc.x = fmaf(coef, v.x, acc.x); acc.y = fmaf(coef, v.y, acc.y); acc.z = fmaf(coef, v.z, acc.z); acc.w = fmaf(coef, v.w, acc.w);
+        for (int k = 0; k < 5; ++k) {
+          const int j = nb_idx[node * 5 + k];
+          if (j < 0) continue;
+          const float coef = nb_coef[node * 5 + k];
+          const size_t off = (size_t)(g0 + j) * H4 + c4;
+          float4 v = in4[off];
+          if (BWD) {
+            const float4 a = act4[off];
+            v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
+          }
+          acc.x = fmaf(coef, v.x, acc.x); acc.y = fmaf(coef, v.y, acc.y); acc.z = fmaf(coef, v.z, acc.z); acc.w = fmaf(coef, v.w, acc.w);
+        }
+        if (!BWD) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        out4[(size_t)(g0 + node) * H4 + c4] = acc;
       }
-      if (!BWD) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-      reinterpret_cast<float4*>(out)[base + i] = acc;
     }
   }
 }
 
 template <bool BWD>
 int launch_grid_aggregate(const float* in, const float* act, int64_t B, int gh, int gw, int H, float* out, cudaStream_t st) {
-  const size_t graph_bytes = (size_t)gh * gw * H * sizeof(float);
-  if (graph_bytes <= 48 * 1024) {
-    const int G = (int)((48 * 1024) / graph_bytes);
-    const int64_t tiles = (B + G - 1) / G;
-    const int grid = (int)(tiles < 148 * 4 ? tiles : 148 * 4);
-    grid_aggregate_smem_kernel<BWD><<<grid, 256, (size_t)G * graph_bytes, st>>>(in, act, B, gh, gw, H, G, out);
-  } else {
-    const int64_t n = B * gh * gw * (H / 4);
-    grid_aggregate_kernel<BWD><<<grid_for(n, 256), 256, 0, st>>>(in, act, B, gh, gw, H, out);
-  }
+  const int H4 = H / 4;
+  const int bx = H4 < 64 ? (H4 < 16 ? 16 : H4) : 64;  // 16..64 channel groups per row of threads
+  dim3 block(bx, 256 / bx);
+  const int grid = (int)(B < 148 * 16 ? B : 148 * 16);
+  grid_aggregate_kernel<BWD><<<grid, block, 0, st>>>(in, act, B, gh, gw, H, out);
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }
