@@ -10,6 +10,9 @@
 #include "azg_common.cuh"
 #include "azg_rules.cuh"
 
+int azg_train_linear_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t M, int N, int K, int relu,
+                         cudaStream_t st);  // azg_train.cu
+
 namespace {
 
 inline int grid_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -351,6 +354,8 @@ int launch_conv(const float* in, const float* w, const float* b, float* out, int
 
 int launch_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K, int relu,
                   cudaStream_t st) {
+  // fewer than ~1.5 waves of 128 x 128 tiles: the split-K / matrix-vector kernels of azg_train.cu fill the SMs instead
+  if (azg_ceil_div(M, SG_BM) * azg_ceil_div(N, SG_BN) < 222) return azg_train_linear_fwd(A, W, bias, C, M, N, K, relu, st);
   AZG_REQUIRE(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
   AZG_REQUIRE(N <= 65535 * SG_BN, "linear: N=%d too large for one launch", N);
   dim3 grid((unsigned)((M + SG_BM - 1) / SG_BM), (N + SG_BN - 1) / SG_BN);

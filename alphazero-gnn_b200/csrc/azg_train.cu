@@ -97,8 +97,382 @@ int gemm_split(bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_
   return AZG_OK;
 }
 
+// ------------------------------------------------------------------------------ tiled SGEMM, asynchronous copies
+// Same contract as gemm_generic_kernel for operands whose rows are 16-byte aligned (leading dimensions and
+// base pointers multiples of 4 floats): 64 x 128 x 32 tiles, 3-stage cp.async pipeline that lands the operands
+// in shared memory in their HBM orientation (no register staging, no transposing stores), 8 x 4 outputs per
+// thread.  A warp owns 8 rows (its A reads are broadcasts), lanes spread over the 128 columns.
+//   AK: A[m*lda + k] (k contiguous), else A[k*lda + m];   BK: B[n*ldb + k], else B[k*ldb + n]
+constexpr int TM = 64, TN = 128, TKC = 32, TST = 3;
+template <bool AK, bool BK>
+struct TileSmem {
+  static constexpr int A_ROWS = AK ? TM : TKC, A_LD = (AK ? TKC : TM) + 4;
+  static constexpr int B_ROWS = BK ? TN : TKC, B_LD = (BK ? TKC : TN) + 4;
+  static constexpr int A_FLOATS = A_ROWS * A_LD, B_FLOATS = B_ROWS * B_LD;
+  static constexpr int STAGE_FLOATS = A_FLOATS + B_FLOATS;
+  static constexpr int BYTES = TST * STAGE_FLOATS * 4;
+};
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(256) gemm_tile_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda,
+                                                        const float* __restrict__ B, int64_t ldb, float* __restrict__ C,
+                                                        int64_t ldc, float beta, int kper, int64_t zstride_c) {
+  using S = TileSmem<AK, BK>;
+  extern __shared__ __align__(16) float tile_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+  const int kbeg = blockIdx.z * kper;
+  const int kend = K < kbeg + kper ? K : kbeg + kper;
+  C += (size_t)blockIdx.z * zstride_c;
+  const int chunks = kend > kbeg ? (kend - kbeg + TKC - 1) / TKC : 0;
+
+  auto issue = [&](int chunk, int stage) {
+    float* As = tile_smem + stage * S::STAGE_FLOATS;
+    float* Bs = As + S::A_FLOATS;
+    const int k0 = kbeg + chunk * TKC;
+    // A: 512 float4
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + 256 * i;
+      if (AK) {
+        const int r = f >> 3, c = (f & 7) * 4;
+        const int64_t m = m0 + r;
+        const int k = k0 + c;
+        int valid = (m < M) ? (kend - k) : 0;
+        valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+        cp_async16(As + r * S::A_LD + c, valid ? A + m * lda + k : A, valid * 4);
+      } else {
+        const int r = f >> 4, c = (f & 15) * 4;
+        const int k = k0 + r;
+        const int64_t m = m0 + c;
+        int64_t valid = (k < kend) ? (M - m) : 0;
+        valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+        cp_async16(As + r * S::A_LD + c, valid ? A + (int64_t)k * lda + m : A, (int)valid * 4);
+      }
+    }
+    // B: 1024 float4
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + 256 * i;
+      if (BK) {
+        const int r = f >> 3, c = (f & 7) * 4;
+        const int n = n0 + r;
+        const int k = k0 + c;
+        int valid = (n < N) ? (kend - k) : 0;
+        valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+        cp_async16(Bs + r * S::B_LD + c, valid ? B + (int64_t)n * ldb + k : B, valid * 4);
+      } else {
+        const int r = f >> 5, c = (f & 31) * 4;
+        const int k = k0 + r;
+        const int n = n0 + c;
+        int valid = (k < kend) ? (N - n) : 0;
+        valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+        cp_async16(Bs + r * S::B_LD + c, valid ? B + (int64_t)k * ldb + n : B, valid * 4);
+      }
+    }
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+#pragma unroll
+  for (int s = 0; s < TST - 1; ++s) {
+    if (s < chunks) issue(s, s);
+    cp_async_commit();
+  }
+  for (int c = 0; c < chunks; ++c) {
+    cp_async_wait<TST - 2>();
+    __syncthreads();
+    if (c + TST - 1 < chunks) issue(c + TST - 1, (c + TST - 1) % TST);
+    cp_async_commit();
+    const float* As = tile_smem + (c % TST) * S::STAGE_FLOATS;
+    const float* Bs = As + S::A_FLOATS;
+#pragma unroll
+    for (int k4 = 0; k4 < TKC; k4 += 4) {
+      float a[8][4], b[4][4];  // [row][kk], [col][kk]
+      if (AK) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(As + (warp * 8 + i) * S::A_LD + k4);
+          a[i][0] = v.x; a[i][1] = v.y; a[i][2] = v.z; a[i][3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 v0 = *reinterpret_cast<const float4*>(As + (k4 + kk) * S::A_LD + warp * 8);
+          const float4 v1 = *reinterpret_cast<const float4*>(As + (k4 + kk) * S::A_LD + warp * 8 + 4);
+          a[0][kk] = v0.x; a[1][kk] = v0.y; a[2][kk] = v0.z; a[3][kk] = v0.w;
+          a[4][kk] = v1.x; a[5][kk] = v1.y; a[6][kk] = v1.z; a[7][kk] = v1.w;
+        }
+      }
+      if (BK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(Bs + (lane + 32 * j) * S::B_LD + k4);
+          b[j][0] = v.x; b[j][1] = v.y; b[j][2] = v.z; b[j][3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 v = *reinterpret_cast<const float4*>(Bs + (k4 + kk) * S::B_LD + lane * 4);
+          b[0][kk] = v.x; b[1][kk] = v.y; b[2][kk] = v.z; b[3][kk] = v.w;
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][kk], b[j][kk], acc[i][j]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + warp * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + (BK ? lane + 32 * j : lane * 4 + j);
+      if (n >= N) continue;
+      float* c = C + m * ldc + n;
+      *c = (beta == 0.0f) ? acc[i][j] : acc[i][j] + beta * (*c);
+    }
+  }
+}
+
+inline bool tile_ok(const float* A, int64_t lda, const float* B, int64_t ldb) {
+  return ((uintptr_t)A & 15u) == 0 && ((uintptr_t)B & 15u) == 0 && (lda & 3) == 0 && (ldb & 3) == 0;
+}
+
+template <bool AK, bool BK>
+int launch_tile(dim3 grid, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                int64_t ldc, float beta, int kper, int64_t zstride_c, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tile_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TileSmem<AK, BK>::BYTES));
+    attr = true;
+  }
+  gemm_tile_kernel<AK, BK><<<grid, 256, TileSmem<AK, BK>::BYTES, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, kper, zstride_c);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+// split-K launch of the tiled kernel (slab z of C = partial product over k range z); ta/tb as in gemm_split
+int gemm_tile_split(bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                    int64_t ldc, float beta, int splits, int64_t zstride_c, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return AZG_OK;
+  const int kper = (int)(((int64_t)(K + splits - 1) / splits + TKC - 1) / TKC * TKC);
+  dim3 grid((unsigned)((M + TM - 1) / TM), (N + TN - 1) / TN, splits);
+  AZG_REQUIRE(grid.y <= 65535 && splits <= 65535, "gemm: N too large");
+  // AK = A is [M,K] row-major = !ta;  BK = B is [N,K] row-major = tb
+  if (!ta && tb) return launch_tile<true, true>(grid, M, N, K, A, lda, B, ldb, C, ldc, beta, kper, zstride_c, st);
+  if (!ta && !tb) return launch_tile<true, false>(grid, M, N, K, A, lda, B, ldb, C, ldc, beta, kper, zstride_c, st);
+  if (ta && tb) return launch_tile<false, true>(grid, M, N, K, A, lda, B, ldb, C, ldc, beta, kper, zstride_c, st);
+  return launch_tile<false, false>(grid, M, N, K, A, lda, B, ldb, C, ldc, beta, kper, zstride_c, st);
+}
+
+// ------------------------------------------------------------------------------ weight streaming, M = 1
+// The GNNLayer works on ONE target row against 39-79 MB weight matrices (gnn_utils.py:66-71), so its
+// contractions are matrix-vector products / rank-1 updates whose only cost is streaming the matrix once.
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+
+// y[n] = act(W[n, :K] . x + bias[n]): one warp per GR rows, 128-bit streaming loads, x staged in shared memory.
+// Fixed summation order per lane + shuffle tree: deterministic.
+constexpr int GR = 2;
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ x,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int N, int K,
+                                                        int relu) {
+  extern __shared__ float4 gemv_xs[];
+  const int K4 = K >> 2;
+  for (int i = threadIdx.x; i < K4; i += blockDim.x) gemv_xs[i] = reinterpret_cast<const float4*>(x)[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 8 + warp) * GR;
+  if (n0 >= N) return;
+  const float4* w[GR];
+  float acc[GR];
+#pragma unroll
+  for (int r = 0; r < GR; ++r) {
+    const int n = n0 + r < N ? n0 + r : N - 1;
+    w[r] = reinterpret_cast<const float4*>(W + (int64_t)n * ldw);
+    acc[r] = 0.0f;
+  }
+#pragma unroll 4
+  for (int k = lane; k < K4; k += 32) {
+    const float4 xv = gemv_xs[k];
+#pragma unroll
+    for (int r = 0; r < GR; ++r) acc[r] = dot4(__ldcs(w[r] + k), xv, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < GR; ++r) {
+    const float s = warp_sum_f(acc[r]);
+    if (lane == 0 && n0 + r < N) {
+      const float v = s + (bias ? bias[n0 + r] : 0.0f);
+      y[n0 + r] = relu ? fmaxf(v, 0.0f) : v;
+    }
+  }
+}
+
+// One pass over a [N, K] weight matrix for the backward of y = W x with upstream gradient g [N]:
+//   DW: dW[n, k] = g[n] * x[k]                       (written, never read)
+//   DX: part[chunk, k] = sum_{n in chunk} g[n] W[n, k]  (reduced over chunks in fixed order afterwards)
+// CTA = 256 threads x float4 = 1024 columns, R1_ROWS rows.
+constexpr int R1_ROWS = 32;
+template <bool DX, bool DW>
+__global__ void __launch_bounds__(256) rank1_bwd_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ g,
+                                                        const float* __restrict__ x, float* __restrict__ dW, int64_t lddw,
+                                                        float* __restrict__ part, int N, int K) {
+  __shared__ float gs[R1_ROWS];
+  const int n0 = blockIdx.y * R1_ROWS;
+  const int rows = N - n0 < R1_ROWS ? N - n0 : R1_ROWS;
+  if (threadIdx.x < R1_ROWS) gs[threadIdx.x] = threadIdx.x < rows ? g[n0 + threadIdx.x] : 0.0f;
+  __syncthreads();
+  const int k = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (k >= K) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (DW) xv = *reinterpret_cast<const float4*>(x + k);
+  const float* wp = W + (int64_t)n0 * ldw + k;
+  float* dp = dW + (int64_t)n0 * lddw + k;
+#pragma unroll 8
+  for (int r = 0; r < rows; ++r) {
+    const float gn = gs[r];
+    if (DX) {
+      const float4 w = __ldcs(reinterpret_cast<const float4*>(wp + (int64_t)r * ldw));
+      acc.x = fmaf(gn, w.x, acc.x);
+      acc.y = fmaf(gn, w.y, acc.y);
+      acc.z = fmaf(gn, w.z, acc.z);
+      acc.w = fmaf(gn, w.w, acc.w);
+    }
+    if (DW) __stcs(reinterpret_cast<float4*>(dp + (int64_t)r * lddw), make_float4(gn * xv.x, gn * xv.y, gn * xv.z, gn * xv.w));
+  }
+  if (DX) *reinterpret_cast<float4*>(part + (size_t)blockIdx.y * K + k) = acc;
+}
+
+// out[m, n] = beta * out[m, n] + sum_z part[z][m, n]   (fixed order; out has leading dimension ldc)
+__global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, int64_t M, int N, float* __restrict__ out,
+                                    int64_t ldc, float beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float s = 0.0f;
+  for (int z = 0; z < splits; ++z) s += part[(size_t)z * M * N + i];
+  float* o = out + (i / N) * ldc + (i % N);
+  *o = beta == 0.0f ? s : s + beta * (*o);
+}
+
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+// stream-ordered scratch for split reductions
+struct Scratch {
+  float* p = nullptr;
+  cudaStream_t st;
+  explicit Scratch(cudaStream_t s) : st(s) {}
+  int get(size_t floats) { return cudaMallocAsync((void**)&p, sizeof(float) * floats, st) == cudaSuccess ? 0 : 1; }
+  ~Scratch() {
+    if (p) cudaFreeAsync(p, st);
+  }
+};
+
+// y[N] = act(W[N, K] x + bias)
+int gemv_rows(const float* W, int64_t ldw, const float* x, const float* bias, float* y, int N, int K, int relu, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (size_t)K;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(gemv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  gemv_rows_kernel<<<grid_for(N, 8 * GR), 256, smem, st>>>(W, ldw, x, bias, y, N, K, relu);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+inline bool gemv_rows_ok(const float* W, int64_t ldw, const float* x, int K) {
+  return (K & 3) == 0 && (ldw & 3) == 0 && aligned16(W) && aligned16(x) && K <= 48 * 1024;
+}
+
+// backward of y = W x (W [N, K]): dW = g x^T (optional), dx = beta * dx + W^T g (optional)
+int rank1_bwd(const float* W, int64_t ldw, const float* g, const float* x, float* dW, int64_t lddw, float* dx, float beta, int N,
+              int K, cudaStream_t st) {
+  dim3 grid(grid_for(K, 1024), grid_for(N, R1_ROWS));
+  Scratch sc(st);
+  if (dx && sc.get((size_t)grid.y * K)) {
+    azg_set_error("rank1_bwd: scratch allocation failed");
+    return AZG_ERR_CUDA;
+  }
+  if (dx && dW) rank1_bwd_kernel<true, true><<<grid, 256, 0, st>>>(W, ldw, g, x, dW, lddw, sc.p, N, K);
+  else if (dx) rank1_bwd_kernel<true, false><<<grid, 256, 0, st>>>(W, ldw, g, x, nullptr, 0, sc.p, N, K);
+  else if (dW) rank1_bwd_kernel<false, true><<<grid, 256, 0, st>>>(nullptr, 0, g, x, dW, lddw, nullptr, N, K);
+  else return AZG_OK;
+  AZG_LAUNCH_CHECK();
+  if (dx) {
+    reduce_parts_kernel<<<grid_for(K, 256), 256, 0, st>>>(sc.p, (int)grid.y, 1, K, dx, K, beta);
+    AZG_LAUNCH_CHECK();
+  }
+  return AZG_OK;
+}
+inline bool rank1_ok(const float* W, int64_t ldw, const float* x, const float* dW, int64_t lddw, int K) {
+  return (K & 3) == 0 && (!W || ((ldw & 3) == 0 && aligned16(W))) && (!dW || ((lddw & 3) == 0 && aligned16(dW) && aligned16(x)));
+}
+
+// C = op(A) op(B) + beta C with shape-driven dispatch:
+//   M = 1 against a [N, K] matrix        -> gemv_rows (one streaming pass)
+//   M = 1 against a [K, N] matrix        -> rank1_bwd DX pass
+//   K = 1 (outer product)                -> rank1_bwd DW pass
+//   few output tiles but a long K        -> split-K over enough CTAs to fill the SMs, fixed-order reduction
 int gemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
          int64_t ldc, float beta, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return AZG_OK;
+  if (M == 1 && !ta && tb && beta == 0.0f && gemv_rows_ok(B, ldb, A, K)) return gemv_rows(B, ldb, A, nullptr, C, N, K, 0, st);
+  if (M == 1 && !ta && !tb && (beta == 0.0f || beta == 1.0f) && K >= 64 && rank1_ok(B, ldb, nullptr, nullptr, 0, N) && aligned16(C))
+    return rank1_bwd(B, ldb, A, nullptr, nullptr, 0, C, beta, K, N, st);  // C[n] = sum_k A[k] B[k, n]
+  if (K == 1 && ta && !tb && beta == 0.0f && rank1_ok(nullptr, 0, B, C, ldc, N))
+    return rank1_bwd(nullptr, 0, A, B, C, ldc, nullptr, 0.0f, (int)M, N, st);  // C[m, n] = A[m] B[n]
+  const bool tiled = tile_ok(A, lda, B, ldb);
+  const int64_t ctas = tiled ? ((M + TM - 1) / TM) * ((N + TN - 1) / TN) : ((M + GT - 1) / GT) * ((N + GT - 1) / GT);
+  if (ctas < 148 && K >= 256) {
+    int splits = (int)((296 + ctas - 1) / ctas);
+    if (splits > K / 64) splits = K / 64;
+    if (splits > 1) {
+      Scratch sc(st);
+      if (sc.get((size_t)splits * M * N)) {
+        azg_set_error("gemm: scratch allocation failed");
+        return AZG_ERR_CUDA;
+      }
+      int rc = tiled ? gemm_tile_split(ta, tb, M, N, K, A, lda, B, ldb, sc.p, N, 0.0f, splits, M * (int64_t)N, st)
+                     : gemm_split(ta, tb, M, N, K, A, lda, B, ldb, sc.p, N, 0.0f, splits, M * (int64_t)N, st);
+      if (rc) return rc;
+      reduce_parts_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(sc.p, splits, M, N, C, ldc, beta);
+      AZG_LAUNCH_CHECK();
+      return AZG_OK;
+    }
+  }
+  if (tiled) return gemm_tile_split(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta, 1, 0, st);
   return gemm_split(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta, 1, 0, st);
 }
 
@@ -205,6 +579,53 @@ __global__ void conv_bwd_data_kernel(const float* __restrict__ w, const float* _
         if (out[o] > 0.0f) s = fmaf(dout[o], w[((size_t)co * Cin + ci) * 9 + kx * 3 + ky], s);
       }
     }
+  din[idx] = s;
+}
+
+// conv backward as contractions over (board, output cell): one pass writes
+//   gt [(b,p), Cout]   = dout * (out > 0)        (ReLU gate applied, transposed so that (b,p) is the row index)
+//   col[(b,p), Cin*9]  = 3x3 patch of `in` around output cell p (zero outside the board)
+// then dw = gt^T col (split-K GEMM), db = column sums of gt, dcol = gt w, din = col2im(dcol).
+__global__ void conv_bwd_pack_kernel(const float* __restrict__ in, const float* __restrict__ out, const float* __restrict__ dout,
+                                     float* __restrict__ gt, float* __restrict__ col, int64_t B, int Cin, int Cout, int H, int W,
+                                     int pad) {
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, P = Ho * Wo, C9 = Cin * 9;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_g = B * P * Cout, n_c = B * P * C9;
+  if (i < n_g) {
+    const int co = (int)(i % Cout);
+    const int64_t bp = i / Cout;
+    const int64_t o = ((bp / P) * Cout + co) * P + bp % P;
+    gt[i] = out[o] > 0.0f ? dout[o] : 0.0f;
+  } else if (i < n_g + n_c) {
+    const int64_t j = i - n_g;
+    const int r = (int)(j % C9), ci = r / 9, kx = (r % 9) / 3, ky = r % 3;
+    const int64_t bp = j / C9;
+    const int p = (int)(bp % P), x = p / Wo + kx - pad, y = p % Wo + ky - pad;
+    col[j] = (x >= 0 && x < H && y >= 0 && y < W) ? in[(((bp / P) * Cin + ci) * H + x) * W + y] : 0.0f;
+  }
+}
+
+// din[b,ci,x,y] = sum_{kx,ky} dcol[(b, x-kx+pad, y-ky+pad), ci*9 + kx*3 + ky]
+__global__ void conv_col2im_kernel(const float* __restrict__ dcol, float* __restrict__ din, int64_t B, int Cin, int H, int W,
+                                   int pad) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Cin * H * W) return;
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, C9 = Cin * 9;
+  const int y = (int)(idx % W), x = (int)((idx / W) % H), ci = (int)((idx / ((int64_t)W * H)) % Cin);
+  const int64_t b = idx / ((int64_t)W * H * Cin);
+  float s = 0.0f;
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) {
+    const int ox = x - kx + pad;
+    if (ox < 0 || ox >= Ho) continue;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int oy = y - ky + pad;
+      if (oy < 0 || oy >= Wo) continue;
+      s += dcol[((b * Ho + ox) * Wo + oy) * C9 + ci * 9 + kx * 3 + ky];
+    }
+  }
   din[idx] = s;
 }
 
@@ -439,6 +860,7 @@ struct LayerSaved {
 
 int linear_fwd(const float* X, const float* W, int64_t ldw, const float* bias, float* Y, int64_t M, int N, int K, int relu,
                cudaStream_t st) {
+  if (M == 1 && gemv_rows_ok(W, ldw, X, K)) return gemv_rows(W, ldw, X, bias, Y, N, K, relu, st);
   int rc = gemm(false, true, M, N, K, X, K, W, ldw, Y, N, 0.0f, st);
   if (rc) return rc;
   add_bias_act_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(Y, bias, M, N, relu);
@@ -447,6 +869,12 @@ int linear_fwd(const float* X, const float* W, int64_t ldw, const float* bias, f
 }
 
 }  // namespace
+
+// small-batch Linear forward (azg_nets.cu routes azg_linear_f32 here when M is too small to fill its 128 x 128 tiles)
+int azg_train_linear_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t M, int N, int K, int relu,
+                         cudaStream_t st) {
+  return linear_fwd(X, W, K, bias, Y, M, N, K, relu, st);
+}
 
 extern "C" {
 
@@ -516,6 +944,35 @@ int azg_conv3x3_relu_backward(const float* in, const float* w, const float* out,
                               float* db, int64_t B, int Cin, int Cout, int H, int W, int pad, azg_stream stream) {
   AZG_REQUIRE(in && w && out && dout && dw && db, "azg_conv3x3_relu_backward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, C9 = Cin * 9;
+  const int64_t R = B * Ho * Wo;  // rows of the contraction: (board, output cell)
+  const size_t n_g = (size_t)R * Cout, n_c = (size_t)R * C9;
+  if (R >= 256 && n_g + 2 * n_c <= ((size_t)1 << 28)) {
+    const int splits = (int)(R / 64 < 64 ? R / 64 : 64);
+    Scratch sc(st);
+    if (sc.get(n_g + 2 * n_c + (size_t)splits * Cout + 256)) {
+      azg_set_error("azg_conv3x3_relu_backward: scratch allocation failed");
+      return AZG_ERR_CUDA;
+    }
+    float* gt = sc.p;
+    float* col = gt + (n_g + 63) / 64 * 64;
+    float* dcol = col + (n_c + 63) / 64 * 64;
+    float* bpart = dcol + (n_c + 63) / 64 * 64;
+    conv_bwd_pack_kernel<<<grid_for((int64_t)(n_g + n_c), 256), 256, 0, st>>>(in, out, dout, gt, col, B, Cin, Cout, H, W, pad);
+    AZG_LAUNCH_CHECK();
+    int rc;
+    if ((rc = gemm(true, false, Cout, C9, (int)R, gt, Cout, col, C9, dw, C9, 0.0f, st))) return rc;
+    col_sum_split_kernel<<<dim3(grid_for(Cout, 128), splits), 128, 0, st>>>(gt, R, Cout, (R + splits - 1) / splits, bpart);
+    AZG_LAUNCH_CHECK();
+    reduce_splits_kernel<<<grid_for(Cout, 256), 256, 0, st>>>(bpart, splits, Cout, db);
+    AZG_LAUNCH_CHECK();
+    if (din) {
+      if ((rc = gemm(false, false, R, C9, Cout, gt, Cout, w, C9, dcol, C9, 0.0f, st))) return rc;
+      conv_col2im_kernel<<<grid_for(B * Cin * H * W, 256), 256, 0, st>>>(dcol, din, B, Cin, H, W, pad);
+      AZG_LAUNCH_CHECK();
+    }
+    return AZG_OK;
+  }
   conv_bwd_weight_kernel<<<grid_for(Cout * Cin * 9 + Cout, 128), 128, 0, st>>>(in, out, dout, dw, db, B, Cin, Cout, H, W, pad);
   AZG_LAUNCH_CHECK();
   if (din) {
@@ -617,19 +1074,34 @@ int azg_gnn_layer_backward(const azg_gnn_layer_params* p, const float* f0, const
   int rc;
   gate_bwd_kernel<<<grid_for(F, 256), 256, 0, st>>>(d_out0, L.gate, L.upd, dgpre, dupd, F);
   AZG_LAUNCH_CHECK();
+  // each weight matrix is streamed ONCE: its gradient (rank-1) is written and its input gradient accumulated in one pass
+  const bool fused = rank1_ok(p->gate_w, F2, L.cat2, g->gate_w, F2, (int)F2) && rank1_ok(p->upd2_w, F, L.u1, g->upd2_w, F, F) &&
+                     rank1_ok(p->upd0_w, F2, L.cat2, g->upd0_w, F2, (int)F2);
   // gate = sigmoid(Wg cat2 + bg)
-  if ((rc = gemm(true, false, F, (int)F2, 1, dgpre, F, L.cat2, F2, g->gate_w, F2, 0.0f, st))) return rc;
+  if (fused) {
+    if ((rc = rank1_bwd(p->gate_w, F2, dgpre, L.cat2, g->gate_w, F2, dcat2, 0.0f, F, (int)F2, st))) return rc;
+  } else {
+    if ((rc = gemm(true, false, F, (int)F2, 1, dgpre, F, L.cat2, F2, g->gate_w, F2, 0.0f, st))) return rc;
+    if ((rc = gemm(false, false, 1, (int)F2, F, dgpre, F, p->gate_w, F2, dcat2, F2, 0.0f, st))) return rc;
+  }
   AZG_CUDA_CHECK(cudaMemcpyAsync(g->gate_b, dgpre, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
-  if ((rc = gemm(false, false, 1, (int)F2, F, dgpre, F, p->gate_w, F2, dcat2, F2, 0.0f, st))) return rc;
   // upd = W2 relu(W0 cat2 + b0) + b2
-  if ((rc = gemm(true, false, F, F, 1, dupd, F, L.u1, F, g->upd2_w, F, 0.0f, st))) return rc;
+  if (fused) {
+    if ((rc = rank1_bwd(p->upd2_w, F, dupd, L.u1, g->upd2_w, F, du1, 0.0f, F, F, st))) return rc;
+  } else {
+    if ((rc = gemm(true, false, F, F, 1, dupd, F, L.u1, F, g->upd2_w, F, 0.0f, st))) return rc;
+    if ((rc = gemm(false, false, 1, F, F, dupd, F, p->upd2_w, F, du1, F, 0.0f, st))) return rc;
+  }
   AZG_CUDA_CHECK(cudaMemcpyAsync(g->upd2_b, dupd, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
-  if ((rc = gemm(false, false, 1, F, F, dupd, F, p->upd2_w, F, du1, F, 0.0f, st))) return rc;
   relu_bwd_kernel<<<grid_for(F, 256), 256, 0, st>>>(du1, L.u1, du1, F);
   AZG_LAUNCH_CHECK();
-  if ((rc = gemm(true, false, F, (int)F2, 1, du1, F, L.cat2, F2, g->upd0_w, F2, 0.0f, st))) return rc;
+  if (fused) {
+    if ((rc = rank1_bwd(p->upd0_w, F2, du1, L.cat2, g->upd0_w, F2, dcat2, 1.0f, F, (int)F2, st))) return rc;
+  } else {
+    if ((rc = gemm(true, false, F, (int)F2, 1, du1, F, L.cat2, F2, g->upd0_w, F2, 0.0f, st))) return rc;
+    if ((rc = gemm(false, false, 1, (int)F2, F, du1, F, p->upd0_w, F2, dcat2, F2, 1.0f, st))) return rc;
+  }
   AZG_CUDA_CHECK(cudaMemcpyAsync(g->upd0_b, du1, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
-  if ((rc = gemm(false, false, 1, (int)F2, F, du1, F, p->upd0_w, F2, dcat2, F2, 1.0f, st))) return rc;
   // cat2 = [f0, agg];  out0 = f0 + ...
   AZG_CUDA_CHECK(cudaMemcpyAsync(d_f0, d_out0, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
   axpy_kernel<<<grid_for(F, 256), 256, 0, st>>>(d_f0, dcat2, F);

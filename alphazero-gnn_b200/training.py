@@ -378,9 +378,12 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
     epochs, batch_size = int(arg(w.args, "epochs")), int(arg(w.args, "batch_size"))
     dev = w.device
     nnet_params = list(w.nnet.parameters())
-    nnet_opt = torch.optim.Adam(nnet_params, lr=lr)
+    # torch's own Adam, as in the reference; its single-kernel (`fused`) implementation moves each of p, g, m, v once
+    # instead of once per foreach pass (1.8 ms -> 0.8 ms for the 120 M GNN parameters)
+    kw = {"fused": True} if dev.type == "cuda" else {}
+    nnet_opt = torch.optim.Adam(nnet_params, lr=lr, **kw)
     gnn_params = list(w.gnn.parameters()) if getattr(w, "gnn", None) is not None else []
-    gnn_opt = torch.optim.Adam(gnn_params, lr=lr) if gnn_params else None
+    gnn_opt = torch.optim.Adam(gnn_params, lr=lr, **kw) if gnn_params else None
     for _ in range(epochs):
         if examples:
             idx = _sample(examples, batch_size)
