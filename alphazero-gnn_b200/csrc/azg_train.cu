@@ -303,19 +303,17 @@ __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   return fmaf(a.w, b.w, acc);
 }
 
-// y[n] = act(W[n, :K] . x + bias[n]): one warp per GR rows, 128-bit streaming loads, x staged in shared memory.
-// Fixed summation order per lane + shuffle tree: deterministic.
-constexpr int GR = 2;
-__global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ x,
-                                                        const float* __restrict__ bias, float* __restrict__ y, int N, int K,
-                                                        int relu) {
-  extern __shared__ float4 gemv_xs[];
+// y[n] = act(W[n, :K] . x + bias[n]): one warp per GR rows, 128-bit streaming loads (8 x GR in flight per lane);
+// x (<= 25 KB) is re-read through L1 by every warp.  Fixed summation order per lane + shuffle tree: deterministic.
+constexpr int GR = 2, GEMV_WARPS = 4;
+__global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_rows_kernel(const float* __restrict__ W, int64_t ldw,
+                                                                    const float* __restrict__ x, const float* __restrict__ bias,
+                                                                    float* __restrict__ y, int N, int K, int relu) {
   const int K4 = K >> 2;
-  for (int i = threadIdx.x; i < K4; i += blockDim.x) gemv_xs[i] = reinterpret_cast<const float4*>(x)[i];
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * 8 + warp) * GR;
+  const int n0 = (blockIdx.x * GEMV_WARPS + warp) * GR;
   if (n0 >= N) return;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
   const float4* w[GR];
   float acc[GR];
 #pragma unroll
@@ -324,9 +322,22 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict_
     w[r] = reinterpret_cast<const float4*>(W + (int64_t)n * ldw);
     acc[r] = 0.0f;
   }
-#pragma unroll 4
-  for (int k = lane; k < K4; k += 32) {
-    const float4 xv = gemv_xs[k];
+  int k = lane;
+  for (; k + 7 * 32 < K4; k += 8 * 32) {
+    float4 wv[GR][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int r = 0; r < GR; ++r) wv[r][u] = __ldcs(w[r] + k + 32 * u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 xv = __ldg(x4 + k + 32 * u);
+#pragma unroll
+      for (int r = 0; r < GR; ++r) acc[r] = dot4(wv[r][u], xv, acc[r]);
+    }
+  }
+  for (; k < K4; k += 32) {
+    const float4 xv = __ldg(x4 + k);
 #pragma unroll
     for (int r = 0; r < GR; ++r) acc[r] = dot4(__ldcs(w[r] + k), xv, acc[r]);
   }
@@ -402,18 +413,12 @@ struct Scratch {
 
 // y[N] = act(W[N, K] x + bias)
 int gemv_rows(const float* W, int64_t ldw, const float* x, const float* bias, float* y, int N, int K, int relu, cudaStream_t st) {
-  const size_t smem = sizeof(float) * (size_t)K;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AZG_CUDA_CHECK(cudaFuncSetAttribute(gemv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  gemv_rows_kernel<<<grid_for(N, 8 * GR), 256, smem, st>>>(W, ldw, x, bias, y, N, K, relu);
+  gemv_rows_kernel<<<grid_for(N, GEMV_WARPS * GR), GEMV_WARPS * 32, 0, st>>>(W, ldw, x, bias, y, N, K, relu);
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }
 inline bool gemv_rows_ok(const float* W, int64_t ldw, const float* x, int K) {
-  return (K & 3) == 0 && (ldw & 3) == 0 && aligned16(W) && aligned16(x) && K <= 48 * 1024;
+  return (K & 3) == 0 && (ldw & 3) == 0 && aligned16(W) && aligned16(x);
 }
 
 // backward of y = W x (W [N, K]): dW = g x^T (optional), dx = beta * dx + W^T g (optional)

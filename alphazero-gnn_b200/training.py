@@ -22,6 +22,7 @@ weight-bandwidth bound) layers run replicated, while output_transform + heads + 
 rows; only the rank that owns row 0 contributes layer gradients.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -373,17 +374,95 @@ def _sample(examples, batch_size):
     return idx
 
 
+class _GraphedStep:
+    """One optimizer step (zero_grad -> loss -> backward -> Adam.step) of a fixed batch shape, captured in a CUDA
+    graph: the ~120 launches of a step are replayed by one `cudaGraphLaunch` instead of being issued from Python
+    (the step is launch-bound otherwise: 3.1 ms eager vs 1.9 ms of kernel time per epoch)."""
+
+    def __init__(self, step_fn, w, params, opt, shapes):
+        dev = w.device
+        self.static = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
+        self.graph = None
+        self.step_fn, self.w, self.params, self.opt = step_fn, w, params, opt
+
+    def _body(self):
+        self.opt.zero_grad(set_to_none=True)
+        loss = self.step_fn(CudaOps, self.w, *self.static)
+        loss.backward()
+        self.opt.step()
+
+    def run(self, tensors, eager):
+        for dst, src in zip(self.static, tensors):
+            dst.copy_(src, non_blocking=True)
+        if eager:  # first step after the optimizer was created: Adam allocates its state here
+            self._body()
+            return
+        if self.graph is None:
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            self.opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self.graph):
+                self._body()
+        self.graph.replay()
+
+
+def _reset_adam(opt):
+    """fresh-Adam semantics (the reference re-creates its optimizers on every train call) for a cached optimizer"""
+    for st in opt.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+
+
+def _train_cache(w, key, builder):
+    cache = w.__dict__.setdefault("_train_cache", {})
+    if key not in cache:
+        cache[key] = builder()
+    return cache[key]
+
+
 def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
     lr = float(arg(w.args, "lr"))
     epochs, batch_size = int(arg(w.args, "epochs")), int(arg(w.args, "batch_size"))
     dev = w.device
+    rank, world = _world()
     nnet_params = list(w.nnet.parameters())
+    gnn_params = list(w.gnn.parameters()) if getattr(w, "gnn", None) is not None else []
     # torch's own Adam, as in the reference; its single-kernel (`fused`) implementation moves each of p, g, m, v once
     # instead of once per foreach pass (1.8 ms -> 0.8 ms for the 120 M GNN parameters)
-    kw = {"fused": True} if dev.type == "cuda" else {}
-    nnet_opt = torch.optim.Adam(nnet_params, lr=lr, **kw)
-    gnn_params = list(w.gnn.parameters()) if getattr(w, "gnn", None) is not None else []
-    gnn_opt = torch.optim.Adam(gnn_params, lr=lr, **kw) if gnn_params else None
+    graphed = dev.type == "cuda" and world == 1 and ops is CudaOps and not os.environ.get("AZG_TRAIN_EAGER")
+    if graphed:
+        # optimizers (state zeroed = re-created) and captured steps persist across train() calls
+        def build():
+            o1 = torch.optim.Adam(nnet_params, lr=lr, fused=True, capturable=True)
+            o2 = torch.optim.Adam(gnn_params, lr=lr, fused=True, capturable=True) if gnn_params else None
+            return {"nnet_opt": o1, "gnn_opt": o2, "steps": {}, "warm": set()}
+        cache = _train_cache(w, ("opt", lr), build)
+        nnet_opt, gnn_opt = cache["nnet_opt"], cache["gnn_opt"]
+        _reset_adam(nnet_opt)
+        if gnn_opt is not None:
+            _reset_adam(gnn_opt)
+    else:
+        kw = {"fused": True} if dev.type == "cuda" else {}
+        nnet_opt = torch.optim.Adam(nnet_params, lr=lr, **kw)
+        gnn_opt = torch.optim.Adam(gnn_params, lr=lr, **kw) if gnn_params else None
+
+    def run_step(which, step_fn, params, opt, tensors):
+        if not graphed:
+            opt.zero_grad()
+            loss = step_fn(ops, w, *tensors)
+            if loss is not None:
+                loss.backward()
+            allreduce_grads(params)
+            opt.step()
+            return
+        key = (which, tuple(tuple(t.shape) for t in tensors))
+        if key not in cache["steps"]:
+            cache["steps"][key] = _GraphedStep(step_fn, w, params, opt, [t.shape for t in tensors])
+        eager = which not in cache["warm"]
+        cache["steps"][key].run(tensors, eager)
+        cache["warm"].add(which)
+
     for _ in range(epochs):
         if examples:
             idx = _sample(examples, batch_size)
@@ -391,24 +470,14 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
             boards = torch.FloatTensor(np.array(boards)).to(dev)
             target_pis = torch.FloatTensor(np.array(pis)).to(dev)
             target_vs = torch.FloatTensor(np.array(vs).astype(np.float64)).to(dev)
-            nnet_opt.zero_grad()
-            loss = std_step(ops, w, boards, target_pis, target_vs)
-            if loss is not None:
-                loss.backward()
-            allreduce_grads(nnet_params)
-            nnet_opt.step()
+            run_step("std", std_step, nnet_params, nnet_opt, (boards, target_pis, target_vs))
         if gnn_opt is not None and gnn_examples and len(gnn_examples) > 0:
             idx = _sample(gnn_examples, batch_size)
             batch = [gnn_examples[i] for i in idx]
             boards = torch.FloatTensor(np.array([b[0] for b in batch])).to(dev)
             expanded_pis = torch.FloatTensor(np.array([b[4] for b in batch])).to(dev)
             expanded_vs = torch.FloatTensor(np.array([b[5] for b in batch]).astype(np.float64)).to(dev)
-            gnn_opt.zero_grad()
-            loss = gnn_step(ops, w, boards, expanded_pis, expanded_vs)
-            if loss is not None:
-                loss.backward()
-            allreduce_grads(gnn_params)
-            gnn_opt.step()
+            run_step("gnn", gnn_step, gnn_params, gnn_opt, (boards, expanded_pis, expanded_vs))
     w.weights_changed()
 
 

@@ -122,6 +122,38 @@ def test_train_runs_and_learns():
     assert not np.allclose(out0["pi_gnn"], w.predict_batch(boards)["pi_gnn"])
 
 
+@pytest.mark.parametrize("kind,n", [("c4", 5), ("ttt", 3)])
+def test_captured_steps_equal_eager_steps(kind, n, monkeypatch):
+    """train() replays CUDA-graph captures of its optimizer steps (Adam state zeroed per call = the reference's
+    per-call optimizers).  Two calls of train() must leave the same weights as the eager loop (dropout off)."""
+    rng = np.random.default_rng(3)
+    ws = {}
+    for mode in ("eager", "graph"):
+        if mode == "eager":
+            monkeypatch.setenv("AZG_TRAIN_EAGER", "1")
+        else:
+            monkeypatch.delenv("AZG_TRAIN_EAGER", raising=False)
+        w = _wrapper(kind, n, dropout=0.0, epochs=4, batch_size=8)
+        A = w.action_size
+        r = np.random.default_rng(3)
+        boards = r.integers(-1, 2, size=(24, n, n)).astype(np.int64)
+        pis = r.dirichlet(np.ones(A), size=24)
+        vs = r.choice([-1, 1], size=24)
+        examples = [(boards[i], list(pis[i]), int(vs[i])) for i in range(24)]
+        gnn_examples = [(boards[i], 1, pis[i], np.float32(0.1), pis[i], np.float32(vs[i] * 0.5), int(vs[i])) for i in range(24)]
+        np.random.seed(5)
+        w.train(examples, gnn_examples)
+        w.train(examples[:6], gnn_examples[:6])  # a second call, and a different minibatch shape (6 < batch_size)
+        w.train(examples, gnn_examples)
+        ws[mode] = w
+    for mod in ("nnet", "gnn"):
+        a, b = dict(getattr(ws["eager"], mod).named_parameters()), dict(getattr(ws["graph"], mod).named_parameters())
+        for k in a:
+            assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), (mod, k, (a[k] - b[k]).abs().max().item())
+    o1, o2 = ws["eager"].predict_batch(boards), ws["graph"].predict_batch(boards)
+    assert np.allclose(o1["pi_gnn"], o2["pi_gnn"], atol=1e-5) and np.allclose(o1["v"], o2["v"], atol=1e-5)
+
+
 # ------------------------------------------------------------------------------------ FrozenLake training
 @pytest.mark.parametrize("n,layers", [(4, 3), (8, 2)])
 def test_frozenlake_training_step(n, layers):
