@@ -285,7 +285,8 @@ def shard_rows(B, rank, world):
 
 
 def allreduce_grads(params):
-    """one summed all-reduce over a flat bucket of all parameter gradients (NCCL over NVLink on GPUs)"""
+    """Summed all-reduce of the parameter gradients (NCCL over NVLink on GPUs): tensors of >= 1 M elements are
+    reduced in place (no staging copies of the 39 MB weight gradients), the small ones travel in one flat bucket."""
     rank, world = _world()
     if world == 1:
         return
@@ -293,10 +294,43 @@ def allreduce_grads(params):
     for p in params:
         if p.grad is None:
             p.grad = torch.zeros_like(p)
-    flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
-        p.grad.copy_(g)
+    big = [p for p in params if p.grad.numel() >= (1 << 20) and p.grad.is_contiguous()]
+    small = [p for p in params if not (p.grad.numel() >= (1 << 20) and p.grad.is_contiguous())]
+    works = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in big]
+    if small:
+        flat = torch._utils._flatten_dense_tensors([p.grad for p in small])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        for p, g in zip(small, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in small])):
+            p.grad.copy_(g)
+    for wk in works:
+        wk.wait()
+
+
+class _ShareRow0Grad(torch.autograd.Function):
+    """Identity on the updated target row; its backward sums d(loss)/d(row 0) over ranks.  Only the rank that owns
+    row 0 has a non-zero contribution, so afterwards EVERY rank holds the true gradient and runs the GNNLayer
+    backward itself: the 100 M layer gradients are recomputed (0.35 ms of weight streaming) instead of being
+    moved (400 MB all-reduce), and stay bit-identical across ranks."""
+
+    @staticmethod
+    def forward(ctx, f0):
+        return f0.view_as(f0)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return g
+
+
+def exchange_grads(w, which):
+    """The one exchange of a data-parallel step.  "std": every trunk/head gradient.
+    "gnn": the row-sharded output_transform gradients only -- the GNNLayer gradients are already complete and
+    identical on every rank (see _ShareRow0Grad)."""
+    if which == "std":
+        allreduce_grads(list(w.nnet.parameters()))
+    else:
+        allreduce_grads(list(w.gnn.output_transform.parameters()))
 
 
 def std_step(ops, w, boards, target_pi, target_v):
@@ -330,19 +364,24 @@ def gnn_step(ops, w, boards, target_pi, target_v):
             feats = mine
     gnn = w.gnn
     x = feats
+    f0 = None
     if B > 1:
         f0, path = feats[0], feats[1:]
         for layer in gnn.layers:
             f0 = ops.gnn_layer(f0, path, layer)
+        if world > 1:
+            f0 = _ShareRow0Grad.apply(f0)
         x = torch.cat([f0.unsqueeze(0), path], dim=0)
+    # ranks that do not own row 0 still take part in its gradient exchange (with a zero contribution)
+    anchor = (f0 * 0.0).sum().reshape(1) if (world > 1 and f0 is not None and rank != 0) else None
     if hi <= lo:
-        return None
+        return anchor
     ot = gnn.output_transform
     enh = ops.linear(ops.linear(x[lo:hi], ot[0], relu=True), ot[2])
     heads = _FrozenHeads(w)
     logits, vraw = head_logits(ops, heads, enh)
     loss, _, _ = ops.pv_loss(logits, vraw, target_pi[lo:hi], target_v[lo:hi], B)
-    return loss
+    return loss if anchor is None else loss + anchor
 
 
 class _FrozenHeads:
@@ -453,7 +492,7 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
             loss = step_fn(ops, w, *tensors)
             if loss is not None:
                 loss.backward()
-            allreduce_grads(params)
+            exchange_grads(w, which)
             opt.step()
             return
         key = (which, tuple(tuple(t.shape) for t in tensors))

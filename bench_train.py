@@ -111,7 +111,7 @@ def main():
         if loss is not None:
             loss.backward()
         marks.append(ev())
-        training.allreduce_grads(nnet_params)
+        training.exchange_grads(w, "std")
         marks.append(ev())
         o1.step()
         marks.append(ev())
@@ -121,7 +121,7 @@ def main():
         if loss is not None:
             loss.backward()
         marks.append(ev())
-        training.allreduce_grads(gnn_params)
+        training.exchange_grads(w, "gnn")
         marks.append(ev())
         o2.step()
         marks.append(ev())
@@ -183,7 +183,7 @@ def main():
                 "train_api_ms_per_epoch": api_ms,
                 "params": {"nnet": n_std, "gnn": n_gnn, "feature_dim": F},
                 "hbm_bytes_algorithmic": {"gnn_forward_weights": fwd_bytes, "gnn_backward": 2 * grad_bytes,
-                                          "adam": 7 * grad_bytes, "allreduce_payload": grad_bytes if world > 1 else 0},
+                                          "adam": 7 * grad_bytes, "allreduce_payload": 4 * sum(p.numel() for p in w.gnn.output_transform.parameters()) if world > 1 else 0},
                 "adam": "torch fused" if a.fused_adam else "torch default (as the reference)"}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

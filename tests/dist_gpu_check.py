@@ -27,7 +27,7 @@ def grads(w, boards, tpi, tv):
         if loss is not None:
             loss.backward()
         params = list(mod.parameters())
-        training.allreduce_grads(params)
+        training.exchange_grads(w, name)
         out[name] = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in params]
     return out
 

@@ -53,7 +53,7 @@ def _grads(kind, n, B):
         if loss is not None:
             loss.backward()
         params = list(mod.parameters())
-        training.allreduce_grads(params)
+        training.exchange_grads(w, name)
         out[name] = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in params]
     return out
 
@@ -63,8 +63,7 @@ def _worker(rank, world, port, kind, n, B, q):
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = _grads(kind, n, B)
-    if rank == 0:
-        q.put({k: [t.numpy() for t in v] for k, v in g.items()})
+    q.put((rank, {k: [t.numpy() for t in v] for k, v in g.items()}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -79,13 +78,14 @@ def test_two_ranks_reproduce_single_process_gradients(kind, n, B):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, kind, n, B, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=120)
+    got = dict(q.get(timeout=120) for _ in range(2))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for name in ("std", "gnn"):
-        for a, b in zip(got[name], single[name]):
-            np.testing.assert_allclose(a, b.numpy(), rtol=1e-4, atol=1e-6)
+    for rank in (0, 1):  # every rank ends the exchange with the full-batch gradients (replicated optimizer step)
+        for name in ("std", "gnn"):
+            for a, b in zip(got[rank][name], single[name]):
+                np.testing.assert_allclose(a, b.numpy(), rtol=1e-4, atol=1e-6)
 
 
 def test_shard_rows_cover_the_batch_once():
