@@ -1,0 +1,415 @@
+// azg_grid_tc.cu -- one fused kernel per grid-graph GNN layer on the 5th-gen tensor cores
+// (BASELINE configs[4]; operator = FrozenLakeNet.GNNLayer, frozenlake/FrozenLakeNet.py:8-33, on gh x gw
+// 4-neighbour grids normalised as create_adjacency, :68-72):
+//
+//     forward    out = relu( A^ (X W^T + b) )                    X, out: [B*n, H] fp32 row-major
+//     backward   dX  = A^ ( (dOut * [out > 0]) W )               (A^ is symmetric, so A^ (G W) = (A^ G) W)
+//
+// Each CTA owns tiles of WHOLE graphs (G = 128 / n graphs = G*n <= 128 GEMM rows), one persistent CTA per SM:
+//   warps 0-7    producers: 128-bit loads of the tile's fp32 rows (one k-block = 64 channels at a time, issued one
+//                item ahead), split into bf16 hi/lo, stored as the SWIZZLE_128B operand image of the stage;
+//                thread 0 also starts the bulk copy of the k-block's weight image (L2-resident, <= 64 KB)
+//   warp 8       MMA issuer (one thread): M=128 x N=H x K=16 tcgen05.mma, 3 products per k-block in bf16x3
+//   warp 9       TMEM allocation (2 accumulators of H fp32 columns), barrier init
+//   warps 12-15  epilogue: TMEM -> registers -> fp32 staging tile in shared memory (32 columns at a time) ->
+//                each row gathers its <= 5 neighbours (coefficients d_i d_j tabulated per CTA) -> + rowsum*bias,
+//                ReLU -> 128-byte row segments to HBM
+// so the support matrix X W^T never exists in HBM: algorithmic bytes per layer = 4H read + 4H written per node.
+#include "azg_tc.cuh"
+
+namespace gridtc {
+using namespace tc;
+
+constexpr int GT_THREADS = 512;
+constexpr int EC = 32;             // epilogue chunk (columns per tcgen05.ld)
+constexpr int ST_LD = EC + 4;      // staging row stride in floats (144 B: conflict-free 128-bit accesses)
+constexpr int ST_BYTES = 128 * ST_LD * 4;
+constexpr int MISC_BYTES = 8192;   // barriers, neighbour table
+
+template <int H, bool X3>
+struct GridSmem {
+  static constexpr int KB = H / BK;
+  static constexpr int A_BYTES = (X3 ? 2 : 1) * A_STAGE_BYTES;
+  static constexpr int W_HALF = H * 128;  // one k-block of one weight image
+  static constexpr int W_BYTES = (X3 ? 2 : 1) * W_HALF;
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int BUDGET = 232448 - 1024 - MISC_BYTES - ST_BYTES;
+  static constexpr int NST = BUDGET / STAGE_BYTES < 4 ? BUDGET / STAGE_BYTES : 4;
+  static constexpr int ST_OFF = NST * STAGE_BYTES;
+  static constexpr int MISC_OFF = ST_OFF + ST_BYTES;
+  static constexpr int TOTAL = MISC_OFF + MISC_BYTES + 1024;
+  static_assert(NST >= 2, "at least two pipeline stages");
+};
+
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// 4 fp32 -> 8 bytes of the hi (and lo) operand image
+__device__ __forceinline__ void split_store4(float4 x, uint8_t* hi, uint8_t* lo, uint32_t off) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z),
+                      h3 = __float2bfloat16_rn(x.w);
+  *reinterpret_cast<uint2*>(hi + off) = make_uint2((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16),
+                                                   (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16));
+  if (lo) {
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x.y - __bfloat162float(h1)),
+                        l2 = __float2bfloat16_rn(x.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(x.w - __bfloat162float(h3));
+    *reinterpret_cast<uint2*>(lo + off) = make_uint2((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16),
+                                                     (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16));
+  }
+}
+
+struct GridArgs {
+  const float* x;      // FWD: layer input; BWD: upstream gradient dOut
+  const float* act;    // BWD: the layer's output (ReLU gate), else null
+  const uint8_t* w_hi; // weight image, k-block major: [KB][H rows x 64] (BWD: of W^T)
+  const uint8_t* w_lo;
+  const float* bias;   // FWD: [H] or null
+  float* out;
+  int64_t B;           // graphs
+  int gh, gw;
+  int relu;
+};
+
+template <int H, bool X3, bool BWD>
+__global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g) {
+  using S = GridSmem<H, X3>;
+  constexpr int KB = S::KB, NST = S::NST;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* staging = (float*)(smem + S::ST_OFF);
+  uint64_t* full = (uint64_t*)(smem + S::MISC_OFF);
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* nb_coef = (float*)(smem + S::MISC_OFF + 256);  // [128][5]
+  float* row_sum = nb_coef + 128 * 5;                   // [128]
+  int16_t* nb_row = (int16_t*)(row_sum + 128);          // [128][5] tile rows
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = g.gh * g.gw;
+  const int G = 128 / n;          // graphs per tile
+  const int R = G * n;            // valid tile rows
+  const int64_t tiles = (g.B + G - 1) / G;
+  const int64_t total_rows = g.B * n;
+  constexpr uint32_t TMEM_COLS = 2 * H < 32 ? 32 : 2 * H;
+
+  // neighbour table of a tile row: (tile row of the neighbour, d_i * d_j); identical for every tile
+  for (int i = threadIdx.x; i < 128 * 5; i += blockDim.x) {
+    const int r = i / 5, k = i % 5;
+    float coef = 0.0f;
+    int row = r;
+    if (r < R) {
+      const int slot = r / n, node = r - slot * n, x = node / g.gw, y = node - x * g.gw;
+      const int dx = (k == 1) ? -1 : (k == 2) ? 1 : 0, dy = (k == 3) ? -1 : (k == 4) ? 1 : 0;
+      const int nx = x + dx, ny = y + dy;
+      if (nx >= 0 && nx < g.gh && ny >= 0 && ny < g.gw) {
+        const int di = 1 + (x > 0) + (x < g.gh - 1) + (y > 0) + (y < g.gw - 1);
+        const int dj = 1 + (nx > 0) + (nx < g.gh - 1) + (ny > 0) + (ny < g.gw - 1);
+        coef = (1.0f / sqrtf((float)di)) * (1.0f / sqrtf((float)dj));
+        row = slot * n + nx * g.gw + ny;
+      }
+    }
+    nb_coef[i] = coef;
+    nb_row[i] = (int16_t)row;
+  }
+  if (warp == 9 && lane == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 256);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+  __syncthreads();
+  if (threadIdx.x < 128) {  // rowsum in the same order as the gather below
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s += nb_coef[threadIdx.x * 5 + k];
+    row_sum[threadIdx.x] = s;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // =========================== producers ===========================
+    // A step = RS rows per thread of one (tile, k-block) item; the loads of step s+1 are in flight while step s is
+    // converted and stored.  A half-warp reads one row's 256 B of the k-block in one fully coalesced request.
+    // FWD: 8 rows = the whole item (32 KB in flight per SM); BWD loads two tensors, so it works in half items to
+    // keep the same bytes in flight within the register budget.
+    constexpr int RS = BWD ? 4 : 8, SPI = 8 / RS;
+    const int j4 = threadIdx.x & 15, r0 = threadIdx.x >> 4;  // rows r0 + 16 i, float4 j4 (4 channels) of the k-block
+    const int64_t items = ((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * KB;
+    const int64_t steps = items * SPI;
+    float4 cur[RS], nxt[RS];
+    float4 cura[BWD ? RS : 1], nxta[BWD ? RS : 1];
+    auto load = [&](int64_t step, float4* v, float4* a) {
+      const int64_t it = step / SPI;
+      const int half = (int)(step % SPI);
+      const int64_t tile = blockIdx.x + (it / KB) * (int64_t)gridDim.x;
+      const int kb = (int)(it % KB);
+#pragma unroll
+      for (int i = 0; i < RS; ++i) {
+        const int r = r0 + 16 * (half * RS + i);
+        const int64_t row = tile * R + r;
+        if (r < R && row < total_rows) {
+          v[i] = __ldcs(reinterpret_cast<const float4*>(g.x + row * H + kb * BK) + j4);
+          if (BWD) a[i] = __ldcs(reinterpret_cast<const float4*>(g.act + row * H + kb * BK) + j4);
+        } else {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (BWD) a[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+      }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    if (steps > 0) load(0, cur, cura);
+    for (int64_t step = 0; step < steps; ++step) {
+      if (step + 1 < steps) load(step + 1, nxt, nxta);
+      const int kb = (int)((step / SPI) % KB);
+      const int half = (int)(step % SPI);
+      uint8_t* sa = smem + stage * S::STAGE_BYTES;
+      if (half == 0) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (threadIdx.x == 0) {  // this k-block of the weight image(s): contiguous in HBM/L2, one bulk copy each
+          mbar_expect_tx_only(&full[stage], S::W_BYTES);
+          bulk_g2s(sa + S::A_BYTES, g.w_hi + (size_t)kb * S::W_HALF, S::W_HALF, &full[stage]);
+          if (X3) bulk_g2s(sa + S::A_BYTES + S::W_HALF, g.w_lo + (size_t)kb * S::W_HALF, S::W_HALF, &full[stage]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RS; ++i) {
+        float4 v = cur[i];
+        if (BWD) {
+          const float4 a = cura[i];
+          v.x = a.x > 0.0f ? v.x : 0.0f; v.y = a.y > 0.0f ? v.y : 0.0f; v.z = a.z > 0.0f ? v.z : 0.0f; v.w = a.w > 0.0f ? v.w : 0.0f;
+        }
+        split_store4(v, sa, X3 ? sa + A_STAGE_BYTES : nullptr, image_offset(r0 + 16 * (half * RS + i), j4 * 4));
+      }
+#pragma unroll
+      for (int i = 0; i < RS; ++i) {
+        cur[i] = nxt[i];
+        if (BWD) cura[i] = nxta[i];
+      }
+      if (half == SPI - 1) {
+        fence_async_smem();
+        mbar_arrive(&full[stage]);
+        if (++stage == NST) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, H);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * H);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_STAGE_BYTES);
+          const uint64_t b_hi = make_smem_desc(sa + S::A_BYTES), b_lo = make_smem_desc(sa + S::A_BYTES + S::W_HALF);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+          if (X3) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == NST) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    // =========================== epilogue ===========================
+    const int q = warp & 3, r = q * 32 + lane;
+    int nrow[5];
+    float ncoef[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      nrow[k] = nb_row[r * 5 + k];
+      ncoef[k] = nb_coef[r * 5 + k];
+    }
+    const float rs = row_sum[r];
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t row = tile * R + r;
+      const bool valid = r < R && row < total_rows;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H);
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += EC) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + (uint32_t)c0, rr);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(staging + r * ST_LD);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          dst[e] = make_float4(__uint_as_float(rr[4 * e]), __uint_as_float(rr[4 * e + 1]), __uint_as_float(rr[4 * e + 2]),
+                               __uint_as_float(rr[4 * e + 3]));
+        named_bar(3, 128);  // the chunk of every row is staged
+        float o[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const float cf = ncoef[k];
+          if (cf != 0.0f) {
+            const float4* src = reinterpret_cast<const float4*>(staging + nrow[k] * ST_LD);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 v = src[e];
+              o[4 * e] = fmaf(cf, v.x, o[4 * e]);
+              o[4 * e + 1] = fmaf(cf, v.y, o[4 * e + 1]);
+              o[4 * e + 2] = fmaf(cf, v.z, o[4 * e + 2]);
+              o[4 * e + 3] = fmaf(cf, v.w, o[4 * e + 3]);
+            }
+          }
+        }
+        if (valid) {
+          float4* po = reinterpret_cast<float4*>(g.out + row * H + c0);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float4 v = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+            if (g.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + e);
+              v.x = fmaf(rs, b.x, v.x); v.y = fmaf(rs, b.y, v.y); v.z = fmaf(rs, b.z, v.z); v.w = fmaf(rs, b.w, v.w);
+            }
+            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            __stcs(po + e, v);
+          }
+        }
+        named_bar(4, 128);  // every row has gathered: the staging tile may be overwritten
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// W [H, H] fp32 row-major (nn.Linear weight: [out, in]) -> B-operand images, k-block major.
+//   transpose = 0: B[nrow = out][k = in] = W[out][in]       (forward,  X W^T)
+//   transpose = 1: B[nrow = in][k = out] = W[out][in]       (backward, G W)
+__global__ void grid_weight_image_kernel(const float* __restrict__ w, int H, int transpose, uint8_t* __restrict__ hi,
+                                         uint8_t* __restrict__ lo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (nrow, 8-wide k chunk)
+  const int chunks = H / 8;
+  if (idx >= H * chunks) return;
+  const int nrow = idx / chunks, k0 = (idx % chunks) * 8;
+  float x8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x8[e] = transpose ? w[(size_t)(k0 + e) * H + nrow] : w[(size_t)nrow * H + k0 + e];
+  const size_t off = (size_t)(k0 / BK) * ((size_t)H * 128) + image_offset(nrow, k0 % BK);
+  split_store(x8, hi, lo, off);
+}
+
+template <int H, bool X3, bool BWD>
+int launch(const GridArgs& g, cudaStream_t st) {
+  static bool configured = false;
+  using S = GridSmem<H, X3>;
+  int dev = 0, sms = 0;
+  AZG_CUDA_CHECK(cudaGetDevice(&dev));
+  AZG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!configured) {
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(grid_layer_tc_kernel<H, X3, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  const int G = 128 / (g.gh * g.gw);
+  const int64_t tiles = (g.B + G - 1) / G;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  grid_layer_tc_kernel<H, X3, BWD><<<grid, GT_THREADS, S::TOTAL, st>>>(g);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+template <bool BWD>
+int dispatch(const GridArgs& g, int H, int prec, cudaStream_t st) {
+  const bool x3 = prec == AZG_PREC_BF16X3;
+  switch (H) {
+    case 64: return x3 ? launch<64, true, BWD>(g, st) : launch<64, false, BWD>(g, st);
+    case 128: return x3 ? launch<128, true, BWD>(g, st) : launch<128, false, BWD>(g, st);
+    case 256: return x3 ? launch<256, true, BWD>(g, st) : launch<256, false, BWD>(g, st);
+  }
+  azg_set_error("grid layer: hidden size %d not in {64, 128, 256}", H);
+  return AZG_ERR_INVALID;
+}
+
+}  // namespace gridtc
+
+extern "C" {
+
+size_t azg_grid_packed_bytes(int H) { return (size_t)H * H * 2 * 2; }  // hi image, lo image
+
+int azg_grid_tc_supported(int gh, int gw, int H) {
+  const int n = gh * gw;
+  return n >= 1 && n <= 128 && (H == 64 || H == 128 || H == 256);
+}
+
+int azg_grid_pack_weights(const float* w, int H, int transpose, void* packed, azg_stream stream) {
+  AZG_REQUIRE(w && packed && (H == 64 || H == 128 || H == 256), "azg_grid_pack_weights: bad argument");
+  uint8_t* hi = (uint8_t*)packed;
+  uint8_t* lo = hi + (size_t)H * H * 2;
+  const int threads = H * (H / 8);
+  gridtc::grid_weight_image_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, H, transpose, hi, lo);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+int azg_grid_layer_tc_forward(const float* x, const void* packed_w, const float* bias, int64_t B, int gh, int gw, int H, int prec,
+                              float* out, azg_stream stream) {
+  AZG_REQUIRE(x && packed_w && out, "azg_grid_layer_tc_forward: null pointer");
+  AZG_REQUIRE(azg_grid_tc_supported(gh, gw, H), "azg_grid_layer_tc_forward: unsupported shape %dx%d, H=%d", gh, gw, H);
+  AZG_REQUIRE(prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16, "azg_grid_layer_tc_forward: precision must be bf16x3 or bf16");
+  if (B <= 0) return AZG_OK;
+  gridtc::GridArgs g{x, nullptr, (const uint8_t*)packed_w, (const uint8_t*)packed_w + (size_t)H * H * 2, bias, out, B, gh, gw, 1};
+  return gridtc::dispatch<false>(g, H, prec, (cudaStream_t)stream);
+}
+
+int azg_grid_layer_tc_backward_input(const float* dout, const float* act, const void* packed_wt, int64_t B, int gh, int gw, int H,
+                                     int prec, float* dx, azg_stream stream) {
+  AZG_REQUIRE(dout && act && packed_wt && dx, "azg_grid_layer_tc_backward_input: null pointer");
+  AZG_REQUIRE(azg_grid_tc_supported(gh, gw, H), "azg_grid_layer_tc_backward_input: unsupported shape %dx%d, H=%d", gh, gw, H);
+  AZG_REQUIRE(prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16, "azg_grid_layer_tc_backward_input: precision must be bf16x3 or bf16");
+  if (B <= 0) return AZG_OK;
+  gridtc::GridArgs g{dout, act, (const uint8_t*)packed_wt, (const uint8_t*)packed_wt + (size_t)H * H * 2, nullptr, dx, B, gh, gw, 0};
+  return gridtc::dispatch<true>(g, H, prec, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -192,6 +192,20 @@ int azg_graph_mean_relu_backward(const float* dout, const float* out, const int3
 int azg_grid_aggregate_relu_forward(const float* sup, int64_t B, int gh, int gw, int H, float* out, azg_stream stream);
 int azg_grid_aggregate_relu_backward(const float* dout, const float* out, int64_t B, int gh, int gw, int H,
                                      float* dsup, azg_stream stream);
+/* The same layer as ONE fused tensor-core kernel (csrc/azg_grid_tc.cu): each CTA owns tiles of whole graphs,
+ * X W^T runs on tcgen05 (bf16x3 = fp32-level accuracy, or bf16), the <= 5-neighbour aggregation, rowsum*bias and
+ * ReLU happen in the epilogue, so the support matrix never reaches HBM.
+ *   forward:         out = relu(adj * (x W^T + b))                    x, out [B, gh*gw, H] fp32
+ *   backward_input:  dx  = adj * ((dout * (out > 0)) W)
+ * Weights are passed as operand images made by azg_grid_pack_weights (transpose = 1 for backward_input);
+ * azg_grid_tc_supported: gh*gw <= 128 and H in {64, 128, 256}.  prec: AZG_PREC_BF16X3 or AZG_PREC_BF16. */
+size_t azg_grid_packed_bytes(int H);
+int azg_grid_tc_supported(int gh, int gw, int H);
+int azg_grid_pack_weights(const float* w, int H, int transpose, void* packed, azg_stream stream);
+int azg_grid_layer_tc_forward(const float* x, const void* packed_w, const float* bias, int64_t B, int gh, int gw, int H,
+                              int prec, float* out, azg_stream stream);
+int azg_grid_layer_tc_backward_input(const float* dout, const float* act, const void* packed_wt, int64_t B, int gh, int gw,
+                                     int H, int prec, float* dx, azg_stream stream);
 /* GNNLayer.forward / backward at B = P + 1 > 1 (gnn_utils.py:34-74): row 0 (f0) is the target, rows
  * 1.. (path) are attended over; only the target row changes. */
 typedef struct azg_gnn_layer_params {

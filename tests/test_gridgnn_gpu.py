@@ -5,7 +5,9 @@ import pytest
 import torch
 
 from oracle import nets as onets
-from azgnn_b200.gridgnn import GridGNNStack
+import torch.nn.functional as F
+
+from azgnn_b200.gridgnn import GridGNNStack, _GridLayerTC
 
 pytestmark = pytest.mark.gpu
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -14,9 +16,11 @@ torch.backends.cuda.matmul.allow_tf32 = False
 @pytest.mark.parametrize("gh,gw", [(3, 3), (4, 4), (6, 7), (7, 7), (8, 8), (16, 16)])
 @pytest.mark.parametrize("hidden", [64, 128, 256])
 def test_grid_gnn_forward_backward(gh, gw, hidden):
+    """fp32 path: SGEMM + aggregation kernels vs the dense-adjacency oracle."""
     torch.manual_seed(gh * 100 + hidden)
     B = 37
-    net = GridGNNStack(gh, gw, hidden, layers=2).cuda()
+    net = GridGNNStack(gh, gw, hidden, layers=2, precision="fp32").cuda()
+    assert not net.fused
     x = torch.randn(B, gh * gw, hidden, device="cuda", requires_grad=True)
     y = net(x)
     g = torch.randn_like(y)
@@ -32,3 +36,52 @@ def test_grid_gnn_forward_backward(gh, gw, hidden):
     for a, b in zip(got, ref):
         bad = (a - b).abs() > 1e-3 * b.abs().max() + 2e-6
         assert bad.float().mean().item() < 1e-3, (a - b).abs().max().item()  # isolated ReLU knife-edge flips only
+
+
+@pytest.mark.parametrize("gh,gw", [(3, 3), (4, 4), (6, 7), (7, 7), (8, 8), (11, 11)])
+@pytest.mark.parametrize("hidden", [64, 128, 256])
+def test_fused_tensor_core_layer(gh, gw, hidden):
+    """bf16x3 = the fused tcgen05 layer kernel.  Outputs: the fp32 contract (1e-5) against the oracle.  Gradients:
+    against autograd through the oracle operator evaluated WITH THE KERNEL'S OWN ReLU pattern -- a hidden unit whose
+    pre-activation is within rounding of 0 may land on either side of the ReLU in two correct implementations, and
+    with a random upstream gradient one such flip moves a whole row of the weight gradient, so comparing gradients
+    across different activation patterns says nothing about the backward kernels."""
+    torch.manual_seed(gh * 100 + hidden)
+    B = 1531  # the persistent CTAs walk several tiles each
+    net = GridGNNStack(gh, gw, hidden, layers=2, precision="bf16x3").cuda()
+    assert net.fused
+    x = torch.randn(B, gh * gw, hidden, device="cuda", requires_grad=True)
+    outs, h = [], x
+    for lin in net.gnn_layers:
+        h = _GridLayerTC.apply(h, lin.weight, lin.bias, gh, gw, net.precision)
+        outs.append(h)
+    g = torch.randn_like(h)
+    h.backward(g)
+    got = [x.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+    x2 = x.detach().clone().requires_grad_(True)
+    ws = [l.weight.detach().clone().requires_grad_(True) for l in net.gnn_layers]
+    bs = [l.bias.detach().clone().requires_grad_(True) for l in net.gnn_layers]
+    with torch.no_grad():
+        y_ref = onets.grid_gnn_forward(ws, bs, x2, gh, gw)
+    assert (h - y_ref).abs().max().item() <= 1e-5 * max(1.0, y_ref.abs().max().item())
+    adj = onets.grid_adjacency(gh, gw).cuda().unsqueeze(0).expand(B, -1, -1)
+    h2 = x2
+    for w, b, o in zip(ws, bs, outs):
+        h2 = torch.bmm(adj, F.linear(h2, w, b)) * (o.detach() > 0)
+    h2.backward(g)
+    ref = [x2.grad] + [t.grad for pair in zip(ws, bs) for t in pair]
+    for a, b in zip(got, ref):
+        assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-6, (a - b).abs().max().item()
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 148 * 2 + 1])
+def test_fused_layer_ragged_batches(B):
+    """tiles with empty graph slots / a partial last tile, bf16 single-product mode at its stated tolerance (2e-2)"""
+    torch.manual_seed(B)
+    for precision, tol in (("bf16x3", 1e-5), ("bf16", 2e-2)):
+        net = GridGNNStack(7, 7, 128, layers=2, precision=precision).cuda()
+        x = torch.randn(B, 49, 128, device="cuda")
+        with torch.no_grad():
+            y = net(x)
+            y2 = onets.grid_gnn_forward([l.weight for l in net.gnn_layers], [l.bias for l in net.gnn_layers], x, 7, 7)
+        assert (y - y2).abs().max().item() <= tol * max(1.0, y2.abs().max().item())
