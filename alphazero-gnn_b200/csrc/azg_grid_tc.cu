@@ -47,16 +47,11 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t byte
 
 // 4 fp32 -> 8 bytes of the hi (and lo) operand image
 __device__ __forceinline__ void split_store4(float4 x, uint8_t* hi, uint8_t* lo, uint32_t off) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z),
-                      h3 = __float2bfloat16_rn(x.w);
-  *reinterpret_cast<uint2*>(hi + off) = make_uint2((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16),
-                                                   (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16));
-  if (lo) {
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x.y - __bfloat162float(h1)),
-                        l2 = __float2bfloat16_rn(x.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(x.w - __bfloat162float(h3));
-    *reinterpret_cast<uint2*>(lo + off) = make_uint2((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16),
-                                                     (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16));
-  }
+  uint32_t h0, h1, l0, l1;
+  split_pair(x.x, x.y, h0, l0);
+  split_pair(x.z, x.w, h1, l1);
+  *reinterpret_cast<uint2*>(hi + off) = make_uint2(h0, h1);
+  if (lo) *reinterpret_cast<uint2*>(lo + off) = make_uint2(l0, l1);
 }
 
 struct GridArgs {
@@ -140,65 +135,60 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
 
   if (warp < 8) {
     // =========================== producers ===========================
-    // A step = RS rows per thread of one (tile, k-block) item; the loads of step s+1 are in flight while step s is
-    // converted and stored.  A half-warp reads one row's 256 B of the k-block in one fully coalesced request.
-    // FWD: 8 rows = the whole item (32 KB in flight per SM); BWD loads two tensors, so it works in half items to
-    // keep the same bytes in flight within the register budget.
-    constexpr int RS = BWD ? 4 : 8, SPI = 8 / RS;
+    // An item = one (tile, k-block): 128 rows x 64 channels = 8 row groups of 16 rows; a half-warp reads one row's
+    // 256 B in one fully coalesced request.  Each thread keeps PF items (8 x PF float4) of loads in flight in a
+    // register ring with static indices: a slot is refilled with the same row group of item + PF right after it has
+    // been converted, so the global loads never wait for the pipeline (32-64 KB in flight per SM).
+    constexpr int PF = BWD ? 1 : 2;
     const int j4 = threadIdx.x & 15, r0 = threadIdx.x >> 4;  // rows r0 + 16 i, float4 j4 (4 channels) of the k-block
     const int64_t items = ((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * KB;
-    const int64_t steps = items * SPI;
-    float4 cur[RS], nxt[RS];
-    float4 cura[BWD ? RS : 1], nxta[BWD ? RS : 1];
-    auto load = [&](int64_t step, float4* v, float4* a) {
-      const int64_t it = step / SPI;
-      const int half = (int)(step % SPI);
+    float4 v[PF][8];
+    float4 a[PF][BWD ? 8 : 1];
+    auto load = [&](int64_t it, int i, float4& vv, float4& aa) {
       const int64_t tile = blockIdx.x + (it / KB) * (int64_t)gridDim.x;
       const int kb = (int)(it % KB);
-#pragma unroll
-      for (int i = 0; i < RS; ++i) {
-        const int r = r0 + 16 * (half * RS + i);
-        const int64_t row = tile * R + r;
-        if (r < R && row < total_rows) {
-          v[i] = __ldcs(reinterpret_cast<const float4*>(g.x + row * H + kb * BK) + j4);
-          if (BWD) a[i] = __ldcs(reinterpret_cast<const float4*>(g.act + row * H + kb * BK) + j4);
-        } else {
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (BWD) a[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-        }
+      const int r = r0 + 16 * i;
+      const int64_t row = tile * R + r;
+      if (r < R && row < total_rows) {
+        vv = __ldcs(reinterpret_cast<const float4*>(g.x + row * H + kb * BK) + j4);
+        if (BWD) aa = __ldcs(reinterpret_cast<const float4*>(g.act + row * H + kb * BK) + j4);
+      } else {
+        vv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BWD) aa = make_float4(1.f, 1.f, 1.f, 1.f);
       }
     };
+#pragma unroll
+    for (int p = 0; p < PF; ++p)
+      if (p < items) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) load(p, i, v[p][i], a[p][BWD ? i : 0]);
+      }
     int stage = 0;
     uint32_t phase = 0;
-    if (steps > 0) load(0, cur, cura);
-    for (int64_t step = 0; step < steps; ++step) {
-      if (step + 1 < steps) load(step + 1, nxt, nxta);
-      const int kb = (int)((step / SPI) % KB);
-      const int half = (int)(step % SPI);
-      uint8_t* sa = smem + stage * S::STAGE_BYTES;
-      if (half == 0) {
+    for (int64_t it0 = 0; it0 < items; it0 += PF) {
+#pragma unroll
+      for (int p = 0; p < PF; ++p) {
+        const int64_t it = it0 + p;
+        if (it >= items) break;
+        const int kb = (int)(it % KB);
+        const bool more = it + PF < items;
+        uint8_t* sa = smem + stage * S::STAGE_BYTES;
         mbar_wait(&empty[stage], phase ^ 1);
         if (threadIdx.x == 0) {  // this k-block of the weight image(s): contiguous in HBM/L2, one bulk copy each
           mbar_expect_tx_only(&full[stage], S::W_BYTES);
           bulk_g2s(sa + S::A_BYTES, g.w_hi + (size_t)kb * S::W_HALF, S::W_HALF, &full[stage]);
           if (X3) bulk_g2s(sa + S::A_BYTES + S::W_HALF, g.w_lo + (size_t)kb * S::W_HALF, S::W_HALF, &full[stage]);
         }
-      }
 #pragma unroll
-      for (int i = 0; i < RS; ++i) {
-        float4 v = cur[i];
-        if (BWD) {
-          const float4 a = cura[i];
-          v.x = a.x > 0.0f ? v.x : 0.0f; v.y = a.y > 0.0f ? v.y : 0.0f; v.z = a.z > 0.0f ? v.z : 0.0f; v.w = a.w > 0.0f ? v.w : 0.0f;
+        for (int i = 0; i < 8; ++i) {
+          float4 x = v[p][i];
+          if (BWD) {
+            const float4 m = a[p][BWD ? i : 0];
+            x.x = m.x > 0.0f ? x.x : 0.0f; x.y = m.y > 0.0f ? x.y : 0.0f; x.z = m.z > 0.0f ? x.z : 0.0f; x.w = m.w > 0.0f ? x.w : 0.0f;
+          }
+          split_store4(x, sa, X3 ? sa + A_STAGE_BYTES : nullptr, image_offset(r0 + 16 * i, j4 * 4));
+          if (more) load(it + PF, i, v[p][i], a[p][BWD ? i : 0]);
         }
-        split_store4(v, sa, X3 ? sa + A_STAGE_BYTES : nullptr, image_offset(r0 + 16 * (half * RS + i), j4 * 4));
-      }
-#pragma unroll
-      for (int i = 0; i < RS; ++i) {
-        cur[i] = nxt[i];
-        if (BWD) cura[i] = nxta[i];
-      }
-      if (half == SPI - 1) {
         fence_async_smem();
         mbar_arrive(&full[stage]);
         if (++stage == NST) {
@@ -246,20 +236,34 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
     }
   } else if (warp >= 12) {
     // =========================== epilogue ===========================
+    // Staging: thread = TMEM lane = tile row writes d_row * D[row, 32 columns] (d = deg^-1/2).  Gather: a warp
+    // covers 4 rows x 8 float4 per step (lanes 0-7 = 128 contiguous bytes of one row), so both the shared-memory
+    // reads and the global stores are whole 128-byte lines; out = d_row * (sum over {self, valid neighbours} of the
+    // staged rows) + rowsum * bias.  Neighbours of row r: r -/+ gw (x -/+ 1), r -/+ 1 (y -/+ 1).
     const int q = warp & 3, r = q * 32 + lane;
-    int nrow[5];
-    float ncoef[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      nrow[k] = nb_row[r * 5 + k];
-      ncoef[k] = nb_coef[r * 5 + k];
+    const int c4 = lane & 7;
+    float my_d = 0.0f;
+    {
+      float self = nb_coef[r * 5];  // d_r * d_r
+      my_d = sqrtf(self);
     }
-    const float rs = row_sum[r];
+    uint32_t it_mask[8];
+    float it_d[8], it_rs[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = q * 32 + it * 4 + (lane >> 3);
+      uint32_t m = 0;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) m |= (nb_coef[row * 5 + k] != 0.0f ? 1u : 0u) << k;
+      it_mask[it] = m;
+      it_d[it] = sqrtf(nb_coef[row * 5]);
+      it_rs[it] = row_sum[row];
+    }
+    const int gw = g.gw;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int64_t row = tile * R + r;
-      const bool valid = r < R && row < total_rows;
+      const int64_t row_base = tile * R;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H);
@@ -271,39 +275,27 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
         float4* dst = reinterpret_cast<float4*>(staging + r * ST_LD);
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          dst[e] = make_float4(__uint_as_float(rr[4 * e]), __uint_as_float(rr[4 * e + 1]), __uint_as_float(rr[4 * e + 2]),
-                               __uint_as_float(rr[4 * e + 3]));
+          dst[e] = make_float4(my_d * __uint_as_float(rr[4 * e]), my_d * __uint_as_float(rr[4 * e + 1]),
+                               my_d * __uint_as_float(rr[4 * e + 2]), my_d * __uint_as_float(rr[4 * e + 3]));
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + c4);
         named_bar(3, 128);  // the chunk of every row is staged
-        float o[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o[e] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const float cf = ncoef[k];
-          if (cf != 0.0f) {
-            const float4* src = reinterpret_cast<const float4*>(staging + nrow[k] * ST_LD);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 v = src[e];
-              o[4 * e] = fmaf(cf, v.x, o[4 * e]);
-              o[4 * e + 1] = fmaf(cf, v.y, o[4 * e + 1]);
-              o[4 * e + 2] = fmaf(cf, v.z, o[4 * e + 2]);
-              o[4 * e + 3] = fmaf(cf, v.w, o[4 * e + 3]);
-            }
-          }
-        }
-        if (valid) {
-          float4* po = reinterpret_cast<float4*>(g.out + row * H + c0);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float4 v = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
-            if (g.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + e);
-              v.x = fmaf(rs, b.x, v.x); v.y = fmaf(rs, b.y, v.y); v.z = fmaf(rs, b.z, v.z); v.w = fmaf(rs, b.w, v.w);
-            }
-            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            __stcs(po + e, v);
-          }
+        for (int it = 0; it < 8; ++it) {
+          const int row = q * 32 + it * 4 + (lane >> 3);
+          const uint32_t m = it_mask[it];
+          const float4* src = reinterpret_cast<const float4*>(staging + row * ST_LD) + c4;
+          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m & 1u) s = *src;
+          if (m & 2u) { const float4 t = *(src - gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+          if (m & 4u) { const float4 t = *(src + gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+          if (m & 8u) { const float4 t = *(src - (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+          if (m & 16u) { const float4 t = *(src + (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+          const float d = it_d[it], rs = it_rs[it];
+          float4 v = make_float4(fmaf(d, s.x, rs * b4.x), fmaf(d, s.y, rs * b4.y), fmaf(d, s.z, rs * b4.z), fmaf(d, s.w, rs * b4.w));
+          if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          const int64_t grow = row_base + row;
+          if (m != 0u && grow < total_rows) __stcs(reinterpret_cast<float4*>(g.out + grow * H + c0) + c4, v);
         }
         named_bar(4, 128);  // every row has gathered: the staging tile may be overwritten
       }
