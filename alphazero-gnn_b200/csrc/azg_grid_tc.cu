@@ -8,23 +8,21 @@
 // Each CTA owns tiles of WHOLE graphs (G = 128 / n graphs = G*n <= 128 GEMM rows), one persistent CTA per SM:
 //   warps 0-7    producers: 128-bit loads of the tile's fp32 rows (one k-block = 64 channels at a time, issued one
 //                item ahead), split into bf16 hi/lo, stored as the SWIZZLE_128B operand image of the stage;
-//                thread 0 also starts the bulk copy of the k-block's weight image (L2-resident, <= 64 KB)
+//                the weight images are resident in shared memory (one bulk copy per CTA) except for H = 256 in
+//                bf16x3 (256 KB), where thread 0 streams the k-block's weight images into the stage from L2
 //   warp 8       MMA issuer (one thread): M=128 x N=H x K=16 tcgen05.mma, 3 products per k-block in bf16x3
 //   warp 9       TMEM allocation (2 accumulators of H fp32 columns), barrier init
-//   warps 12-15  epilogue: TMEM -> registers -> fp32 staging tile in shared memory (32 columns at a time) ->
-//                each row gathers its <= 5 neighbours (coefficients d_i d_j tabulated per CTA) -> + rowsum*bias,
-//                ReLU -> 128-byte row segments to HBM
+//   warps 10-17  epilogue, two groups of four warps alternating 32-column chunks: TMEM -> registers -> fp32 staging
+//                tile in shared memory (pre-scaled by d_row) -> every row sums its <= 5 neighbours -> * d_row
+//                + rowsum*bias, ReLU -> whole 128-byte row segments to HBM
 // so the support matrix X W^T never exists in HBM: algorithmic bytes per layer = 4H read + 4H written per node.
 #include "azg_tc.cuh"
 
 namespace gridtc {
 using namespace tc;
 
-constexpr int GT_THREADS = 512;
-constexpr int EC = 32;             // epilogue chunk (columns per tcgen05.ld)
-constexpr int ST_LD = EC + 4;      // staging row stride in floats (144 B: conflict-free 128-bit accesses)
-constexpr int ST_BYTES = 128 * ST_LD * 4;
-constexpr int MISC_BYTES = 8192;   // barriers, neighbour table
+constexpr int GT_THREADS = 576;    // 8 producer warps, MMA, TMEM/barrier setup, 2 x 4 epilogue warps
+constexpr int MISC_BYTES = 5120;   // barriers, neighbour table
 
 template <int H, bool X3>
 struct GridSmem {
@@ -32,11 +30,25 @@ struct GridSmem {
   static constexpr int A_BYTES = (X3 ? 2 : 1) * A_STAGE_BYTES;
   static constexpr int W_HALF = H * 128;  // one k-block of one weight image
   static constexpr int W_BYTES = (X3 ? 2 : 1) * W_HALF;
-  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  static constexpr int BUDGET = 232448 - 1024 - MISC_BYTES - ST_BYTES;
-  static constexpr int NST = BUDGET / STAGE_BYTES < 4 ? BUDGET / STAGE_BYTES : 4;
-  static constexpr int ST_OFF = NST * STAGE_BYTES;
-  static constexpr int MISC_OFF = ST_OFF + ST_BYTES;
+  static constexpr int W_TOTAL = KB * W_BYTES;  // the whole weight operand (hi and lo images)
+  static constexpr int AVAIL = 232448 - 1024 - MISC_BYTES;
+  static constexpr int ST32 = 2 * 128 * 36 * 4;  // two staging tiles of 32-column chunks
+  // WRES: the weight images stay resident in shared memory for the life of the CTA (one bulk copy at start) and a
+  // pipeline stage holds only the A operand; otherwise (H = 256 in bf16x3: 256 KB of weights) every stage also
+  // carries its k-block of the weights, re-streamed from L2 per tile.
+  static constexpr bool WRES = (AVAIL - ST32 - W_TOTAL) / A_BYTES >= 2;
+  static constexpr int STAGE_BYTES = A_BYTES + (WRES ? 0 : W_BYTES);
+  static constexpr int W_RES_BYTES = WRES ? W_TOTAL : 0;
+  // epilogue chunk = columns per tcgen05.ld; two staging tiles (one per epilogue group) of 128 rows x (EC + 4) floats
+  // (row stride 144 / 80 B: conflict-free 128-bit accesses).  32 columns unless that leaves fewer than two stages.
+  static constexpr int EC = (AVAIL - W_RES_BYTES - ST32) / STAGE_BYTES >= 2 ? 32 : 16;
+  static constexpr int ST_LD = EC + 4;
+  static constexpr int ST_BYTES = 128 * ST_LD * 4;
+  static constexpr int BUDGET = AVAIL - W_RES_BYTES - 2 * ST_BYTES;
+  static constexpr int NST = BUDGET / STAGE_BYTES < 6 ? BUDGET / STAGE_BYTES : 6;
+  static constexpr int STAGE_OFF = W_RES_BYTES;
+  static constexpr int ST_OFF = STAGE_OFF + NST * STAGE_BYTES;
+  static constexpr int MISC_OFF = ST_OFF + 2 * ST_BYTES;
   static constexpr int TOTAL = MISC_OFF + MISC_BYTES + 1024;
   static_assert(NST >= 2, "at least two pipeline stages");
 };
@@ -67,9 +79,9 @@ struct GridArgs {
 };
 
 template <int H, bool X3, bool BWD>
-__global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g) {
+__global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g) {  // 18 warps: 96 registers per thread
   using S = GridSmem<H, X3>;
-  constexpr int KB = S::KB, NST = S::NST;
+  constexpr int KB = S::KB, NST = S::NST, EC = S::EC, ST_LD = S::ST_LD;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* staging = (float*)(smem + S::ST_OFF);
@@ -77,10 +89,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
   uint64_t* empty = full + NST;
   uint64_t* tfull = empty + NST;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
   float* nb_coef = (float*)(smem + S::MISC_OFF + 256);  // [128][5]
   float* row_sum = nb_coef + 128 * 5;                   // [128]
-  int16_t* nb_row = (int16_t*)(row_sum + 128);          // [128][5] tile rows
+  float* row_d = row_sum + 128;                         // [128] deg^-1/2 (0 for unused tile rows)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = g.gh * g.gw;
@@ -94,7 +107,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
   for (int i = threadIdx.x; i < 128 * 5; i += blockDim.x) {
     const int r = i / 5, k = i % 5;
     float coef = 0.0f;
-    int row = r;
     if (r < R) {
       const int slot = r / n, node = r - slot * n, x = node / g.gw, y = node - x * g.gw;
       const int dx = (k == 1) ? -1 : (k == 2) ? 1 : 0, dy = (k == 3) ? -1 : (k == 4) ? 1 : 0;
@@ -103,11 +115,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
         const int di = 1 + (x > 0) + (x < g.gh - 1) + (y > 0) + (y < g.gw - 1);
         const int dj = 1 + (nx > 0) + (nx < g.gh - 1) + (ny > 0) + (ny < g.gw - 1);
         coef = (1.0f / sqrtf((float)di)) * (1.0f / sqrtf((float)dj));
-        row = slot * n + nx * g.gw + ny;
       }
     }
     nb_coef[i] = coef;
-    nb_row[i] = (int16_t)row;
   }
   if (warp == 9 && lane == 0) {
     for (int s = 0; s < NST; ++s) {
@@ -116,8 +126,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 256);
     }
+    mbar_init(wbar, 1);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -127,19 +138,27 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
 #pragma unroll
     for (int k = 0; k < 5; ++k) s += nb_coef[threadIdx.x * 5 + k];
     row_sum[threadIdx.x] = s;
+    row_d[threadIdx.x] = sqrtf(nb_coef[threadIdx.x * 5]);  // coefficient 0 of a row is d_r * d_r
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (S::WRES && warp == 9 && lane == 0) {  // weight images -> shared memory, once per CTA
+    mbar_expect_tx(wbar, S::W_TOTAL);
+    for (int kb = 0; kb < KB; ++kb) {
+      bulk_g2s(smem + kb * S::W_HALF, g.w_hi + (size_t)kb * S::W_HALF, S::W_HALF, wbar);
+      if (X3) bulk_g2s(smem + (KB + kb) * S::W_HALF, g.w_lo + (size_t)kb * S::W_HALF, S::W_HALF, wbar);
+    }
+  }
   if (warp < 8) {
     // =========================== producers ===========================
     // An item = one (tile, k-block): 128 rows x 64 channels = 8 row groups of 16 rows; a half-warp reads one row's
     // 256 B in one fully coalesced request.  Each thread keeps PF items (8 x PF float4) of loads in flight in a
     // register ring with static indices: a slot is refilled with the same row group of item + PF right after it has
-    // been converted, so the global loads never wait for the pipeline (32-64 KB in flight per SM).
-    constexpr int PF = BWD ? 1 : 2;
+    // been converted, so the global loads never wait for the pipeline.
+    constexpr int PF = 1;  // 8 float4 (x2 in BWD) per thread = 32 KB (64 KB) of loads in flight per SM
     const int j4 = threadIdx.x & 15, r0 = threadIdx.x >> 4;  // rows r0 + 16 i, float4 j4 (4 channels) of the k-block
     const int64_t items = ((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * KB;
     float4 v[PF][8];
@@ -172,9 +191,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
         if (it >= items) break;
         const int kb = (int)(it % KB);
         const bool more = it + PF < items;
-        uint8_t* sa = smem + stage * S::STAGE_BYTES;
+        uint8_t* sa = smem + S::STAGE_OFF + stage * S::STAGE_BYTES;
         mbar_wait(&empty[stage], phase ^ 1);
-        if (threadIdx.x == 0) {  // this k-block of the weight image(s): contiguous in HBM/L2, one bulk copy each
+        if (!S::WRES && threadIdx.x == 0) {  // this k-block of the weight image(s): contiguous in HBM/L2, one bulk copy each
           mbar_expect_tx_only(&full[stage], S::W_BYTES);
           bulk_g2s(sa + S::A_BYTES, g.w_hi + (size_t)kb * S::W_HALF, S::W_HALF, &full[stage]);
           if (X3) bulk_g2s(sa + S::A_BYTES + S::W_HALF, g.w_lo + (size_t)kb * S::W_HALF, S::W_HALF, &full[stage]);
@@ -203,6 +222,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
       constexpr uint32_t idesc = make_idesc(BM, H);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      if (S::WRES) mbar_wait(wbar, 0);
+      const uint32_t w_res = smem_u32(smem);
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -210,9 +231,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + S::STAGE_OFF + stage * S::STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_STAGE_BYTES);
-          const uint64_t b_hi = make_smem_desc(sa + S::A_BYTES), b_lo = make_smem_desc(sa + S::A_BYTES + S::W_HALF);
+          const uint64_t b_hi = make_smem_desc(S::WRES ? w_res + kb * S::W_HALF : sa + S::A_BYTES);
+          const uint64_t b_lo = make_smem_desc(S::WRES ? w_res + (KB + kb) * S::W_HALF : sa + S::A_BYTES + S::W_HALF);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
           if (X3) {
@@ -234,30 +256,26 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
         }
       }
     }
-  } else if (warp >= 12) {
-    // =========================== epilogue ===========================
-    // Staging: thread = TMEM lane = tile row writes d_row * D[row, 32 columns] (d = deg^-1/2).  Gather: a warp
-    // covers 4 rows x 8 float4 per step (lanes 0-7 = 128 contiguous bytes of one row), so both the shared-memory
-    // reads and the global stores are whole 128-byte lines; out = d_row * (sum over {self, valid neighbours} of the
-    // staged rows) + rowsum * bias.  Neighbours of row r: r -/+ gw (x -/+ 1), r -/+ 1 (y -/+ 1).
+  } else if (warp >= 10) {
+    // =========================== epilogue: two groups of four warps, alternating column chunks ===========================
+    // Staging: thread = TMEM lane = tile row writes d_row * D[row, EC columns] (d = deg^-1/2).  Gather: a warp covers
+    // RPS rows x EC/4 float4 per step (a row's chunk is contiguous in shared memory and in HBM), so shared-memory
+    // reads and global stores are whole lines; out = d_row * (sum over {self, valid neighbours} of the staged rows)
+    // + rowsum * bias.  Neighbours of row r: r -/+ gw (x -/+ 1), r -/+ 1 (y -/+ 1).
+    constexpr int LPR = EC / 4, RPS = 32 / LPR, STEPS = 32 / RPS;  // lanes per row, rows per step, steps per quarter
+    const int grp = (warp - 10) >> 2;
     const int q = warp & 3, r = q * 32 + lane;
-    const int c4 = lane & 7;
-    float my_d = 0.0f;
-    {
-      float self = nb_coef[r * 5];  // d_r * d_r
-      my_d = sqrtf(self);
-    }
-    uint32_t it_mask[8];
-    float it_d[8], it_rs[8];
+    const int c4 = lane % LPR;
+    float* stg = staging + grp * (S::ST_BYTES / 4);
+    const float my_d = row_d[r];
+    uint32_t it_mask[STEPS];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = q * 32 + it * 4 + (lane >> 3);
+    for (int it = 0; it < STEPS; ++it) {
+      const int row = q * 32 + it * RPS + lane / LPR;
       uint32_t m = 0;
 #pragma unroll
       for (int k = 0; k < 5; ++k) m |= (nb_coef[row * 5 + k] != 0.0f ? 1u : 0u) << k;
       it_mask[it] = m;
-      it_d[it] = sqrtf(nb_coef[row * 5]);
-      it_rs[it] = row_sum[row];
     }
     const int gw = g.gw;
     int acc = 0;
@@ -268,36 +286,37 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H);
 #pragma unroll 1
-      for (int c0 = 0; c0 < H; c0 += EC) {
-        uint32_t rr[32];
-        tmem_ld32(taddr + (uint32_t)c0, rr);
+      for (int c0 = grp * EC; c0 < H; c0 += 2 * EC) {
+        uint32_t rr[EC];
+        if (EC == 32) tmem_ld32(taddr + (uint32_t)c0, rr);
+        else tmem_ld16(taddr + (uint32_t)c0, rr);
         tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(staging + r * ST_LD);
+        float4* dst = reinterpret_cast<float4*>(stg + r * ST_LD);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
+        for (int e = 0; e < EC / 4; ++e)
           dst[e] = make_float4(my_d * __uint_as_float(rr[4 * e]), my_d * __uint_as_float(rr[4 * e + 1]),
                                my_d * __uint_as_float(rr[4 * e + 2]), my_d * __uint_as_float(rr[4 * e + 3]));
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + c4);
-        named_bar(3, 128);  // the chunk of every row is staged
+        named_bar(3 + 2 * grp, 128);  // the chunk of every row is staged
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = q * 32 + it * 4 + (lane >> 3);
+        for (int it = 0; it < STEPS; ++it) {
+          const int row = q * 32 + it * RPS + lane / LPR;
           const uint32_t m = it_mask[it];
-          const float4* src = reinterpret_cast<const float4*>(staging + row * ST_LD) + c4;
+          const float4* src = reinterpret_cast<const float4*>(stg + row * ST_LD) + c4;
           float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
           if (m & 1u) s = *src;
           if (m & 2u) { const float4 t = *(src - gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
           if (m & 4u) { const float4 t = *(src + gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
           if (m & 8u) { const float4 t = *(src - (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
           if (m & 16u) { const float4 t = *(src + (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-          const float d = it_d[it], rs = it_rs[it];
+          const float d = row_d[row], rs = row_sum[row];
           float4 v = make_float4(fmaf(d, s.x, rs * b4.x), fmaf(d, s.y, rs * b4.y), fmaf(d, s.z, rs * b4.z), fmaf(d, s.w, rs * b4.w));
           if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
           const int64_t grow = row_base + row;
           if (m != 0u && grow < total_rows) __stcs(reinterpret_cast<float4*>(g.out + grow * H + c0) + c4, v);
         }
-        named_bar(4, 128);  // every row has gathered: the staging tile may be overwritten
+        named_bar(4 + 2 * grp, 128);  // every row has gathered: the staging tile may be overwritten
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);

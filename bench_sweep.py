@@ -25,6 +25,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--precisions", default="bf16x3,bf16,fp32")
+    ap.add_argument("--grids", default="3x3,4x4,6x7,7x7,8x8,16x16")
+    ap.add_argument("--hiddens", default="64,128,256")
+    ap.add_argument("--batches", default="1024,16384,262144")
     args = ap.parse_args()
     peaks = {}
     try:
@@ -32,8 +35,8 @@ def main():
     except Exception:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
-    grids = [(3, 3), (4, 4), (6, 7), (7, 7), (8, 8), (16, 16)]
-    hiddens = [64, 128, 256]
+    grids = [tuple(int(v) for v in gs.split("x")) for gs in args.grids.split(",")]
+    hiddens = [int(v) for v in args.hiddens.split(",")]
     budget = 2 ** 31  # elements per activation tensor
     rows = []
 
@@ -52,7 +55,7 @@ def main():
     for gh, gw in grids:
         for H in hiddens:
             n = gh * gw
-            for B in ([4096] if args.quick else [1024, 16384, 262144]):
+            for B in ([4096] if args.quick else [int(v) for v in args.batches.split(",")]):
                 if B * n * H > budget // 4:
                     continue
                 for prec in args.precisions.split(","):
