@@ -638,6 +638,34 @@ __global__ void __launch_bounds__(256) heads_image_kernel(const uint8_t* __restr
 }
 
 // logits = fixed-order sum of the per-tile partial head sums + bias; then exp(log_softmax) and tanh
+// AZG_EVAL_FOLD: no non-linearity lies between output_transform.2 and the policy/value heads
+// (gnn_utils.py:99-103 -> Connect4GNN.py:48-57), so   heads(W2 h + b2) = ([Wp; Wv] W2) h + ([Wp; Wv] b2 + [bp; bv]).
+// fold_w[a, j] = sum_n hc[a, n] W2[n, j]  (fp64 accumulation, once per weight version); hc = concatenated heads [32, F].
+__global__ void __launch_bounds__(128) fold_heads_kernel(const float* __restrict__ hc, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, const float* __restrict__ bias32, int rows,
+                                                         int F, float* __restrict__ fold_w, float* __restrict__ fold_b) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < F) {
+    double acc[HEAD_ROWS];
+#pragma unroll
+    for (int a = 0; a < HEAD_ROWS; ++a) acc[a] = 0.0;
+    for (int n = 0; n < F; ++n) {
+      const double w = (double)w2[(size_t)n * F + j];
+#pragma unroll
+      for (int a = 0; a < HEAD_ROWS; ++a)
+        if (a < rows) acc[a] += (double)__ldg(hc + (size_t)a * F + n) * w;
+    }
+#pragma unroll
+    for (int a = 0; a < HEAD_ROWS; ++a)
+      if (a < rows) fold_w[(size_t)a * F + j] = (float)acc[a];
+  } else if (j - F < rows) {
+    const int a = j - F;
+    double acc = (double)bias32[a];
+    for (int n = 0; n < F; ++n) acc += (double)hc[(size_t)a * F + n] * (double)b2[n];
+    fold_b[a] = (float)acc;
+  }
+}
+
 __global__ void heads_finalize_kernel(const float* __restrict__ part, int n_tiles, int A, const float* __restrict__ bp,
                                       const float* __restrict__ bv, int64_t B, const int32_t* __restrict__ dyn_rows,
                                       float* __restrict__ pi, float* __restrict__ v) {
@@ -995,7 +1023,7 @@ int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R
 //   W2 (output_transform.2) hi [lo] | conv2 [64 x 320] hi [lo] | head weights permuted, fp32
 namespace {
 struct PackLayout {
-  size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, heads_cat, hd_hi, hd_lo, bias32, total;
+  size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, heads_cat, hd_hi, hd_lo, bias32, fold_w, fold_b, total;
   bool x3, gnn;
 };
 
@@ -1021,6 +1049,8 @@ PackLayout pack_layout(int n, int prec, bool gnn) {
   L.hd_hi = take((size_t)32 * F * 2);           // std heads as a [32 x F] weight image (feature-image order)
   L.hd_lo = L.x3 ? take((size_t)32 * F * 2) : 0;
   L.bias32 = take(32 * 4);
+  L.fold_w = gnn ? take((size_t)tc::HEAD_ROWS * F * 4) : 0;  // [Wp; Wv] W2 (AZG_EVAL_FOLD)
+  L.fold_b = gnn ? take(32 * 4) : 0;                         // [Wp; Wv] b2 + [bp; bv]
   L.total = off;
   return L;
 }
@@ -1134,12 +1164,27 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   g.pair_ok = 1;
   g.dyn_rows = dyn_rows;
   g.a_hi = f_hi; g.a_lo = f_lo; g.w_hi = w + L.w0_hi; g.w_lo = x3 ? w + L.w0_lo : nullptr; g.bias = p->ot0_b; g.relu = 1;
+  AZG_REQUIRE(g.n_tiles <= 16 && A + 1 <= tc::HEAD_ROWS, "tcgen05 path: head fusion limits exceeded");
+  if (eval_mask & AZG_EVAL_FOLD) {
+    // output_transform.2 and the heads folded into one [A+1, F] matrix (see fold_heads_kernel): GEMM-1's epilogue
+    // applies it to relu(H) tile by tile; H and E never exist in HBM and the second F x F contraction is gone
+    g.out_mode = tc::OUT_HEADS; g.out_hi = g.out_lo = nullptr; g.out_f32 = nullptr;
+    g.head_w = (const float*)(w + L.fold_w); g.head_rows = A + 1; g.head_part = (float*)(sc + S.part);
+    if ((rc = tc::run_gemm(BN, g, st))) return rc;
+    azg_phase_end(AZG_PHASE_GEMM, st);
+    azg_phase_begin(AZG_PHASE_HEADS, st);
+    const float* fb = (const float*)(w + L.fold_b);
+    tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles, A, fb, fb + A, B, dyn_rows,
+                                                                          pi_gnn, v_gnn);
+    AZG_LAUNCH_CHECK();
+    azg_phase_end(AZG_PHASE_HEADS, st);
+    return AZG_OK;
+  }
   g.out_mode = x3 ? tc::OUT_IMG_HILO : tc::OUT_IMG; g.out_hi = h_hi; g.out_lo = h_lo;
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
   g.a_hi = h_hi; g.a_lo = h_lo; g.w_hi = w + L.w2_hi; g.w_lo = x3 ? w + L.w2_lo : nullptr; g.bias = p->ot2_b; g.relu = 0;
   g.out_mode = tc::OUT_HEADS; g.out_hi = g.out_lo = nullptr; g.out_f32 = nullptr;
   g.head_w = (const float*)(w + L.heads_cat); g.head_rows = A + 1; g.head_part = (float*)(sc + S.part);
-  AZG_REQUIRE(g.n_tiles <= 16 && A + 1 <= tc::HEAD_ROWS, "tcgen05 path: head fusion limits exceeded");
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
   azg_phase_end(AZG_PHASE_GEMM, st);
   azg_phase_begin(AZG_PHASE_HEADS, st);
@@ -1184,6 +1229,12 @@ int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t pa
   tc::concat_heads_kernel<<<(unsigned)(((int64_t)32 * F + 255) / 256), 256, 0, st>>>(
       p->fc_policy_w, p->fc_value_w, p->fc_policy_b, p->fc_value_b, A, F, (float*)(w + L.heads_cat), (float*)(w + L.bias32));
   AZG_LAUNCH_CHECK();
+  if (p->ot2_w && p->ot2_b) {
+    tc::fold_heads_kernel<<<(F + 32 + 127) / 128, 128, 0, st>>>((const float*)(w + L.heads_cat), p->ot2_w, p->ot2_b,
+                                                                (const float*)(w + L.bias32), A + 1, F, (float*)(w + L.fold_w),
+                                                                (float*)(w + L.fold_b));
+    AZG_LAUNCH_CHECK();
+  }
   {
     const int64_t cnt = (int64_t)32 * (F / 8);
     tc::permuted_weight_image_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((const float*)(w + L.heads_cat), 32, F, nn, 32,

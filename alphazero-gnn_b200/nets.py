@@ -139,6 +139,8 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         self.nnet = modules.Connect4Trunk(self.n, self.action_size, 0.3 if dropout is None else dropout).to(self.device)
         self.gnn = None
         self.precision = _lib.PRECISIONS[arg(args, "b200_precision", "fp32") or "fp32"]
+        # opt-in: evaluate predict_with_gnn with output_transform.2 folded into the heads (_lib.EVAL_FOLD)
+        self.fold_heads = bool(arg(args, "b200_fold_heads", False))
         self._packed, self._packed_ok = {}, False
 
     def _params(self, prec, need_packed):
@@ -173,6 +175,8 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         if (eval_mask & _lib.EVAL_GNN) and self.gnn is None:
             raise RuntimeError("predict_with_gnn needs the GNN wrapper")
         prec = self.precision if precision is None else precision
+        if self.fold_heads and prec != _lib.PREC_FP32 and (eval_mask & _lib.EVAL_GNN):
+            eval_mask |= _lib.EVAL_FOLD
         B = int(states.shape[0])
         o = self._outputs(B, eval_mask)
         if B == 0:

@@ -300,6 +300,26 @@ def run_gpu_arm(args, rank, local_rank, world):
                        "note": {"bf16": "single bf16 product, fp32 accumulate; stated tolerance 5e-3 on pi and v",
                                 "bf16x3": "3-term bf16 split, fp32 accumulate; pi and v within 1e-5 of the reference"}[other]}
 
+    # ---- opt-in algebraic fold of output_transform.2 into the heads (same outputs, one F x F contraction) ----
+    if args.precision != "fp32":
+        net.fold_heads = True
+        for i in range(3):
+            net.forward_states(dev_states[i % n_rot], mask)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(10):
+            net.forward_states(dev_states[i % n_rot], mask)
+        a1.record()
+        torch.cuda.synchronize()
+        net.fold_heads = False
+        also[args.precision + "_folded_heads"] = {
+            "value": B * 10 / (a0.elapsed_time(a1) / 1e3), "unit": "leaf_evals/s per GPU", "ms_per_step": a0.elapsed_time(a1) / 10,
+            "note": "b200_fold_heads=True: no non-linearity lies between output_transform.2 and the policy/value heads, so "
+                    "[Wp;Wv] W2 is folded once per weight version and applied in GEMM-1's epilogue; pi and v stay within the "
+                    "fp32 contract (tests/test_nets_gpu.py::test_folded_heads_match_reference). Not the headline: `value` "
+                    "runs both F x F contractions as the reference does."}
+
     # ---- end-to-end through the host-facing API ----
     for i in range(3):
         step_e2e(i)

@@ -42,6 +42,9 @@ extern "C" {
 /* which predictions to produce (MCTS.py:169-178 evaluates both when use_gnn) */
 #define AZG_EVAL_STD 1 /* NeuralNet.predict            */
 #define AZG_EVAL_GNN 2 /* NeuralNet.predict_with_gnn   */
+#define AZG_EVAL_FOLD 4 /* with AZG_EVAL_GNN on the tensor-core path: output_transform.2 folded into the policy/value heads
+                         (no non-linearity between them, gnn_utils.py:99-103 -> Connect4GNN.py:48-57): same pi/v within the
+                         fp32 contract, half the F x F contractions.  Opt-in; ignored by the fp32 path. */
 
 /* arithmetic of the dense F x F contractions (output_transform, gnn_utils.py:99-103) */
 #define AZG_PREC_FP32 0   /* fp32 FFMA on CUDA cores                                  */

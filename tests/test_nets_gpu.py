@@ -240,3 +240,39 @@ def test_bf16x3_margin_under_weight_scale(scale):
     e_v = np.abs(o3["v_gnn"].cpu().numpy() - gv.numpy()).max()
     print(f"scale {scale}: max |dpi| = {e_pi:.2e}, max |dv| = {e_v:.2e}, max pi = {gpi.max().item():.3f}")
     assert e_pi <= 1e-5 and e_v <= 2e-5
+
+
+@pytest.mark.parametrize("n,B", [(7, 1), (7, 777), (5, 300), (8, 300)])
+@pytest.mark.parametrize("scale", [1.0, 3.0])
+def test_folded_heads_match_reference(n, B, scale):
+    """EVAL_FOLD: heads(W2 h + b2) evaluated as ([Wp; Wv] W2) h + const in GEMM-1's epilogue (no second F x F
+    contraction).  Same pi / v as the reference module within the fp32 contract, also with scaled weights, and it
+    follows weight updates."""
+    w = _wrapper("c4", n)
+    if scale != 1.0:
+        with torch.no_grad():
+            for p_ in list(w.nnet.parameters()) + list(w.gnn.output_transform.parameters()):
+                if p_.dim() > 1:
+                    p_.mul_(scale ** 0.5)
+        w.weights_changed()
+    rng = np.random.default_rng(B + n)
+    boards = rng.integers(-1, 2, size=(B, n, n)).astype(np.int64)
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    with torch.no_grad():
+        gpi, gv = onets.c4_predict_with_gnn(p, q, onets.boards_to_tensor(boards), n)
+    states = w.states_from_boards(boards)
+    w.fold_heads = True
+    o = w.forward_states(states, _lib.EVAL_STD | _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
+    e_pi = np.abs(o["pi_gnn"].cpu().numpy() - gpi.numpy()).max()
+    e_v = np.abs(o["v_gnn"].cpu().numpy() - gv.numpy()).max()
+    print(f"folded n={n} B={B} scale={scale}: max |dpi| = {e_pi:.2e}, max |dv| = {e_v:.2e}")
+    assert e_pi <= 1e-5 and e_v <= 2e-5
+    w.fold_heads = False
+    ref = w.forward_states(states, _lib.EVAL_STD | _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
+    assert torch.equal(ref["pi"], o["pi"])  # the standard prediction is untouched
+    with torch.no_grad():
+        w.gnn.output_transform[2].bias.add_(0.25)
+    w.weights_changed()
+    w.fold_heads = True
+    o2 = w.forward_states(states, _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
+    assert not np.allclose(o2["v_gnn"].cpu().numpy(), o["v_gnn"].cpu().numpy())
