@@ -354,8 +354,6 @@ int launch_conv(const float* in, const float* w, const float* b, float* out, int
 
 int launch_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K, int relu,
                   cudaStream_t st) {
-  // fewer than ~1.5 waves of 128 x 128 tiles: the split-K / matrix-vector kernels of azg_train.cu fill the SMs instead
-  if (azg_ceil_div(M, SG_BM) * azg_ceil_div(N, SG_BN) < 222) return azg_train_linear_fwd(A, W, bias, C, M, N, K, relu, st);
   AZG_REQUIRE(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
   AZG_REQUIRE(N <= 65535 * SG_BN, "linear: N=%d too large for one launch", N);
   dim3 grid((unsigned)((M + SG_BM - 1) / SG_BM), (N + SG_BN - 1) / SG_BN);
@@ -439,6 +437,10 @@ int azg_linear_f32(const float* A, const float* W, const float* bias, float* C, 
                    azg_stream stream) {
   AZG_REQUIRE(A && W && C, "azg_linear_f32: null pointer");
   if (M <= 0) return AZG_OK;
+  // Training-step entry point: with fewer than ~1.5 waves of 128 x 128 tiles the split-K / matrix-vector kernels of
+  // azg_train.cu fill the SMs instead.  The inference path (launch_linear) never takes this route: there a row's
+  // result must not depend on how many other rows share the batch (bit-exact tree statistics, tests/test_arena_gpu.py).
+  if (azg_ceil_div(M, SG_BM) * azg_ceil_div(N, SG_BN) < 222) return azg_train_linear_fwd(A, W, bias, C, M, N, K, relu, (cudaStream_t)stream);
   return launch_linear(A, W, bias, C, M, N, K, relu, (cudaStream_t)stream);
 }
 
