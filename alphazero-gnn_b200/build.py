@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libazgnn_b200.so")
-SOURCES = ["azg_api.cu", "azg_arena.cu", "azg_nets.cu", "azg_gemm_tc.cu", "azg_train.cu", "azg_grid_tc.cu"]
+SOURCES = ["azg_api.cu", "azg_arena.cu", "azg_nets.cu", "azg_gemm_tc.cu", "azg_train.cu", "azg_grid_tc.cu", "azg_replay.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
               "-cudart", "static"]

@@ -8,12 +8,15 @@ Coach.py:16-176) on top of the arena.
 * `learn()` keeps the reference's iteration structure (self-play -> history window -> train ->
   pit new vs previous -> accept/reject -> checkpoints, Coach.py:87-176) but collects the
   `numEps` episodes with `BatchedSelfPlay` (`n_parallel_games` concurrent games, default
-  min(numEps, 4096)) and pits with the arena-backed MCTS.  Example pickling and `--load_model`
-  resume stay in the reference's own Coach (out of scope).
+  min(numEps, 4096)) and pits with the arena-backed MCTS.  On a GPU the standard examples never
+  leave HBM (`replay.DeviceExamples`: symmetries, value signing, history window, shuffle and
+  minibatch gather on the device); `saveTrainExamples` / `loadTrainExamples` read and write the
+  reference's pickle format (Coach.py:178-201).
 """
 import logging
 import os
 from collections import deque
+from pickle import Pickler, Unpickler
 from random import shuffle
 
 import numpy as np
@@ -100,6 +103,45 @@ class Coach:
     def getCheckpointFile(self, iteration):
         return f"checkpoint_{iteration}" + ("_gnn" if self._use_gnn() else "") + ".pth.tar"
 
+    @staticmethod
+    def _clip(examples, maxlen):
+        """deque(maxlen) semantics for a device buffer: keep the newest `maxlen` examples"""
+        if maxlen is not None and len(examples) > maxlen:
+            from .replay import DeviceExamples
+            out = DeviceExamples.__new__(DeviceExamples)
+            out.__dict__.update(examples.__dict__)
+            k = len(examples) - maxlen
+            out.states, out.pi, out.v, out.vtag, out.sym = (t[k:] for t in (examples.states, examples.pi, examples.v,
+                                                                            examples.vtag, examples.sym))
+            return out
+        return examples
+
+    def _folder(self):
+        return arg(self.args, "checkpoint", arg(self.args, "checkpoint_path", "./checkpoints/"))
+
+    # ------------------------------------------------------------------ Coach.py:178-201
+    def saveTrainExamples(self, iteration):
+        """the reference's file: a pickled list of (deque of (board, pi, v), deque of GNN tuples) per iteration"""
+        folder = self._folder()
+        if not os.path.exists(folder):
+            os.makedirs(folder)
+        maxlen = arg(self.args, "maxlenOfQueue")
+        history = [(deque(std.to_examples() if hasattr(std, "to_examples") else std, maxlen=maxlen), deque(gnn, maxlen=maxlen))
+                   for std, gnn in self.trainExamplesHistory]
+        with open(os.path.join(folder, self.getCheckpointFile(iteration) + ".examples"), "wb+") as f:
+            Pickler(f).dump(history)
+
+    def loadTrainExamples(self, examples_file=None):
+        if examples_file is None:
+            lf = arg(self.args, "load_folder_file")
+            examples_file = os.path.join(lf[0], lf[1]) + ".examples"
+        with open(examples_file, "rb") as f:
+            history = Unpickler(f).load()
+        if self._arena_factory is None:
+            from .replay import DeviceExamples
+            history = [(DeviceExamples.from_examples(self.game, list(std)), gnn) for std, gnn in history]
+        self.trainExamplesHistory = history
+
     # ------------------------------------------------------------------ Coach.py:87-176
     def learn(self):
         a = self.args
@@ -109,19 +151,32 @@ class Coach:
             it_gnn = deque([], maxlen=arg(a, "maxlenOfQueue"))
             n_eps = arg(a, "numEps")
             games = int(arg(a, "n_parallel_games", min(n_eps, 4096)) or min(n_eps, 4096))
-            sp = BatchedSelfPlay(self.game, self.nnet, a, games, seed=i,
+            on_device = self._arena_factory is None  # the CPU check arena of the tests keeps host tuples
+            sp = BatchedSelfPlay(self.game, self.nnet, a, games, seed=i, collect_examples="device" if on_device else True,
                                  arena=self._arena_factory(games) if self._arena_factory else None)
             for std, gnn in sp.play(n_eps):
                 it_std += std
                 it_gnn += gnn
+            if on_device:
+                it_std = self._clip(sp.device_examples, arg(a, "maxlenOfQueue"))
             self.trainExamplesHistory.append((it_std, it_gnn))
             if len(self.trainExamplesHistory) > arg(a, "numItersForTrainExamplesHistory"):
                 self.trainExamplesHistory.pop(0)
-            trainExamples, gnnExamples = [], []
-            for std, gnn in self.trainExamplesHistory:
-                trainExamples.extend(std)
+            self.saveTrainExamples(i - 1)
+            gnnExamples = []
+            for _std, gnn in self.trainExamplesHistory:
                 gnnExamples.extend(gnn)
-            shuffle(trainExamples)
+            if on_device:
+                from .replay import DeviceExamples
+                trainExamples = DeviceExamples(self.game)
+                for std, _gnn in self.trainExamplesHistory:
+                    trainExamples.extend(std)
+                trainExamples = trainExamples.shuffled()  # random.shuffle's permutation, applied on the device
+            else:
+                trainExamples = []
+                for std, _gnn in self.trainExamplesHistory:
+                    trainExamples.extend(std)
+                shuffle(trainExamples)
             shuffle(gnnExamples)
             folder = arg(a, "checkpoint", arg(a, "checkpoint_path", "./checkpoints/"))
             self.nnet.save_checkpoint(folder=folder, filename="temp.pth.tar")

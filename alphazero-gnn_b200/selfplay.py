@@ -84,7 +84,11 @@ class BatchedSelfPlay:
         self.mcts = BatchedMCTS(game, nnet, args, n_games=self.G, arena=arena)
         self.kind, self.n, self.A = self.mcts.kind, self.mcts.n, self.mcts.A
         self.rng = np.random.default_rng(seed)
+        # collect_examples: False (throughput runs), True (host lists, the reference's tuples), or "device": standard
+        # examples are assembled on the GPU (replay.DeviceExamples: history in HBM, symmetries + value signing in one
+        # kernel per batch of finished episodes) and `play` returns them as ONE DeviceExamples
         self.collect = collect_examples
+        self.device_collect = collect_examples == "device"
         self.temp_threshold = int(arg(args, "tempThreshold", 15))
         self.expand_by = int(arg(args, "expand_by", 5))
         self.two_player = bool(getattr(game, "is_two_player", True))
@@ -94,6 +98,19 @@ class BatchedSelfPlay:
         self.max_episode_steps = max_episode_steps
         self.moves_played = 0
         self.episodes_done = 0
+        self._budget = None
+        if self.device_collect:
+            from .replay import DeviceExamples
+            dev = self.mcts.arena.device if hasattr(self.mcts.arena, "device") else torch.device("cuda", torch.cuda.current_device())
+            nn = self.n * self.n
+            self.t_cap = int(max_episode_steps) if max_episode_steps is not None else nn + 2
+            assert self.two_player or max_episode_steps is not None, "device collection of single-player episodes needs max_episode_steps"
+            self.dev = dev
+            self.h_states = torch.zeros(self.t_cap, self.G, 2, dtype=torch.int64, device=dev)
+            self.h_pi = torch.zeros(self.t_cap, self.G, self.A, dtype=torch.float64, device=dev)
+            self.h_player = torch.zeros(self.t_cap, self.G, dtype=torch.int32, device=dev)
+            self.h_int = torch.zeros(self.t_cap, self.G, dtype=torch.int8, device=dev)
+            self.device_examples = DeviceExamples(game, dev)
         self._start_all()
 
     # ------------------------------------------------------------------ episode bookkeeping
@@ -130,6 +147,41 @@ class BatchedSelfPlay:
                 gnn.append((board, pl, ip, iv, ep, ev, sign))
         return std, gnn
 
+    def _finish_device(self, done, ended):
+        """Coach.py:68-79 for all episodes that ended on this move: one gather of their history slots and one
+        emit kernel (symmetries + signed values) append the standard examples to `self.device_examples`; GNN
+        records (no symmetries, host-computed by expand_tree) are returned as the reference's tuples."""
+        done = np.asarray(done, dtype=np.int64)
+        lens = self.step[done]
+        E = int(lens.sum())
+        gcol = np.repeat(done, lens)
+        tcol = np.concatenate([np.arange(k) for k in lens]) if E else np.zeros(0, dtype=np.int64)
+        grow = np.repeat(np.arange(len(done)), lens).astype(np.int32)
+        dev = self.dev
+        t = torch.as_tensor(tcol, dtype=torch.int64).to(dev)
+        gi = torch.as_tensor(gcol, dtype=torch.int64).to(dev)
+        res = np.array([float(ended[g]) for g in done], dtype=np.float64)
+        tag = np.array([_lib.TAG_F32 if isinstance(ended[g], np.floating) and not isinstance(ended[g], float) else
+                        _lib.TAG_PYINT if isinstance(ended[g], (int, np.integer)) else _lib.TAG_PYFLOAT for g in done], dtype=np.int8)
+        self.device_examples.emit(self.h_states[t, gi], self.h_pi[t, gi], self.h_player[t, gi], torch.as_tensor(grow).to(dev),
+                                  torch.as_tensor(res).to(dev), torch.as_tensor(tag).to(dev),
+                                  torch.as_tensor(self.player[done].astype(np.int32)).to(dev), pi_int=self.h_int[t, gi])
+        out = []
+        if self.use_gnn:
+            states = self.h_states[t, gi].cpu().numpy()
+            boards = unpack_boards(self.kind, self.n, states)
+            off = 0
+            for j, g in enumerate(done):
+                r, cur, gnn = ended[g], self.player[g], []
+                for k, (pl, rec) in enumerate(self.history[g]):
+                    ip, iv, ep, ev = rec
+                    gnn.append((boards[off + k], pl, ip, iv, ep, ev, r * ((-1) ** (pl != cur))))
+                off += int(lens[j])
+                out.append(([], gnn))
+        else:
+            out = [([], []) for _ in done]
+        return out
+
     # ------------------------------------------------------------------ one lock-step move
     def step_all(self):
         """Every live game plays one move.  Returns the list of (std_examples, gnn_examples) of the
@@ -143,7 +195,18 @@ class BatchedSelfPlay:
         recs = None
         if self.use_gnn:
             recs = m.expand_tree(self.expand_by) if self.collect else self._expand_only()
-        if self.collect:
+        if self.device_collect:
+            # history stays in HBM: slot (episode step, game) <- root state, player to move, pi
+            t = torch.as_tensor(self.step - 1, dtype=torch.int64).to(self.dev)
+            gi = torch.arange(G, device=self.dev)
+            self.h_states[t, gi] = m.arena.get_roots().view(G, 2)
+            self.h_pi[t, gi] = torch.as_tensor(probs, dtype=torch.float64).to(self.dev)
+            self.h_player[t, gi] = torch.as_tensor(self.player, dtype=torch.int32).to(self.dev)
+            self.h_int[t, gi] = torch.as_tensor(temps == 0, dtype=torch.int8).to(self.dev)
+            if recs is not None:
+                for g in range(G):
+                    self.history[g].append((int(self.player[g]), recs[g]))
+        elif self.collect:
             boards = unpack_boards(self.kind, self.n, m.arena.to_host(m.arena.get_roots()))
             for g in range(G):
                 self.history[g].append((boards[g], int(self.player[g]), list(probs[g]),
@@ -159,8 +222,16 @@ class BatchedSelfPlay:
         else:
             done = [g for g in range(G) if ended[g] != 0]
         out = []
-        for g in done:
-            out.append(self._finish(g, ended[g]) if self.collect else ([], []))
+        if self.device_collect and done:
+            # `play(n)` keeps exactly n episodes (the reference runs numEps of them): later finishers of the same
+            # move-step are restarted without contributing examples
+            keep = done if self._budget is None else done[:max(self._budget, 0)]
+            if self._budget is not None:
+                self._budget -= len(keep)
+            out = self._finish_device(keep, ended) + [([], []) for _ in done[len(keep):]]
+        else:
+            for g in done:
+                out.append(self._finish(g, ended[g]) if self.collect else ([], []))
         if done:
             self.episodes_done += len(done)
             self._restart(done)
@@ -176,6 +247,8 @@ class BatchedSelfPlay:
     def play(self, n_episodes):
         """Run until n_episodes episodes have finished; returns their example lists."""
         finished = []
+        self._budget = n_episodes if self.device_collect else None
         while len(finished) < n_episodes:
             finished.extend(self.step_all())
+        self._budget = None
         return finished[:n_episodes]

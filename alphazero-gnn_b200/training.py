@@ -503,12 +503,15 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
         cache["warm"].add(which)
 
     for _ in range(epochs):
-        if examples:
+        if examples is not None and len(examples) > 0:
             idx = _sample(examples, batch_size)
-            boards, pis, vs = list(zip(*[examples[i] for i in idx]))
-            boards = torch.FloatTensor(np.array(boards)).to(dev)
-            target_pis = torch.FloatTensor(np.array(pis)).to(dev)
-            target_vs = torch.FloatTensor(np.array(vs).astype(np.float64)).to(dev)
+            if hasattr(examples, "sample"):  # replay.DeviceExamples: the minibatch is gathered on the device
+                boards, target_pis, target_vs = examples.sample(batch_size, idx=idx)
+            else:
+                boards, pis, vs = list(zip(*[examples[i] for i in idx]))
+                boards = torch.FloatTensor(np.array(boards)).to(dev)
+                target_pis = torch.FloatTensor(np.array(pis)).to(dev)
+                target_vs = torch.FloatTensor(np.array(vs).astype(np.float64)).to(dev)
             run_step("std", std_step, nnet_params, nnet_opt, (boards, target_pis, target_vs))
         if gnn_opt is not None and gnn_examples and len(gnn_examples) > 0:
             idx = _sample(gnn_examples, batch_size)

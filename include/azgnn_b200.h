@@ -209,6 +209,20 @@ int azg_grid_layer_tc_forward(const float* x, const void* packed_w, const float*
                               int prec, float* out, azg_stream stream);
 int azg_grid_layer_tc_backward_input(const float* dout, const float* act, const void* packed_wt, int64_t B, int gh, int gw,
                                      int H, int prec, float* dx, azg_stream stream);
+/* Example pipeline between self-play and training, on the device (csrc/azg_replay.cu).
+ * azg_emit_examples: every stored position of finished episodes -> S symmetric training examples with signed values
+ *   (Coach.py:45-49, 68-79; Connect4Game.getSymmetries :189-215, TicTacToeGame.getSymmetries :187-200).
+ *   states [E] packed positions, pi [E,A] float64, player [E], game [E] -> row of result / result_tag / cur (finished
+ *   games); board_perm [S,ncells] and pi_perm [S,A]: output cell d / action a takes input cell board_perm[s][d] /
+ *   entry pi_perm[s][a] (tables built on the host from the reference's own numpy calls).  Outputs: example e*S+s.
+ *   out_v may be NULL (positions without a value, e.g. GNN records).  frozenlake != 0: S = 1, states copied.
+ * azg_gather_examples: minibatch assembly (Connect4GNN.py:141-148): boards float32 [B,n,n], pi, v float32. */
+int azg_emit_examples(int frozenlake, const uint64_t* states, const double* pi, const int32_t* player, const int32_t* game,
+                      const double* result, const int8_t* result_tag, const int32_t* cur, int64_t E, int ncells, int A, int S,
+                      const int32_t* board_perm, const int32_t* pi_perm, uint64_t* out_states, double* out_pi, double* out_v,
+                      int8_t* out_vtag, azg_stream stream);
+int azg_gather_examples(int frozenlake, const uint64_t* states, const double* pi, const double* v, const int64_t* idx, int B,
+                        int ncells, int A, float* boards, float* out_pi, float* out_v, azg_stream stream);
 /* GNNLayer.forward / backward at B = P + 1 > 1 (gnn_utils.py:34-74): row 0 (f0) is the target, rows
  * 1.. (path) are attended over; only the target row changes. */
 typedef struct azg_gnn_layer_params {
