@@ -189,7 +189,13 @@ class Coach:
             else:
                 self.nnet.train(trainExamples)
             nmcts = self._new_mcts(self.nnet)
-            pwins, nwins, draws = self._pit(pmcts, nmcts, arg(a, "arenaCompare"))
+            if on_device and arg(a, "batched_arena", True):
+                # all arenaCompare games in flight at once (pit.BatchedArena; per-game trees instead of the reference's
+                # persistent pair -- set args.batched_arena = False for the sequential reference semantics)
+                from .pit import BatchedArena
+                pwins, nwins, draws = BatchedArena(self.game, self.pnet, self.nnet, a).playGames(arg(a, "arenaCompare"))
+            else:
+                pwins, nwins, draws = self._pit(pmcts, nmcts, arg(a, "arenaCompare"))
             log.info("NEW/PREV WINS : %d / %d ; DRAWS : %d" % (nwins, pwins, draws))
             accept = i == 1 or ((pwins + nwins > 0) and float(nwins) / (pwins + nwins) >= arg(a, "updateThreshold"))
             if not accept:

@@ -1,0 +1,77 @@
+"""Batched Arena for two-player games (Arena.py:106-152, 249-283; Coach.py:139-152): all `num` evaluation games
+in flight at once on the GPU arena instead of one after the other.
+
+    BatchedArena(game, nnet1, nnet2, args).playGames(num) -> (oneWon, twoWon, draws)
+
+Players are what Coach.learn pits (Coach.py:140-141): `argmax(MCTS(game, net, args).getActionProb(board, temp=0))`.
+As in `Arena.playGamesForTwoPlayer`, player 1 moves first in the first num/2 games and second in the others.
+Every ply is two lock-step searches (one per network, each over the games in which that network is to move) with
+ONE batched leaf evaluation per simulation round.
+
+Semantics that differ from the reference, on purpose and flagged (SURVEY.md section 8e "Arena pitting"): the
+reference plays the games sequentially with ONE persistent MCTS object per network, so visit statistics leak from
+game k into game k+1 and results depend on game order.  Here every game has its own tree per network; the tree
+persists across the plies of its game (the table is keyed by position), not across games.  With `fresh trees per
+game` in the sequential loop the two are identical move for move (tests/test_pit_gpu.py).
+Single-player evaluation (Arena.py:166-247) is not batched here.
+"""
+import numpy as np
+
+from .mcts import BatchedMCTS, arg
+
+
+class BatchedArena:
+    def __init__(self, game, nnet1, nnet2, args, arena_factory=None):
+        assert getattr(game, "is_two_player", True), "BatchedArena pits two-player games"
+        self.game, self.nets, self.args = game, (nnet1, nnet2), args
+        self._arena_factory = arena_factory
+
+    def _mcts(self, net, n_games):
+        arena = self._arena_factory(n_games) if self._arena_factory else None
+        a = self.args
+        sims = int(arg(a, "numMCTSSims"))
+        n = self.game.getBoardSize()[0]
+        # a game's tree lives for the whole game: every simulation of every ply it is searched on adds <= 1 entry
+        cap = max(4096, 2 * sims * (n * n + 2))
+        return BatchedMCTS(self.game, net, a, n_games=n_games, arena=arena, capacity=cap)
+
+    def playGames(self, num):
+        half = int(num / 2)
+        if half == 0:
+            return 0, 0, 0
+        g = self.game
+        # group 0: net 0 is player +1 (moves first); group 1: net 1 is player +1
+        mcts = [[self._mcts(self.nets[k], half) for _grp in range(2)] for k in range(2)]
+        boards = [[g.getInitBoard() for _ in range(half)] for _grp in range(2)]
+        cur = 1
+        alive = [np.ones(half, dtype=bool) for _grp in range(2)]
+        result = [np.zeros(half) for _grp in range(2)]  # from player +1's point of view
+        while alive[0].any() or alive[1].any():
+            for grp in range(2):
+                if not alive[grp].any():
+                    continue
+                net_idx = grp if cur == 1 else 1 - grp  # which network is to move in this group
+                m = mcts[net_idx][grp]
+                canon = [g.getCanonicalForm(b, cur) for b in boards[grp]]
+                m.set_root_boards(canon)
+                probs = m.getActionProbs(temp=0)
+                for i in np.flatnonzero(alive[grp]):
+                    action = int(np.argmax(probs[i]))
+                    valids = g.getValidMoves(canon[i], 1)
+                    assert valids[action] > 0, f"action {action} is not valid"
+                    boards[grp][i], _ = g.getNextState(boards[grp][i], cur, action)
+                    ended = g.getGameEnded(boards[grp][i], -cur)
+                    if ended != 0:
+                        alive[grp][i] = False
+                        result[grp][i] = -cur * ended  # Arena.py:152: curPlayer * getGameEnded(board, curPlayer)
+            cur = -cur
+        one = two = draws = 0
+        for grp in range(2):
+            for r in result[grp]:
+                if r == 1:
+                    one, two = (one + 1, two) if grp == 0 else (one, two + 1)
+                elif r == -1:
+                    one, two = (one, two + 1) if grp == 0 else (one + 1, two)
+                else:
+                    draws += 1
+        return one, two, draws

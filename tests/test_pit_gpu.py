@@ -1,0 +1,57 @@
+"""Batched Arena: all evaluation games in flight at once.  With fresh trees per game in the
+sequential loop (the flagged difference from the reference's persistent trees) it reproduces the sequential games
+move for move; the tie-break among equally visited moves is pinned to the lowest index in both runs."""
+import numpy as np
+import pytest
+import torch
+
+from azgnn_b200 import games
+from azgnn_b200.mcts import MCTS
+from azgnn_b200.nets import B200Connect4GNNWrapper, B200TicTacToeGNNWrapper
+from azgnn_b200.pit import BatchedArena
+from helpers import dotdict
+
+pytestmark = pytest.mark.gpu
+
+
+def _sequential(game, nets, args, num):
+    """Arena.playGamesForTwoPlayer (Arena.py:249-283) with a new MCTS pair per game"""
+    half = num // 2
+    one = two = draws = 0
+    for grp in range(2):
+        for _ in range(half):
+            first, second = (nets[0], nets[1]) if grp == 0 else (nets[1], nets[0])
+            players = {1: MCTS(game, first, args), -1: MCTS(game, second, args)}
+            board, cur = game.getInitBoard(), 1
+            while game.getGameEnded(board, cur) == 0:
+                canon = game.getCanonicalForm(board, cur)
+                action = int(np.argmax(players[cur].getActionProb(canon, temp=0)))
+                assert game.getValidMoves(canon, 1)[action] > 0
+                board, cur = game.getNextState(board, cur, action)
+            r = cur * game.getGameEnded(board, cur)
+            if r == 1:
+                one, two = (one + 1, two) if grp == 0 else (one, two + 1)
+            elif r == -1:
+                one, two = (one, two + 1) if grp == 0 else (one + 1, two)
+            else:
+                draws += 1
+    return one, two, draws
+
+
+@pytest.mark.parametrize("kind,n", [("c4", 5), ("ttt", 3)])
+def test_batched_arena_equals_sequential_games_with_fresh_trees(kind, n, monkeypatch):
+    monkeypatch.setattr(np.random, "choice", lambda a, *args, **kw: np.asarray(a).reshape(-1)[0])
+    game = games.Connect4Game(n) if kind == "c4" else games.TicTacToeGame(n)
+    args = dotdict(dict(lr=1e-3, dropout=0.3, gnn_layers=2, use_gnn=True, numMCTSSims=8, cpuct=1.0, expand_by=3,
+                        b200_precision="fp32"))
+    W = B200Connect4GNNWrapper if kind == "c4" else B200TicTacToeGNNWrapper
+    torch.manual_seed(0)
+    net_a = W(game, args)
+    torch.manual_seed(1)
+    net_b = W(game, args)
+    got = BatchedArena(game, net_a, net_b, args).playGames(6)
+    want = _sequential(game, (net_a, net_b), args, 6)
+    assert got == want and sum(got) == 6
+    # the two halves mirror each other when a network meets itself
+    one, two, draws = BatchedArena(game, net_a, net_a, args).playGames(4)
+    assert one == two and one + two + draws == 4
