@@ -142,27 +142,83 @@ class Coach:
             history = [(DeviceExamples.from_examples(self.game, list(std)), gnn) for std, gnn in history]
         self.trainExamplesHistory = history
 
+    # ------------------------------------------------------------------ multi-GPU plumbing
+    @staticmethod
+    def _world():
+        import torch.distributed as dist
+        return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+    def _gather_examples(self, std, gnn):
+        """Whole games were sharded over the ranks with no communication; the data-parallel training step works on ONE
+        shared minibatch, so after self-play every rank receives every rank's examples (rank order): one padded
+        all-gather per column for the device buffer, an object gather for the host GNN tuples."""
+        import torch
+        import torch.distributed as dist
+        rank, world = self._world()
+        if world == 1:
+            return std, gnn
+        from .replay import DeviceExamples
+        dev = std.device
+        n = torch.tensor([len(std)], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(x.item()) for x in sizes]
+        cap = max(sizes)
+        out = DeviceExamples(self.game, dev)
+        cols = {}
+        for name in ("states", "pi", "v", "vtag", "sym"):
+            t = getattr(std, name)
+            pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            pad[:t.shape[0]] = t
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)
+            cols[name] = torch.cat([p_[:k] for p_, k in zip(parts, sizes)])
+        out._append(cols["states"], cols["pi"], cols["v"], cols["vtag"], cols["sym"])
+        objs = [None] * world
+        dist.all_gather_object(objs, list(gnn))
+        return out, deque([e for part in objs for e in part], maxlen=arg(self.args, "maxlenOfQueue"))
+
     # ------------------------------------------------------------------ Coach.py:87-176
     def learn(self):
+        """One process per GPU (torch.distributed initialised by the caller, NCCL): self-play episodes and arena games
+        are sharded over the ranks with no communication, the examples are all-gathered once per iteration, and the
+        training step is the only collective on the compute path (row-sharded minibatch, gradient all-reduce).
+        `self.timings` keeps the wall time of every phase of the last iteration."""
+        import time
+        import torch
         a = self.args
+        rank, world = self._world()
+        on_device = self._arena_factory is None  # the CPU check arena of the tests keeps host tuples
+        assert world == 1 or on_device
+        folder = self._folder()
+
+        def sync():
+            if on_device:
+                torch.cuda.synchronize()
+            return time.perf_counter()
         for i in range(1, arg(a, "numIters") + 1):
             log.info(f"Starting Iter #{i} ...")
+            t0 = sync()
             it_std = deque([], maxlen=arg(a, "maxlenOfQueue"))
             it_gnn = deque([], maxlen=arg(a, "maxlenOfQueue"))
             n_eps = arg(a, "numEps")
-            games = int(arg(a, "n_parallel_games", min(n_eps, 4096)) or min(n_eps, 4096))
-            on_device = self._arena_factory is None  # the CPU check arena of the tests keeps host tuples
-            sp = BatchedSelfPlay(self.game, self.nnet, a, games, seed=i, collect_examples="device" if on_device else True,
+            my_eps = (n_eps + world - 1) // world  # whole games per rank
+            games = int(arg(a, "n_parallel_games", min(my_eps, 4096)) or min(my_eps, 4096))
+            sp = BatchedSelfPlay(self.game, self.nnet, a, games, seed=i * 1000 + rank,
+                                 collect_examples="device" if on_device else True,
                                  arena=self._arena_factory(games) if self._arena_factory else None)
-            for std, gnn in sp.play(n_eps):
+            for std, gnn in sp.play(my_eps):
                 it_std += std
                 it_gnn += gnn
+            self.selfplay_moves = sp.moves_played
+            t1 = sync()
             if on_device:
-                it_std = self._clip(sp.device_examples, arg(a, "maxlenOfQueue"))
+                it_std, it_gnn = self._gather_examples(self._clip(sp.device_examples, arg(a, "maxlenOfQueue")), it_gnn)
             self.trainExamplesHistory.append((it_std, it_gnn))
             if len(self.trainExamplesHistory) > arg(a, "numItersForTrainExamplesHistory"):
                 self.trainExamplesHistory.pop(0)
-            self.saveTrainExamples(i - 1)
+            if rank == 0 and arg(a, "save_examples", True):
+                self.saveTrainExamples(i - 1)
             gnnExamples = []
             for _std, gnn in self.trainExamplesHistory:
                 gnnExamples.extend(gnn)
@@ -171,6 +227,12 @@ class Coach:
                 trainExamples = DeviceExamples(self.game)
                 for std, _gnn in self.trainExamplesHistory:
                     trainExamples.extend(std)
+                if world > 1:  # every rank applies rank 0's shuffles
+                    import random
+                    import torch.distributed as dist
+                    seed = [random.getrandbits(62)]
+                    dist.broadcast_object_list(seed, src=0)
+                    random.seed(seed[0])
                 trainExamples = trainExamples.shuffled()  # random.shuffle's permutation, applied on the device
             else:
                 trainExamples = []
@@ -178,29 +240,46 @@ class Coach:
                     trainExamples.extend(std)
                 shuffle(trainExamples)
             shuffle(gnnExamples)
-            folder = arg(a, "checkpoint", arg(a, "checkpoint_path", "./checkpoints/"))
-            self.nnet.save_checkpoint(folder=folder, filename="temp.pth.tar")
+            t2 = sync()
+            if rank == 0:
+                self.nnet.save_checkpoint(folder=folder, filename="temp.pth.tar")
+            if world > 1:
+                import torch.distributed as dist
+                dist.barrier()
             if self.pnet is None:
                 self.pnet = self.nnet.__class__(self.game, a)
             self.pnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
             pmcts = self._new_mcts(self.pnet)
+            t3 = sync()
             if self._use_gnn() and gnnExamples:
                 self.nnet.train(trainExamples, gnnExamples)
             else:
                 self.nnet.train(trainExamples)
+            t4 = sync()
             nmcts = self._new_mcts(self.nnet)
+            n_arena = arg(a, "arenaCompare")
             if on_device and arg(a, "batched_arena", True):
                 # all arenaCompare games in flight at once (pit.BatchedArena; per-game trees instead of the reference's
                 # persistent pair -- set args.batched_arena = False for the sequential reference semantics)
                 from .pit import BatchedArena
-                pwins, nwins, draws = BatchedArena(self.game, self.pnet, self.nnet, a).playGames(arg(a, "arenaCompare"))
+                mine = 2 * ((n_arena // 2 + world - 1 - rank) // world) if world > 1 else n_arena  # pairs of games per rank
+                pwins, nwins, draws = BatchedArena(self.game, self.pnet, self.nnet, a).playGames(mine)
+                if world > 1:
+                    import torch.distributed as dist
+                    c = torch.tensor([pwins, nwins, draws], dtype=torch.int64, device=self.nnet.device)
+                    dist.all_reduce(c)
+                    pwins, nwins, draws = (int(x) for x in c.tolist())
             else:
-                pwins, nwins, draws = self._pit(pmcts, nmcts, arg(a, "arenaCompare"))
+                pwins, nwins, draws = self._pit(pmcts, nmcts, n_arena)
+            t5 = sync()
+            self.timings = {"selfplay_s": t1 - t0, "gather_shuffle_s": t2 - t1, "checkpoint_s": t3 - t2, "train_s": t4 - t3,
+                            "arena_s": t5 - t4, "iteration_s": t5 - t0}
+            self.arena_result = (pwins, nwins, draws)
             log.info("NEW/PREV WINS : %d / %d ; DRAWS : %d" % (nwins, pwins, draws))
             accept = i == 1 or ((pwins + nwins > 0) and float(nwins) / (pwins + nwins) >= arg(a, "updateThreshold"))
             if not accept:
                 self.nnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
-            else:
+            elif rank == 0:
                 best = "best_gnn.pth.tar" if self._use_gnn() else "best.pth.tar"
                 self.nnet.save_checkpoint(folder=folder, filename=self.getCheckpointFile(i))
                 self.nnet.save_checkpoint(folder=folder, filename=best)

@@ -82,6 +82,52 @@ def typed_value(d, tag):
     return 0
 
 
+def expanded_values(N1, Q1, T1, v0):
+    """MCTS.py:132-143 for all games at once: `expanded_value = sum_a Qsa * Nsa / sum_a Nsa` over the root edges, with
+    the value types of the reference's scalar loop.  Q is an np.float32 once a network value has joined its running
+    mean and a Python int/float before, and under NumPy >= 2 (NEP 50) a Python scalar is "weak":
+        python (+|*) python -> python (float64 arithmetic);   np.float32 (+|*|/) python -> float32 arithmetic.
+    So per game the accumulator is a Python number until the first float32 term arrives, is rounded to float32 there,
+    and stays float32.  Returns (float64 payload [G], type tag [G]); no visited edge -> the network's root value."""
+    G, A = N1.shape
+    acc64 = np.zeros(G, dtype=np.float64)
+    acc32 = np.zeros(G, dtype=np.float32)
+    is32 = np.zeros(G, dtype=bool)
+    cnt = np.zeros(G, dtype=np.int64)
+    for a in range(A):
+        n = N1[:, a].astype(np.int64)
+        valid = (T1[:, a] != _lib.TAG_NONE) & (n > 0)
+        f32 = valid & (T1[:, a] == _lib.TAG_F32)
+        py = valid & ~f32
+        term64 = Q1[:, a] * n                                            # python number * int
+        term32 = Q1[:, a].astype(np.float32) * n.astype(np.float32)      # np.float32 * int -> float32
+        m_py_py, m_py_32 = py & ~is32, py & is32
+        m_32_first, m_32_32 = f32 & ~is32, f32 & is32
+        acc64[m_py_py] += term64[m_py_py]
+        acc32[m_py_32] = acc32[m_py_32] + term64[m_py_32].astype(np.float32)
+        acc32[m_32_first] = acc64[m_32_first].astype(np.float32) + term32[m_32_first]
+        acc32[m_32_32] = acc32[m_32_32] + term32[m_32_32]
+        is32 |= f32
+        cnt[valid] += n[valid]
+    have = cnt > 0
+    safe = np.where(have, cnt, 1)
+    val = np.where(is32, (acc32 / safe.astype(np.float32)).astype(np.float64), acc64 / safe)
+    tag = np.where(is32, _lib.TAG_F32, _lib.TAG_PYFLOAT).astype(np.int8)
+    val = np.where(have, val, np.asarray(v0, dtype=np.float32).astype(np.float64))
+    tag = np.where(have, tag, _lib.TAG_F32).astype(np.int8)
+    return val, tag
+
+
+def expanded_value_scalar(N, Q, T, v0):
+    """the reference's loop for one game (MCTS.py:132-143), kept as the checker of `expanded_values`"""
+    expanded_value, valid_count = 0, 0
+    for a in range(len(N)):
+        if T[a] != _lib.TAG_NONE and N[a] > 0:
+            expanded_value += typed_value(Q[a], T[a]) * int(N[a])
+            valid_count += int(N[a])
+    return expanded_value / valid_count if valid_count > 0 else v0
+
+
 class BatchedMCTS:
     def __init__(self, game, nnet, args, n_games=1, arena=None, capacity=None, max_depth=None):
         self.game, self.nnet, self.args = game, nnet, args
@@ -223,42 +269,40 @@ class BatchedMCTS:
         return vals
 
     def expand_tree(self, expand_by=5):
-        A = self.A
+        """per game: (initial_policy, initial_value, expanded_policy, expanded_value), MCTS.py:60-149"""
+        ip, v0, ep, ev, evtag = self.expand_tree_arrays(expand_by)
+        return [(ip[g], v0[g], ep[g], typed_value(ev[g], int(evtag[g]))) for g in range(self.G)]
+
+    def expand_tree_arrays(self, expand_by=5):
+        """expand_tree for all games at once, as arrays: initial_policy [G,A] f64, initial_value [G] f32,
+        expanded_policy [G,A] f64, expanded_value [G] f64 payload + type tag [G] (see `expanded_values`)."""
         N0, _, _ = self.root_stats()
         if (N0.sum(axis=1) == 0).any():  # MCTS.py:83-92: no counts yet -> run the standard simulations first
             if not (N0.sum(axis=1) == 0).all():
                 raise RuntimeError("expand_tree: some games have root visits and some do not; call getActionProbs first")
             self.search(int(arg(self.args, "numMCTSSims")))
             N0, _, _ = self.root_stats()
-        v0 = self._root_std_values()
+        v0 = np.asarray(self._root_std_values(), dtype=np.float32)
         self.search(expand_by)
         N1, Q1, T1 = self.root_stats()
-        results = []
-        for g in range(self.G):
-            initial_policy = np.zeros(A)
-            for a in range(A):
-                if N0[g, a] > 0:
-                    initial_policy[a] = int(N0[g, a])
-            isum = np.sum(initial_policy)
-            if isum > 0:
-                initial_policy = initial_policy / isum
+        ip = self._visit_policy(N0, None)
+        ep = self._visit_policy(N1, ip)
+        ev, evtag = expanded_values(N1, Q1, T1, v0)
+        return ip, v0, ep, ev, evtag
+
+    def _visit_policy(self, N, fallback):
+        """counts -> policy as MCTS.py:95-103 / 125-130: N / sum(N); with no visits the fallback (the initial policy for
+        the expanded one, the uniform-over-valid-moves vector for the initial one)"""
+        pol = np.where(N > 0, N, 0).astype(np.float64)
+        tot = pol.sum(axis=1)  # small integers: exact in any order
+        out = pol / np.where(tot > 0, tot, 1.0)[:, None]
+        for g in np.flatnonzero(tot <= 0):
+            if fallback is not None:
+                out[g] = fallback[g]
             else:
                 valids = self.game.getValidMoves(self.root_boards()[g], 1)
-                initial_policy = valids / np.sum(valids)
-            expanded_policy = np.zeros(A)
-            for a in range(A):
-                if N1[g, a] > 0:
-                    expanded_policy[a] = int(N1[g, a])
-            esum = np.sum(expanded_policy)
-            expanded_policy = expanded_policy / esum if esum > 0 else initial_policy
-            expanded_value, valid_count = 0, 0  # MCTS.py:132-143, same promotion rules
-            for a in range(A):
-                if T1[g, a] != _lib.TAG_NONE and N1[g, a] > 0:
-                    expanded_value += typed_value(Q1[g, a], T1[g, a]) * int(N1[g, a])
-                    valid_count += int(N1[g, a])
-            expanded_value = expanded_value / valid_count if valid_count > 0 else v0[g]
-            results.append((initial_policy, v0[g], expanded_policy, expanded_value))
-        return results
+                out[g] = valids / np.sum(valids)
+        return out
 
     # ------------------------------------------------------------------ moves
     def advance(self, actions):

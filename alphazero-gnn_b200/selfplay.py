@@ -111,6 +111,11 @@ class BatchedSelfPlay:
             self.h_player = torch.zeros(self.t_cap, self.G, dtype=torch.int32, device=dev)
             self.h_int = torch.zeros(self.t_cap, self.G, dtype=torch.int8, device=dev)
             self.device_examples = DeviceExamples(game, dev)
+            # GNN records (expand_tree, MCTS.py:60-149) per (episode step, game): initial policy, initial value,
+            # expanded policy, expanded value payload + type tag -- host arrays, tuples are formed at episode end
+            self.g_rec = (np.zeros((self.t_cap, self.G, self.A)), np.zeros((self.t_cap, self.G), dtype=np.float32),
+                          np.zeros((self.t_cap, self.G, self.A)), np.zeros((self.t_cap, self.G)),
+                          np.zeros((self.t_cap, self.G), dtype=np.int8))
         self._start_all()
 
     # ------------------------------------------------------------------ episode bookkeeping
@@ -168,14 +173,17 @@ class BatchedSelfPlay:
                                   torch.as_tensor(self.player[done].astype(np.int32)).to(dev), pi_int=self.h_int[t, gi])
         out = []
         if self.use_gnn:
+            from .mcts import typed_value
             states = self.h_states[t, gi].cpu().numpy()
             boards = unpack_boards(self.kind, self.n, states)
+            players = self.h_player[t, gi].cpu().numpy()
+            ip, iv, ep, ev, evtag = (x[tcol, gcol] for x in self.g_rec)
             off = 0
             for j, g in enumerate(done):
-                r, cur, gnn = ended[g], self.player[g], []
-                for k, (pl, rec) in enumerate(self.history[g]):
-                    ip, iv, ep, ev = rec
-                    gnn.append((boards[off + k], pl, ip, iv, ep, ev, r * ((-1) ** (pl != cur))))
+                r, cur, gnn = ended[g], int(self.player[g]), []
+                for k in range(off, off + int(lens[j])):
+                    pl = int(players[k])
+                    gnn.append((boards[k], pl, ip[k], iv[k], ep[k], typed_value(ev[k], int(evtag[k])), r * ((-1) ** (pl != cur))))
                 off += int(lens[j])
                 out.append(([], gnn))
         else:
@@ -194,7 +202,10 @@ class BatchedSelfPlay:
         probs = probs_from_counts(N, temps, self.rng)
         recs = None
         if self.use_gnn:
-            recs = m.expand_tree(self.expand_by) if self.collect else self._expand_only()
+            if self.device_collect:
+                recs = m.expand_tree_arrays(self.expand_by)  # arrays over all games, no per-game Python work
+            else:
+                recs = m.expand_tree(self.expand_by) if self.collect else self._expand_only()
         if self.device_collect:
             # history stays in HBM: slot (episode step, game) <- root state, player to move, pi
             t = torch.as_tensor(self.step - 1, dtype=torch.int64).to(self.dev)
@@ -204,8 +215,9 @@ class BatchedSelfPlay:
             self.h_player[t, gi] = torch.as_tensor(self.player, dtype=torch.int32).to(self.dev)
             self.h_int[t, gi] = torch.as_tensor(temps == 0, dtype=torch.int8).to(self.dev)
             if recs is not None:
-                for g in range(G):
-                    self.history[g].append((int(self.player[g]), recs[g]))
+                th, gh = self.step - 1, np.arange(G)
+                for dst, src in zip(self.g_rec, recs):
+                    dst[th, gh] = src
         elif self.collect:
             boards = unpack_boards(self.kind, self.n, m.arena.to_host(m.arena.get_roots()))
             for g in range(G):

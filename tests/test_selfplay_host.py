@@ -76,3 +76,24 @@ def test_episodes_are_well_formed(kind, n, use_gnn):
         rs = [std[i * n_sym][2] for i in range(plies)]
         if abs(rs[0]) == 1:
             assert all(rs[i] == -rs[i + 1] for i in range(plies - 1))
+
+
+def test_vectorised_expanded_value_has_the_scalar_loops_values_and_types():
+    """expand_tree's value (MCTS.py:132-143) for all games at once vs the reference's scalar loop, including roots
+    whose edges mix Python-number Q values (pure-terminal subtrees) with np.float32 ones (NEP 50 promotion order)."""
+    from azgnn_b200 import _lib
+    from azgnn_b200.mcts import expanded_value_scalar, expanded_values, typed_value
+    rng = np.random.default_rng(0)
+    G, A = 4000, 8
+    N = rng.integers(0, 6, size=(G, A))
+    T = rng.choice([_lib.TAG_NONE, _lib.TAG_F32, _lib.TAG_F32, _lib.TAG_PYFLOAT, _lib.TAG_PYINT], size=(G, A)).astype(np.int8)
+    Q = np.where(T == _lib.TAG_F32, rng.uniform(-1, 1, (G, A)).astype(np.float32).astype(np.float64),
+                 np.where(T == _lib.TAG_PYINT, rng.choice([-1.0, 1.0, 0.0], size=(G, A)), rng.choice([1e-4, -1e-4, 0.5], size=(G, A))))
+    N[:50] = 0  # no visited edge: the network's root value is returned
+    v0 = rng.uniform(-1, 1, G).astype(np.float32)
+    val, tag = expanded_values(N, Q, T, v0)
+    for g in range(G):
+        want = expanded_value_scalar(N[g], Q[g], T[g], v0[g])
+        got = typed_value(val[g], int(tag[g]))
+        assert type(got) is type(want), (g, type(got), type(want))
+        assert got == want, (g, got, want)
