@@ -103,19 +103,6 @@ class Coach:
     def getCheckpointFile(self, iteration):
         return f"checkpoint_{iteration}" + ("_gnn" if self._use_gnn() else "") + ".pth.tar"
 
-    @staticmethod
-    def _clip(examples, maxlen):
-        """deque(maxlen) semantics for a device buffer: keep the newest `maxlen` examples"""
-        if maxlen is not None and len(examples) > maxlen:
-            from .replay import DeviceExamples
-            out = DeviceExamples.__new__(DeviceExamples)
-            out.__dict__.update(examples.__dict__)
-            k = len(examples) - maxlen
-            out.states, out.pi, out.v, out.vtag, out.sym = (t[k:] for t in (examples.states, examples.pi, examples.v,
-                                                                            examples.vtag, examples.sym))
-            return out
-        return examples
-
     def _folder(self):
         return arg(self.args, "checkpoint", arg(self.args, "checkpoint_path", "./checkpoints/"))
 
@@ -126,8 +113,8 @@ class Coach:
         if not os.path.exists(folder):
             os.makedirs(folder)
         maxlen = arg(self.args, "maxlenOfQueue")
-        history = [(deque(std.to_examples() if hasattr(std, "to_examples") else std, maxlen=maxlen), deque(gnn, maxlen=maxlen))
-                   for std, gnn in self.trainExamplesHistory]
+        host = lambda x: x.to_examples() if hasattr(x, "to_examples") else x
+        history = [(deque(host(std), maxlen=maxlen), deque(host(gnn), maxlen=maxlen)) for std, gnn in self.trainExamplesHistory]
         with open(os.path.join(folder, self.getCheckpointFile(iteration) + ".examples"), "wb+") as f:
             Pickler(f).dump(history)
 
@@ -138,8 +125,9 @@ class Coach:
         with open(examples_file, "rb") as f:
             history = Unpickler(f).load()
         if self._arena_factory is None:
-            from .replay import DeviceExamples
-            history = [(DeviceExamples.from_examples(self.game, list(std)), gnn) for std, gnn in history]
+            from .replay import DeviceExamples, DeviceGnnExamples
+            history = [(DeviceExamples.from_examples(self.game, list(std)), DeviceGnnExamples.from_examples(self.game, list(gnn)))
+                       for std, gnn in history]
         self.trainExamplesHistory = history
 
     # ------------------------------------------------------------------ multi-GPU plumbing
@@ -147,36 +135,6 @@ class Coach:
     def _world():
         import torch.distributed as dist
         return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
-
-    def _gather_examples(self, std, gnn):
-        """Whole games were sharded over the ranks with no communication; the data-parallel training step works on ONE
-        shared minibatch, so after self-play every rank receives every rank's examples (rank order): one padded
-        all-gather per column for the device buffer, an object gather for the host GNN tuples."""
-        import torch
-        import torch.distributed as dist
-        rank, world = self._world()
-        if world == 1:
-            return std, gnn
-        from .replay import DeviceExamples
-        dev = std.device
-        n = torch.tensor([len(std)], dtype=torch.int64, device=dev)
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        sizes = [int(x.item()) for x in sizes]
-        cap = max(sizes)
-        out = DeviceExamples(self.game, dev)
-        cols = {}
-        for name in ("states", "pi", "v", "vtag", "sym"):
-            t = getattr(std, name)
-            pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-            pad[:t.shape[0]] = t
-            parts = [torch.empty_like(pad) for _ in range(world)]
-            dist.all_gather(parts, pad)
-            cols[name] = torch.cat([p_[:k] for p_, k in zip(parts, sizes)])
-        out._append(cols["states"], cols["pi"], cols["v"], cols["vtag"], cols["sym"])
-        objs = [None] * world
-        dist.all_gather_object(objs, list(gnn))
-        return out, deque([e for part in objs for e in part], maxlen=arg(self.args, "maxlenOfQueue"))
 
     # ------------------------------------------------------------------ Coach.py:87-176
     def learn(self):
@@ -213,20 +171,22 @@ class Coach:
             self.selfplay_moves = sp.moves_played
             t1 = sync()
             if on_device:
-                it_std, it_gnn = self._gather_examples(self._clip(sp.device_examples, arg(a, "maxlenOfQueue")), it_gnn)
+                # whole games were sharded over the ranks with no communication; the data-parallel training step works
+                # on ONE shared minibatch, so every rank now receives every rank's examples (padded all-gather per column)
+                maxlen = arg(a, "maxlenOfQueue")
+                it_std = sp.device_examples.newest(maxlen).all_gathered().newest(maxlen)
+                it_gnn = sp.device_gnn_examples.newest(maxlen).all_gathered().newest(maxlen)
             self.trainExamplesHistory.append((it_std, it_gnn))
             if len(self.trainExamplesHistory) > arg(a, "numItersForTrainExamplesHistory"):
                 self.trainExamplesHistory.pop(0)
             if rank == 0 and arg(a, "save_examples", True):
                 self.saveTrainExamples(i - 1)
-            gnnExamples = []
-            for _std, gnn in self.trainExamplesHistory:
-                gnnExamples.extend(gnn)
             if on_device:
-                from .replay import DeviceExamples
-                trainExamples = DeviceExamples(self.game)
-                for std, _gnn in self.trainExamplesHistory:
+                from .replay import DeviceExamples, DeviceGnnExamples
+                trainExamples, gnnExamples = DeviceExamples(self.game), DeviceGnnExamples(self.game)
+                for std, gnn in self.trainExamplesHistory:
                     trainExamples.extend(std)
+                    gnnExamples.extend(gnn)
                 if world > 1:  # every rank applies rank 0's shuffles
                     import random
                     import torch.distributed as dist
@@ -234,12 +194,14 @@ class Coach:
                     dist.broadcast_object_list(seed, src=0)
                     random.seed(seed[0])
                 trainExamples = trainExamples.shuffled()  # random.shuffle's permutation, applied on the device
+                gnnExamples = gnnExamples.shuffled()
             else:
-                trainExamples = []
-                for std, _gnn in self.trainExamplesHistory:
+                trainExamples, gnnExamples = [], []
+                for std, gnn in self.trainExamplesHistory:
                     trainExamples.extend(std)
+                    gnnExamples.extend(gnn)
                 shuffle(trainExamples)
-            shuffle(gnnExamples)
+                shuffle(gnnExamples)
             t2 = sync()
             if rank == 0:
                 self.nnet.save_checkpoint(folder=folder, filename="temp.pth.tar")
@@ -251,10 +213,19 @@ class Coach:
             self.pnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
             pmcts = self._new_mcts(self.pnet)
             t3 = sync()
-            if self._use_gnn() and gnnExamples:
+            prof = None
+            if os.environ.get("AZG_PROFILE_TRAIN") and rank == 0 and i > 1:
+                import cProfile
+                prof = cProfile.Profile()
+                prof.enable()
+            if self._use_gnn() and len(gnnExamples) > 0:
                 self.nnet.train(trainExamples, gnnExamples)
             else:
                 self.nnet.train(trainExamples)
+            if prof is not None:
+                import pstats
+                prof.disable()
+                pstats.Stats(prof).sort_stats("cumulative").print_stats(25)
             t4 = sync()
             nmcts = self._new_mcts(self.nnet)
             n_arena = arg(a, "arenaCompare")

@@ -37,33 +37,100 @@ def symmetry_tables(game):
     return bp, pp
 
 
-class DeviceExamples:
-    def __init__(self, game, device=None):
+class _Columns:
+    """a list of records stored as named device tensors with a common first dimension"""
+    COLS = ()  # (name, dtype, trailing shape as a function of A)
+
+    def _init_columns(self, game, device):
         self.game = game
         self.kind = game_kind(game)
         self.n = game.getBoardSize()[0]
         self.A = game.getActionSize()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        bp, pp = symmetry_tables(game)
-        self.S = bp.shape[0]
-        self._bp = torch.from_numpy(bp).to(self.device)
-        self._pp = torch.from_numpy(pp).to(self.device)
-        d = self.device
-        self.states = torch.empty(0, 2, dtype=torch.int64, device=d)
-        self.pi = torch.empty(0, self.A, dtype=torch.float64, device=d)
-        self.v = torch.empty(0, dtype=torch.float64, device=d)
-        self.vtag = torch.empty(0, dtype=_I8, device=d)
-        self.sym = torch.empty(0, dtype=_I8, device=d)
+        for name, dtype, per_action in self.COLS:
+            shape = (0, 2) if name == "states" else ((0, self.A) if per_action else (0,))
+            setattr(self, name, torch.empty(shape, dtype=dtype, device=self.device))
 
     def __len__(self):
         return int(self.states.shape[0])
 
-    def _append(self, states, pi, v, vtag, sym):
-        self.states = torch.cat([self.states, states])
-        self.pi = torch.cat([self.pi, pi])
-        self.v = torch.cat([self.v, v])
-        self.vtag = torch.cat([self.vtag, vtag])
-        self.sym = torch.cat([self.sym, sym])
+    def _append(self, *cols):
+        for (name, _d, _p), t in zip(self.COLS, cols):
+            setattr(self, name, torch.cat([getattr(self, name), t]))
+
+    def extend(self, other):
+        self._append(*[getattr(other, name) for name, _d, _p in self.COLS])
+
+    def _like(self, index):
+        out = self.__class__.__new__(self.__class__)
+        out.__dict__.update(self.__dict__)
+        for name, _d, _p in self.COLS:
+            setattr(out, name, getattr(self, name)[index])
+        return out
+
+    def shuffled(self):
+        """`random.shuffle` of the example list (Coach.py:118): the swaps depend only on the length, so shuffling an
+        index list with the same `random` state gives the permutation the reference's list would get."""
+        idx = list(range(len(self)))
+        random.shuffle(idx)
+        return self._like(torch.as_tensor(idx, dtype=torch.int64, device=self.device))
+
+    def newest(self, maxlen):
+        """deque(maxlen) semantics: keep the newest `maxlen` records"""
+        if maxlen is None or len(self) <= maxlen:
+            return self
+        return self._like(slice(len(self) - maxlen, None))
+
+    def all_gathered(self):
+        """every rank's records on every rank, in rank order (one padded all-gather per column)"""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self
+        world = dist.get_world_size()
+        n = torch.tensor([len(self)], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(x.item()) for x in sizes]
+        cap = max(sizes)
+        out = self._like(slice(0, 0))
+        for name, _d, _p in self.COLS:
+            t = getattr(self, name)
+            pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+            pad[:t.shape[0]] = t
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)
+            setattr(out, name, torch.cat([p_[:k] for p_, k in zip(parts, sizes)]))
+        return out
+
+    def _gather(self, pi_col, v_col, batch_size, idx):
+        if idx is None:
+            idx = np.random.randint(0, len(self), min(len(self), batch_size))
+        B = len(idx)
+        d = self.device
+        t = torch.as_tensor(np.asarray(idx, dtype=np.int64)).to(d)
+        boards = torch.empty(B, self.n, self.n, dtype=torch.float32, device=d)
+        pi = torch.empty(B, self.A, dtype=torch.float32, device=d)
+        v = torch.empty(B, dtype=torch.float32, device=d)
+        _lib.check(_lib.lib().azg_gather_examples(int(self.kind == "frozenlake"), ptr(self.states), ptr(pi_col), ptr(v_col),
+                                                  ptr(t), B, self.n * self.n, self.A, ptr(boards), ptr(pi), ptr(v), stream()))
+        return boards, pi, v
+
+
+def _value_tags(values):
+    return np.array([_lib.TAG_F32 if isinstance(v, np.floating) and not isinstance(v, float) else
+                     _lib.TAG_PYINT if isinstance(v, (int, np.integer)) else _lib.TAG_PYFLOAT for v in values], dtype=np.int8)
+
+
+class DeviceExamples(_Columns):
+    COLS = (("states", torch.int64, False), ("pi", torch.float64, True), ("v", torch.float64, False), ("vtag", _I8, False),
+            ("sym", _I8, False))
+
+    def __init__(self, game, device=None):
+        self._init_columns(game, device)
+        bp, pp = symmetry_tables(game)
+        self.S = bp.shape[0]
+        self._bp = torch.from_numpy(bp).to(self.device)
+        self._pp = torch.from_numpy(pp).to(self.device)
 
     # ------------------------------------------------------------------ Coach.py:45-49, 68-79
     def emit(self, states, pi, player, game, result, result_tag, cur, pi_int=None):
@@ -89,36 +156,11 @@ class DeviceExamples:
             sym = sym + 16 * pi_int.to(_I8).repeat_interleave(S)
         self._append(out_states, out_pi, out_v, out_tag, sym)
 
-    def extend(self, other):
-        self._append(other.states, other.pi, other.v, other.vtag, other.sym)
-
-    def shuffled(self):
-        """`random.shuffle` of the example list (Coach.py:118): the swaps depend only on the length, so shuffling an
-        index list with the same `random` state gives the permutation the reference's list would get."""
-        idx = list(range(len(self)))
-        random.shuffle(idx)
-        t = torch.as_tensor(idx, dtype=torch.int64, device=self.device)
-        out = DeviceExamples.__new__(DeviceExamples)
-        out.__dict__.update(self.__dict__)
-        out.states, out.pi, out.v = self.states[t], self.pi[t], self.v[t]
-        out.vtag, out.sym = self.vtag[t], self.sym[t]
-        return out
-
     # ------------------------------------------------------------------ Connect4GNN.py:141-148
     def sample(self, batch_size, idx=None):
         """float32 boards [B,n,n], pi [B,A], v [B] of examples drawn with replacement through the global NumPy RNG
         (`np.random.randint(len(examples), size=...)`), or of the given indices."""
-        if idx is None:
-            idx = np.random.randint(0, len(self), min(len(self), batch_size))
-        B = len(idx)
-        d = self.device
-        t = torch.as_tensor(np.asarray(idx, dtype=np.int64)).to(d)
-        boards = torch.empty(B, self.n, self.n, dtype=torch.float32, device=d)
-        pi = torch.empty(B, self.A, dtype=torch.float32, device=d)
-        v = torch.empty(B, dtype=torch.float32, device=d)
-        _lib.check(_lib.lib().azg_gather_examples(int(self.kind == "frozenlake"), ptr(self.states), ptr(self.pi), ptr(self.v),
-                                                  ptr(t), B, self.n * self.n, self.A, ptr(boards), ptr(pi), ptr(v), stream()))
-        return boards, pi, v
+        return self._gather(self.pi, self.v, batch_size, idx)
 
     # ------------------------------------------------------------------ pickle format (Coach.py:178-201)
     def to_examples(self):
@@ -155,8 +197,7 @@ class DeviceExamples:
         tags, syms = [], []
         for e in examples:
             v = e[2]
-            tags.append(_lib.TAG_F32 if isinstance(v, np.floating) and not isinstance(v, float) else
-                        _lib.TAG_PYINT if isinstance(v, (int, np.integer)) else _lib.TAG_PYFLOAT)
+            tags.append(int(_value_tags([v])[0]))
             first = np.asarray(e[1]).reshape(-1)[0]
             ints = 16 if isinstance(first, (int, np.integer)) and not isinstance(first, bool) else 0
             syms.append((1 if (ex.kind == "connect4" and isinstance(e[1], np.ndarray)) else 0) + ints)
@@ -164,4 +205,51 @@ class DeviceExamples:
                    torch.as_tensor(np.array([np.asarray(e[1], dtype=np.float64) for e in examples])).to(d),
                    torch.as_tensor(np.array([float(e[2]) for e in examples], dtype=np.float64)).to(d),
                    torch.as_tensor(np.array(tags, dtype=np.int8)).to(d), torch.as_tensor(np.array(syms, dtype=np.int8)).to(d))
+        return ex
+
+
+class DeviceGnnExamples(_Columns):
+    """The GNN examples of Coach.executeEpisode (Coach.py:52-60, 72-74) as device columns: one record per stored
+    position (no symmetries): (board, player, initial_pi, initial_v, expanded_pi, expanded_v, signed result).
+    `train` uses board, expanded_pi and expanded_v (Connect4GNN.py:160-166)."""
+    COLS = (("states", torch.int64, False), ("player", torch.int32, False), ("ip", torch.float64, True),
+            ("iv", torch.float32, False), ("ep", torch.float64, True), ("ev", torch.float64, False), ("evtag", _I8, False),
+            ("sign", torch.float64, False), ("signtag", _I8, False))
+
+    def __init__(self, game, device=None):
+        self._init_columns(game, device)
+
+    def append_records(self, states, player, ip, iv, ep, ev, evtag, sign, signtag):
+        """device `states` [E,2]; the other columns as host arrays (expand_tree_arrays output, vectorised signs)"""
+        d = self.device
+        up = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x)).to(d).to(dt)
+        self._append(states, up(player, torch.int32), up(ip, torch.float64), up(iv, torch.float32), up(ep, torch.float64),
+                     up(ev, torch.float64), up(evtag, _I8), up(sign, torch.float64), up(signtag, _I8))
+
+    def sample(self, batch_size, idx=None):
+        """float32 boards [B,n,n], expanded_pi [B,A], expanded_v [B] (Connect4GNN.py:160-166)"""
+        return self._gather(self.ep, self.ev, batch_size, idx)
+
+    def to_examples(self):
+        states = self.states.cpu().numpy()
+        c = {name: getattr(self, name).cpu().numpy() for name, _d, _p in self.COLS[1:]}
+        out = []
+        for i in range(len(states)):
+            out.append((unpack_state(self.kind, self.n, states[i]), int(c["player"][i]), c["ip"][i].copy(), np.float32(c["iv"][i]),
+                        c["ep"][i].copy(), typed_value(c["ev"][i], int(c["evtag"][i])),
+                        typed_value(c["sign"][i], int(c["signtag"][i]))))
+        return out
+
+    @classmethod
+    def from_examples(cls, game, examples, device=None):
+        ex = cls(game, device)
+        if not examples:
+            return ex
+        boards = np.stack([np.asarray(e[0]) for e in examples])
+        ex.append_records(torch.as_tensor(pack_states(ex.kind, boards)).to(ex.device), [e[1] for e in examples],
+                          np.array([np.asarray(e[2], dtype=np.float64) for e in examples]),
+                          np.array([float(np.asarray(e[3]).reshape(-1)[0]) for e in examples], dtype=np.float32),
+                          np.array([np.asarray(e[4], dtype=np.float64) for e in examples]),
+                          np.array([float(np.asarray(e[5]).reshape(-1)[0]) for e in examples]), _value_tags([e[5] for e in examples]),
+                          np.array([float(e[6]) for e in examples]), _value_tags([e[6] for e in examples]))
         return ex

@@ -100,7 +100,7 @@ class BatchedSelfPlay:
         self.episodes_done = 0
         self._budget = None
         if self.device_collect:
-            from .replay import DeviceExamples
+            from .replay import DeviceExamples, DeviceGnnExamples
             dev = self.mcts.arena.device if hasattr(self.mcts.arena, "device") else torch.device("cuda", torch.cuda.current_device())
             nn = self.n * self.n
             self.t_cap = int(max_episode_steps) if max_episode_steps is not None else nn + 2
@@ -111,6 +111,7 @@ class BatchedSelfPlay:
             self.h_player = torch.zeros(self.t_cap, self.G, dtype=torch.int32, device=dev)
             self.h_int = torch.zeros(self.t_cap, self.G, dtype=torch.int8, device=dev)
             self.device_examples = DeviceExamples(game, dev)
+            self.device_gnn_examples = DeviceGnnExamples(game, dev)
             # GNN records (expand_tree, MCTS.py:60-149) per (episode step, game): initial policy, initial value,
             # expanded policy, expanded value payload + type tag -- host arrays, tuples are formed at episode end
             self.g_rec = (np.zeros((self.t_cap, self.G, self.A)), np.zeros((self.t_cap, self.G), dtype=np.float32),
@@ -140,7 +141,7 @@ class BatchedSelfPlay:
 
     def _finish(self, g, r):
         """Coach.py:68-79: sign the result for every stored position; symmetries as the reference."""
-        cur = self.player[g]
+        cur = int(self.player[g])  # Python ints as Coach.curPlayer: the signed results keep the reference's types
         std, gnn = [], []
         for board, pl, pi, rec in self.history[g]:
             sign = r * ((-1) ** (pl != cur))
@@ -154,8 +155,8 @@ class BatchedSelfPlay:
 
     def _finish_device(self, done, ended):
         """Coach.py:68-79 for all episodes that ended on this move: one gather of their history slots and one
-        emit kernel (symmetries + signed values) append the standard examples to `self.device_examples`; GNN
-        records (no symmetries, host-computed by expand_tree) are returned as the reference's tuples."""
+        emit kernel (symmetries + signed values) append the standard examples to `self.device_examples`; the GNN
+        records (no symmetries; expand_tree_arrays output) go to `self.device_gnn_examples` column by column."""
         done = np.asarray(done, dtype=np.int64)
         lens = self.step[done]
         E = int(lens.sum())
@@ -171,24 +172,13 @@ class BatchedSelfPlay:
         self.device_examples.emit(self.h_states[t, gi], self.h_pi[t, gi], self.h_player[t, gi], torch.as_tensor(grow).to(dev),
                                   torch.as_tensor(res).to(dev), torch.as_tensor(tag).to(dev),
                                   torch.as_tensor(self.player[done].astype(np.int32)).to(dev), pi_int=self.h_int[t, gi])
-        out = []
-        if self.use_gnn:
-            from .mcts import typed_value
-            states = self.h_states[t, gi].cpu().numpy()
-            boards = unpack_boards(self.kind, self.n, states)
+        if self.use_gnn:  # Coach.py:72-74: one GNN record per stored position, no symmetries
             players = self.h_player[t, gi].cpu().numpy()
             ip, iv, ep, ev, evtag = (x[tcol, gcol] for x in self.g_rec)
-            off = 0
-            for j, g in enumerate(done):
-                r, cur, gnn = ended[g], int(self.player[g]), []
-                for k in range(off, off + int(lens[j])):
-                    pl = int(players[k])
-                    gnn.append((boards[k], pl, ip[k], iv[k], ep[k], typed_value(ev[k], int(evtag[k])), r * ((-1) ** (pl != cur))))
-                off += int(lens[j])
-                out.append(([], gnn))
-        else:
-            out = [([], []) for _ in done]
-        return out
+            cur_e = np.repeat(self.player[done], lens)
+            sign = np.repeat(res, lens) * np.where(players != cur_e, -1.0, 1.0)
+            self.device_gnn_examples.append_records(self.h_states[t, gi], players, ip, iv, ep, ev, evtag, sign, np.repeat(tag, lens))
+        return [([], []) for _ in done]
 
     # ------------------------------------------------------------------ one lock-step move
     def step_all(self):

@@ -513,12 +513,15 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
                 target_pis = torch.FloatTensor(np.array(pis)).to(dev)
                 target_vs = torch.FloatTensor(np.array(vs).astype(np.float64)).to(dev)
             run_step("std", std_step, nnet_params, nnet_opt, (boards, target_pis, target_vs))
-        if gnn_opt is not None and gnn_examples and len(gnn_examples) > 0:
+        if gnn_opt is not None and gnn_examples is not None and len(gnn_examples) > 0:
             idx = _sample(gnn_examples, batch_size)
-            batch = [gnn_examples[i] for i in idx]
-            boards = torch.FloatTensor(np.array([b[0] for b in batch])).to(dev)
-            expanded_pis = torch.FloatTensor(np.array([b[4] for b in batch])).to(dev)
-            expanded_vs = torch.FloatTensor(np.array([b[5] for b in batch]).astype(np.float64)).to(dev)
+            if hasattr(gnn_examples, "sample"):  # replay.DeviceGnnExamples
+                boards, expanded_pis, expanded_vs = gnn_examples.sample(batch_size, idx=idx)
+            else:
+                batch = [gnn_examples[i] for i in idx]
+                boards = torch.FloatTensor(np.array([b[0] for b in batch])).to(dev)
+                expanded_pis = torch.FloatTensor(np.array([b[4] for b in batch])).to(dev)
+                expanded_vs = torch.FloatTensor(np.array([b[5] for b in batch]).astype(np.float64)).to(dev)
             run_step("gnn", gnn_step, gnn_params, gnn_opt, (boards, expanded_pis, expanded_vs))
     w.weights_changed()
 

@@ -116,15 +116,24 @@ def test_device_collection_equals_host_collection():
         assert np.array_equal(gb, np.asarray(wb))
         assert np.array_equal(np.asarray(gp, dtype=np.float64), np.asarray(wp, dtype=np.float64))
         assert gv == wv
-    dev_gnn = [e for _, gnn in dev_fin for e in gnn]
-    assert len(dev_gnn) == len(host_gnn)
+    dev_gnn = dev_sp.device_gnn_examples.to_examples()
+    assert len(dev_gnn) >= len(host_gnn) > 0
     for a, b in zip(dev_gnn, host_gnn):
-        assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[6] == b[6]
-        assert np.array_equal(a[2], b[2]) and np.array_equal(a[4], b[4]) and a[3] == b[3] and a[5] == b[5]
-    # training consumes the device buffer directly
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[6] == b[6] and type(a[6]) is type(b[6])
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[4], b[4]) and a[3] == b[3]
+        assert a[5] == b[5] and type(a[5]) is type(b[5])
+    # the GNN minibatch gathered on the device equals the host assembly of Connect4GNN.py:160-166
+    np.random.seed(2)
+    gb, gp, gv = dev_sp.device_gnn_examples.sample(32)
+    np.random.seed(2)
+    idx = np.random.randint(0, len(dev_gnn), 32)
+    batch = [dev_gnn[i] for i in idx]
+    assert torch.equal(gb.cpu(), torch.FloatTensor(np.array([x[0] for x in batch])))
+    assert torch.equal(gp.cpu(), torch.FloatTensor(np.array([x[4] for x in batch])))
+    assert torch.equal(gv.cpu(), torch.FloatTensor(np.array([x[5] for x in batch]).astype(np.float64)))
+    # training consumes both device buffers directly
     np.random.seed(0)
-    net.train(dev_sp.device_examples, host_gnn)
-
+    net.train(dev_sp.device_examples, dev_sp.device_gnn_examples)
 
 def test_coach_learn_keeps_examples_on_device_and_pickles_the_reference_format(tmp_path):
     from collections import deque
@@ -142,7 +151,9 @@ def test_coach_learn_keeps_examples_on_device_and_pickles_the_reference_format(t
     c = Coach(game, B200Connect4GNNWrapper(game, args), args)
     c.learn()
     std, gnn = c.trainExamplesHistory[0]
-    assert isinstance(std, DeviceExamples) and len(std) > 0 and len(std) % 2 == 0 and len(gnn) > 0
+    from azgnn_b200.replay import DeviceGnnExamples
+    assert isinstance(std, DeviceExamples) and len(std) > 0 and len(std) % 2 == 0
+    assert isinstance(gnn, DeviceGnnExamples) and len(gnn) == len(std) // 2
     f = tmp_path / "checkpoint_0_gnn.pth.tar.examples"
     with open(f, "rb") as fh:
         hist = Unpickler(fh).load()
@@ -155,3 +166,6 @@ def test_coach_learn_keeps_examples_on_device_and_pickles_the_reference_format(t
     again = c2.trainExamplesHistory[0][0]
     assert torch.equal(again.states, std.states) and torch.equal(again.pi, std.pi) and torch.equal(again.v, std.v)
     assert torch.equal(again.vtag, std.vtag) and torch.equal(again.sym, std.sym)
+    g2 = c2.trainExamplesHistory[0][1]
+    for name, _d, _p in DeviceGnnExamples.COLS:
+        assert torch.equal(getattr(g2, name), getattr(gnn, name)), name
