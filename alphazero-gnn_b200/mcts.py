@@ -308,9 +308,13 @@ class BatchedMCTS:
     def advance(self, actions):
         """Play actions[g] in game g (Coach.py:63-66); returns getGameEnded of the new position for the
         player to move, with the reference's value types (0 = still running).  action -1 = leave."""
-        ended, tag = self.arena.advance(np.asarray(actions, dtype=np.int32))
-        e, t = self.arena.to_host(ended), self.arena.to_host(tag)
+        e, t = self.advance_arrays(actions)
         return [typed_value(e[g], t[g]) for g in range(self.G)]
+
+    def advance_arrays(self, actions):
+        """`advance` without the per-game Python objects: (float64 payload [G], type tag [G]); payload 0 = still running"""
+        ended, tag = self.arena.advance(np.asarray(actions, dtype=np.int32))
+        return self.arena.to_host(ended), self.arena.to_host(tag)
 
     # ------------------------------------------------------------------ dict views (MCTS.py:15-21)
     def tables(self, g=0):

@@ -214,15 +214,17 @@ class BatchedSelfPlay:
                 self.history[g].append((boards[g], int(self.player[g]), list(probs[g]),
                                         recs[g] if recs is not None else None))
         actions = sample_actions(probs, self.rng)
-        ended = m.advance(actions)
+        e_val, e_tag = m.advance_arrays(actions)  # getGameEnded of the new positions; typed objects only for finished games
         self.moves_played += G
         if self.two_player:
             self.player = -self.player
+        over = e_val != 0
         if self.max_episode_steps is not None:
-            ended = [e if (e != 0 or self.step[g] < self.max_episode_steps) else 0.0 for g, e in enumerate(ended)]
-            done = [g for g in range(G) if ended[g] != 0 or self.step[g] >= self.max_episode_steps]
-        else:
-            done = [g for g in range(G) if ended[g] != 0]
+            capped = (self.step >= self.max_episode_steps) & ~over
+            over = over | capped
+        done = [int(g) for g in np.flatnonzero(over)]
+        from .mcts import typed_value
+        ended = {g: (typed_value(e_val[g], int(e_tag[g])) if e_val[g] != 0 else 0.0) for g in done}
         out = []
         if self.device_collect and done:
             # `play(n)` keeps exactly n episodes (the reference runs numEps of them): later finishers of the same

@@ -337,6 +337,13 @@ def run_gpu_arm(args, rank, local_rank, world):
         barrier()
         sp_moves, sp_leaves, sp_ms = gpu_selfplay(net, a, args.selfplay_games, args.selfplay_moves, seed=rank)
         barrier()
+    sp_fold = None
+    if args.selfplay_games > 0 and args.precision != "fp32" and world == 1:
+        net.fold_heads = True  # same search, leaves evaluated with output_transform.2 folded into the heads (opt-in mode)
+        f_moves, f_leaves, f_ms = gpu_selfplay(net, a, args.selfplay_games, args.selfplay_moves, seed=rank)
+        net.fold_heads = False
+        sp_fold = {"value": f_moves, "unit": "moves/s", "leaf_evals_per_s_in_search": f_leaves,
+                   "ms_per_move_step": f_ms / max(args.selfplay_moves, 1), "note": "b200_fold_heads=True (see also.*_folded_heads)"}
     t = torch.tensor([ms, ms_e2e, sp_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([sp_moves * sp_ms, sp_leaves * sp_ms], dtype=torch.float64, device=dev)  # counts
     if world > 1:
@@ -408,6 +415,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                         "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_host.values())),
                         "ms_per_step": ms_e2e / args.steps},
                 "selfplay": selfplay,
+                "selfplay_folded_heads": sp_fold,
                 "also": also,
                 "gpu_launches": int(launches),
                 "clocks": clocks.summary()}
