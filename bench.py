@@ -139,8 +139,11 @@ def run_reference_arm(args, rank):
     line = {"impl": "reference", "metric": "connect4_gnn_leaf_evals_per_s", "value": value, "unit": "leaf_evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "connect4_7x7_gnn_leaf_eval_per_position_b1", "positions_per_step": sample,
-                       "board": "7x7", "use_gnn": True},
+            "config": {"workload": "connect4_7x7_gnn_leaf_eval_batch_65536", "positions_per_step_per_gpu": BATCH,
+                       "board": "7x7 (reference geometry; 6x7 is not constructible, SURVEY 8d)", "use_gnn": True,
+                       "eval": "predict + predict_with_gnn (shared trunk)", "weights": "random-init seed 0", "precision": "fp32",
+                       "sample": f"each step = {sample} positions of the workload, evaluated as the reference's MCTS does: one "
+                                 "B=1 predict + predict_with_gnn per position (MCTS.py:169-173), all host threads"},
             "cpu_baseline": {"value": value, "unit": "leaf_evals/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} positions per step, predict + predict_with_gnn per position (B=1), "
                                        "oracle/nets.py on torch CPU"},
