@@ -69,13 +69,36 @@ def cpu_leaf_evals(sample, threads=None):
         with torch.no_grad():
             onets.c4_predict(p, bt, N_BOARD)
             onets.c4_predict_with_gnn(p, q, bt, N_BOARD)
-    for b in boards[:8]:
-        leaf(b)
+    for i in range(30):  # >= 30 warm-up calls
+        leaf(boards[i % 8])
     t0 = time.perf_counter()
     for b in boards[8:]:
         leaf(b)
     dt = time.perf_counter() - t0
     return sample / dt, dt, torch.get_num_threads()
+
+
+def cpu_fairness_notes():
+    """the same CPU path with one thread (300 timed B=1 call pairs) and the vectorised number
+    (one batch of 4096 positions through the same modules, all threads) -- context for the B=1 baseline."""
+    import numpy as np
+    import torch
+    from oracle import nets as onets
+    from azgnn_b200 import modules
+    one, _dt, _ = cpu_leaf_evals(300, threads=1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    nnet = modules.Connect4Trunk(N_BOARD, N_BOARD + 1)
+    gnn = modules.PolicyValueGNN(64 * N_BOARD * N_BOARD, 2)
+    p, q = dict(nnet.state_dict()), dict(gnn.state_dict())
+    bt = onets.boards_to_tensor(synthetic_boards(4096, 2).astype(np.int64))
+    with torch.no_grad():
+        onets.c4_predict_with_gnn(p, q, bt[:256], N_BOARD)
+        t0 = time.perf_counter()
+        onets.c4_predict(p, bt, N_BOARD)
+        onets.c4_predict_with_gnn(p, q, bt, N_BOARD)
+        dt = time.perf_counter() - t0
+    return {"one_thread_b1": one, "vectorised_batch_4096_all_threads": 4096 / dt}
 
 
 def cpu_selfplay(episodes):
@@ -412,7 +435,8 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "cpu_baseline": None if cpu_rate is None else
                 {"value": cpu_rate, "unit": "leaf_evals/s", "cores": cores, "kind": "port",
                  "sample": f"{args.cpu_sample} positions, predict + predict_with_gnn per position "
-                           f"(B=1) as MCTS.py:169-173, {cpu_dt:.1f} s"},
+                           f"(B=1) as MCTS.py:169-173, {cpu_dt:.1f} s",
+                 "fairness_notes_leaf_evals_per_s": cpu_fairness_notes()},
                 "e2e": {"value": total / (ms_e2e / 1e3), "unit": "leaf_evals/s",
                         "h2d_bytes_per_step": int(B * N_BOARD * N_BOARD),
                         "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_host.values())),
