@@ -8,7 +8,10 @@ layer (bf16x3 / bf16, csrc/azg_grid_tc.cu) the achieved HBM rate on the ALGORITH
 (4H read + 4H written per node) against the measured copy peak, and the issued tensor TFLOP/s; for the
 fp32 path (SGEMM + aggregation kernel) the aggregation kernel's rate.  Not the headline metric (bench.py);
 a parity-tested (tests/test_gridgnn_gpu.py) roofline table for the graph operator.
-usage: python bench_sweep.py [--quick] [--precisions bf16x3,bf16,fp32]"""
+usage: python bench_sweep.py [--quick] [--precisions bf16x3,bf16,fp32] [--grids 7x7,8x8] [--hiddens 128] [--batches 65536]
+       python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 bench_sweep.py ...
+         (graphs are independent: every rank runs `batch` graphs of its own, no collective on the data path; times are
+          the max over ranks, graphs/s the whole-job aggregate -- weak scaling)"""
 import argparse
 import json
 import os
@@ -20,6 +23,11 @@ sys.path.insert(0, ROOT)
 
 def main():
     import torch
+    import torch.distributed as dist
+    rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from azgnn_b200 import _lib
     from azgnn_b200.gridgnn import GridGNNStack, _GridAggRelu
     ap = argparse.ArgumentParser()
@@ -50,7 +58,12 @@ def main():
             fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
+        t = e0.elapsed_time(e1) / reps
+        if world > 1:  # max over ranks
+            tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = tt.item()
+        return t
 
     for gh, gw in grids:
         for H in hiddens:
@@ -59,7 +72,7 @@ def main():
                 if B * n * H > budget // 4:
                     continue
                 for prec in args.precisions.split(","):
-                    torch.manual_seed(0)
+                    torch.manual_seed(rank)
                     net = GridGNNStack(gh, gw, H, layers=2, precision=prec).cuda()
                     x = torch.randn(B, n, H, device="cuda")
                     with torch.no_grad():
@@ -81,23 +94,28 @@ def main():
                     lin_flops = 2 * B * n * H * H
                     terms = 3 if prec == "bf16x3" else 1
                     r = dict(nodes=n, grid=f"{gh}x{gw}", hidden=H, batch=B, precision=prec, fused=bool(net.fused), fwd_ms=t_fwd,
-                             fwd_bwd_ms=t_fb, graphs_per_s_fwd=B / t_fwd * 1e3)
+                             fwd_bwd_ms=t_fb, graphs_per_s_fwd=world * B / t_fwd * 1e3, n_gpus=world)
                     if net.fused:
                         r.update(layer_gbs=2 * layer_bytes / t_fwd / 1e6, frac_hbm=2 * layer_bytes / t_fwd / 1e6 / hbm,
-                                 issued_tflops=2 * lin_flops * terms / t_fwd / 1e9)
+                                 issued_tflops=2 * lin_flops * terms / t_fwd / 1e9)  # per GPU
                     else:
                         r.update(agg_ms=t_agg, layer_gbs=layer_bytes / t_agg / 1e6, frac_hbm=layer_bytes / t_agg / 1e6 / hbm,
                                  issued_tflops=lin_flops * 2 / max(t_fwd - 2 * t_agg, 1e-6) / 1e9)
                     rows.append(r)
                     del net, x, xg
                     torch.cuda.empty_cache()
-    print(f"# grid-graph sweep, 2 layers; HBM peak {hbm:.0f} GB/s ({'measured' if peaks else 'fallback'}); fused rows: GB/s = "
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    print(f"# grid-graph sweep, 2 layers, {world} GPU(s), batch = graphs per GPU; HBM peak {hbm:.0f} GB/s ({'measured' if peaks else 'fallback'}); fused rows: GB/s = "
           "algorithmic layer bytes / forward time; fp32 rows: GB/s of the aggregation kernel alone, TF/s of the SGEMM alone")
     print(f"{'grid':>6} {'H':>4} {'batch':>7} {'prec':>7} {'fwd ms':>9} {'fwd+bwd ms':>11} {'graphs/s fwd':>13} {'GB/s':>9} {'/HBM':>6} {'TF/s':>8}")
     for r in rows:
         print(f"{r['grid']:>6} {r['hidden']:>4} {r['batch']:>7} {r['precision']:>7} {r['fwd_ms']:>9.3f} {r['fwd_bwd_ms']:>11.3f} "
               f"{r['graphs_per_s_fwd']:>13.3e} {r['layer_gbs']:>9.0f} {r['frac_hbm']:>6.2f} {r['issued_tflops']:>8.1f}")
-    print(json.dumps({"metric": "grid_gnn_sweep", "rows": rows}))
+    print(json.dumps({"metric": "grid_gnn_sweep", "n_gpus": world, "rows": rows}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
