@@ -86,6 +86,8 @@ SIGNATURES = {
     "azg_grid_layer_tc_backward_input": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "azg_emit_examples": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "azg_gather_examples": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "azg_grid_dw_scratch_floats": (_sz, [_i]),
+    "azg_grid_layer_tc_backward_weights": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     "azg_gnn_layer_saved_floats": (_sz, [_i, _i]),
     "azg_gnn_layer_scratch_floats": (_sz, [_i, _i]),
     "azg_gnn_layer_forward": (_i, [C.POINTER(GNNLayerParams), _vp, _vp, _i, _i, _vp, _vp, _vp]),

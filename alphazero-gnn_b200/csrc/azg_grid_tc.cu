@@ -370,6 +370,229 @@ int launch(const GridArgs& g, cudaStream_t st) {
   return AZG_OK;
 }
 
+// ---- weight / bias gradient of the layer on the tensor cores ---------------------------------------------------
+//   dW[o, i] = sum_r S[r, o] X[r, i],   db[o] = sum_r S[r, o]      S = A^ (dOut * [out > 0]),  r over all B*n rows
+// The contraction index is the ROW of two row-major fp32 matrices, i.e. both operands are MN-major for the tensor
+// core: a k-block of KR rows is stored as H/64 blocks of [KR k-rows x 64 elements] (128-byte rows, 8-row swizzle
+// atoms) -- the same byte pattern the K-major images use, read through descriptors with the MN-major bits set
+// (a_major = b_major = 1; LBO = block stride, SBO = 1024).  Split-K over persistent CTAs: each CTA accumulates its
+// k-blocks in TMEM (M = 128 output features per accumulator, two accumulators for H = 256) and writes one partial
+// [H, H]; a fixed-order reduction adds the partials (deterministic).
+template <int H, bool X3>
+struct DwSmem {
+  static constexpr int KR = H == 256 ? 32 : 64;           // rows per k-block (16 float4 of loads in flight per thread)
+  static constexpr int BLK = KR * 128;                    // one [KR x 64] block
+  static constexpr int OPER = (H / 64) * BLK;             // one operand image (hi or lo)
+  static constexpr int STAGE_BYTES = 2 * (X3 ? 2 : 1) * OPER;  // S and X
+  static constexpr int NST = 3;
+  static constexpr int MISC_OFF = NST * STAGE_BYTES;
+  static constexpr int TOTAL = MISC_OFF + 4096 + 1024;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;  // stride between 64-element blocks along M/N
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride between 8-row groups along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+struct DwArgs {
+  const float* s;   // [rows, H]
+  const float* x;   // [rows, H]
+  float* part_w;    // [grid, H, H]
+  float* part_b;    // [grid, H]
+  int64_t rows;
+};
+
+template <int H, bool X3>
+__global__ void __launch_bounds__(512, 1) grid_dw_tc_kernel(DwArgs g) {
+  using S = DwSmem<H, X3>;
+  constexpr int KR = S::KR, NST = S::NST, MH = H / 128;  // M halves
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = (uint64_t*)(smem + S::MISC_OFF);
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
+  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t kblocks = (g.rows + KR - 1) / KR;
+  const int64_t items = kblocks > blockIdx.x ? (kblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  constexpr uint32_t TMEM_COLS = MH * H < 32 ? 32 : MH * H;
+
+  if (warp == 9 && lane == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 256);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // producers: thread = (row group, float4 column); rows rg + RG*i of the k-block
+    constexpr int C4 = H / 4, RG = 256 / C4, NI = KR / RG;
+    const int c4 = threadIdx.x % C4, rg = threadIdx.x / C4;
+    const int blk = (c4 * 4) / 64, col = (c4 * 4) % 64;
+    float4 sv[NI], xv[NI];
+    float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load = [&](int64_t it, int i, float4& a, float4& b) {
+      const int64_t row = (blockIdx.x + it * (int64_t)gridDim.x) * KR + rg + RG * i;
+      if (row < g.rows) {
+        a = __ldcs(reinterpret_cast<const float4*>(g.s + row * H) + c4);
+        b = __ldcs(reinterpret_cast<const float4*>(g.x + row * H) + c4);
+      } else {
+        a = b = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (items > 0) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) load(0, i, sv[i], xv[i]);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t it = 0; it < items; ++it) {
+      uint8_t* sa = smem + stage * S::STAGE_BYTES;  // [S hi][S lo][X hi][X lo]
+      uint8_t* sx = sa + (X3 ? 2 : 1) * S::OPER;
+      mbar_wait(&empty[stage], phase ^ 1);
+      const bool more = it + 1 < items;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const float4 a = sv[i], b = xv[i];
+        dbacc.x += a.x; dbacc.y += a.y; dbacc.z += a.z; dbacc.w += a.w;
+        const uint32_t off = (uint32_t)blk * S::BLK + image_offset(rg + RG * i, col);
+        split_store4(a, sa, X3 ? sa + S::OPER : nullptr, off);
+        split_store4(b, sx, X3 ? sx + S::OPER : nullptr, off);
+        if (more) load(it + 1, i, sv[i], xv[i]);
+      }
+      fence_async_smem();
+      mbar_arrive(&full[stage]);
+      if (++stage == NST) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    // db partial: sum the row groups' column sums in fixed order (rg = 0 .. RG-1)
+    named_bar(1, 256);  // every producer is past its last stage write; reuse stage 0 as scratch once the MMAs are done
+    mbar_wait(tfull, 0);
+    float4* scratch = reinterpret_cast<float4*>(smem);
+    scratch[rg * C4 + c4] = dbacc;
+    named_bar(1, 256);
+    if (rg == 0) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < RG; ++r) {
+        const float4 v = scratch[r * C4 + c4];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      reinterpret_cast<float4*>(g.part_b + (size_t)blockIdx.x * H)[c4] = t;
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, H) | (1u << 15) | (1u << 16);  // A and B MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t it = 0; it < items; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+        const uint32_t sx = sa + (X3 ? 2 : 1) * S::OPER;
+#pragma unroll
+        for (int m = 0; m < MH; ++m) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(m * H);
+          const uint32_t a0 = sa + m * 2 * S::BLK;  // output features [128 m, 128 m + 128) = blocks 2m, 2m+1
+#pragma unroll
+          for (int k = 0; k < KR / 16; ++k) {
+            const uint64_t a_hi = make_smem_desc_mn(a0 + k * 2048, S::BLK), b_hi = make_smem_desc_mn(sx + k * 2048, S::BLK);
+            umma_bf16(d_tmem, a_hi, b_hi, idesc, (it | k) != 0);
+            if (X3) {
+              const uint64_t a_lo = make_smem_desc_mn(a0 + S::OPER + k * 2048, S::BLK);
+              const uint64_t b_lo = make_smem_desc_mn(sx + S::OPER + k * 2048, S::BLK);
+              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+              umma_bf16(d_tmem, a_lo, b_hi, idesc, 1);
+            }
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == NST) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull);  // also arrives when nothing was issued
+    }
+  } else if (warp >= 12) {
+    const int q = warp & 3, r = q * 32 + lane;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int m = 0; m < MH; ++m) {
+      float* dst = g.part_w + ((size_t)blockIdx.x * H + m * 128 + r) * H;
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        uint32_t rr[32];
+        if (items > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * H + c0), rr);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) rr[e] = 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          reinterpret_cast<float4*>(dst + c0)[e] = make_float4(__uint_as_float(rr[4 * e]), __uint_as_float(rr[4 * e + 1]),
+                                                              __uint_as_float(rr[4 * e + 2]), __uint_as_float(rr[4 * e + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// out[i] = sum over CTAs of part[cta][i], fixed order
+__global__ void reduce_cta_partials_kernel(const float* __restrict__ part, int ctas, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int c = 0; c < ctas; ++c) s += part[(size_t)c * n + i];
+  out[i] = s;
+}
+
+template <int H, bool X3>
+int launch_dw(const float* s, const float* x, int64_t rows, float* dw, float* db, float* scratch, cudaStream_t st) {
+  static bool configured = false;
+  using S = DwSmem<H, X3>;
+  int dev = 0, sms = 0;
+  AZG_CUDA_CHECK(cudaGetDevice(&dev));
+  AZG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!configured) {
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(grid_dw_tc_kernel<H, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  const int64_t kblocks = (rows + S::KR - 1) / S::KR;
+  const int grid = (int)(kblocks < sms ? kblocks : sms);
+  DwArgs g{s, x, scratch, scratch + (size_t)grid * H * H, rows};
+  grid_dw_tc_kernel<H, X3><<<grid, 512, S::TOTAL, st>>>(g);
+  AZG_LAUNCH_CHECK();
+  reduce_cta_partials_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(g.part_w, grid, (int64_t)H * H, dw);
+  AZG_LAUNCH_CHECK();
+  reduce_cta_partials_kernel<<<(H + 255) / 256, 256, 0, st>>>(g.part_b, grid, H, db);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
 template <bool BWD>
 int dispatch(const GridArgs& g, int H, int prec, cudaStream_t st) {
   const bool x3 = prec == AZG_PREC_BF16X3;
@@ -421,6 +644,20 @@ int azg_grid_layer_tc_backward_input(const float* dout, const float* act, const 
   if (B <= 0) return AZG_OK;
   gridtc::GridArgs g{dout, act, (const uint8_t*)packed_wt, (const uint8_t*)packed_wt + (size_t)H * H * 2, nullptr, dx, B, gh, gw, 0};
   return gridtc::dispatch<true>(g, H, prec, (cudaStream_t)stream);
+}
+
+size_t azg_grid_dw_scratch_floats(int H) { return (size_t)160 * ((size_t)H * H + H); }  // one partial per CTA (<= 160 SMs)
+
+int azg_grid_layer_tc_backward_weights(const float* s, const float* x, int64_t rows, int H, int prec, float* dw, float* db,
+                                       float* scratch, azg_stream stream) {
+  AZG_REQUIRE(s && x && dw && db && scratch, "azg_grid_layer_tc_backward_weights: null pointer");
+  AZG_REQUIRE(H == 128 || H == 256, "azg_grid_layer_tc_backward_weights: hidden size %d not in {128, 256}", H);
+  AZG_REQUIRE(prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16, "azg_grid_layer_tc_backward_weights: precision must be bf16x3 or bf16");
+  AZG_REQUIRE(rows > 0, "azg_grid_layer_tc_backward_weights: no rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool x3 = prec == AZG_PREC_BF16X3;
+  if (H == 128) return x3 ? gridtc::launch_dw<128, true>(s, x, rows, dw, db, scratch, st) : gridtc::launch_dw<128, false>(s, x, rows, dw, db, scratch, st);
+  return x3 ? gridtc::launch_dw<256, true>(s, x, rows, dw, db, scratch, st) : gridtc::launch_dw<256, false>(s, x, rows, dw, db, scratch, st);
 }
 
 }  // extern "C"

@@ -209,6 +209,13 @@ int azg_grid_layer_tc_forward(const float* x, const void* packed_w, const float*
                               int prec, float* out, azg_stream stream);
 int azg_grid_layer_tc_backward_input(const float* dout, const float* act, const void* packed_wt, int64_t B, int gh, int gw,
                                      int H, int prec, float* dx, azg_stream stream);
+/*   backward_weights: dW[o,i] = sum_r S[r,o] x[r,i], db[o] = sum_r S[r,o] over all rows r of two row-major [rows, H]
+ *   matrices (S = adj * (dout * (out > 0)), from azg_grid_aggregate_relu_backward): split-K over persistent CTAs on
+ *   tcgen05 with MN-major operands, fixed-order reduction of the per-CTA partials.  H in {128, 256};
+ *   scratch: azg_grid_dw_scratch_floats(H) floats. */
+size_t azg_grid_dw_scratch_floats(int H);
+int azg_grid_layer_tc_backward_weights(const float* s, const float* x, int64_t rows, int H, int prec, float* dw, float* db,
+                                       float* scratch, azg_stream stream);
 /* Example pipeline between self-play and training, on the device (csrc/azg_replay.cu).
  * azg_emit_examples: every stored position of finished episodes -> S symmetric training examples with signed values
  *   (Coach.py:45-49, 68-79; Connect4Game.getSymmetries :189-215, TicTacToeGame.getSymmetries :187-200).
