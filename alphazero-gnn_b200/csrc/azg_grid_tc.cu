@@ -385,7 +385,8 @@ struct DwSmem {
   static constexpr int OPER = (H / 64) * BLK;             // one operand image (hi or lo)
   static constexpr int STAGE_BYTES = 2 * (X3 ? 2 : 1) * OPER;  // S and X
   static constexpr int NST = 3;
-  static constexpr int MISC_OFF = NST * STAGE_BYTES;
+  static constexpr int ZERO_OFF = NST * STAGE_BYTES;      // H = 64: an all-zero block stands in for output features 64..127
+  static constexpr int MISC_OFF = ZERO_OFF + (H < 128 ? BLK : 0);
   static constexpr int TOTAL = MISC_OFF + 4096 + 1024;
 };
 
@@ -410,7 +411,7 @@ struct DwArgs {
 template <int H, bool X3>
 __global__ void __launch_bounds__(512, 1) grid_dw_tc_kernel(DwArgs g) {
   using S = DwSmem<H, X3>;
-  constexpr int KR = S::KR, NST = S::NST, MH = H / 128;  // M halves
+  constexpr int KR = S::KR, NST = S::NST, MH = H < 128 ? 1 : H / 128;  // accumulators of 128 output features
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = (uint64_t*)(smem + S::MISC_OFF);
@@ -431,6 +432,10 @@ __global__ void __launch_bounds__(512, 1) grid_dw_tc_kernel(DwArgs g) {
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (H < 128) {
+    for (int i = threadIdx.x; i < S::BLK / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + S::ZERO_OFF)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -508,12 +513,15 @@ __global__ void __launch_bounds__(512, 1) grid_dw_tc_kernel(DwArgs g) {
         for (int m = 0; m < MH; ++m) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(m * H);
           const uint32_t a0 = sa + m * 2 * S::BLK;  // output features [128 m, 128 m + 128) = blocks 2m, 2m+1
+          // H = 64: the operand has one block; the second block of the 128-row MMA is the zero block
+          const uint32_t lbo_hi = H < 128 ? smem_u32(smem + S::ZERO_OFF) - a0 : (uint32_t)S::BLK;
+          const uint32_t lbo_lo = H < 128 ? lbo_hi - S::OPER : (uint32_t)S::BLK;
 #pragma unroll
           for (int k = 0; k < KR / 16; ++k) {
-            const uint64_t a_hi = make_smem_desc_mn(a0 + k * 2048, S::BLK), b_hi = make_smem_desc_mn(sx + k * 2048, S::BLK);
+            const uint64_t a_hi = make_smem_desc_mn(a0 + k * 2048, lbo_hi), b_hi = make_smem_desc_mn(sx + k * 2048, S::BLK);
             umma_bf16(d_tmem, a_hi, b_hi, idesc, (it | k) != 0);
             if (X3) {
-              const uint64_t a_lo = make_smem_desc_mn(a0 + S::OPER + k * 2048, S::BLK);
+              const uint64_t a_lo = make_smem_desc_mn(a0 + S::OPER + k * 2048, lbo_lo);
               const uint64_t b_lo = make_smem_desc_mn(sx + S::OPER + k * 2048, S::BLK);
               umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
               umma_bf16(d_tmem, a_lo, b_hi, idesc, 1);
@@ -536,7 +544,7 @@ __global__ void __launch_bounds__(512, 1) grid_dw_tc_kernel(DwArgs g) {
     for (int m = 0; m < MH; ++m) {
       float* dst = g.part_w + ((size_t)blockIdx.x * H + m * 128 + r) * H;
 #pragma unroll 1
-      for (int c0 = 0; c0 < H; c0 += 32) {
+      for (int c0 = 0; c0 < H && m * 128 + r < H; c0 += 32) {
         uint32_t rr[32];
         if (items > 0) {
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * H + c0), rr);
@@ -651,11 +659,12 @@ size_t azg_grid_dw_scratch_floats(int H) { return (size_t)160 * ((size_t)H * H +
 int azg_grid_layer_tc_backward_weights(const float* s, const float* x, int64_t rows, int H, int prec, float* dw, float* db,
                                        float* scratch, azg_stream stream) {
   AZG_REQUIRE(s && x && dw && db && scratch, "azg_grid_layer_tc_backward_weights: null pointer");
-  AZG_REQUIRE(H == 128 || H == 256, "azg_grid_layer_tc_backward_weights: hidden size %d not in {128, 256}", H);
+  AZG_REQUIRE(H == 64 || H == 128 || H == 256, "azg_grid_layer_tc_backward_weights: hidden size %d not in {64, 128, 256}", H);
   AZG_REQUIRE(prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16, "azg_grid_layer_tc_backward_weights: precision must be bf16x3 or bf16");
   AZG_REQUIRE(rows > 0, "azg_grid_layer_tc_backward_weights: no rows");
   cudaStream_t st = (cudaStream_t)stream;
   const bool x3 = prec == AZG_PREC_BF16X3;
+  if (H == 64) return x3 ? gridtc::launch_dw<64, true>(s, x, rows, dw, db, scratch, st) : gridtc::launch_dw<64, false>(s, x, rows, dw, db, scratch, st);
   if (H == 128) return x3 ? gridtc::launch_dw<128, true>(s, x, rows, dw, db, scratch, st) : gridtc::launch_dw<128, false>(s, x, rows, dw, db, scratch, st);
   return x3 ? gridtc::launch_dw<256, true>(s, x, rows, dw, db, scratch, st) : gridtc::launch_dw<256, false>(s, x, rows, dw, db, scratch, st);
 }

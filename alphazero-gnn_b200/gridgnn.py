@@ -46,8 +46,7 @@ def _pack(weight, transpose):
 class _GridLayerTC(torch.autograd.Function):
     """One GNNLayer as the fused tensor-core kernel (csrc/azg_grid_tc.cu): out = relu(adj (x W^T + b)).
     Backward: dx from the same kernel on (dout * [out > 0]) with the transposed weight image; the weight and bias
-    gradients contract over all B*n rows (S = adj (dout * [out > 0]), dW = S^T x): on tcgen05 with MN-major operands for
-    hidden 128 / 256, on the fp32 split-K path for hidden 64."""
+    gradients contract over all B*n rows (S = adj (dout * [out > 0]), dW = S^T x): on tcgen05 with MN-major operands."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, gh, gw, prec):
@@ -77,7 +76,7 @@ class _GridLayerTC(torch.autograd.Function):
             s = torch.empty_like(out)
             _lib.check(lib.azg_grid_aggregate_relu_backward(ptr(dout), ptr(out), B, gh, gw, H, ptr(s), stream()))
             dw, db = torch.empty_like(weight), torch.empty(H, dtype=torch.float32, device=x.device)
-            if H in (128, 256):  # contraction over all B*n rows on the tensor cores (MN-major operands, split-K over CTAs)
+            if H in (64, 128, 256):  # contraction over all B*n rows on the tensor cores (MN-major operands, split-K over CTAs)
                 scratch = torch.empty(int(lib.azg_grid_dw_scratch_floats(H)), dtype=torch.float32, device=x.device)
                 _lib.check(lib.azg_grid_layer_tc_backward_weights(ptr(s), ptr(x), B * n, H, prec, ptr(dw), ptr(db), ptr(scratch),
                                                                   stream()))

@@ -211,7 +211,7 @@ int azg_grid_layer_tc_backward_input(const float* dout, const float* act, const 
                                      int H, int prec, float* dx, azg_stream stream);
 /*   backward_weights: dW[o,i] = sum_r S[r,o] x[r,i], db[o] = sum_r S[r,o] over all rows r of two row-major [rows, H]
  *   matrices (S = adj * (dout * (out > 0)), from azg_grid_aggregate_relu_backward): split-K over persistent CTAs on
- *   tcgen05 with MN-major operands, fixed-order reduction of the per-CTA partials.  H in {128, 256};
+ *   tcgen05 with MN-major operands, fixed-order reduction of the per-CTA partials.  H in {64, 128, 256};
  *   scratch: azg_grid_dw_scratch_floats(H) floats. */
 size_t azg_grid_dw_scratch_floats(int H);
 int azg_grid_layer_tc_backward_weights(const float* s, const float* x, int64_t rows, int H, int prec, float* dw, float* db,

@@ -85,3 +85,23 @@ def test_fused_layer_ragged_batches(B):
             y = net(x)
             y2 = onets.grid_gnn_forward([l.weight for l in net.gnn_layers], [l.bias for l in net.gnn_layers], x, 7, 7)
         assert (y - y2).abs().max().item() <= tol * max(1.0, y2.abs().max().item())
+
+
+@pytest.mark.parametrize("H", [64, 128, 256])
+@pytest.mark.parametrize("rows", [1, 63, 64, 65, 4097, 333333])
+def test_weight_gradient_kernel_ragged_row_counts(H, rows):
+    """dW = S^T X, db = colsum(S) on tcgen05 with MN-major operands: partial k-blocks, fewer k-blocks than CTAs"""
+    from azgnn_b200 import _lib
+    from azgnn_b200._lib import ptr, stream
+    g = torch.Generator(device="cuda").manual_seed(rows + H)
+    S = torch.randn(rows, H, device="cuda", generator=g)
+    X = torch.randn(rows, H, device="cuda", generator=g)
+    lib = _lib.lib()
+    dw, db = torch.empty(H, H, device="cuda"), torch.empty(H, device="cuda")
+    scratch = torch.empty(int(lib.azg_grid_dw_scratch_floats(H)), device="cuda")
+    for prec, tol in ((_lib.PREC_BF16X3, 2e-5), (_lib.PREC_BF16, 2e-2)):
+        _lib.check(lib.azg_grid_layer_tc_backward_weights(ptr(S), ptr(X), rows, H, prec, ptr(dw), ptr(db), ptr(scratch), stream()))
+        want = S.double().t() @ X.double()
+        scale = (S.double().abs().t() @ X.double().abs()).max().item() + 1.0
+        assert (dw.double() - want).abs().max().item() <= tol * scale, (prec, (dw.double() - want).abs().max().item(), scale)
+        assert (db.double() - S.double().sum(0)).abs().max().item() <= 1e-5 * (S.abs().sum(0).max().item() + 1.0)
