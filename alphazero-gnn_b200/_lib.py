@@ -67,6 +67,10 @@ SIGNATURES = {
     "azg_tc_linear": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _sz, _vp]),
     "azg_ttt_workspace_bytes": (_sz, [_i, _i64, _i]),
     "azg_ttt_forward": (_i, [C.POINTER(TTTParams), _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "azg_ttt_packed_bytes": (_sz, [_i, _i]),
+    "azg_ttt_pack": (_i, [C.POINTER(TTTParams), _i, _i, _vp, _sz, _vp]),
+    "azg_ttt_tc_workspace_bytes": (_sz, [_i, _i64, _i]),
+    "azg_ttt_forward_tc": (_i, [C.POINTER(TTTParams), _vp, _i, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "azg_fl_forward": (_i, [C.POINTER(FLParams), _i, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "azg_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
     "azg_gemm_f32": (_i, [_i, _i, _i64, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, C.c_float, _vp]),

@@ -1244,6 +1244,230 @@ int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t pa
   return AZG_OK;
 }
 
+}  // extern "C" (reopened below)
+
+// ---- TicTacToe on the tensor cores (tictactoe/TicTacToeNet.py:28-48, TicTacToeGNN.py:25-87) ------------------------
+// conv2 / conv3 as im2col GEMMs whose A operand is written straight as tile images (the fp32 patch matrix never
+// exists), fc1 / fc2 / output_transform as GEMMs over image copies of their fp32 inputs; conv1 and the two small
+// heads stay on the fp32 kernels.  Weight images: one blob per precision, rebuilt after weight updates.
+namespace {
+
+// patches of boards [b0, b0+nb) -> A operand images, rows (board, cell), K = (ci, kx, ky) zero-padded to Kp
+__global__ void im2col3x3_image_kernel(const float* __restrict__ in, int in_nhwc, int64_t b0, int64_t nb, int Cin, int H, int W,
+                                       int pad, int Kp, int64_t rows_padded, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, P = Ho * Wo, K = Cin * 9, chunks = Kp / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_padded * chunks) return;
+  const int64_t row = idx / chunks;
+  const int c = (int)(idx % chunks);
+  float x8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x8[e] = 0.0f;
+  if (row < nb * P) {
+    const int64_t b = b0 + row / P;
+    const int p = (int)(row % P), ox = p / Wo, oy = p % Wo;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = c * 8 + e;
+      if (k < K) {
+        const int ci = k / 9, kx = (k % 9) / 3, ky = k % 3, x = ox + kx - pad, y = oy + ky - pad;
+        if (x >= 0 && x < H && y >= 0 && y < W)
+          x8[e] = in_nhwc ? in[((b * H + x) * W + y) * Cin + ci] : in[((b * Cin + ci) * H + x) * W + y];
+      }
+    }
+  }
+  const int KB = Kp / tc::BK;
+  const size_t off = ((size_t)(row / 128) * KB + (c * 8) / tc::BK) * ((size_t)128 * 128) + tc::image_offset((int)(row % 128), (c * 8) % tc::BK);
+  tc::split_store(x8, hi, lo, off);
+}
+
+// W [N, K] fp32 -> [N x Kp] weight images with BN-row tiles (columns K..Kp-1 zero)
+__global__ void weight_image_padded_kernel(const float* __restrict__ w, int N, int K, int Kp, int BN, uint8_t* __restrict__ hi,
+                                           uint8_t* __restrict__ lo) {
+  const int chunks = Kp / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * chunks) return;
+  const int n = idx / chunks, c = idx % chunks;
+  float x8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x8[e] = (c * 8 + e < K) ? w[(size_t)n * K + c * 8 + e] : 0.0f;
+  const int KB = Kp / tc::BK;
+  const size_t off = ((size_t)(n / BN) * KB + (c * 8) / tc::BK) * ((size_t)BN * 128) + tc::image_offset(n % BN, (c * 8) % tc::BK);
+  tc::split_store(x8, hi, lo, off);
+}
+
+struct TttLayer {
+  int N, K, Kp, BN;
+  size_t hi, lo;
+};
+struct TttPack {
+  TttLayer conv2, conv3, fc1, fc2, ot0, ot2;
+  size_t total;
+};
+
+int ttt_bn(int N) { return N % 256 == 0 ? 256 : 64; }
+
+TttPack ttt_pack_layout(int n, bool x3) {
+  const int F = 128 * (n - 2) * (n - 2);
+  TttPack L{};
+  size_t off = 0;
+  auto lay = [&](int N, int K) {
+    TttLayer l{N, K, (K + 63) / 64 * 64, ttt_bn(N), 0, 0};
+    const size_t img = (size_t)N * l.Kp * 2;
+    l.hi = off; off = up1k(off + img);
+    if (x3) { l.lo = off; off = up1k(off + img); }
+    return l;
+  };
+  L.conv2 = lay(64, 288); L.conv3 = lay(128, 576); L.fc1 = lay(512, F); L.fc2 = lay(512, F); L.ot0 = lay(F, F); L.ot2 = lay(F, F);
+  L.total = off;
+  return L;
+}
+
+constexpr size_t TTT_IMG_BYTES = (size_t)128 << 20;  // per image (hi or lo) of an im2col chunk
+
+struct TttScratch {
+  size_t planes, c1, c2, f_nhwc, feat, hid, enh, h1, h2, a_hi, a_lo, total;
+};
+TttScratch ttt_scratch_layout(int n, int64_t B, bool gnn) {
+  const size_t nn = (size_t)n * n, P = (size_t)(n - 2) * (n - 2), F = 128 * P;
+  TttScratch S{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = up1k(off + bytes); return o; };
+  S.planes = take(B * nn * 4); S.c1 = take(B * 32 * nn * 4); S.c2 = take(B * 64 * nn * 4); S.f_nhwc = take(B * F * 4);
+  S.feat = take(B * F * 4); S.h1 = take(B * 512 * 4); S.h2 = take(B * 512 * 4);
+  if (gnn) { S.hid = take(B * F * 4); S.enh = take(B * F * 4); }
+  const size_t Mp = (size_t)azg_ceil_div(B, 256) * 256;
+  const size_t fc_img = Mp * (F > 512 ? F : 512) * 2;
+  const size_t img = fc_img > TTT_IMG_BYTES ? fc_img : TTT_IMG_BYTES;
+  S.a_hi = take(img + 65536); S.a_lo = take(img + 65536);
+  S.total = off;
+  return S;
+}
+
+// C[M, N] = act(image(A) W^T + b): the A images are already in a_hi / a_lo
+int ttt_gemm(const uint8_t* a_hi, const uint8_t* a_lo, int64_t M, const TttLayer& l, const uint8_t* w, const float* bias, int relu,
+             bool x3, float* C, cudaStream_t st) {
+  tc::GemmArgs g{};
+  g.M = M; g.m_tiles = (int)azg_ceil_div(M, tc::BM); g.n_tiles = l.N / l.BN; g.KB = l.Kp / tc::BK; g.x3 = x3;
+  g.pair_ok = l.BN == 256 ? 1 : 0;
+  g.a_hi = a_hi; g.a_lo = x3 ? a_lo : nullptr; g.w_hi = w + l.hi; g.w_lo = x3 ? w + l.lo : nullptr; g.bias = bias; g.relu = relu;
+  g.out_mode = tc::OUT_F32; g.out_f32 = C;
+  return tc::run_gemm(l.BN, g, st);
+}
+
+// relu(conv3x3) over all boards in chunks: im2col images -> GEMM -> (board, cell, channel) rows
+int ttt_conv_tc(const float* in, int in_nhwc, const TttLayer& l, const uint8_t* w, const float* bias, float* out_nhwc, int64_t B,
+                int Cin, int H, int W, int pad, bool x3, uint8_t* a_hi, uint8_t* a_lo, cudaStream_t st) {
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, P = Ho * Wo;
+  int64_t chunk = (int64_t)(TTT_IMG_BYTES / ((size_t)P * l.Kp * 2)) / 256 * 256;
+  if (chunk < 256) chunk = 256;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    const int64_t nb = B - b0 < chunk ? B - b0 : chunk;
+    const int64_t rows = nb * P, rows_p = azg_ceil_div(rows, 256) * 256;
+    AZG_REQUIRE((size_t)rows_p * l.Kp * 2 <= TTT_IMG_BYTES + 65536, "ttt_conv_tc: image chunk overflow");
+    const int64_t n = rows_p * (l.Kp / 8);
+    im2col3x3_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, in_nhwc, b0, nb, Cin, H, W, pad, l.Kp, rows_p, a_hi,
+                                                                       x3 ? a_lo : nullptr);
+    AZG_LAUNCH_CHECK();
+    int rc = ttt_gemm(a_hi, a_lo, rows, l, w, bias, 1, x3, out_nhwc + (size_t)b0 * P * l.N, st);
+    if (rc) return rc;
+  }
+  return AZG_OK;
+}
+
+int ttt_linear_tc(const float* A, int64_t M, const TttLayer& l, const uint8_t* w, const float* bias, int relu, bool x3, float* C,
+                  uint8_t* a_hi, uint8_t* a_lo, bool reuse_image, cudaStream_t st) {
+  int rc;
+  if (!reuse_image && (rc = tc::to_image(A, M, azg_ceil_div(M, 256) * 256, l.Kp, tc::BM, a_hi, x3 ? a_lo : nullptr, st))) return rc;
+  return ttt_gemm(a_hi, a_lo, M, l, w, bias, relu, x3, C, st);
+}
+
+}  // namespace
+
+// fp32 pieces of azg_nets.cu
+int azg_ttt_fp32_front(const float* conv1_w, const float* conv1_b, int n, const uint64_t* states, int64_t B, float* planes, float* c1,
+                       cudaStream_t st);
+int azg_ttt_fp32_heads(const float* h1, const float* pw, const float* pb, int A, const float* h2, const float* vw, const float* vb,
+                       int64_t B, float* pi, float* v, cudaStream_t st);
+int azg_nhwc_to_nchw(const float* src, int64_t B, int P, int C, float* dst, cudaStream_t st);
+
+extern "C" {
+
+size_t azg_ttt_packed_bytes(int n, int prec) {
+  if (n < 3 || n > 8 || prec == AZG_PREC_FP32) return 0;
+  return ttt_pack_layout(n, prec == AZG_PREC_BF16X3).total + 1024;
+}
+
+int azg_ttt_pack(const azg_ttt_params* p, int n, int prec, void* packed, size_t packed_bytes, azg_stream stream) {
+  AZG_REQUIRE(p && packed && n >= 3 && n <= 8 && (prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16), "azg_ttt_pack: bad argument");
+  AZG_REQUIRE(packed_bytes >= azg_ttt_packed_bytes(n, prec) && ((uintptr_t)packed & 1023) == 0, "azg_ttt_pack: buffer too small or not 1 KB aligned");
+  const bool x3 = prec == AZG_PREC_BF16X3;
+  const TttPack L = ttt_pack_layout(n, x3);
+  uint8_t* w = (uint8_t*)packed;
+  cudaStream_t st = (cudaStream_t)stream;
+  struct { const TttLayer* l; const float* src; } items[] = {{&L.conv2, p->conv2_w}, {&L.conv3, p->conv3_w}, {&L.fc1, p->fc1_w},
+                                                            {&L.fc2, p->fc2_w}, {&L.ot0, p->ot0_w}, {&L.ot2, p->ot2_w}};
+  for (auto& it : items) {
+    if (!it.src) continue;  // output_transform is absent without the GNN
+    const int n_thr = it.l->N * (it.l->Kp / 8);
+    weight_image_padded_kernel<<<(n_thr + 255) / 256, 256, 0, st>>>(it.src, it.l->N, it.l->K, it.l->Kp, it.l->BN, w + it.l->hi,
+                                                                    x3 ? w + it.l->lo : nullptr);
+    AZG_LAUNCH_CHECK();
+  }
+  return AZG_OK;
+}
+
+size_t azg_ttt_tc_workspace_bytes(int n, int64_t B, int eval_mask) {
+  return ttt_scratch_layout(n, B, (eval_mask & AZG_EVAL_GNN) != 0).total + 1024;
+}
+
+int azg_ttt_forward_tc(const azg_ttt_params* p, const void* packed, int n, int prec, const uint64_t* states, int64_t B, int eval_mask,
+                       float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* workspace, size_t workspace_bytes,
+                       azg_stream stream) {
+  AZG_REQUIRE(p && packed && states && workspace, "azg_ttt_forward_tc: null pointer");
+  AZG_REQUIRE(n >= 3 && n <= 8 && (eval_mask & ~3) == 0 && eval_mask != 0, "azg_ttt_forward_tc: bad n=%d or eval_mask=%d", n, eval_mask);
+  AZG_REQUIRE(prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16, "azg_ttt_forward_tc: precision must be bf16x3 or bf16");
+  if (B <= 0) return AZG_OK;
+  const bool x3 = prec == AZG_PREC_BF16X3, gnn = (eval_mask & AZG_EVAL_GNN) != 0;
+  const TttPack L = ttt_pack_layout(n, x3);
+  const TttScratch S = ttt_scratch_layout(n, B, gnn);
+  AZG_REQUIRE(workspace_bytes >= S.total + 1024, "azg_ttt_forward_tc: workspace %zu < %zu", workspace_bytes, S.total + 1024);
+  uint8_t* sc = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  const uint8_t* w = (const uint8_t*)packed;
+  cudaStream_t st = (cudaStream_t)stream;
+  float *planes = (float*)(sc + S.planes), *c1 = (float*)(sc + S.c1), *c2 = (float*)(sc + S.c2), *f_nhwc = (float*)(sc + S.f_nhwc);
+  float *feat = (float*)(sc + S.feat), *h1 = (float*)(sc + S.h1), *h2 = (float*)(sc + S.h2);
+  float *hid = gnn ? (float*)(sc + S.hid) : nullptr, *enh = gnn ? (float*)(sc + S.enh) : nullptr;
+  uint8_t *a_hi = sc + S.a_hi, *a_lo = sc + S.a_lo;
+  const int P = (n - 2) * (n - 2), A = n * n + 1;
+  int rc;
+  if ((rc = azg_ttt_fp32_front(p->conv1_w, p->conv1_b, n, states, B, planes, c1, st))) return rc;
+  if ((rc = ttt_conv_tc(c1, 0, L.conv2, w, p->conv2_b, c2, B, 32, n, n, 1, x3, a_hi, a_lo, st))) return rc;
+  if ((rc = ttt_conv_tc(c2, 1, L.conv3, w, p->conv3_b, f_nhwc, B, 64, n, n, 0, x3, a_hi, a_lo, st))) return rc;
+  if ((rc = azg_nhwc_to_nchw(f_nhwc, B, P, 128, feat, st))) return rc;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int bit = pass == 0 ? AZG_EVAL_STD : AZG_EVAL_GNN;
+    if (!(eval_mask & bit)) continue;
+    const float* f = feat;
+    float *pi = pi_std, *v = v_std;
+    if (pass == 1) {
+      AZG_REQUIRE(p->ot0_w && p->ot2_w, "azg_ttt_forward_tc: null output_transform weights");
+      if ((rc = ttt_linear_tc(feat, B, L.ot0, w, p->ot0_b, 1, x3, hid, a_hi, a_lo, false, st))) return rc;
+      if ((rc = ttt_linear_tc(hid, B, L.ot2, w, p->ot2_b, 0, x3, enh, a_hi, a_lo, false, st))) return rc;
+      f = enh; pi = pi_gnn; v = v_gnn;
+    }
+    AZG_REQUIRE(pi && v, "azg_ttt_forward_tc: null outputs");
+    if ((rc = ttt_linear_tc(f, B, L.fc1, w, p->fc1_b, 1, x3, h1, a_hi, a_lo, false, st))) return rc;
+    if ((rc = ttt_linear_tc(f, B, L.fc2, w, p->fc2_b, 1, x3, h2, a_hi, a_lo, true, st))) return rc;  // same A image
+    if ((rc = azg_ttt_fp32_heads(h1, p->fc_policy_w, p->fc_policy_b, A, h2, p->fc_value_w, p->fc_value_b, B, pi, v, st))) return rc;
+  }
+  return AZG_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
 // Stand-alone dense layer on the tensor-core path, for parity tests of the GEMM itself:
 // C[M,F] = act(A[M,F] . W[F,F]^T + bias), fp32 in/out, operands converted on the fly.
 int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int F, int prec, int relu,

@@ -439,6 +439,22 @@ struct Carver {
 
 }  // namespace
 
+// fp32 pieces used by the TicTacToe tensor-core path (azg_gemm_tc.cu)
+int azg_ttt_fp32_front(const float* conv1_w, const float* conv1_b, int n, const uint64_t* states, int64_t B, float* planes, float* c1,
+                       cudaStream_t st) {
+  if (B <= 0) return AZG_OK;
+  encode_planes_kernel<<<grid_for(B * n * n, 256), 256, 0, st>>>((const AzgState*)states, n * n, B, planes);
+  AZG_LAUNCH_CHECK();
+  return launch_conv(planes, conv1_w, conv1_b, c1, B, 1, 32, n, n, 1, st);
+}
+int azg_ttt_fp32_heads(const float* h1, const float* pw, const float* pb, int A, const float* h2, const float* vw, const float* vb,
+                       int64_t B, float* pi, float* v, cudaStream_t st) {
+  return launch_heads(h1, 512, pw, pb, A, h2, 512, vw, vb, B, pi, v, st);
+}
+int azg_nhwc_to_nchw(const float* src, int64_t B, int P, int C, float* dst, cudaStream_t st) {
+  return launch_nhwc_to_nchw(src, B, P, C, dst, st);
+}
+
 // tcgen05 path (azg_gemm_tc.cu)
 int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int prec, const uint64_t* states, int64_t B,
                       int eval_mask, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* scratch,

@@ -210,6 +210,22 @@ class B200TicTacToeNNetWrapper(_TwoPlayer):
         self._common(game, args)
         self.nnet = modules.TicTacToeTrunk(self.n, self.action_size).to(self.device)
         self.gnn = None
+        self.precision = _lib.PRECISIONS[arg(args, "b200_precision", "fp32") or "fp32"]
+        self._packed, self._packed_ok = {}, False
+
+    def _ensure_packed(self, prec, params):
+        """tcgen05 weight images (conv2, conv3, fc1, fc2, output_transform), rebuilt lazily after weights_changed()"""
+        if not self._packed_ok:
+            self._packed = {}
+            self._packed_ok = True
+        if prec not in self._packed:
+            nbytes = int(self.lib.azg_ttt_packed_bytes(self.n, prec))
+            blob = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-blob.data_ptr()) % 1024
+            view = blob[off:off + nbytes]
+            _lib.check(self.lib.azg_ttt_pack(C.byref(params), self.n, prec, ptr(view), nbytes, stream()))
+            self._packed[prec] = (blob, view)
+        return self._packed[prec][1]
 
     def _params(self):
         n, g = self.nnet, self.gnn
@@ -222,15 +238,23 @@ class B200TicTacToeNNetWrapper(_TwoPlayer):
             p.ot0_w, p.ot0_b, p.ot2_w, p.ot2_b = ptr(ot[0].weight), ptr(ot[0].bias), ptr(ot[2].weight), ptr(ot[2].bias)
         return p
 
-    def forward_states(self, states, eval_mask=None):
+    def forward_states(self, states, eval_mask=None, precision=None):
         eval_mask = self._default_mask() if eval_mask is None else eval_mask
         if (eval_mask & _lib.EVAL_GNN) and self.gnn is None:
             raise RuntimeError("predict_with_gnn needs the GNN wrapper")
+        prec = self.precision if precision is None else precision
         B = int(states.shape[0])
         o = self._outputs(B, eval_mask)
         if B == 0:
             return o
         p = self._params()
+        if prec != _lib.PREC_FP32:  # conv2 / conv3 / fc / output_transform on tcgen05
+            packed = self._ensure_packed(prec, p)
+            ws = self._workspace(self.lib.azg_ttt_tc_workspace_bytes(self.n, B, eval_mask))
+            _lib.check(self.lib.azg_ttt_forward_tc(C.byref(p), ptr(packed), self.n, prec, ptr(states), B, eval_mask, ptr(o.get("pi")),
+                                                   ptr(o.get("v")), ptr(o.get("pi_gnn")), ptr(o.get("v_gnn")), ptr(ws), ws.numel(),
+                                                   stream()))
+            return o
         ws = self._workspace(self.lib.azg_ttt_workspace_bytes(self.n, B, eval_mask))
         _lib.check(self.lib.azg_ttt_forward(C.byref(p), self.n, ptr(states), B, eval_mask, ptr(o.get("pi")), ptr(o.get("v")),
                                             ptr(o.get("pi_gnn")), ptr(o.get("v_gnn")), ptr(ws), ws.numel(), stream()))

@@ -29,9 +29,9 @@ class Args(dict):
     __getattr__ = dict.__getitem__
 
 
-def ttt_args(use_gnn):
+def ttt_args(use_gnn, precision="bf16x3"):
     return Args(lr=1e-3, dropout=0.3, epochs=20, batch_size=64, gnn_layers=2, use_gnn=use_gnn, numMCTSSims=10, cpuct=1.0,
-                expand_by=5, tempThreshold=15)
+                expand_by=5, tempThreshold=15, b200_precision=precision)
 
 
 def fl_args():
@@ -142,11 +142,11 @@ def main():
     from azgnn_b200 import games
     from azgnn_b200.nets import B200FrozenLakeNet, B200TicTacToeGNNWrapper, B200TicTacToeNNetWrapper
     torch.cuda.set_device(0)
-    for n, use_gnn in ((4, False), (4, True), (3, True)):
-        game, ar = games.TicTacToeGame(n), ttt_args(use_gnn)
+    for n, use_gnn, prec in ((4, False, "bf16x3"), (4, True, "bf16x3"), (3, True, "bf16x3"), (4, True, "fp32")):
+        game, ar = games.TicTacToeGame(n), ttt_args(use_gnn, prec)
         torch.manual_seed(0)
         w = (B200TicTacToeGNNWrapper if use_gnn else B200TicTacToeNNetWrapper)(game, ar)
-        run(f"tictactoe_{n}x{n}_{'gnn' if use_gnn else 'std'}", game, w, ar, a.games, a.leaf_batch, a.moves, a.cpu_episodes,
+        run(f"tictactoe_{n}x{n}_{'gnn' if use_gnn else 'std'}_{prec}", game, w, ar, a.games, a.leaf_batch, a.moves, a.cpu_episodes,
             None, OracleTTTNet(w, n), None)
     for n in (4, 8):
         game, ar = games.FrozenLakeGame(n), fl_args()

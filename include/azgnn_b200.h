@@ -141,6 +141,17 @@ int azg_ttt_forward(const azg_ttt_params* p, int n, const uint64_t* states, int6
                     float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* workspace,
                     size_t workspace_bytes, azg_stream stream);
 
+/* The same forward with conv2 / conv3 (im2col GEMMs whose A operand is written directly as tile images), fc1 / fc2
+ * and output_transform on tcgen05 (prec = AZG_PREC_BF16X3: pi, v within 1e-5 of the fp32 module; AZG_PREC_BF16:
+ * stated tolerance 5e-3); conv1 and the two small heads stay fp32.  `packed` = weight images from azg_ttt_pack
+ * (azg_ttt_packed_bytes bytes, 1 KB aligned), rebuilt after every weight update. */
+size_t azg_ttt_packed_bytes(int n, int prec);
+int azg_ttt_pack(const azg_ttt_params* p, int n, int prec, void* packed, size_t packed_bytes, azg_stream stream);
+size_t azg_ttt_tc_workspace_bytes(int n, int64_t B, int eval_mask);
+int azg_ttt_forward_tc(const azg_ttt_params* p, const void* packed, int n, int prec, const uint64_t* states, int64_t B,
+                       int eval_mask, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* workspace,
+                       size_t workspace_bytes, azg_stream stream);
+
 /* FrozenLake (frozenlake/FrozenLakeNet.py:178-230 predict, :297-334 EnhancedNNet.forward) */
 typedef struct azg_fl_params {
   const float *fe0_w, *fe0_b; /* feature_extractor.0: [128, n^2] */

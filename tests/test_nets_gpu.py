@@ -276,3 +276,32 @@ def test_folded_heads_match_reference(n, B, scale):
     w.fold_heads = True
     o2 = w.forward_states(states, _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
     assert not np.allclose(o2["v_gnn"].cpu().numpy(), o["v_gnn"].cpu().numpy())
+
+
+@pytest.mark.parametrize("n,B", [(3, 1), (3, 1000), (4, 1), (4, 777), (4, 5000), (5, 300), (8, 130)])
+def test_tictactoe_tensor_core_forward(n, B):
+    """TicTacToe with conv2 / conv3 / fc / output_transform on tcgen05: bf16x3 within the fp32 contract (1e-5 on pi, v),
+    bf16 within its stated 5e-3; std and GNN predictions; follows weight updates."""
+    w = _wrapper("ttt", n)
+    rng = np.random.default_rng(B + n)
+    boards = rng.integers(-1, 2, size=(B, n, n)).astype(np.int64)
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    bt = onets.boards_to_tensor(boards)
+    with torch.no_grad():
+        pi, v = onets.ttt_predict(p, bt, n)
+        gpi, gv = onets.ttt_predict_with_gnn(p, q, bt, n)
+    states = w.states_from_boards(boards)
+    both = _lib.EVAL_STD | _lib.EVAL_GNN
+    o3 = w.forward_states(states, both, precision=_lib.PREC_BF16X3)
+    for got, want in ((o3["pi"], pi), (o3["v"], v), (o3["pi_gnn"], gpi), (o3["v_gnn"], gv)):
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=0, atol=1e-5)
+    o1 = w.forward_states(states, both, precision=_lib.PREC_BF16)
+    for got, want in ((o1["pi"], pi), (o1["v"], v), (o1["pi_gnn"], gpi), (o1["v_gnn"], gv)):
+        assert np.abs(got.cpu().numpy() - want.numpy()).max() <= 5e-3
+    std_only = w.forward_states(states, _lib.EVAL_STD, precision=_lib.PREC_BF16X3)
+    assert torch.equal(std_only["pi"], o3["pi"])
+    with torch.no_grad():
+        w.nnet.fc2.bias.add_(0.5)
+    w.weights_changed()
+    o3b = w.forward_states(states, _lib.EVAL_STD, precision=_lib.PREC_BF16X3)
+    assert not np.allclose(o3b["v"].cpu().numpy(), o3["v"].cpu().numpy())
