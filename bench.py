@@ -358,6 +358,15 @@ def run_gpu_arm(args, rank, local_rank, world):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
+    # ---- latency of the reference-shaped single call (NeuralNet.predict_with_gnn(board): host board in, numpy out) ----
+    one = synthetic_boards(1, 7)[0].astype(np.int64)
+    for _ in range(5):
+        net.predict_with_gnn(one)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        net.predict_with_gnn(one)
+    single_ms = (time.perf_counter() - t0) / 50 * 1e3
+
     sp_moves, sp_leaves, sp_ms = (0.0, 0.0, 0.0)
     if args.selfplay_games > 0:
         barrier()
@@ -441,6 +450,8 @@ def run_gpu_arm(args, rank, local_rank, world):
                         "h2d_bytes_per_step": int(B * N_BOARD * N_BOARD),
                         "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_host.values())),
                         "ms_per_step": ms_e2e / args.steps},
+                "single_call_ms": {"predict_with_gnn": single_ms, "note": "one position, host board in, numpy pi/v out (B=1 "
+                                   "through the same kernels; the reference's CPU call takes ~7.8 ms on one thread)"},
                 "selfplay": selfplay,
                 "selfplay_folded_heads": sp_fold,
                 "also": also,

@@ -76,7 +76,7 @@ class _AsReference:
 
 
 @pytest.mark.parametrize("kind,n,prec", [("connect4", 7, "fp32"), ("connect4", 7, "bf16x3"), ("connect4", 5, "bf16"),
-                                         ("tictactoe", 4, "fp32"), ("frozenlake", 4, "fp32")])
+                                         ("tictactoe", 4, "fp32"), ("tictactoe", 4, "bf16x3"), ("frozenlake", 4, "fp32")])
 def test_search_with_device_networks_matches_oracle_search(kind, n, prec):
     """Lock-step search of several games whose leaves are evaluated in ONE batched CUDA pass per round
     gives the visit counts and Q values of the sequential oracle search that calls the same network
