@@ -21,14 +21,16 @@ from .mcts import BatchedMCTS, arg
 
 
 class BatchedArena:
-    def __init__(self, game, nnet1, nnet2, args, arena_factory=None):
+    def __init__(self, game, nnet1, nnet2, args, arena_factory=None, args2=None):
+        """args2: search settings of player 2 when they differ from player 1's (e.g. use_gnn, main.py:96-103)"""
         assert getattr(game, "is_two_player", True), "BatchedArena pits two-player games"
-        self.game, self.nets, self.args = game, (nnet1, nnet2), args
+        self.game, self.nets = game, (nnet1, nnet2)
+        self.args = (args, args if args2 is None else args2)
         self._arena_factory = arena_factory
 
     def _mcts(self, net, n_games):
         arena = self._arena_factory(n_games) if self._arena_factory else None
-        a = self.args
+        a = self.args[self.nets.index(net)] if self.nets[0] is not self.nets[1] else self.args[0]
         sims = int(arg(a, "numMCTSSims"))
         n = self.game.getBoardSize()[0]
         # a game's tree lives for the whole game: every simulation of every ply it is searched on adds <= 1 entry
@@ -75,3 +77,14 @@ class BatchedArena:
                 else:
                     draws += 1
         return one, two, draws
+
+
+def pit_gnn_vs_regular(game, gnn_nnet, reg_nnet, config_args, num=None):
+    """main.py:60-138 (`--pit_gnn`): the GNN-enhanced model (searching with predict_with_gnn) against the regular
+    model (predict), `arenaCompare` games, all in flight.  Returns (gnn_wins, reg_wins, draws)."""
+    def with_gnn(flag):
+        a = type(config_args)(config_args) if isinstance(config_args, dict) else dict(vars(config_args))
+        a["use_gnn"] = flag
+        return a if isinstance(config_args, dict) else type("Args", (), a)()
+    num = arg(config_args, "arenaCompare") if num is None else num
+    return BatchedArena(game, gnn_nnet, reg_nnet, with_gnn(True), args2=with_gnn(False)).playGames(num)

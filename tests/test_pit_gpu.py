@@ -55,3 +55,18 @@ def test_batched_arena_equals_sequential_games_with_fresh_trees(kind, n, monkeyp
     # the two halves mirror each other when a network meets itself
     one, two, draws = BatchedArena(game, net_a, net_a, args).playGames(4)
     assert one == two and one + two + draws == 4
+
+
+def test_pit_gnn_vs_regular():
+    """--pit_gnn (main.py:60-138): GNN wrapper searching with predict_with_gnn vs regular wrapper searching with predict"""
+    from azgnn_b200.nets import B200Connect4NNetWrapper
+    from azgnn_b200.pit import pit_gnn_vs_regular
+    game = games.Connect4Game(5)
+    args = dotdict(dict(lr=1e-3, dropout=0.3, gnn_layers=2, use_gnn=True, numMCTSSims=6, cpuct=1.0, expand_by=3, arenaCompare=6,
+                        b200_precision="fp32"))
+    torch.manual_seed(0)
+    gnn_net = B200Connect4GNNWrapper(game, args)
+    torch.manual_seed(1)
+    reg_net = B200Connect4NNetWrapper(game, args)
+    g, r, d = pit_gnn_vs_regular(game, gnn_net, reg_net, args)
+    assert g + r + d == 6
