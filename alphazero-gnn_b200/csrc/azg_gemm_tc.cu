@@ -726,16 +726,16 @@ __global__ void heads32_finalize_kernel(const float* __restrict__ lg, int A, int
 
 // ---- fused trunk: encode + conv1 + im2col in shared memory -> tcgen05 conv2 --------------------
 // One persistent CTA per SM, 16 warps.  A tile is G = 128 / n^2 whole boards (G*n^2 <= 128 GEMM rows).
-//   warps 0-7   builders: relu(conv1) of the tile's boards into smem (bf16 hi/lo, zero border, 80-byte
-//               cell stride = conflict-free 16-byte gathers), then per k-block copy the 3x3 patches
-//               into the SWIZZLE_128B operand stage (pure 16-byte smem->smem moves, two threads per
-//               row), fence.proxy.async, arrive on the stage's mbarrier
+//   warps 0-7   builders: relu(conv1) of the tile's boards into smem (bf16 hi/lo, zero border, 64-byte
+//               cells), then per k-block copy the 3x3 patches into the SWIZZLE_128B operand stage (pure
+//               16-byte smem->smem moves, a quarter-warp per tile row), fence.proxy.async, arrive on the
+//               stage's mbarrier
 //   warp 8      MMA issuer (one thread): M=128 x N=64 x K=16, conv2 weight images resident in smem
 //   warp 9      TMEM allocation, barrier init, one-time bulk copy of the conv2 weight images
 //   warps 12-15 epilogue: TMEM -> +bias, ReLU -> feature image (the A operand of GEMM-1)
 // The im2col matrix never exists in HBM (the split version moved 2 x 4.1 GB per 65,536 positions).
 constexpr int TR_THREADS = 512;
-constexpr int TR_CELL_STRIDE = 80;   // bytes per padded cell: 32 channels x bf16 + 16 B pad
+constexpr int TR_CELL_STRIDE = 64;   // bytes per padded cell: 32 channels x bf16, no pad (see the patch copies)
 constexpr int TR_MAX_CELLS = 288;    // max over n of G * (n+2)^2
 constexpr int TR_W_BYTES = C2_KB * 64 * 128;  // conv2 weight image [64 x 320] bf16 = 40 KB
 
@@ -831,6 +831,14 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
     const bool row_valid = bl < G;
     const int cell0 = bl * cells + x * np + y;  // padded cell of tap (0,0); tap (kx,ky) adds kx*np + ky
     const int cw = warp;                        // conv1 worker index 0..7
+    // patch-copy mapping: lane & 7 = chunk of the k-block, rows grow0 + 32 i
+    const int gj = threadIdx.x & 7, grow0 = threadIdx.x >> 3;
+    int gcell[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr_ = grow0 + 32 * i, b_ = rr_ / nn, p_ = rr_ - b_ * nn, x_ = p_ / n;
+      gcell[i] = b_ < G ? b_ * cells + x_ * np + (p_ - x_ * n) : -1;
+    }
     float w9[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) w9[k] = w1s[lane * 9 + k];
@@ -882,19 +890,24 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
       for (int kb = 0; kb < C2_KB; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = stages + stage * S::STAGE_BYTES;
-        if (row_valid) {
+        // Patch copies: the 8 lanes of a quarter-warp move the 8 chunks (two taps x 64 B) of ONE tile row, so a
+        // 128-bit shared load touches two 64-byte cells whose offsets differ by an odd number of cells (tap +1, or
+        // n cells across a kernel row for odd n): distinct bank groups.  (One row per lane with an 80-byte cell
+        // stride conflicted 2-way whenever the 8 rows of a quarter-warp crossed a board-row end: +48 % wavefronts.)
+        const int c = kb * 8 + gj;  // 16-byte chunk of the K = (tap, cin) axis
+        const bool chunk_live = c < 36;
+        const int tap = c >> 2, kx = tap / 3, ky = tap - kx * 3;
+        const uint32_t toff = (uint32_t)((kx * np + ky) * TR_CELL_STRIDE + (c & 3) * 16);
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = half * 4 + jj;
-            const int c = kb * 8 + j;  // 16-byte chunk of the K = (tap, cin) axis
+        for (int i = 0; i < 4; ++i) {
+          if (gcell[i] >= 0) {
             uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-            if (c < 36) {
-              const int tap = c >> 2, kx = tap / 3, ky = tap - kx * 3;
-              const size_t src = (size_t)(cell0 + kx * np + ky) * TR_CELL_STRIDE + (c & 3) * 16;
+            if (chunk_live) {
+              const uint32_t src = (uint32_t)gcell[i] * TR_CELL_STRIDE + toff;
               vh = *reinterpret_cast<const uint4*>(a1hi + src);
               if (X3) vl = *reinterpret_cast<const uint4*>(a1lo + src);
             }
-            const uint32_t dst = image_offset(r, j * 8);
+            const uint32_t dst = image_offset(grow0 + 32 * i, gj * 8);
             *reinterpret_cast<uint4*>(sa + dst) = vh;
             if (X3) *reinterpret_cast<uint4*>(sa + A_STAGE_BYTES + dst) = vl;
           }
