@@ -13,7 +13,9 @@ reference plays the games sequentially with ONE persistent MCTS object per netwo
 game k into game k+1 and results depend on game order.  Here every game has its own tree per network; the tree
 persists across the plies of its game (the table is keyed by position), not across games.  With `fresh trees per
 game` in the sequential loop the two are identical move for move (tests/test_pit_gpu.py).
-Single-player evaluation (Arena.py:166-247) is not batched here.
+`BatchedSinglePlayerArena` is the single-player comparison (Arena.py:29-100, 166-247: FrozenLake): both models play
+`num` episodes from the initial board, all episodes in flight, and each pair of episodes is scored by the reference's
+rules (success beats failure, fewer steps to succeed, more steps survived before failing).
 """
 import numpy as np
 
@@ -76,6 +78,66 @@ class BatchedArena:
                     one, two = (one, two + 1) if grp == 0 else (one + 1, two)
                 else:
                     draws += 1
+        return one, two, draws
+
+
+class BatchedSinglePlayerArena:
+    def __init__(self, game, nnet1, nnet2, args, arena_factory=None):
+        assert not getattr(game, "is_two_player", True), "single-player games only (Arena.py:27)"
+        self.game, self.nets, self.args = game, (nnet1, nnet2), args
+        self._arena_factory = arena_factory
+
+    def _play(self, net, num):
+        """`num` concurrent episodes of Arena.playGameForSinglePlayer (Arena.py:29-100); returns (results, steps)"""
+        g = self.game
+        n = g.getBoardSize()[0]
+        max_steps = g.getBoardSize()[0] * g.getBoardSize()[1] * 5  # Arena.py:45
+        arena = self._arena_factory(num) if self._arena_factory else None
+        sims = int(arg(self.args, "numMCTSSims"))
+        m = BatchedMCTS(g, net, self.args, n_games=num, arena=arena, capacity=max(4096, 2 * sims * (n * n + 2)), max_depth=4 * n * n)
+        boards = [g.getInitBoard() for _ in range(num)]
+        steps = np.zeros(num, dtype=np.int64)
+        alive = np.ones(num, dtype=bool)
+        while alive.any():
+            for i in np.flatnonzero(alive):
+                if g.getGameEnded(boards[i], 1) != 0 or steps[i] >= max_steps:
+                    alive[i] = False
+            if not alive.any():
+                break
+            canon = [g.getCanonicalForm(b, 1) for b in boards]
+            m.set_root_boards(canon)
+            probs = m.getActionProbs(temp=0)
+            for i in np.flatnonzero(alive):
+                steps[i] += 1
+                action = int(np.argmax(probs[i]))
+                valids = g.getValidMoves(canon[i], 1)
+                if valids[action] == 0:  # Arena.py:74-85: fall back to a random valid action
+                    va = np.where(np.asarray(valids) == 1)[0]
+                    if len(va) == 0:
+                        alive[i] = False
+                        continue
+                    action = int(np.random.choice(va))
+                boards[i], _ = g.getNextState(boards[i], 1, action)
+        results = [0 if (steps[i] >= max_steps and g.getGameEnded(boards[i], 1) == 0) else g.getGameEnded(boards[i], 1)
+                   for i in range(num)]
+        return results, steps
+
+    def playGames(self, num):
+        """(oneWon, twoWon, draws) with the pairing rules of Arena.playGamesForSinglePlayer (Arena.py:166-247)"""
+        r1, s1 = self._play(self.nets[0], num)
+        r2, s2 = self._play(self.nets[1], num)
+        one = two = draws = 0
+        for a, b, sa, sb in zip(r1, r2, s1, s2):
+            if a > 0 and b <= 0:
+                one += 1
+            elif b > 0 and a <= 0:
+                two += 1
+            elif a > 0 and b > 0:
+                one, two, draws = (one + 1, two, draws) if sa < sb else (one, two + 1, draws) if sb < sa else (one, two, draws + 1)
+            elif a < 0 and b < 0:
+                one, two, draws = (one + 1, two, draws) if sa > sb else (one, two + 1, draws) if sb > sa else (one, two, draws + 1)
+            else:
+                draws += 1
         return one, two, draws
 
 

@@ -70,3 +70,29 @@ def test_pit_gnn_vs_regular():
     reg_net = B200Connect4NNetWrapper(game, args)
     g, r, d = pit_gnn_vs_regular(game, gnn_net, reg_net, args)
     assert g + r + d == 6
+
+
+def test_single_player_arena_frozenlake():
+    """Arena.playGamesForSinglePlayer semantics on FrozenLake 4x4: results partition the games; a network that was
+    trained to walk to the goal beats an untrained one."""
+    from azgnn_b200.nets import B200FrozenLakeNet
+    from azgnn_b200.pit import BatchedSinglePlayerArena
+    game = games.FrozenLakeGame(4)
+    args = dotdict(dict(lr=1e-2, epochs=30, batch_size=8, embedding_dim=128, gnn_layers=2, numMCTSSims=25, cpuct=2.0, use_gnn=False))
+    torch.manual_seed(0)
+    fresh = B200FrozenLakeNet(game, args)
+    torch.manual_seed(1)
+    taught = B200FrozenLakeNet(game, args)
+    # teach the safe path of the standard map: down, down, right, down, right, right (cells 0,4,8,9,13,14 -> 15);
+    # actions: 0 up, 1 right, 2 down, 3 left (FrozenLakeGame.py:88-110)
+    path = [(0, 2), (4, 2), (8, 1), (9, 2), (13, 1), (14, 1)]
+    examples = []
+    for cell, act in path * 4:
+        b = np.zeros((4, 4)); b[cell // 4, cell % 4] = 1
+        pi = np.zeros(4); pi[act] = 1.0
+        examples.append((b, list(pi), 1.0))
+    np.random.seed(0)
+    taught.train(examples)
+    one, two, draws = BatchedSinglePlayerArena(game, fresh, taught, args).playGames(8)
+    assert one + two + draws == 8
+    assert two >= one
