@@ -123,6 +123,57 @@ class _TwoPlayer(_Base):
     def _default_mask(self):
         return (_lib.EVAL_STD | _lib.EVAL_GNN) if self.has_gnn else _lib.EVAL_STD
 
+    def predict_batches(self, host_batches, eval_mask=None):
+        """Pipelined `predict_batch` over an iterable of equally shaped PINNED host board tensors [B,n,n]: the host->device
+        copy of batch i+1 and the device->host copy of batch i-1 run on a copy stream while the kernels of batch i run
+        on the compute stream.  Yields, per batch, a dict of pinned host tensors (valid until two batches later)."""
+        eval_mask = self._default_mask() if eval_mask is None else eval_mask
+        compute = torch.cuda.current_stream()
+        if getattr(self, "_copy_streams", None) is None:
+            self._copy_streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        up, down = self._copy_streams  # host->device, device->host
+        slots = [None, None]
+        pending = []  # (slot index, d2h-done event)
+
+        def make_slot(hb):
+            B = hb.shape[0]
+            dev_out = self._outputs(B, eval_mask)
+            return {"boards": torch.empty(hb.shape, dtype=hb.dtype, device=self.device), "out": dev_out,
+                    "host": {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in dev_out.items()},
+                    "states": torch.empty(B, 2, dtype=torch.int64, device=self.device), "done": None}
+        for i, hb in enumerate(host_batches):
+            k = i & 1
+            if slots[k] is None or slots[k]["boards"].shape != hb.shape or slots[k]["boards"].dtype != hb.dtype:
+                slots[k] = make_slot(hb)
+            sl = slots[k]
+            if len(pending) == 2:  # slot k is about to be reused: its previous results must have reached the host
+                j, ev = pending.pop(0)
+                ev.synchronize()
+                yield slots[j]["host"]
+            with torch.cuda.stream(up):
+                if sl["done"] is not None:
+                    up.wait_event(sl["done"])  # the kernels of batch i-2 have consumed this slot's device buffers
+                sl["boards"].copy_(hb, non_blocking=True)
+                h2d = torch.cuda.Event()
+                h2d.record(up)
+            compute.wait_event(h2d)
+            _lib.check(self.lib.azg_pack_boards(ptr(sl["boards"]), _CELL[sl["boards"].dtype], self.n, hb.shape[0], ptr(sl["states"]),
+                                                stream()))
+            self.forward_states(sl["states"], eval_mask, out=sl["out"])
+            sl["done"] = torch.cuda.Event()
+            sl["done"].record(compute)
+            with torch.cuda.stream(down):
+                down.wait_event(sl["done"])
+                for name, t in sl["out"].items():
+                    sl["host"][name].copy_(t, non_blocking=True)
+                d2h = torch.cuda.Event()
+                d2h.record(down)
+            pending.append((k, d2h))
+        for j, ev in pending:
+            ev.synchronize()
+            yield slots[j]["host"]
+
+
     def _init_gnn(self, args, feature_dim):
         self.feature_dim = feature_dim
         self.gnn = modules.PolicyValueGNN(feature_dim, arg(args, "gnn_layers", 2) or 2).to(self.device)
@@ -167,7 +218,7 @@ class B200Connect4NNetWrapper(_TwoPlayer):
             self._packed[prec] = blob
         return self._packed[prec]
 
-    def forward_states(self, states, eval_mask=None, precision=None, count=None):
+    def forward_states(self, states, eval_mask=None, precision=None, count=None, out=None):
         """states: int64 [B,2] on the device.  Returns device tensors pi/v (+pi_gnn/v_gnn).
         count: optional device int32 scalar -- only the first `count` rows are live (compacted leaf batches,
         read by the kernels on the device; rows beyond it are left untouched on the tensor-core path)."""
@@ -178,7 +229,7 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         if self.fold_heads and prec != _lib.PREC_FP32 and (eval_mask & _lib.EVAL_GNN):
             eval_mask |= _lib.EVAL_FOLD
         B = int(states.shape[0])
-        o = self._outputs(B, eval_mask)
+        o = self._outputs(B, eval_mask) if out is None else out
         if B == 0:
             return o
         p = self._params(prec, prec != _lib.PREC_FP32)

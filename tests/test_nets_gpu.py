@@ -305,3 +305,18 @@ def test_tictactoe_tensor_core_forward(n, B):
     w.weights_changed()
     o3b = w.forward_states(states, _lib.EVAL_STD, precision=_lib.PREC_BF16X3)
     assert not np.allclose(o3b["v"].cpu().numpy(), o3["v"].cpu().numpy())
+
+
+def test_predict_batches_pipeline_equals_predict_batch():
+    """the pipelined host-facing call returns, in order, exactly what predict_batch returns per batch"""
+    w = _wrapper("c4", 7)
+    rng = np.random.default_rng(0)
+    host = [torch.from_numpy(rng.integers(-1, 2, size=(257, 7, 7)).astype(np.int8)).pin_memory() for _ in range(5)]
+    want = [w.predict_batch(h) for h in host]
+    got = []
+    for res in w.predict_batches(iter(host)):
+        got.append({k: v.clone().numpy() for k, v in res.items()})
+    assert len(got) == len(want)
+    for g, e in zip(got, want):
+        for k in e:
+            assert np.array_equal(g[k], e[k]), k
