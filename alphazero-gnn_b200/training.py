@@ -497,6 +497,12 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
             return
         key = (which, tuple(tuple(t.shape) for t in tensors))
         if key not in cache["steps"]:
+            if len(cache["steps"]) >= 6:  # every capture pins its own gradient pool (0.5 GB for the GNN step): odd batch
+                opt.zero_grad()           # shapes beyond a handful run eagerly instead of being captured
+                step_fn(ops, w, *tensors).backward()
+                opt.step()
+                cache["warm"].add(which)
+                return
             cache["steps"][key] = _GraphedStep(step_fn, w, params, opt, [t.shape for t in tensors])
         eager = which not in cache["warm"]
         cache["steps"][key].run(tensors, eager)
