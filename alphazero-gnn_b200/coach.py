@@ -210,7 +210,15 @@ class Coach:
                 dist.barrier()
             if self.pnet is None:
                 self.pnet = self.nnet.__class__(self.game, a)
-            self.pnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
+            if on_device and hasattr(self.pnet, "nnet"):
+                # same weights as reading temp.pth.tar back (Coach.py:123-124), copied device to device; the file stays on
+                # disk for the reject path
+                self.pnet.nnet.load_state_dict(self.nnet.nnet.state_dict())
+                if getattr(self.nnet, "gnn", None) is not None:
+                    self.pnet.gnn.load_state_dict(self.nnet.gnn.state_dict())
+                self.pnet.weights_changed()
+            else:
+                self.pnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
             pmcts = self._new_mcts(self.pnet)
             t3 = sync()
             prof = None
