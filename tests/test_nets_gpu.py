@@ -20,7 +20,9 @@ TOL = dict(rtol=0, atol=1e-5)
 
 
 def _args(**kw):
-    return dotdict(dict(dict(lr=1e-3, dropout=0.3, epochs=1, batch_size=64, gnn_layers=2, use_gnn=True), **kw))
+    # the fp32 CUDA-core path unless a test asks otherwise (the wrappers' own default is bf16x3; the tensor-core tests
+    # pass `precision=` per call and test_default_precision_is_the_tensor_core_path checks the default)
+    return dotdict(dict(dict(lr=1e-3, dropout=0.3, epochs=1, batch_size=64, gnn_layers=2, use_gnn=True, b200_precision="fp32"), **kw))
 
 
 def _wrapper(kind, n, **kw):
@@ -320,3 +322,26 @@ def test_predict_batches_pipeline_equals_predict_batch():
     for g, e in zip(got, want):
         for k in e:
             assert np.array_equal(g[k], e[k]), k
+
+
+@pytest.mark.parametrize("kind,n", [("c4", 7), ("ttt", 4)])
+def test_default_precision_is_the_tensor_core_path(kind, n):
+    """a config without `b200_precision` (the reference's config.yaml) runs bf16x3 on tcgen05 and still reproduces the
+    reference module's golden outputs within 1e-5"""
+    game = (orules.Connect4Rules if kind == "c4" else orules.TicTacToeRules)(n)
+    torch.manual_seed(0)
+    W = B200Connect4GNNWrapper if kind == "c4" else B200TicTacToeGNNWrapper
+    w = W(game, dotdict(dict(lr=1e-3, dropout=0.3, epochs=1, batch_size=64, gnn_layers=2, use_gnn=True)))
+    assert w.precision == _lib.PREC_BF16X3
+    rng = np.random.default_rng(n)
+    boards = rng.integers(-1, 2, size=(200, n, n)).astype(np.int64)
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    bt = onets.boards_to_tensor(boards)
+    with torch.no_grad():
+        pi, v = (onets.c4_predict if kind == "c4" else onets.ttt_predict)(p, bt, n)
+        gpi, gv = (onets.c4_predict_with_gnn if kind == "c4" else onets.ttt_predict_with_gnn)(p, q, bt, n)
+    out = w.predict_batch(boards)
+    for got, want in ((out["pi"], pi), (out["v"], v), (out["pi_gnn"], gpi), (out["v_gnn"], gv)):
+        np.testing.assert_allclose(got, want.numpy(), rtol=0, atol=1e-5)
+    one_pi, one_v = w.predict_with_gnn(boards[0])
+    assert abs(one_v - gv[0].item()) <= 1e-5 and np.abs(one_pi - gpi[0].numpy()).max() <= 1e-5
