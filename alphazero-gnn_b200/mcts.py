@@ -164,7 +164,10 @@ class BatchedMCTS:
 
     # ------------------------------------------------------------------ leaf evaluation
     def _evaluate_device(self, leaf_states, count=None):
-        mask = (_lib.EVAL_STD | _lib.EVAL_GNN) if self.use_gnn else _lib.EVAL_STD
+        # use_gnn: MCTS.py:169-176 calls predict AND predict_with_gnn at every leaf but searches with the GNN prediction
+        # only; the standard prediction is read back for ROOTS alone (expand_tree, MCTS.py:108-111), and those are
+        # evaluated by _root_std_values.  The device path therefore skips the unused standard heads at the leaves.
+        mask = _lib.EVAL_GNN if self.use_gnn else _lib.EVAL_STD
         out = self.nnet.forward_states(leaf_states, mask, count=count) if count is not None else \
             self.nnet.forward_states(leaf_states, mask)
         return (out["pi_gnn"], out["v_gnn"]) if self.use_gnn else (out["pi"], out["v"])

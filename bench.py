@@ -437,7 +437,8 @@ def run_gpu_arm(args, rank, local_rank, world):
                         "leaf_evals_per_s_in_search": sp_leaves, "games_per_gpu": args.selfplay_games,
                         "move_steps_timed": args.selfplay_moves, "ms_per_move_step": sp_ms / max(args.selfplay_moves, 1),
                         "config": "connect4/config.yaml search settings: numMCTSSims 10, expand_by 5, cpuct 1.0, "
-                                  "tempThreshold 15, use_gnn (std+GNN evaluated per leaf)",
+                                  "tempThreshold 15, use_gnn (leaves searched with the GNN prediction; the standard prediction, "
+                                  "which the reference also computes per leaf but reads only at roots, is evaluated at roots)",
                         "cpu_baseline": None if cpu_mps is None else
                         {"value": cpu_mps, "unit": "moves/s", "cores": cores, "kind": "port",
                          "sample": f"{args.cpu_selfplay_episodes} sequential episodes ({cpu_moves} moves, "
