@@ -640,24 +640,41 @@ __global__ void __launch_bounds__(256) heads_image_kernel(const uint8_t* __restr
 // logits = fixed-order sum of the per-tile partial head sums + bias; then exp(log_softmax) and tanh
 // AZG_EVAL_FOLD: no non-linearity lies between output_transform.2 and the policy/value heads
 // (gnn_utils.py:99-103 -> Connect4GNN.py:48-57), so   heads(W2 h + b2) = ([Wp; Wv] W2) h + ([Wp; Wv] b2 + [bp; bv]).
-// fold_w[a, j] = sum_n hc[a, n] W2[n, j]  (fp64 accumulation, once per weight version); hc = concatenated heads [32, F].
-__global__ void __launch_bounds__(128) fold_heads_kernel(const float* __restrict__ hc, const float* __restrict__ w2,
-                                                         const float* __restrict__ b2, const float* __restrict__ bias32, int rows,
-                                                         int F, float* __restrict__ fold_w, float* __restrict__ fold_b) {
+// fold_w[a, j] = sum_n hc[a, n] W2[n, j]  (fp64 accumulation, once per weight version, n split over FOLD_SPLITS blocks and
+// reduced in fixed order); hc = concatenated heads [32, F].
+constexpr int FOLD_SPLITS = 16;
+// blockIdx.y owns the n range [y*per, (y+1)*per): part[y][a][j] = sum_n hc[a, n] W2[n, j] in fp64
+__global__ void __launch_bounds__(128) fold_heads_partial_kernel(const float* __restrict__ hc, const float* __restrict__ w2, int rows,
+                                                                 int F, int per, double* __restrict__ part) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < F) {
-    double acc[HEAD_ROWS];
+  if (j >= F) return;
+  const int n0 = blockIdx.y * per, n1 = n0 + per < F ? n0 + per : F;
+  double acc[HEAD_ROWS];
 #pragma unroll
-    for (int a = 0; a < HEAD_ROWS; ++a) acc[a] = 0.0;
-    for (int n = 0; n < F; ++n) {
-      const double w = (double)w2[(size_t)n * F + j];
-#pragma unroll
-      for (int a = 0; a < HEAD_ROWS; ++a)
-        if (a < rows) acc[a] += (double)__ldg(hc + (size_t)a * F + n) * w;
-    }
+  for (int a = 0; a < HEAD_ROWS; ++a) acc[a] = 0.0;
+  for (int n = n0; n < n1; ++n) {
+    const double w = (double)w2[(size_t)n * F + j];
 #pragma unroll
     for (int a = 0; a < HEAD_ROWS; ++a)
-      if (a < rows) fold_w[(size_t)a * F + j] = (float)acc[a];
+      if (a < rows) acc[a] += (double)__ldg(hc + (size_t)a * F + n) * w;
+  }
+#pragma unroll
+  for (int a = 0; a < HEAD_ROWS; ++a)
+    if (a < rows) part[((size_t)blockIdx.y * HEAD_ROWS + a) * F + j] = acc[a];
+}
+
+// fold_w = fixed-order sum of the partials; fold_b[a] = sum_n hc[a, n] b2[n] + bias32[a]
+__global__ void __launch_bounds__(128) fold_heads_finish_kernel(const double* __restrict__ part, const float* __restrict__ hc,
+                                                                const float* __restrict__ b2, const float* __restrict__ bias32,
+                                                                int rows, int F, float* __restrict__ fold_w,
+                                                                float* __restrict__ fold_b) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < F) {
+    for (int a = 0; a < rows; ++a) {
+      double s = 0.0;
+      for (int y = 0; y < FOLD_SPLITS; ++y) s += part[((size_t)y * HEAD_ROWS + a) * F + j];
+      fold_w[(size_t)a * F + j] = (float)s;
+    }
   } else if (j - F < rows) {
     const int a = j - F;
     double acc = (double)bias32[a];
@@ -1243,10 +1260,17 @@ int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t pa
       p->fc_policy_w, p->fc_value_w, p->fc_policy_b, p->fc_value_b, A, F, (float*)(w + L.heads_cat), (float*)(w + L.bias32));
   AZG_LAUNCH_CHECK();
   if (p->ot2_w && p->ot2_b) {
-    tc::fold_heads_kernel<<<(F + 32 + 127) / 128, 128, 0, st>>>((const float*)(w + L.heads_cat), p->ot2_w, p->ot2_b,
-                                                                (const float*)(w + L.bias32), A + 1, F, (float*)(w + L.fold_w),
-                                                                (float*)(w + L.fold_b));
+    double* part = nullptr;
+    AZG_CUDA_CHECK(cudaMallocAsync((void**)&part, sizeof(double) * tc::FOLD_SPLITS * tc::HEAD_ROWS * (size_t)F, st));
+    const int per = (F + tc::FOLD_SPLITS - 1) / tc::FOLD_SPLITS;
+    tc::fold_heads_partial_kernel<<<dim3((F + 127) / 128, tc::FOLD_SPLITS), 128, 0, st>>>((const float*)(w + L.heads_cat), p->ot2_w,
+                                                                                         A + 1, F, per, part);
     AZG_LAUNCH_CHECK();
+    tc::fold_heads_finish_kernel<<<(F + 32 + 127) / 128, 128, 0, st>>>(part, (const float*)(w + L.heads_cat), p->ot2_b,
+                                                                       (const float*)(w + L.bias32), A + 1, F,
+                                                                       (float*)(w + L.fold_w), (float*)(w + L.fold_b));
+    AZG_LAUNCH_CHECK();
+    AZG_CUDA_CHECK(cudaFreeAsync(part, st));
   }
   {
     const int64_t cnt = (int64_t)32 * (F / 8);
