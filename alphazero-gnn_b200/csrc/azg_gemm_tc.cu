@@ -54,7 +54,16 @@ struct GemmArgs {
   int pair_ok;          // the A image covers an even number of m-tiles: the CTA-pair kernel may be used
   int feat_nn;          // OUT_FEAT*: rows are (board b, cell p) pairs, m = b*feat_nn + p; the 64 columns (conv2
                         // channels) become k-block p of row b of the feature image  [K' = p*64 + co]
+  // optional side tile (CTA-pair kernel only): one more n-tile of SIDE_N columns per m-unit contracts the same A rows
+  // with a second, narrow weight image and writes fp32 [M, SIDE_N] (no ReLU) -- the standard policy/value heads of
+  // `predict` ride on GEMM-1 instead of re-reading the feature image in their own launch
+  const uint8_t* side_hi;  // [SIDE_N x K] weight image, tiles [SIDE_N x 64] at kb * SIDE_N * 128
+  const uint8_t* side_lo;  // (x3 only)
+  const float* side_bias;  // [SIDE_N]
+  float* side_out;         // row-major [M, SIDE_N]
 };
+constexpr int SIDE_N = 32;
+constexpr int SIDE_STAGE_BYTES = (SIDE_N / 2) * BK * 2;  // one CTA's half of a side weight tile stage
 
 // TWO = CTA pair: cta_group::2 MMAs of 256 x BN (each CTA holds 128 rows of A and of the accumulator and
 // BN/2 rows of the weight tile), which halves the weight bytes each SM reads from shared memory per MMA.
@@ -115,7 +124,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = m_units * g.n_tiles;
+  const int nt_all = g.n_tiles + ((TWO && g.side_hi) ? 1 : 0);  // n-tile index g.n_tiles = the side tile
+  const int total_tiles = m_units * nt_all;
   // CTA pair: a stage holds TWO operand pairs (60 KB per CTA, 3 stages) and feeds 8-12 MMAs per barrier
   // round trip.  bf16x3: hi and lo of both operands of one k-block -> all three products, so every operand
   // byte crosses L2 -> smem once instead of 1.5 times.  Plain bf16: two consecutive k-blocks.
@@ -132,10 +142,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
       int stage = 0;
       uint32_t phase = 0;
       for (int t = unit; t < total_tiles; t += n_units) {
-        const int mt = (t / g.n_tiles) * (TWO ? 2 : 1) + (int)rank, nt = t % g.n_tiles;
+        const int mt = (t / nt_all) * (TWO ? 2 : 1) + (int)rank, nt = t % nt_all;
+        const bool side = TWO && nt == g.n_tiles;
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
+          if (side) {  // same stage layout, the weight part is this CTA's 16 rows of the [32 x 64] side tile
+            const int k0 = dual ? 2 * kb : kb, parts = (fused3 || k0 + 1 < g.KB) ? 2 : 1;
+            mbar_expect_tx(&full[stage], parts * (A_STAGE_BYTES + SIDE_STAGE_BYTES));
+            for (int pt = 0; pt < parts; ++pt) {
+              const int kk = fused3 ? k0 : k0 + pt;
+              const size_t ao = ((size_t)mt * g.KB + kk) * A_STAGE_BYTES;
+              const size_t wo = (size_t)kk * (2 * SIDE_STAGE_BYTES) + (size_t)rank * SIDE_STAGE_BYTES;
+              const bool lo = fused3 && pt == 1;
+              bulk_g2s(sa + pt * S::STAGE_BYTES, (lo ? g.a_lo : g.a_hi) + ao, A_STAGE_BYTES, &full[stage]);
+              bulk_g2s(sa + pt * S::STAGE_BYTES + A_STAGE_BYTES, (lo ? g.side_lo : g.side_hi) + wo, SIDE_STAGE_BYTES, &full[stage]);
+            }
+            if (++stage == NSR) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           if (dual) {  // [A(k0) | W(k0) half | A(k0+1) | W(k0+1) half]; an odd K leaves the last second half unused
             const int k0 = 2 * kb, parts = (k0 + 1 < g.KB) ? 2 : 1;
             mbar_expect_tx(&full[stage], parts * S::STAGE_BYTES);
@@ -178,7 +206,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
   } else if (warp == 1) {
     // ================= MMA issuer: one thread (of the leader CTA when paired) =================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc(TWO ? 2 * BM : BM, BN);
+      constexpr uint32_t idesc_main = make_idesc(TWO ? 2 * BM : BM, BN);
+      constexpr uint32_t idesc_side = make_idesc(TWO ? 2 * BM : BM, SIDE_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -188,6 +217,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
         else mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t idesc = (TWO && t % nt_all == g.n_tiles) ? idesc_side : idesc_main;
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&full[stage], phase);  // operands have landed
           if (TWO) mbar_wait_cluster(&pfull[stage], phase);  // ... in the peer CTA as well
@@ -253,11 +283,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
     const int NKB = (g.n_tiles * BN) / BK;  // k-blocks of the output image
     const uint32_t leader_tempty = TWO ? map_to_cta(&tempty[0], 0) : 0u;
     for (int t = unit; t < total_tiles; t += n_units) {
-      const int mt = (t / g.n_tiles) * (TWO ? 2 : 1) + (int)rank, nt = t % g.n_tiles;
+      const int mt = (t / nt_all) * (TWO ? 2 : 1) + (int)rank, nt = t % nt_all;
       const int64_t row = (int64_t)mt * BM + r_local;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if (TWO && nt == g.n_tiles) {  // side tile: SIDE_N fp32 columns + bias, row-major
+        uint32_t rr[32];
+        tmem_ld32(taddr, rr);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_cluster(leader_tempty + (uint32_t)acc * 8u);
+        if (row < g.M) {
+          float4* dst = reinterpret_cast<float4*>(g.side_out + row * SIDE_N);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.side_bias) + j);
+            dst[j] = make_float4(__uint_as_float(rr[4 * j]) + b4.x, __uint_as_float(rr[4 * j + 1]) + b4.y,
+                                 __uint_as_float(rr[4 * j + 2]) + b4.z, __uint_as_float(rr[4 * j + 3]) + b4.w);
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
       float hacc[HEAD_ROWS];
 #pragma unroll
       for (int a = 0; a < HEAD_ROWS; ++a) hacc[a] = 0.0f;
@@ -416,7 +467,7 @@ int launch_gemm_impl(const GemmArgs& g, cudaStream_t st) {
     AZG_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  const int units = (TWO ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles;
+  const int units = (TWO ? (g.m_tiles + 1) / 2 : g.m_tiles) * (g.n_tiles + ((TWO && g.side_hi) ? 1 : 0));
   int grid = TWO ? 2 * (units < sms / 2 ? units : sms / 2) : (units < sms ? units : sms);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -1121,6 +1172,15 @@ static int azg_trunk_mode() {
   return mode;
 }
 
+static int azg_std_heads_mode() {  // AZG_STD_HEADS=split: predict's heads in their own skinny GEMM launch (A/B measurements)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("AZG_STD_HEADS");
+    mode = (e && strcmp(e, "split") == 0) ? 1 : 0;
+  }
+  return mode;
+}
+
 size_t azg_tc_scratch_bytes(int n, int64_t B, int prec) { return scratch_layout(n, B, prec, true).total; }
 
 // Whole Connect4 leaf evaluation on the tensor-core path: im2col(encode+conv1) -> conv2 GEMM ->
@@ -1163,7 +1223,24 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     if ((rc = tc::run_gemm(64, g, st))) return rc;
   }
   azg_phase_end(AZG_PHASE_TRUNK, st);
-  if (eval_mask & AZG_EVAL_STD) {
+  // predict's heads ride on GEMM-1 as a side tile when the CTA-pair kernel runs it (AZG_STD_HEADS=split: own launch)
+  const bool std_side = (eval_mask & AZG_EVAL_STD) && azg_trunk_mode() == 0 && tc::gemm_pair_mode() && BN >= 128 &&
+                        azg_std_heads_mode() == 0;
+  if (std_side && !gnn) {  // std only: the same side-tile code with no main n-tiles (bit-identical to the combined call)
+    AZG_REQUIRE(pi_std && v_std && A <= 9, "tcgen05 path: bad std outputs");
+    azg_phase_begin(AZG_PHASE_HEADS, st);
+    tc::GemmArgs h{};
+    h.M = B; h.m_tiles = (int)azg_ceil_div(B, tc::BM); h.n_tiles = 0; h.KB = F / tc::BK; h.x3 = x3; h.pair_ok = 1;
+    h.a_hi = f_hi; h.a_lo = f_lo; h.dyn_rows = dyn_rows;
+    h.side_hi = w + L.hd_hi; h.side_lo = x3 ? w + L.hd_lo : nullptr;
+    h.side_bias = (const float*)(w + L.bias32); h.side_out = (float*)(sc + S.lg32);
+    if ((rc = tc::run_gemm(BN, h, st))) return rc;
+    tc::heads32_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const float*)(sc + S.lg32), A, B, dyn_rows, pi_std, v_std);
+    AZG_LAUNCH_CHECK();
+    azg_phase_end(AZG_PHASE_HEADS, st);
+    return AZG_OK;
+  }
+  if ((eval_mask & AZG_EVAL_STD) && !std_side) {
     AZG_REQUIRE(pi_std && v_std && A <= 9, "tcgen05 path: bad std outputs");
     azg_phase_begin(AZG_PHASE_HEADS, st);
     if (azg_trunk_mode() == 0) {  // predict's heads (Connect4Net.py:55-60) as a skinny tcgen05 GEMM: [B,F] x [F,32]
@@ -1195,6 +1272,17 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   g.dyn_rows = dyn_rows;
   g.a_hi = f_hi; g.a_lo = f_lo; g.w_hi = w + L.w0_hi; g.w_lo = x3 ? w + L.w0_lo : nullptr; g.bias = p->ot0_b; g.relu = 1;
   AZG_REQUIRE(g.n_tiles <= 16 && A + 1 <= tc::HEAD_ROWS, "tcgen05 path: head fusion limits exceeded");
+  if (std_side) {
+    AZG_REQUIRE(pi_std && v_std && A <= 9, "tcgen05 path: bad std outputs");
+    g.side_hi = w + L.hd_hi; g.side_lo = x3 ? w + L.hd_lo : nullptr;
+    g.side_bias = (const float*)(w + L.bias32); g.side_out = (float*)(sc + S.lg32);
+  }
+  auto finish_std = [&]() -> int {  // log_softmax / tanh of the side tile's logits (inside the HEADS phase)
+    if (!std_side) return AZG_OK;
+    tc::heads32_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const float*)(sc + S.lg32), A, B, dyn_rows, pi_std, v_std);
+    AZG_LAUNCH_CHECK();
+    return AZG_OK;
+  };
   if (eval_mask & AZG_EVAL_FOLD) {
     // output_transform.2 and the heads folded into one [A+1, F] matrix (see fold_heads_kernel): GEMM-1's epilogue
     // applies it to relu(H) tile by tile; H and E never exist in HBM and the second F x F contraction is gone
@@ -1207,11 +1295,13 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles, A, fb, fb + A, B, dyn_rows,
                                                                           pi_gnn, v_gnn);
     AZG_LAUNCH_CHECK();
+    if ((rc = finish_std())) return rc;
     azg_phase_end(AZG_PHASE_HEADS, st);
     return AZG_OK;
   }
   g.out_mode = x3 ? tc::OUT_IMG_HILO : tc::OUT_IMG; g.out_hi = h_hi; g.out_lo = h_lo;
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
+  g.side_hi = g.side_lo = nullptr;  // GEMM-2 has no side tile
   g.a_hi = h_hi; g.a_lo = h_lo; g.w_hi = w + L.w2_hi; g.w_lo = x3 ? w + L.w2_lo : nullptr; g.bias = p->ot2_b; g.relu = 0;
   g.out_mode = tc::OUT_HEADS; g.out_hi = g.out_lo = nullptr; g.out_f32 = nullptr;
   g.head_w = (const float*)(w + L.heads_cat); g.head_rows = A + 1; g.head_part = (float*)(sc + S.part);
@@ -1221,6 +1311,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles, A, p->fc_policy_b,
                                                                         p->fc_value_b, B, dyn_rows, pi_gnn, v_gnn);
   AZG_LAUNCH_CHECK();
+  if ((rc = finish_std())) return rc;
   azg_phase_end(AZG_PHASE_HEADS, st);
   return AZG_OK;
 }
