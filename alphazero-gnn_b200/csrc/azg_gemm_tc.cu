@@ -794,29 +794,42 @@ __global__ void heads32_finalize_kernel(const float* __restrict__ lg, int A, int
 
 // ---- fused trunk: encode + conv1 + im2col in shared memory -> tcgen05 conv2 --------------------
 // One persistent CTA per SM, 16 warps.  A tile is G = 128 / n^2 whole boards (G*n^2 <= 128 GEMM rows).
-//   warps 0-7   builders: relu(conv1) of the tile's boards into smem (bf16 hi/lo, zero border, 64-byte
-//               cells), then per k-block copy the 3x3 patches into the SWIZZLE_128B operand stage (pure
-//               16-byte smem->smem moves, a quarter-warp per tile row), fence.proxy.async, arrive on the
-//               stage's mbarrier
-//   warp 8      MMA issuer (one thread): M=128 x N=64 x K=16, conv2 weight images resident in smem
+//   warps 0-7   builders, two threads per tile row (r = tid & 127, half = tid >> 7):
+//               (1) K1 encode + conv1 operand: the 3x3 neighbourhood of the row's cell, read straight from the packed
+//                   position (bits -> bf16 {-1, 0, +1}), written three times along K into a ring stage ("C1 slot");
+//                   conv1 itself runs on the tensor core against [w_hi | w_mid | w_lo] (three bf16 terms = the full
+//                   fp32 weight, the {-1,0,1} operand is exact, fp32 accumulation): 3 MMAs of 128 x 32 x 16 per tile;
+//               (2) conv1 "epilogue": TMEM -> +bias, ReLU -> bf16 hi/lo into the padded cell plane in smem (64-byte
+//                   cells, zero border) -- each thread converts 16 channels of its own cell;
+//               (3) per k-block copy the 3x3 patches into the SWIZZLE_128B operand stage (pure 16-byte smem->smem
+//                   moves, a quarter-warp per tile row), fence.proxy.async, arrive on the stage's mbarrier.
+//               The C1 slot of tile i+1 is queued between k-blocks 2 and 3 of tile i, so its MMAs have long completed
+//               when the builders come back for (2).
+//   warp 8      MMA issuer (one thread): conv2 M=128 x N=64 x K=16 (weight images resident in smem), conv1 as above
 //   warp 9      TMEM allocation, barrier init, one-time bulk copy of the conv2 weight images
 //   warps 12-15 epilogue: TMEM -> +bias, ReLU -> feature image (the A operand of GEMM-1)
 // The im2col matrix never exists in HBM (the split version moved 2 x 4.1 GB per 65,536 positions).
+// History of conv1: FFMA with lanes = channels and broadcast LDS of the planes took 42 % of the builders' time
+// (ncu source view, profiles/r01_trunk_fused_v6.txt: 18 LDS per two cells queued behind the tensor core's own
+// shared-memory reads); on the tensor core it is 3 MMAs and one tcgen05.ld per thread.
 constexpr int TR_THREADS = 512;
 constexpr int TR_CELL_STRIDE = 64;   // bytes per padded cell: 32 channels x bf16, no pad (see the patch copies)
 constexpr int TR_MAX_CELLS = 288;    // max over n of G * (n+2)^2
 constexpr int TR_W_BYTES = C2_KB * 64 * 128;  // conv2 weight image [64 x 320] bf16 = 40 KB
+constexpr int TR_W1_BYTES = 32 * 128;         // conv1 weight image [32 x 64] bf16: cols 0-8 hi, 16-24 mid, 32-40 lo
+constexpr int TR_C1_AFTER_KB = 2;             // the next tile's C1 slot follows this k-block in the ring
 
 template <bool X3>
 struct TrunkSmem {
   static constexpr int STAGES = X3 ? 3 : 4;
   static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * A_STAGE_BYTES;
   static constexpr int W_OFF = 0;
-  static constexpr int A1_OFF = (X3 ? 2 : 1) * TR_W_BYTES;
+  static constexpr int W1_OFF = (X3 ? 2 : 1) * TR_W_BYTES;
+  static constexpr int A1_OFF = W1_OFF + TR_W1_BYTES;
   static constexpr int A1_BYTES = ((TR_MAX_CELLS * TR_CELL_STRIDE + 1023) / 1024) * 1024;
   static constexpr int STAGE_OFF = A1_OFF + (X3 ? 2 : 1) * A1_BYTES;
   static constexpr int MISC_OFF = STAGE_OFF + STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = MISC_OFF + 3072 + 1024;  // barriers, conv1 weights, planes, cell table + alignment slack
+  static constexpr int TOTAL = MISC_OFF + 1024 + 1024;  // barriers + alignment slack
 };
 
 struct TrunkArgs {
@@ -835,6 +848,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS)
   uint8_t* w_s = smem + S::W_OFF;
+  uint8_t* w1img = smem + S::W1_OFF;
   uint8_t* a1hi = smem + S::A1_OFF;
   uint8_t* a1lo = a1hi + S::A1_BYTES;
   uint8_t* stages = smem + S::STAGE_OFF;
@@ -843,11 +857,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   uint64_t* tfull = empty + S::STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* wbar = tempty + 2;
-  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
-  float* w1s = (float*)(smem + S::MISC_OFF + 256);  // [32*9] + [32]
-  float* b1s = w1s + 288;
-  float* planes_s = b1s + 32;                       // [G boards][(n+2)^2] cells in {-1,0,1}, zero border
-  uint16_t* cell_tab = (uint16_t*)(planes_s + TR_MAX_CELLS);  // tile row -> padded cell index of its (0,0) tap
+  uint64_t* c1done = wbar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(c1done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = t.n, nn = n * n, np = n + 2, cells = np * np;
@@ -855,18 +866,23 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   if (t.dyn_rows && *t.dyn_rows < t.B) t.B = *t.dyn_rows;
   const int64_t tiles = (t.B + G - 1) / G;
   constexpr int BN = 64;
-  constexpr uint32_t TMEM_COLS = 128;
+  constexpr uint32_t TMEM_COLS = 256;      // 2 x 64 conv2 accumulator columns, conv1 at C1_COL
+  constexpr uint32_t C1_COL = 128;
 
   // one-time setup
   for (int i = threadIdx.x; i < (X3 ? 2 : 1) * S::A1_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(a1hi)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < S::STAGES * S::STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 288; i += blockDim.x) w1s[i] = t.w1[i];
-  for (int i = threadIdx.x; i < TR_MAX_CELLS; i += blockDim.x) planes_s[i] = 0.0f;
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-    const int ib = i / nn, ip = i - ib * nn, ix = ip / n;
-    cell_tab[i] = (uint16_t)(ib * cells + ix * np + (ip - ix * n));
+  for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {  // conv1 weights as three bf16 terms along K (Connect4Net.py:32)
+    const int ch = i >> 6, col = i & 63, term = col >> 4, k = col & 15;
+    float v = 0.0f;
+    if (term < 3 && k < 9) {
+      const float w = t.w1[ch * 9 + k];
+      const float hi = __bfloat162float(__float2bfloat16_rn(w));
+      const float mid = __bfloat162float(__float2bfloat16_rn(w - hi));
+      v = term == 0 ? hi : term == 1 ? mid : (w - hi) - mid;
+    }
+    *reinterpret_cast<__nv_bfloat16*>(w1img + image_offset(ch, col)) = __float2bfloat16_rn(v);
   }
-  if (threadIdx.x < 32) b1s[threadIdx.x] = t.b1[threadIdx.x];
   if (warp == 9 && lane == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
       mbar_init(&full[s], 256);
@@ -877,10 +893,11 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
       mbar_init(&tempty[a], 128);
     }
     mbar_init(wbar, 1);
+    mbar_init(c1done, 1);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
-  fence_async_smem();  // the zero-filled stages are read by the tensor core (async proxy)
+  fence_async_smem();  // the zero-filled stages and the conv1 weight image are read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -893,12 +910,18 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
       if (X3) bulk_g2s(w_s + TR_W_BYTES, t.w_lo, TR_W_BYTES, wbar);
     }
   } else if (warp < 8) {
-    // ============ builders: 8 warps, two threads per tile row (each moves half of a row's chunks) ============
-    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;  // tile row, chunk half
+    // ============ builders: 8 warps, two threads per tile row ============
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;  // tile row, half (16 conv1 channels / 3 operand chunks)
     const int bl = r / nn, pc = r - bl * nn, x = pc / n, y = pc - x * n;
     const bool row_valid = bl < G;
     const int cell0 = bl * cells + x * np + y;  // padded cell of tap (0,0); tap (kx,ky) adds kx*np + ky
-    const int cw = warp;                        // conv1 worker index 0..7
+    // taps of this row's cell that lie on the board (bit k = tap kx*3+ky), fixed for the whole kernel
+    uint32_t tap_ok = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int xx = x + k / 3 - 1, yy = y + k % 3 - 1;
+      if (row_valid && xx >= 0 && xx < n && yy >= 0 && yy < n) tap_ok |= 1u << k;
+    }
     // patch-copy mapping: lane & 7 = chunk of the k-block, rows grow0 + 32 i
     const int gj = threadIdx.x & 7, grow0 = threadIdx.x >> 3;
     int gcell[4];
@@ -907,77 +930,99 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
       const int rr_ = grow0 + 32 * i, b_ = rr_ / nn, p_ = rr_ - b_ * nn, x_ = p_ / n;
       gcell[i] = b_ < G ? b_ * cells + x_ * np + (p_ - x_ * n) : -1;
     }
-    float w9[9];
+    float bias16[16];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) w9[k] = w1s[lane * 9 + k];
-    const float bias = b1s[lane];
+    for (int j = 0; j < 16; ++j) bias16[j] = __ldg(t.b1 + half * 16 + j);
+    const uint32_t c1_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C1_COL + (uint32_t)(half * 16);
     int stage = 0;
-    uint32_t phase = 0;
-    // the packed positions of the next tile are fetched one tile ahead (global latency off the critical path)
+    uint32_t phase = 0, c1_phase = 0;
+    // the packed positions are fetched one tile ahead of their use (global latency off the critical path)
     uint64_t nm = 0, nt = 0;
-    if (row_valid && half == 0) {
-      const int64_t b = (int64_t)blockIdx.x * G + bl;
-      if (b < t.B) { nm = t.states[2 * b]; nt = t.states[2 * b + 1]; }
-    }
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      if (row_valid && half == 0) {  // K1 encode: this row's cell of the packed position -> {-1,0,1} in the padded plane
-        planes_s[cell0 + np + 1] = (float)((int)((nm >> pc) & 1ull) - (int)((nt >> pc) & 1ull));
-        const int64_t b = (tile + gridDim.x) * G + bl;
-        nm = nt = 0;
-        if (b < t.B) { nm = t.states[2 * b]; nt = t.states[2 * b + 1]; }
+    auto fetch = [&](int64_t tile) {
+      nm = nt = 0;
+      const int64_t b = tile * G + bl;
+      if (row_valid && tile < tiles && b < t.B) { nm = t.states[2 * b]; nt = t.states[2 * b + 1]; }
+    };
+    // K1 encode + conv1 operand of the tile whose position is in (nm, nt): 16 bf16 = taps 0..8 and zeros, the same
+    // 32 bytes at K = 0, 16 and 32 (one copy per weight term); this thread writes three of the six 16-byte chunks
+    auto c1_slot = [&]() {
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* sa = stages + stage * S::STAGE_BYTES;
+      uint32_t pk[5];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int sh = (pc + (k / 3 - 1) * n + (k % 3 - 1)) & 63;
+        const uint32_t ok = (tap_ok >> k) & 1u;
+        const uint32_t m = (uint32_t)(nm >> sh) & ok, o = (uint32_t)(nt >> sh) & ok;
+        const uint32_t v = (m ? 0x3F80u : 0u) | (o ? 0xBF80u : 0u);  // bf16 +1 / -1
+        if (k & 1) pk[k >> 1] |= v << 16;
+        else pk[k >> 1] = v;
       }
-      named_bar(1, 256);  // planes ready; every builder is done reading the previous tile's conv1 output
-      // relu(conv1): lanes = channels, six warps walk the cells (Connect4Net.py:45)
-      for (int c = cw; c < G * nn; c += 16) {  // two cells per iteration (independent FMA chains)
-        const int c2 = c + 8;
-        const bool has2 = c2 < G * nn;
-        const int ctap = cell_tab[c], ctap2 = cell_tab[has2 ? c2 : c];
-        const float* pl = planes_s + ctap;
-        const float* pl2 = planes_s + ctap2;
-        float acc = bias, acc2 = bias;
+      const uint4 c_even = make_uint4(pk[0], pk[1], pk[2], pk[3]), c_odd = make_uint4(pk[4], 0, 0, 0);
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
+      for (int j = 0; j < 3; ++j) {
+        const int c = half * 3 + j;  // chunk 0..5 of the row: even chunks = taps 0-7, odd chunks = tap 8
+        *reinterpret_cast<uint4*>(sa + image_offset(r, c * 8)) = (c & 1) ? c_odd : c_even;
+      }
+      fence_async_smem();
+      mbar_arrive(&full[stage]);
+      if (++stage == S::STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    };
+    fetch(blockIdx.x);
+    if ((int64_t)blockIdx.x < tiles) c1_slot();
+    fetch((int64_t)blockIdx.x + gridDim.x);
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const bool has_next = tile + gridDim.x < tiles;
+      // relu(conv1 + bias) of this row's cell, 16 channels: TMEM -> bf16 hi/lo in the padded plane (Connect4Net.py:45)
+      mbar_wait(c1done, c1_phase);
+      c1_phase ^= 1;
+      tc_fence_after();
+      uint32_t rr[16];
+      tmem_ld16(c1_taddr, rr);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (row_valid) {
+        float v[16];
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            acc = fmaf(pl[kx * np + ky], w9[kx * 3 + ky], acc);
-            acc2 = fmaf(pl2[kx * np + ky], w9[kx * 3 + ky], acc2);
-          }
-        acc = fmaxf(acc, 0.0f);
-        acc2 = fmaxf(acc2, 0.0f);
-        const __nv_bfloat16 h = __float2bfloat16_rn(acc), h2 = __float2bfloat16_rn(acc2);
-        const uint32_t off = (uint32_t)(ctap + np + 1) * TR_CELL_STRIDE + lane * 2;
-        const uint32_t off2 = (uint32_t)(ctap2 + np + 1) * TR_CELL_STRIDE + lane * 2;
-        *reinterpret_cast<__nv_bfloat16*>(a1hi + off) = h;
-        if (X3) *reinterpret_cast<__nv_bfloat16*>(a1lo + off) = __float2bfloat16_rn(acc - __bfloat162float(h));
-        if (has2) {
-          *reinterpret_cast<__nv_bfloat16*>(a1hi + off2) = h2;
-          if (X3) *reinterpret_cast<__nv_bfloat16*>(a1lo + off2) = __float2bfloat16_rn(acc2 - __bfloat162float(h2));
-        }
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(rr[j]) + bias16[j], 0.0f);
+        const uint32_t off = (uint32_t)(cell0 + np + 1) * TR_CELL_STRIDE + half * 32;
+        split_store(v, a1hi, X3 ? a1lo : nullptr, off);
+        split_store(v + 8, a1hi, X3 ? a1lo : nullptr, off + 16);
       }
       named_bar(2, 256);  // conv1 output complete
       for (int kb = 0; kb < C2_KB; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = stages + stage * S::STAGE_BYTES;
         // Patch copies: the 8 lanes of a quarter-warp move the 8 chunks (two taps x 64 B) of ONE tile row, so a
         // 128-bit shared load touches two 64-byte cells whose offsets differ by an odd number of cells (tap +1, or
         // n cells across a kernel row for odd n): distinct bank groups.  (One row per lane with an 80-byte cell
         // stride conflicted 2-way whenever the 8 rows of a quarter-warp crossed a board-row end: +48 % wavefronts.)
+        // All loads of the k-block are issued before the wait for a free stage and before any store (the compiler
+        // cannot reorder shared loads over shared stores itself: four dependent round trips became one).
         const int c = kb * 8 + gj;  // 16-byte chunk of the K = (tap, cin) axis
         const bool chunk_live = c < 36;
         const int tap = c >> 2, kx = tap / 3, ky = tap - kx * 3;
         const uint32_t toff = (uint32_t)((kx * np + ky) * TR_CELL_STRIDE + (c & 3) * 16);
+        uint4 vh[4], vl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vh[i] = make_uint4(0, 0, 0, 0);
+          vl[i] = make_uint4(0, 0, 0, 0);
+          if (gcell[i] >= 0 && chunk_live) {
+            const uint32_t src = (uint32_t)gcell[i] * TR_CELL_STRIDE + toff;
+            vh[i] = *reinterpret_cast<const uint4*>(a1hi + src);
+            if (X3) vl[i] = *reinterpret_cast<const uint4*>(a1lo + src);
+          }
+        }
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = stages + stage * S::STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (gcell[i] >= 0) {
-            uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-            if (chunk_live) {
-              const uint32_t src = (uint32_t)gcell[i] * TR_CELL_STRIDE + toff;
-              vh = *reinterpret_cast<const uint4*>(a1hi + src);
-              if (X3) vl = *reinterpret_cast<const uint4*>(a1lo + src);
-            }
             const uint32_t dst = image_offset(grow0 + 32 * i, gj * 8);
-            *reinterpret_cast<uint4*>(sa + dst) = vh;
-            if (X3) *reinterpret_cast<uint4*>(sa + A_STAGE_BYTES + dst) = vl;
+            *reinterpret_cast<uint4*>(sa + dst) = vh[i];
+            if (X3) *reinterpret_cast<uint4*>(sa + A_STAGE_BYTES + dst) = vl[i];
           }
         }
         fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -986,17 +1031,39 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
           stage = 0;
           phase ^= 1;
         }
+        if (kb == TR_C1_AFTER_KB && has_next) {  // conv1 operand of the next tile, then fetch the one after
+          c1_slot();
+          fetch(tile + 2 * (int64_t)gridDim.x);
+        }
       }
+      named_bar(1, 256);  // every builder is done reading this tile's conv1 output
     }
   } else if (warp == 8) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc_c1 = make_idesc(BM, 32);
       mbar_wait(wbar, 0);
       const uint32_t w_addr = smem_u32(w_s);
+      const uint64_t b_c1 = make_smem_desc(smem_u32(w1img));
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      auto c1_slot = [&]() {  // conv1 of one tile: [A | A | A] x [w_hi | w_mid | w_lo]^T -> TMEM columns C1_COL..+31
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t a_c1 = make_smem_desc(smem_u32(stages + stage * S::STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) umma_bf16(tmem_base + C1_COL, a_c1 + 2 * k, b_c1 + 2 * k, idesc_c1, k != 0);
+        umma_commit(&empty[stage]);
+        umma_commit(c1done);
+        if (++stage == S::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      if ((int64_t)blockIdx.x < tiles) c1_slot();
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const bool has_next = tile + gridDim.x < tiles;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -1020,6 +1087,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
             stage = 0;
             phase ^= 1;
           }
+          if (kb == TR_C1_AFTER_KB && has_next) c1_slot();
         }
         umma_commit(&tfull[acc]);
         if (++acc == 2) {
