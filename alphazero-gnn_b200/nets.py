@@ -126,13 +126,18 @@ class _TwoPlayer(_Base):
     def predict_batches(self, host_batches, eval_mask=None):
         """Pipelined `predict_batch` over an iterable of equally shaped PINNED host board tensors [B,n,n]: the host->device
         copy of batch i+1 and the device->host copy of batch i-1 run on a copy stream while the kernels of batch i run
-        on the compute stream.  Yields, per batch, a dict of pinned host tensors (valid until two batches later)."""
+        on the compute stream.  Yields, per batch, a dict of pinned host tensors (valid until two batches later; the
+        staging buffers are reused by the next call with the same shapes)."""
         eval_mask = self._default_mask() if eval_mask is None else eval_mask
         compute = torch.cuda.current_stream()
         if getattr(self, "_copy_streams", None) is None:
             self._copy_streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
         up, down = self._copy_streams  # host->device, device->host
-        slots = [None, None]
+        # the two staging slots (device boards/outputs + pinned host outputs) persist across calls: pinning host memory
+        # costs milliseconds, which a 20-batch call would otherwise pay every time
+        if getattr(self, "_pipe_slots", None) is None:
+            self._pipe_slots = {}
+        slots = self._pipe_slots.setdefault(int(eval_mask), [None, None])
         pending = []  # (slot index, d2h-done event)
 
         def make_slot(hb):
