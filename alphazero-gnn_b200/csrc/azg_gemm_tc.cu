@@ -866,8 +866,12 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   if (t.dyn_rows && *t.dyn_rows < t.B) t.B = *t.dyn_rows;
   const int64_t tiles = (t.B + G - 1) / G;
   constexpr int BN = 64;
-  constexpr uint32_t TMEM_COLS = 256;      // 2 x 64 conv2 accumulator columns, conv1 at C1_COL
-  constexpr uint32_t C1_COL = 128;
+  // bf16x3: A_hi meets [W_hi ; W_lo] in ONE N = 128 MMA (columns 0-63 = hi x hi, 64-127 = hi x lo), A_lo x W_hi
+  // accumulates into columns 0-63, and the epilogue adds the two halves: 14 KB instead of 18 KB of operand reads per
+  // K = 16 step (an N = 64 MMA needs 6 KB per 32 tensor cycles, more than the 128 B/clk shared memory delivers)
+  constexpr int ACC_COLS = X3 ? 128 : 64;  // TMEM columns per accumulator stage
+  constexpr uint32_t TMEM_COLS = X3 ? 512 : 256;
+  constexpr uint32_t C1_COL = 2 * ACC_COLS;  // conv1 result columns
 
   // one-time setup
   for (int i = threadIdx.x; i < (X3 ? 2 : 1) * S::A1_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(a1hi)[i] = make_uint4(0, 0, 0, 0);
@@ -906,8 +910,14 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
   if (warp == 9) {
     if (lane == 0) {  // conv2 weight images -> smem, once
       mbar_expect_tx(wbar, (X3 ? 2 : 1) * TR_W_BYTES);
-      bulk_g2s(w_s, t.w_hi, TR_W_BYTES, wbar);
-      if (X3) bulk_g2s(w_s + TR_W_BYTES, t.w_lo, TR_W_BYTES, wbar);
+      if (X3) {  // per k-block [hi 8 KB | lo 8 KB]: one 128-row B operand
+        for (int kb = 0; kb < C2_KB; ++kb) {
+          bulk_g2s(w_s + kb * 16384, t.w_hi + kb * 8192, 8192, wbar);
+          bulk_g2s(w_s + kb * 16384 + 8192, t.w_lo + kb * 8192, 8192, wbar);
+        }
+      } else {
+        bulk_g2s(w_s, t.w_hi, TR_W_BYTES, wbar);
+      }
     }
   } else if (warp < 8) {
     // ============ builders: 8 warps, two threads per tile row ============
@@ -1043,6 +1053,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       constexpr uint32_t idesc_c1 = make_idesc(BM, 32);
+      constexpr uint32_t idesc_cat = make_idesc(BM, 2 * BN);
       mbar_wait(wbar, 0);
       const uint32_t w_addr = smem_u32(w_s);
       const uint64_t b_c1 = make_smem_desc(smem_u32(w1img));
@@ -1066,21 +1077,21 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
         const bool has_next = tile + gridDim.x < tiles;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         for (int kb = 0; kb < C2_KB; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stages + stage * S::STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_STAGE_BYTES);
-          const uint64_t b_hi = make_smem_desc(w_addr + kb * (64 * 128));
-          const uint64_t b_lo = make_smem_desc(w_addr + TR_W_BYTES + kb * (64 * 128));
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+          const uint64_t b_w = make_smem_desc(w_addr + kb * (X3 ? 2 : 1) * (64 * 128));  // X3: rows 0-63 hi, 64-127 lo
           if (X3) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_w + 2 * k, idesc_cat, (kb | k) != 0);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_w + 2 * k, idesc, 1);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_w + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);
           if (++stage == S::STAGES) {
@@ -1107,20 +1118,25 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
       const bool valid = bl < G && b < t.B;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
       const size_t tbase = ((size_t)(b >> 7) * nn + pc) * A_STAGE_BYTES;
       const int rb = (int)(b & 127);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t rr[32];
-        tmem_ld32(taddr + (uint32_t)c0, rr);
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t rr[16], r2[16];
+        tmem_ld16(taddr + (uint32_t)c0, rr);
+        if (X3) tmem_ld16(taddr + (uint32_t)(BN + c0), r2);  // the hi x lo half
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             float x8[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x8[e] = fmaxf(__uint_as_float(rr[c * 8 + e]) + __ldg(t.b2 + c0 + c * 8 + e), 0.0f);
+            for (int e = 0; e < 8; ++e) {
+              float d = __uint_as_float(rr[c * 8 + e]);
+              if (X3) d += __uint_as_float(r2[c * 8 + e]);
+              x8[e] = fmaxf(d + __ldg(t.b2 + c0 + c * 8 + e), 0.0f);
+            }
             split_store(x8, t.f_hi, X3 ? t.f_lo : nullptr, tbase + image_offset(rb, c0 + c * 8));
           }
         }
