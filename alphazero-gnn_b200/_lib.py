@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libazgnn_b200.so")
+LIB_PATH = os.environ.get("AZG_LIBRARY") or os.path.join(_HERE, "libazgnn_b200.so")  # AZG_LIBRARY: A/B builds
 
 OK = 0
 GAME_CONNECT4, GAME_TICTACTOE, GAME_FROZENLAKE = 0, 1, 2
