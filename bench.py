@@ -415,8 +415,9 @@ def run_gpu_arm(args, rank, local_rank, world):
         # roofline entry always uses the measured bf16 tensor peak (the path's real ceiling).
         terms = 3 if args.precision == "bf16x3" else 1
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this
-        # configuration (profiles/r01_main_kernels_bf16x3_v5.txt: GEMM-1 2.245+0.806 GB, GEMM-2 1.944+0.060 GB)
-        traffic = {"bf16x3": 2.528e9, "bf16": None, "fp32": None}[args.precision] if B == BATCH else None
+        # configuration (profiles/r01_main_kernels_bf16x3_v9.txt: GEMM-1 with the std-heads side tile 1.983+0.813 GB,
+        # GEMM-2 1.681+0.060 GB)
+        traffic = {"bf16x3": 2.268e9, "bf16": None, "fp32": None}[args.precision] if B == BATCH else None
         roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
                 "frac": (gemm_tflops / bf16_peak) if gemm_tflops else None, "traffic": traffic,
                 "traffic_unit": "bytes per launch (average of the two launches)",
@@ -425,7 +426,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "algorithmic_bytes_per_launch": (3 * (B * 3136 * 2) * (2 if terms == 3 else 1) + B * 14 * 16 * 4) / 2,
                 "mma_terms": terms, "issued_tflops": gemm_tflops * terms if gemm_tflops else None,
                 "peak_source": peak_src + " (bf16_tflops_sustained)",
-                "kernel": "output_transform F x F contractions (2 launches per step)",
+                "kernel": "output_transform F x F contractions (2 launches per step; the first also carries the standard heads as a 32-column side tile, not counted in the algorithmic FLOP)",
                 "kernel_ms_per_step": gemm_ms / max(gemm_cnt, 1),
                 "phase_ms_per_step": {k: v[0] / args.steps for k, v in phase.items()}}
         # CPU baselines are timed at N=1 only (rank 0); multi-GPU lines carry null
