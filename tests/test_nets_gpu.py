@@ -345,3 +345,26 @@ def test_default_precision_is_the_tensor_core_path(kind, n):
         np.testing.assert_allclose(got, want.numpy(), rtol=0, atol=1e-5)
     one_pi, one_v = w.predict_with_gnn(boards[0])
     assert abs(one_v - gv[0].item()) <= 1e-5 and np.abs(one_pi - gpi[0].numpy()).max() <= 1e-5
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_tensor_core_forward_is_run_to_run_identical(prec):
+    """The fused trunk (conv1 slot queued inside the previous tile's conv2 k-blocks, one TMEM result region) and GEMM-1's
+    side tile are synchronised by mbarriers only: repeated launches over many tiles per CTA (20,011 positions = 68
+    tiles per SM, ragged tail) must be bit-identical, and a std-only call must equal the std half of the combined call."""
+    w = _wrapper("c4", 7)
+    rng = np.random.default_rng(5)
+    states = w.states_from_boards(rng.integers(-1, 2, size=(20011, 7, 7)).astype(np.int8))
+    both = _lib.EVAL_STD | _lib.EVAL_GNN
+    p = _lib.PRECISIONS[prec]
+    first = {k: v.clone() for k, v in w.forward_states(states, both, precision=p).items()}
+    for _ in range(4):
+        again = w.forward_states(states, both, precision=p)
+        for k in first:
+            assert torch.equal(first[k], again[k]), k
+    only_std = w.forward_states(states, _lib.EVAL_STD, precision=p)
+    assert torch.equal(only_std["pi"], first["pi"]) and torch.equal(only_std["v"], first["v"])
+    # rows do not depend on their neighbours or on the batch they arrive in
+    part = w.forward_states(states[1000:1300].contiguous(), both, precision=p)
+    for k in first:
+        assert torch.equal(part[k], first[k][1000:1300]), k
