@@ -10,11 +10,16 @@
 //     complete on an mbarrier; no tensor maps, no in-kernel shuffling.  Weights are re-tiled
 //     once per optimizer step (azg_c4_pack); activations are written as images by the
 //     producer (the f32->image kernel for X, the GEMM epilogue for H).
-//   * One persistent CTA per SM, warp-specialised: warp 0 = bulk-copy producer, warp 1 = MMA
-//     issuer (a single thread issues tcgen05.mma, M=128 x N=BN x K=16 per instruction),
-//     warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/ReLU -> store).
-//     Accumulators live in TMEM, double-buffered (2 x BN fp32 columns) so the epilogue of tile
-//     i overlaps the main loop of tile i+1.  smem ring: 4 stages x (16 KB A + BN*128 B W).
+//   * Persistent, warp-specialised kernel: warp 0 = bulk-copy producer, warp 1 = MMA issuer (a single thread
+//     issues tcgen05.mma), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/ReLU -> store).
+//     Accumulators live in TMEM, double-buffered (2 x BN fp32 columns) so the epilogue of tile i overlaps the
+//     main loop of tile i+1.  Two instantiations per tile width:
+//       TWO = 0  one CTA per SM, M=128 x N=BN x K=16 MMAs, smem ring of 4 stages x (16 KB A + BN*128 B W);
+//       TWO = 1  CTA pairs (cluster of 2, cta_group::2): 256 x BN x 16 MMAs issued by the leader CTA, each CTA holds
+//                128 rows of A and of the accumulator and BN/2 rows of the weight tile; a stage carries two operand
+//                pairs (bf16x3: hi and lo of one k-block -> all three products; bf16: two k-blocks).  This is the
+//                kernel of the Connect4 F x F contractions; it can also carry a 32-column side tile per m-unit
+//                (GemmArgs::side_*: the standard policy/value heads ride on GEMM-1).
 //   * AZG_PREC_BF16X3 (the 1e-5 parity mode): x = hi + lo with hi = bf16(x), lo = bf16(x - hi);
 //     X W^T ~= Xhi Whi^T + Xhi Wlo^T + Xlo Whi^T, fp32 accumulate.  Implemented as ONE GEMM with a
 //     3x longer K: the producer walks the k-blocks of [Xhi|Xhi|Xlo] against [Whi|Wlo|Whi]; the
