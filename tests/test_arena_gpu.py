@@ -141,3 +141,54 @@ def test_batched_selfplay_on_device(kind, n):
             assert np.asarray(b).shape == (n, n) and len(p) == A and abs(sum(p) - 1) < 1e-6
         if use_gnn:
             assert len(gnn) > 0
+
+
+def test_many_concurrent_trees_properties():
+    """8,192 Connect4 7x7 trees searched in lock step with the device network (bf16x3, one batched leaf evaluation
+    per simulation round): every copy of a root position gets bit-identical visit statistics whatever its slot in
+    the arena and in the leaf batches (512 distinct legal roots x 16 copies), a sample of games equals the sequential
+    oracle search that calls the same network per leaf, and the policies are distributions that leave illegal moves their 1e-8 floor."""
+    from azgnn_b200 import games
+    from azgnn_b200.mcts import BatchedMCTS
+    from azgnn_b200.nets import B200Connect4GNNWrapper
+    from oracle.mcts import OracleMCTS
+    from helpers import dotdict
+    n, distinct, copies = 7, 512, 16
+    args = dotdict(dict(lr=1e-3, dropout=0.3, gnn_layers=2, numMCTSSims=10, cpuct=1.0, use_gnn=True, expand_by=5,
+                        b200_precision="bf16x3"))
+    game = games.Connect4Game(n)
+    torch.manual_seed(0)
+    net = B200Connect4GNNWrapper(game, args)
+    rng = np.random.default_rng(8192)
+    roots = []
+    while len(roots) < distinct:  # legal positions from random playouts of 0..12 plies
+        b, player, ok = game.getInitBoard(), 1, True
+        for _ in range(int(rng.integers(0, 13))):
+            valid = np.flatnonzero(game.getValidMoves(b, player))
+            b, player = game.getNextState(b, player, int(rng.choice(valid)))
+            if game.getGameEnded(b, player) != 0:
+                ok = False
+                break
+        if ok:
+            roots.append(game.getCanonicalForm(b, player))
+    G = distinct * copies
+    order = rng.permutation(G)  # copy c of root r sits in an arbitrary slot
+    slot_root = np.empty(G, dtype=np.int64)
+    slot_root[order] = np.arange(G) % distinct
+    bm = BatchedMCTS(game, net, args, n_games=G)
+    bm.set_root_boards([roots[r] for r in slot_root])
+    probs = np.asarray(bm.getActionProbs(temp=1), dtype=np.float64)
+    assert probs.shape == (G, game.getActionSize())
+    first = {}
+    for g in range(G):
+        r = int(slot_root[g])
+        if r in first:
+            assert np.array_equal(probs[g], probs[first[r]]), (g, first[r])
+        else:
+            first[r] = g
+    assert np.abs(probs.sum(axis=1) - 1).max() < 1e-9
+    for r in range(0, distinct, 64):
+        valid = np.asarray(game.getValidMoves(roots[r], 1))
+        assert np.all(probs[first[r]][valid == 0] < 1e-8)  # MCTS.py:55-57 adds 1e-8 to every count
+        want = OracleMCTS(game, _AsReference(net), args).getActionProb(roots[r], temp=1)
+        assert np.array_equal(np.asarray(want), probs[first[r]]), r

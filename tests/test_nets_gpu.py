@@ -368,3 +368,45 @@ def test_tensor_core_forward_is_run_to_run_identical(prec):
     part = w.forward_states(states[1000:1300].contiguous(), both, precision=p)
     for k in first:
         assert torch.equal(part[k], first[k][1000:1300]), k
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] at its full size (65,536 positions, 7x7, std + GNN predictions, bf16x3), checked through
+    size-independent properties: a random sample of rows against the oracle at 1e-5; rows evaluated alone or in
+    another order give bit-identical outputs (no dependence on tile position or neighbours); duplicated positions
+    give duplicated outputs; policies are distributions, values lie in [-1, 1]."""
+    w = _wrapper("c4", 7)
+    B = 65536
+    rng = np.random.default_rng(65536)
+    boards = rng.integers(-1, 2, size=(B, 7, 7)).astype(np.int8)
+    boards[B // 2:B // 2 + 100] = boards[:100]  # duplicates
+    both = _lib.EVAL_STD | _lib.EVAL_GNN
+    states = w.states_from_boards(boards)
+    full = {k: v.clone() for k, v in w.forward_states(states, both).items()}
+    # (1) sample vs oracle
+    idx = np.sort(rng.choice(B, size=384, replace=False))
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    bt = onets.boards_to_tensor(boards[idx].astype(np.int64))
+    with torch.no_grad():
+        spi, sv = onets.c4_predict(p, bt, 7)
+        gpi, gv = onets.c4_predict_with_gnn(p, q, bt, 7)
+    tidx = torch.from_numpy(idx).to(full["pi"].device)
+    for name, want in (("pi", spi), ("v", sv), ("pi_gnn", gpi), ("v_gnn", gv)):
+        got = full[name][tidx].cpu().numpy().reshape(want.shape)
+        np.testing.assert_allclose(got, want.numpy(), rtol=0, atol=1e-5, err_msg=name)
+    # (2) the same rows evaluated alone, and the whole batch in another order
+    alone = w.forward_states(states[tidx].contiguous(), both)
+    for name in full:
+        assert torch.equal(alone[name], full[name][tidx]), name
+    perm = torch.from_numpy(rng.permutation(B)).to(states.device)
+    shuffled = w.forward_states(states[perm].contiguous(), both)
+    for name in full:
+        assert torch.equal(shuffled[name], full[name][perm]), name
+    # (3) duplicates, (4) ranges
+    for name in full:
+        assert torch.equal(full[name][B // 2:B // 2 + 100], full[name][:100]), name
+    for name in ("pi", "pi_gnn"):
+        s = full[name].sum(dim=1)
+        assert float((s - 1).abs().max()) <= 1e-5 and float(full[name].min()) >= 0.0
+    for name in ("v", "v_gnn"):
+        assert float(full[name].abs().max()) <= 1.0
