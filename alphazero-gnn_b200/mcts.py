@@ -271,6 +271,13 @@ class BatchedMCTS:
             vals.append(self.standard_predictions[g][s][1])
         return vals
 
+    def _root_std_values_array(self):
+        """`_root_std_values` as one float32 array (no per-game Python scalars: 4 ms per move-step at 16,384 games)"""
+        if self.device_eval:
+            out = self.nnet.forward_states(self.arena.get_roots(), _lib.EVAL_STD)
+            return np.asarray(self.arena.to_host(out["v"]), dtype=np.float32).reshape(-1)
+        return np.asarray(self._root_std_values(), dtype=np.float32)
+
     def expand_tree(self, expand_by=5):
         """per game: (initial_policy, initial_value, expanded_policy, expanded_value), MCTS.py:60-149"""
         ip, v0, ep, ev, evtag = self.expand_tree_arrays(expand_by)
@@ -285,7 +292,7 @@ class BatchedMCTS:
                 raise RuntimeError("expand_tree: some games have root visits and some do not; call getActionProbs first")
             self.search(int(arg(self.args, "numMCTSSims")))
             N0, _, _ = self.root_stats()
-        v0 = np.asarray(self._root_std_values(), dtype=np.float32)
+        v0 = self._root_std_values_array()
         self.search(expand_by)
         N1, Q1, T1 = self.root_stats()
         ip = self._visit_policy(N0, None)
