@@ -191,8 +191,9 @@ class BatchedMCTS:
             self.leaf_evals += 1
         return ar.to_device(pi, torch.float32), ar.to_device(v, torch.float32), int(mask.sum())
 
-    def search(self, n_sims):
-        """n_sims MCTS.search calls per game (MCTS.py:33-34), in lock step."""
+    def search(self, n_sims, check=True):
+        """n_sims MCTS.search calls per game (MCTS.py:33-34), in lock step.  check=False leaves the (synchronising)
+        arena status read-back to the caller, so that host work can overlap the queued rounds (device evaluation only)."""
         ar = self.arena
         ar.begin(n_sims)
         if self.compact:
@@ -214,7 +215,8 @@ class BatchedMCTS:
                 if pending == 0:
                     break
                 ar.expand_backup(pi, v)
-        ar.check_status()
+        if check or not self.device_eval:
+            ar.check_status()
 
     def leaf_evaluations(self):
         """number of leaf positions evaluated so far (synchronises when the count lives on the device)"""
@@ -294,6 +296,30 @@ class BatchedMCTS:
             N0, _, _ = self.root_stats()
         v0 = self._root_std_values_array()
         self.search(expand_by)
+        N1, Q1, T1 = self.root_stats()
+        ip = self._visit_policy(N0, None)
+        ep = self._visit_policy(N1, ip)
+        ev, evtag = expanded_values(N1, Q1, T1, v0)
+        return ip, v0, ep, ev, evtag
+
+    def expand_tree_launch(self, expand_by, N0):
+        """First half of `expand_tree_arrays` for device evaluation, WITHOUT synchronising: the standard prediction of the
+        roots (MCTS.py:108-111) and the `expand_by` extra searches are queued on the stream; the caller may do host work
+        (policies from counts, action sampling) before `expand_tree_finish`.  N0 = root visit counts before the expansion.
+        Returns None when the synchronous path has to be used (host evaluation, or roots without visits)."""
+        if not self.device_eval or (N0.sum(axis=1) == 0).any():
+            return None
+        v_dev = self.nnet.forward_states(self.arena.get_roots(), _lib.EVAL_STD)["v"]
+        self.search(expand_by, check=False)
+        return N0.copy(), v_dev
+
+    def expand_tree_finish(self, pending, expand_by=5):
+        """Second half: read back, same outputs as `expand_tree_arrays`."""
+        if pending is None:
+            return self.expand_tree_arrays(expand_by)
+        N0, v_dev = pending
+        v0 = np.asarray(self.arena.to_host(v_dev), dtype=np.float32).reshape(-1)
+        self.arena.check_status()
         N1, Q1, T1 = self.root_stats()
         ip = self._visit_policy(N0, None)
         ep = self._visit_policy(N1, ip)

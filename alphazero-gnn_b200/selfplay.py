@@ -189,13 +189,28 @@ class BatchedSelfPlay:
         temps = (self.step < self.temp_threshold).astype(np.int64)   # Coach.py:37
         m.search(int(arg(self.args, "numMCTSSims")))
         N, _, _ = m.root_stats()
+        # expand_tree's device work (root evaluation + expand_by searches) is queued first; the host turns the counts
+        # into policies and actions while it runs.  Neither consumes `self.rng` inside expand_tree, so drawing the
+        # actions here keeps the reference's random stream (policy tie-breaks, then the sampled moves).
+        recs, pending, launched = None, None, False
+        if self.use_gnn and m.device_eval:
+            if self.device_collect:
+                pending = m.expand_tree_launch(self.expand_by, N)
+                launched = pending is not None
+            elif not self.collect:
+                self._expand_only(check=False)
+                launched = True
         probs = probs_from_counts(N, temps, self.rng)
-        recs = None
+        actions = sample_actions(probs, self.rng)
         if self.use_gnn:
             if self.device_collect:
-                recs = m.expand_tree_arrays(self.expand_by)  # arrays over all games, no per-game Python work
+                recs = m.expand_tree_finish(pending, self.expand_by)  # arrays over all games, no per-game Python work
+            elif self.collect:
+                recs = m.expand_tree(self.expand_by)
+            elif launched:
+                m.arena.check_status()
             else:
-                recs = m.expand_tree(self.expand_by) if self.collect else self._expand_only()
+                self._expand_only()
         if self.device_collect:
             # history stays in HBM: slot (episode step, game) <- root state, player to move, pi
             t = torch.as_tensor(self.step - 1, dtype=torch.int64).to(self.dev)
@@ -213,7 +228,6 @@ class BatchedSelfPlay:
             for g in range(G):
                 self.history[g].append((boards[g], int(self.player[g]), list(probs[g]),
                                         recs[g] if recs is not None else None))
-        actions = sample_actions(probs, self.rng)
         e_val, e_tag = m.advance_arrays(actions)  # getGameEnded of the new positions; typed objects only for finished games
         self.moves_played += G
         if self.two_player:
@@ -241,11 +255,11 @@ class BatchedSelfPlay:
             self._restart(done)
         return out
 
-    def _expand_only(self):
+    def _expand_only(self, check=True):
         """expand_tree's searches without building the example records (throughput runs)."""
         if self.mcts.device_eval:
             self.mcts.nnet.forward_states(self.mcts.arena.get_roots(), _lib.EVAL_STD)  # MCTS.py:108-111
-        self.mcts.search(self.expand_by)
+        self.mcts.search(self.expand_by, check=check)
         return None
 
     def play(self, n_episodes):
