@@ -313,18 +313,31 @@ class BatchedMCTS:
         self.search(expand_by, check=False)
         return N0.copy(), v_dev
 
-    def expand_tree_finish(self, pending, expand_by=5):
-        """Second half: read back, same outputs as `expand_tree_arrays`."""
+    def expand_tree_readback(self, pending, expand_by=5):
+        """Second half, part 1: everything that must be read from the arena BEFORE the roots move on (synchronises)."""
         if pending is None:
-            return self.expand_tree_arrays(expand_by)
+            return "records", self.expand_tree_arrays(expand_by)
         N0, v_dev = pending
         v0 = np.asarray(self.arena.to_host(v_dev), dtype=np.float32).reshape(-1)
         self.arena.check_status()
         N1, Q1, T1 = self.root_stats()
+        return "raw", (N0, v0, N1, Q1, T1)
+
+    def expand_tree_records(self, readback):
+        """Part 2, host arithmetic only (may run while later device work is in flight): the outputs of
+        `expand_tree_arrays`."""
+        kind, payload = readback
+        if kind == "records":
+            return payload
+        N0, v0, N1, Q1, T1 = payload
         ip = self._visit_policy(N0, None)
         ep = self._visit_policy(N1, ip)
         ev, evtag = expanded_values(N1, Q1, T1, v0)
         return ip, v0, ep, ev, evtag
+
+    def expand_tree_finish(self, pending, expand_by=5):
+        """Second half: read back, same outputs as `expand_tree_arrays`."""
+        return self.expand_tree_records(self.expand_tree_readback(pending, expand_by))
 
     def _visit_policy(self, N, fallback):
         """counts -> policy as MCTS.py:95-103 / 125-130: N / sum(N); with no visits the fallback (the initial policy for

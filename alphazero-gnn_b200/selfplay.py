@@ -110,6 +110,7 @@ class BatchedSelfPlay:
             self.h_pi = torch.zeros(self.t_cap, self.G, self.A, dtype=torch.float64, device=dev)
             self.h_player = torch.zeros(self.t_cap, self.G, dtype=torch.int32, device=dev)
             self.h_int = torch.zeros(self.t_cap, self.G, dtype=torch.int8, device=dev)
+            self.h_player_host = np.zeros((self.t_cap, self.G), dtype=np.int32)
             self.device_examples = DeviceExamples(game, dev)
             self.device_gnn_examples = DeviceGnnExamples(game, dev)
             # GNN records (expand_tree, MCTS.py:60-149) per (episode step, game): initial policy, initial value,
@@ -122,6 +123,7 @@ class BatchedSelfPlay:
     # ------------------------------------------------------------------ episode bookkeeping
     def _start_all(self):
         G = self.G
+        self._inflight = False  # numMCTSSims searches of the coming move already queued (step_all)
         self.mcts.reset()
         self.mcts.arena.set_roots(np.tile(self.init_state, (G, 1)))
         self.step = np.zeros(G, dtype=np.int64)      # episodeStep (Coach.py:32-35)
@@ -153,12 +155,12 @@ class BatchedSelfPlay:
                 gnn.append((board, pl, ip, iv, ep, ev, sign))
         return std, gnn
 
-    def _finish_device(self, done, ended):
+    def _finish_device(self, done, ended, lens, cur_players):
         """Coach.py:68-79 for all episodes that ended on this move: one gather of their history slots and one
         emit kernel (symmetries + signed values) append the standard examples to `self.device_examples`; the GNN
         records (no symmetries; expand_tree_arrays output) go to `self.device_gnn_examples` column by column."""
-        done = np.asarray(done, dtype=np.int64)
-        lens = self.step[done]
+        done = np.asarray(done, dtype=np.int64)  # lens / cur_players: episode lengths and players to move at the end,
+        # taken before the games were restarted
         E = int(lens.sum())
         gcol = np.repeat(done, lens)
         tcol = np.concatenate([np.arange(k) for k in lens]) if E else np.zeros(0, dtype=np.int64)
@@ -171,11 +173,11 @@ class BatchedSelfPlay:
                         _lib.TAG_PYINT if isinstance(ended[g], (int, np.integer)) else _lib.TAG_PYFLOAT for g in done], dtype=np.int8)
         self.device_examples.emit(self.h_states[t, gi], self.h_pi[t, gi], self.h_player[t, gi], torch.as_tensor(grow).to(dev),
                                   torch.as_tensor(res).to(dev), torch.as_tensor(tag).to(dev),
-                                  torch.as_tensor(self.player[done].astype(np.int32)).to(dev), pi_int=self.h_int[t, gi])
+                                  torch.as_tensor(cur_players.astype(np.int32)).to(dev), pi_int=self.h_int[t, gi])
         if self.use_gnn:  # Coach.py:72-74: one GNN record per stored position, no symmetries
-            players = self.h_player[t, gi].cpu().numpy()
+            players = self.h_player_host[tcol, gcol]  # host mirror of h_player: no read-back behind the queued searches
             ip, iv, ep, ev, evtag = (x[tcol, gcol] for x in self.g_rec)
-            cur_e = np.repeat(self.player[done], lens)
+            cur_e = np.repeat(cur_players, lens)
             sign = np.repeat(res, lens) * np.where(players != cur_e, -1.0, 1.0)
             self.device_gnn_examples.append_records(self.h_states[t, gi], players, ip, iv, ep, ev, evtag, sign, np.repeat(tag, lens))
         return [([], []) for _ in done]
@@ -183,15 +185,23 @@ class BatchedSelfPlay:
     # ------------------------------------------------------------------ one lock-step move
     def step_all(self):
         """Every live game plays one move.  Returns the list of (std_examples, gnn_examples) of the
-        episodes that finished on this move."""
+        episodes that finished on this move.
+
+        Device evaluation is software-pipelined against the host: expand_tree's device work is queued before the host
+        turns counts into policies and actions, and the numMCTSSims searches of the NEXT move are queued (status check
+        pending, `self._inflight`) before this move's records are computed and its finished episodes are emitted.  The
+        arena state each search starts from and the order in which `self.rng` is consumed (policy tie-breaks, then the
+        sampled moves) are those of the sequential loop."""
         m, G = self.mcts, self.G
+        n_sims = int(arg(self.args, "numMCTSSims"))
         self.step += 1
         temps = (self.step < self.temp_threshold).astype(np.int64)   # Coach.py:37
-        m.search(int(arg(self.args, "numMCTSSims")))
+        if self._inflight:
+            m.arena.check_status()  # the searches queued at the end of the previous move
+            self._inflight = False
+        else:
+            m.search(n_sims)
         N, _, _ = m.root_stats()
-        # expand_tree's device work (root evaluation + expand_by searches) is queued first; the host turns the counts
-        # into policies and actions while it runs.  Neither consumes `self.rng` inside expand_tree, so drawing the
-        # actions here keeps the reference's random stream (policy tie-breaks, then the sampled moves).
         recs, pending, launched = None, None, False
         if self.use_gnn and m.device_eval:
             if self.device_collect:
@@ -202,9 +212,11 @@ class BatchedSelfPlay:
                 launched = True
         probs = probs_from_counts(N, temps, self.rng)
         actions = sample_actions(probs, self.rng)
+        th, gh = self.step - 1, np.arange(G)  # history slot of this move (the arrays below change on restart)
+        readback = None
         if self.use_gnn:
             if self.device_collect:
-                recs = m.expand_tree_finish(pending, self.expand_by)  # arrays over all games, no per-game Python work
+                readback = m.expand_tree_readback(pending, self.expand_by)  # root statistics, before the roots move on
             elif self.collect:
                 recs = m.expand_tree(self.expand_by)
             elif launched:
@@ -213,16 +225,13 @@ class BatchedSelfPlay:
                 self._expand_only()
         if self.device_collect:
             # history stays in HBM: slot (episode step, game) <- root state, player to move, pi
-            t = torch.as_tensor(self.step - 1, dtype=torch.int64).to(self.dev)
+            t = torch.as_tensor(th, dtype=torch.int64).to(self.dev)
             gi = torch.arange(G, device=self.dev)
             self.h_states[t, gi] = m.arena.get_roots().view(G, 2)
             self.h_pi[t, gi] = torch.as_tensor(probs, dtype=torch.float64).to(self.dev)
             self.h_player[t, gi] = torch.as_tensor(self.player, dtype=torch.int32).to(self.dev)
             self.h_int[t, gi] = torch.as_tensor(temps == 0, dtype=torch.int8).to(self.dev)
-            if recs is not None:
-                th, gh = self.step - 1, np.arange(G)
-                for dst, src in zip(self.g_rec, recs):
-                    dst[th, gh] = src
+            self.h_player_host[th, gh] = self.player
         elif self.collect:
             boards = unpack_boards(self.kind, self.n, m.arena.to_host(m.arena.get_roots()))
             for g in range(G):
@@ -240,19 +249,29 @@ class BatchedSelfPlay:
         from .mcts import typed_value
         ended = {g: (typed_value(e_val[g], int(e_tag[g])) if e_val[g] != 0 else 0.0) for g in done}
         out = []
+        if not self.device_collect:
+            for g in done:
+                out.append(self._finish(g, ended[g]) if self.collect else ([], []))
+        keep, lens, cur = [], None, None
         if self.device_collect and done:
             # `play(n)` keeps exactly n episodes (the reference runs numEps of them): later finishers of the same
             # move-step are restarted without contributing examples
             keep = done if self._budget is None else done[:max(self._budget, 0)]
             if self._budget is not None:
                 self._budget -= len(keep)
-            out = self._finish_device(keep, ended) + [([], []) for _ in done[len(keep):]]
-        else:
-            for g in done:
-                out.append(self._finish(g, ended[g]) if self.collect else ([], []))
+            lens, cur = self.step[keep].copy(), self.player[keep].copy()
         if done:
             self.episodes_done += len(done)
             self._restart(done)
+        if m.device_eval:  # next move's searches: the GPU works while the host finishes this move's records
+            m.search(n_sims, check=False)
+            self._inflight = True
+        if self.device_collect:
+            if readback is not None:
+                for dst, src in zip(self.g_rec, m.expand_tree_records(readback)):
+                    dst[th, gh] = src
+            if done:
+                out = (self._finish_device(keep, ended, lens, cur) if keep else []) + [([], []) for _ in done[len(keep):]]
         return out
 
     def _expand_only(self, check=True):
