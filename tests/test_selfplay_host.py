@@ -97,3 +97,110 @@ def test_vectorised_expanded_value_has_the_scalar_loops_values_and_types():
         got = typed_value(val[g], int(tag[g]))
         assert type(got) is type(want), (g, type(got), type(want))
         assert got == want, (g, got, want)
+
+
+class _FakeDeviceNet:
+    """FakeNet behind the batched `forward_states` interface of the CUDA wrappers (CPU tensors, with the device-count
+    contract of the compacted leaf batches), so that the device-evaluation code paths of BatchedMCTS / BatchedSelfPlay
+    -- searches queued without a status check, expand_tree launched before the host turns counts into policies, the
+    next move's searches queued before this move's records -- run on the host check arena."""
+    def __init__(self, kind, n, A, salt, dynamic):
+        self.kind, self.n, self.A = kind, n, A
+        self.net = FakeNet(A, salt=salt)
+        self.supports_dynamic_count = dynamic
+        self.calls = 0
+
+    def predict(self, board):
+        return self.net.predict(board)
+
+    def predict_with_gnn(self, board):
+        return self.net.predict_with_gnn(board)
+
+    def forward_states(self, states, eval_mask=None, precision=None, count=None, out=None):
+        import torch
+        from azgnn_b200 import _lib
+        self.calls += 1
+        B = int(states.shape[0])
+        live = B if count is None else int(count.reshape(-1)[0])
+        boards = unpack_boards(self.kind, self.n, states.numpy()[:live])
+        o = {}
+        for bit, names, fn in ((_lib.EVAL_STD, ("pi", "v"), self.net.predict), (_lib.EVAL_GNN, ("pi_gnn", "v_gnn"), self.net.predict_with_gnn)):
+            if eval_mask & bit:
+                pi = np.full((B, self.A), np.nan, dtype=np.float32)  # rows beyond the count must never be read
+                v = np.full(B, np.nan, dtype=np.float32)
+                for i, b in enumerate(boards):
+                    pi[i], v[i] = fn(b)
+                o[names[0]], o[names[1]] = torch.from_numpy(pi), torch.from_numpy(v)
+        return o
+
+
+def _play_fixed_moves(kind, n, net, moves, collect, G=6, seed=11):
+    game = games.Connect4Game(n) if kind == "connect4" else games.TicTacToeGame(n)
+    args = dotdict(dict(numMCTSSims=7, cpuct=1.0, use_gnn=True, expand_by=3, tempThreshold=3))
+    arena = HostArena(kind, n, G, 10, 1.0, capacity=10 * (n * n + 2) + 16)
+    sp = BatchedSelfPlay(game, net, args, G, seed=seed, collect_examples=collect, arena=arena)
+    out = []
+    for _ in range(moves):
+        out.append(sp.step_all())
+    return sp, out
+
+
+def _same_examples(a, b):
+    assert len(a) == len(b)
+    for (s1, g1), (s2, g2) in zip(a, b):
+        assert len(s1) == len(s2) and len(g1) == len(g2)
+        for (b1, p1, r1), (b2, p2, r2) in zip(s1, s2):
+            assert np.array_equal(b1, b2) and list(p1) == list(p2) and r1 == r2 and type(r1) is type(r2)
+        for x, y in zip(g1, g2):
+            assert np.array_equal(x[0], y[0]) and x[1] == y[1] and np.array_equal(x[2], y[2]) and x[3] == y[3]
+            assert np.array_equal(x[4], y[4]) and x[5] == y[5] and type(x[5]) is type(y[5]) and x[6] == y[6]
+
+
+@pytest.mark.parametrize("kind,n", [("connect4", 5), ("tictactoe", 3)])
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_pipelined_device_loop_equals_the_sequential_host_loop(kind, n, dynamic):
+    """The move loop with batched ("device") evaluation -- pipelined against the host -- produces, move by move, the
+    episodes of the sequential per-leaf loop: same examples, same types, same random stream."""
+    A = n + 1 if kind == "connect4" else n * n + 1
+    sp_h, host = _play_fixed_moves(kind, n, FakeNet(A, salt=5), 30, True)
+    sp_d, dev = _play_fixed_moves(kind, n, _FakeDeviceNet(kind, n, A, 5, dynamic), 30, True)
+    assert sp_d.mcts.device_eval and sp_d.mcts.compact == dynamic and not sp_h.mcts.device_eval
+    assert sum(len(x) for x in host) >= 2  # episodes did finish (and restart) inside the window
+    for h, d in zip(host, dev):
+        _same_examples(h, d)
+    assert sp_h.moves_played == sp_d.moves_played and sp_h.episodes_done == sp_d.episodes_done
+    assert np.array_equal(sp_h.step, sp_d.step) and np.array_equal(sp_h.player, sp_d.player)
+    # throughput mode (no examples): the same games are played
+    sp_t, _ = _play_fixed_moves(kind, n, _FakeDeviceNet(kind, n, A, 5, dynamic), 30, False)
+    assert sp_t.episodes_done == sp_h.episodes_done and np.array_equal(sp_t.step, sp_h.step)
+    roots_t = sp_t.mcts.arena.to_host(sp_t.mcts.arena.get_roots())
+    roots_h = sp_h.mcts.arena.to_host(sp_h.mcts.arena.get_roots())
+    assert np.array_equal(roots_t, roots_h)
+
+
+def test_expand_tree_in_two_halves_equals_expand_tree_arrays():
+    """expand_tree_launch + expand_tree_readback + expand_tree_records (the split used by the pipelined loop) ==
+    expand_tree_arrays, outputs and arena statistics alike."""
+    from azgnn_b200.mcts import BatchedMCTS
+    kind, n, G = "connect4", 5, 4
+    game = games.Connect4Game(n)
+    A = game.getActionSize()
+    args = dotdict(dict(numMCTSSims=9, cpuct=1.0, use_gnn=True, expand_by=4))
+    res = []
+    for split in (False, True):
+        arena = HostArena(kind, n, G, 13, 1.0, capacity=13 * (n * n + 2) + 16)
+        bm = BatchedMCTS(game, _FakeDeviceNet(kind, n, A, 9, True), args, n_games=G, arena=arena)
+        bm.set_root_boards([game.getInitBoard()] * G)
+        bm.search(9)
+        N0, _, _ = bm.root_stats()
+        if split:
+            pending = bm.expand_tree_launch(4, N0)
+            assert pending is not None
+            recs = bm.expand_tree_records(bm.expand_tree_readback(pending, 4))
+        else:
+            recs = bm.expand_tree_arrays(4)
+        res.append((recs, bm.root_stats()))
+    for x, y in zip(res[0][0], res[1][0]):
+        assert np.array_equal(x, y) and x.dtype == y.dtype
+    for x, y in zip(res[0][1], res[1][1]):
+        assert np.array_equal(x, y)
