@@ -66,7 +66,15 @@ struct GemmArgs {
   const uint8_t* side_lo;  // (x3 only)
   const float* side_bias;  // [SIDE_N]
   float* side_out;         // row-major [M, SIDE_N]
+  // AZG_PREC_F16F8 (x3 = 1 and f8 = 1, CTA-pair kernel only): the "hi" images are fp16, the "lo" images are the FP8
+  // correction rows of azg_tc.cuh; w_exp / side_exp point at the weight images' power-of-two scales (device ints
+  // written by the pack kernels); activations use the fixed scale F8_A_SCALE
+  int f8;
+  const int32_t* w_exp;
+  const int32_t* side_exp;
 };
+// TMEM columns of the constant UE8M0 scale-factor regions (f8 mode; accumulators use 2 x BN <= 448 columns)
+constexpr uint32_t SF_A_COL = 448, SF_W_COL = 464, SF_SIDE_COL = 480;
 constexpr int SIDE_N = 32;
 constexpr int SIDE_STAGE_BYTES = (SIDE_N / 2) * BK * 2;  // one CTA's half of a side weight tile stage
 
@@ -128,6 +136,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
   if (TWO) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (TWO && g.f8) {
+    // uniform block scales: every scale-factor byte the tensor core can read is the same power of two, so the
+    // regions are written once (whatever the scale-factor layout) -- A: 2^-(sa+11), W: 2^-sw
+    if (warp >= 4) {
+      const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      tmem_st16_const(lane_base + SF_A_COL, ue8m0x4(-(F8_A_SCALE + F8_LO_SHIFT)));
+      tmem_st16_const(lane_base + SF_W_COL, ue8m0x4(g.w_exp ? -(*g.w_exp) : 0));
+      tmem_st16_const(lane_base + SF_SIDE_COL, ue8m0x4(g.side_exp ? -(*g.side_exp) : 0));
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+  }
 
   const int nt_all = g.n_tiles + ((TWO && g.side_hi) ? 1 : 0);  // n-tile index g.n_tiles = the side tile
   const int total_tiles = m_units * nt_all;
@@ -213,6 +236,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc_main = make_idesc(TWO ? 2 * BM : BM, BN);
       constexpr uint32_t idesc_side = make_idesc(TWO ? 2 * BM : BM, SIDE_N);
+      constexpr uint32_t idesc_main_h = make_idesc_f16(2 * BM, BN), idesc_side_h = make_idesc_f16(2 * BM, SIDE_N);
+      constexpr uint32_t idesc_main_q = make_idesc_mxf8(2 * BM, BN), idesc_side_q = make_idesc_mxf8(2 * BM, SIDE_N);
+      const bool f8 = TWO && g.f8;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -222,7 +248,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
         else mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        const uint32_t idesc = (TWO && t % nt_all == g.n_tiles) ? idesc_side : idesc_main;
+        const bool side_tile = TWO && t % nt_all == g.n_tiles;
+        const uint32_t idesc = side_tile ? (f8 ? idesc_side_h : idesc_side) : (f8 ? idesc_main_h : idesc_main);
+        const uint32_t idesc_q = side_tile ? idesc_side_q : idesc_main_q;
+        const uint32_t sfa = tmem_base + SF_A_COL, sfb = tmem_base + (side_tile ? SF_SIDE_COL : SF_W_COL);
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&full[stage], phase);  // operands have landed
           if (TWO) mbar_wait_cluster(&pfull[stage], phase);  // ... in the peer CTA as well
@@ -230,10 +259,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa);
           const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+          uint32_t accf = kb != 0;  // f8 mode with a term switched off (AZG_F8_TERMS, diagnostics): first MMA of the tile overwrites
+          if (!f8 || (g.f8 & 1)) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {  // advance 32 bytes (2 x 16-byte units) per K=16 step
-            if (TWO) umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-            else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {  // advance 32 bytes (2 x 16-byte units) per K=16 step
+              if (TWO) umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
+            accf = 1;
           }
           if (TWO && dual && 2 * kb + 1 < g.KB) {  // second k-block of the stage
             const uint64_t adesc1 = make_smem_desc(sa + S::STAGE_BYTES);
@@ -241,7 +274,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma2_bf16(d_tmem, adesc1 + (uint64_t)(2 * k), bdesc1 + (uint64_t)(2 * k), idesc, 1);
           }
-          if (TWO && fused3) {  // + Xhi Wlo^T + Xlo Whi^T from the same stage
+          if (TWO && fused3 && f8) {  // + the K-concatenated FP8 correction product (4 x K = 32) from the same stage
+            if (g.f8 & 2) {
+              const uint64_t adesc_lo = make_smem_desc(sa + S::STAGE_BYTES);
+              const uint64_t bdesc_lo = make_smem_desc(sa + S::STAGE_BYTES + A_STAGE_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma2_mxf8(d_tmem, adesc_lo + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc_q, sfa, sfb, accf | (uint32_t)k);
+            }
+          } else if (TWO && fused3) {  // + Xhi Wlo^T + Xlo Whi^T from the same stage
             const uint64_t adesc_lo = make_smem_desc(sa + S::STAGE_BYTES);
             const uint64_t bdesc_lo = make_smem_desc(sa + S::STAGE_BYTES + A_STAGE_BYTES);
 #pragma unroll
@@ -374,6 +415,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
           // next GEMM's A operand: columns are its K index; 32 columns = 4 x 16-byte chunks of one image row
           const int kb = n0 / BK, koff = n0 % BK;
           const size_t tile = ((size_t)mt * NKB + kb) * A_STAGE_BYTES;
+          if (TWO && g.f8) {  // fp16 image + FP8 correction rows [2^sa h | 2^(sa+11) h_lo], 16 elements per 16-byte chunk
+            const float s_main = (float)(1 << F8_A_SCALE), s_lo = (float)(1 << (F8_A_SCALE + F8_LO_SHIFT));
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint4 h0, h1;
+              uint2 m0, m1, l0, l1;
+              split8_f16f8(v + c * 16, s_main, s_lo, h0, m0, l0);
+              split8_f16f8(v + c * 16 + 8, s_main, s_lo, h1, m1, l1);
+              const int k0 = koff + c * 16;
+              *reinterpret_cast<uint4*>(g.out_hi + tile + image_offset(r_local, k0)) = h0;
+              *reinterpret_cast<uint4*>(g.out_hi + tile + image_offset(r_local, k0 + 8)) = h1;
+              *reinterpret_cast<uint4*>(g.out_lo + tile + image_offset_bytes(r_local, k0)) = make_uint4(m0.x, m0.y, m1.x, m1.y);
+              *reinterpret_cast<uint4*>(g.out_lo + tile + image_offset_bytes(r_local, 64 + k0)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            }
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t hi[4], lo[4];
@@ -416,8 +473,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
 // ---- image builders --------------------------------------------------------------------------
 // fp32 row-major [rows, K] -> bf16 tile images (hi, optionally lo) with R-row tiles.
 // One thread per 16-byte output chunk (8 elements): 32-byte coalesced reads, 16-byte writes.
+// f8_mode 1 / 2: AZG_PREC_F16F8 activation / weight format (fp16 image + FP8 correction rows, scale 2^*f8_exp for weights)
 __global__ void __launch_bounds__(256) f32_to_image_kernel(const float* __restrict__ src, int64_t rows, int64_t rows_padded,
-                                                           int K, int R, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+                                                           int K, int R, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                                                           int f8_mode = 0, const int32_t* __restrict__ f8_exp = nullptr) {
   const int chunks_per_row = K / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows_padded * chunks_per_row) return;
@@ -432,14 +491,20 @@ __global__ void __launch_bounds__(256) f32_to_image_kernel(const float* __restri
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = 0.0f;
   }
+  const int KB = K / BK;
+  const int64_t tile_row = row / R;
+  const int r = (int)(row % R), kb = (c * 8) / BK, k = (c * 8) % BK;
+  if (f8_mode) {
+    const int e = f8_mode == 2 ? *f8_exp : F8_A_SCALE;
+    split_store_f16f8(x, hi, lo, ((size_t)tile_row * KB + kb) * ((size_t)R * 128), r, k, ldexpf(1.0f, e), ldexpf(1.0f, e + F8_LO_SHIFT),
+                      f8_mode == 2);
+    return;
+  }
   uint32_t h[4], l[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     split_pair(x[2 * e], x[2 * e + 1], h[e], l[e]);
   }
-  const int KB = K / BK;
-  const int64_t tile_row = row / R;
-  const int r = (int)(row % R), kb = (c * 8) / BK, k = (c * 8) % BK;
   const size_t off = ((size_t)tile_row * KB + kb) * ((size_t)R * 128) + image_offset(r, k);
   *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
   if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -450,6 +515,54 @@ inline int pick_bn(int F) {
   if (F % 256 == 0) return 256;
   if (F % 160 == 0) return 160;
   return 0;
+}
+// AZG_PREC_F16F8 keeps 64 TMEM columns for its scale factors: two accumulator stages of <= 224 columns
+inline int pick_bn_f8(int F) {
+  if (F % 224 == 0) return 224;
+  if (F % 160 == 0) return 160;
+  if (F % 128 == 0) return 128;
+  return 0;
+}
+
+// max |w| over a tensor (bits of a non-negative float order like unsigned integers) -> *exp = the largest e with
+// 2^e max|w| <= 448 (e4m3 range), so the scaled weights use the top binades of the format
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ w, int64_t n, uint32_t* __restrict__ bits) {
+  float m = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(bits, __float_as_uint(m));
+}
+__global__ void scale_exp_kernel(const uint32_t* __restrict__ bits, int32_t* __restrict__ exp_out) {
+  const float m = __uint_as_float(*bits);
+  int e = 0;
+  if (m > 0.0f && m < INFINITY) {
+    e = (int)floorf(log2f(448.0f / m));
+    while (ldexpf(m, e) > 448.0f) --e;  // log2f rounding
+    while (ldexpf(m, e + 1) <= 448.0f) ++e;
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  }
+  *exp_out = e;
+}
+// writes the scale exponent of `w` to *exp_out (device); `bits` is a 4-byte device scratch word
+int weight_scale_exp(const float* w, int64_t n, uint32_t* bits, int32_t* exp_out, cudaStream_t st) {
+  AZG_CUDA_CHECK(cudaMemsetAsync(bits, 0, 4, st));
+  const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  absmax_kernel<<<grid, 256, 0, st>>>(w, n, bits);
+  AZG_LAUNCH_CHECK();
+  scale_exp_kernel<<<1, 1, 0, st>>>(bits, exp_out);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+static int f8_terms() {  // AZG_F8_TERMS=1 / 2: only the fp16 product / only the FP8 correction product (diagnostics)
+  static int terms = -1;
+  if (terms < 0) {
+    const char* e = getenv("AZG_F8_TERMS");
+    terms = e ? (atoi(e) & 3) : 3;
+    if (terms == 0) terms = 3;
+  }
+  return terms;
 }
 
 static int gemm_pair_mode() {  // AZG_GEMM=1cta disables the CTA-pair kernels (A/B measurements)
@@ -494,6 +607,15 @@ int launch_gemm_impl(const GemmArgs& g, cudaStream_t st) {
 // the CTA-pair kernel needs BN/2 to be a multiple of 8 rows and an even number of padded m-tiles
 template <int BN>
 int launch_gemm(const GemmArgs& g, cudaStream_t st) {
+  if (g.f8) {
+    if constexpr (BN >= 128 && BN <= 224) {
+      AZG_REQUIRE(g.pair_ok && g.x3, "tcgen05 GEMM: the fp16+FP8 split runs on the CTA-pair kernel only");
+      return launch_gemm_impl<BN, true>(g, st);
+    } else {
+      azg_set_error("tcgen05 GEMM: the fp16+FP8 split needs a tile width of 128..224 columns");
+      return AZG_ERR_INVALID;
+    }
+  }
   if (gemm_pair_mode() && g.pair_ok && BN >= 128) return launch_gemm_impl<BN, true>(g, st);
   return launch_gemm_impl<BN, false>(g, st);
 }
@@ -503,6 +625,7 @@ int run_gemm(int BN, const GemmArgs& g, cudaStream_t st) {
     case 224: return launch_gemm<224>(g, st);
     case 256: return launch_gemm<256>(g, st);
     case 160: return launch_gemm<160>(g, st);
+    case 128: return launch_gemm<128>(g, st);
     case 64: return launch_gemm<64>(g, st);
     case 32: return launch_gemm<32>(g, st);
   }
@@ -510,9 +633,10 @@ int run_gemm(int BN, const GemmArgs& g, cudaStream_t st) {
   return AZG_ERR_INVALID;
 }
 
-int to_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R, uint8_t* hi, uint8_t* lo, cudaStream_t st) {
+int to_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R, uint8_t* hi, uint8_t* lo, cudaStream_t st,
+             int f8_mode = 0, const int32_t* f8_exp = nullptr) {
   const int64_t n = rows_padded * (K / 8);
-  f32_to_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, rows, rows_padded, K, R, hi, lo);
+  f32_to_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, rows, rows_padded, K, R, hi, lo, f8_mode, f8_exp);
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }
@@ -595,7 +719,8 @@ __global__ void conv2_weight_image_kernel(const float* __restrict__ w2, uint8_t*
 // Linear weight [N, F] whose input index is the reference's flatten order k = co*nn + p
 // (Connect4Net.py:49) -> image over the feature image's order k' = p*64 + co
 __global__ void __launch_bounds__(256) permuted_weight_image_kernel(const float* __restrict__ w, int N, int F, int nn, int R,
-                                                                    uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+                                                                    uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                                                                    const int32_t* __restrict__ f8_exp = nullptr) {
   const int chunks = F / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * chunks) return;
@@ -607,6 +732,12 @@ __global__ void __launch_bounds__(256) permuted_weight_image_kernel(const float*
     x8[e] = w[(size_t)row * F + co * nn + pc];
   }
   const int KB = F / BK;
+  if (f8_exp) {  // AZG_PREC_F16F8 weight format
+    const int e = *f8_exp;
+    split_store_f16f8(x8, hi, lo, ((size_t)(row / R) * KB + (c >> 3)) * ((size_t)R * 128), row % R, (c & 7) * 8, ldexpf(1.0f, e),
+                      ldexpf(1.0f, e + F8_LO_SHIFT), true);
+    return;
+  }
   const size_t off = ((size_t)(row / R) * KB + (c >> 3)) * ((size_t)R * 128) + image_offset(row % R, (c & 7) * 8);
   split_store(x8, hi, lo, off);
 }
@@ -845,6 +976,7 @@ struct TrunkArgs {
   int64_t B;
   int n;
   const int32_t* dyn_rows;  // optional device scalar: number of positions this launch (<= B)
+  int out_f8;               // feature image in the AZG_PREC_F16F8 activation format (the convolutions stay bf16x3)
 };
 
 template <bool X3>
@@ -1132,7 +1264,21 @@ __global__ void __launch_bounds__(TR_THREADS, 1) c4_trunk_tc_kernel(TrunkArgs t)
         tmem_ld16(taddr + (uint32_t)c0, rr);
         if (X3) tmem_ld16(taddr + (uint32_t)(BN + c0), r2);  // the hi x lo half
         tmem_ld_wait();
-        if (valid) {
+        if (valid && X3 && t.out_f8) {  // fp16 image + FP8 correction rows, one 16-byte chunk of each half per 16 channels
+          float x16[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            x16[e] = fmaxf(__uint_as_float(rr[e]) + __uint_as_float(r2[e]) + __ldg(t.b2 + c0 + e), 0.0f);
+          const float s_main = (float)(1 << F8_A_SCALE), s_lo = (float)(1 << (F8_A_SCALE + F8_LO_SHIFT));
+          uint4 h0, h1;
+          uint2 m0, m1, l0, l1;
+          split8_f16f8(x16, s_main, s_lo, h0, m0, l0);
+          split8_f16f8(x16 + 8, s_main, s_lo, h1, m1, l1);
+          *reinterpret_cast<uint4*>(t.f_hi + tbase + image_offset(rb, c0)) = h0;
+          *reinterpret_cast<uint4*>(t.f_hi + tbase + image_offset(rb, c0 + 8)) = h1;
+          *reinterpret_cast<uint4*>(t.f_lo + tbase + image_offset_bytes(rb, c0)) = make_uint4(m0.x, m0.y, m1.x, m1.y);
+          *reinterpret_cast<uint4*>(t.f_lo + tbase + image_offset_bytes(rb, 64 + c0)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        } else if (valid) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             float x8[8];
@@ -1181,8 +1327,9 @@ int launch_trunk(const TrunkArgs& t, cudaStream_t st) {
   return AZG_OK;
 }
 
-int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R, uint8_t* hi, uint8_t* lo, cudaStream_t st) {
-  return to_image(src, rows, rows_padded, K, R, hi, lo, st);
+int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R, uint8_t* hi, uint8_t* lo, cudaStream_t st,
+               int f8_mode = 0, const int32_t* f8_exp = nullptr) {
+  return to_image(src, rows, rows_padded, K, R, hi, lo, st, f8_mode, f8_exp);
 }
 
 }  // namespace tc
@@ -1193,16 +1340,19 @@ int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R
 //   W2 (output_transform.2) hi [lo] | conv2 [64 x 320] hi [lo] | head weights permuted, fp32
 namespace {
 struct PackLayout {
-  size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, heads_cat, hd_hi, hd_lo, bias32, fold_w, fold_b, total;
-  bool x3, gnn;
+  size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, heads_cat, hd_hi, hd_lo, bias32, fold_w, fold_b, scales, total;
+  bool x3, gnn, f8;  // x3: hi + lo images (bf16x3 and the fp16+FP8 split); f8: the latter
 };
+inline bool prec_is_tc(int prec) { return prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16 || prec == AZG_PREC_F16F8; }
+inline int prec_bn(int F, int prec) { return prec == AZG_PREC_F16F8 ? tc::pick_bn_f8(F) : tc::pick_bn(F); }
 
 size_t up1k(size_t v) { return (v + 1023) / 1024 * 1024; }
 
 PackLayout pack_layout(int n, int prec, bool gnn) {
   PackLayout L{};
   const size_t F = 64 * (size_t)n * n, wimg = F * F * 2, cimg = 64 * (size_t)tc::C2_K * 2;
-  L.x3 = prec == AZG_PREC_BF16X3;
+  L.x3 = prec == AZG_PREC_BF16X3 || prec == AZG_PREC_F16F8;
+  L.f8 = prec == AZG_PREC_F16F8;
   L.gnn = gnn;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = up1k(off + bytes); return o; };
@@ -1221,6 +1371,7 @@ PackLayout pack_layout(int n, int prec, bool gnn) {
   L.bias32 = take(32 * 4);
   L.fold_w = gnn ? take((size_t)tc::HEAD_ROWS * F * 4) : 0;  // [Wp; Wv] W2 (AZG_EVAL_FOLD)
   L.fold_b = gnn ? take(32 * 4) : 0;                         // [Wp; Wv] b2 + [bp; bv]
+  L.scales = take(64);  // f8: int32 scale exponents of the W0, W2 and std-heads images [0..2], absmax scratch words [8..10]
   L.total = off;
   return L;
 }
@@ -1231,7 +1382,7 @@ struct ScratchLayout {
 
 ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
   ScratchLayout S{};
-  const bool x3 = prec == AZG_PREC_BF16X3;
+  const bool x3 = prec == AZG_PREC_BF16X3 || prec == AZG_PREC_F16F8;
   const size_t nn = (size_t)n * n, F = 64 * nn;
   const size_t M2p = (size_t)azg_ceil_div(B * (int64_t)nn, tc::BM) * tc::BM, Mp = (size_t)azg_ceil_div(B, 2 * tc::BM) * 2 * tc::BM;  // even number of m-tiles (CTA pairs)
   const size_t a2 = M2p * tc::C2_K * 2, fimg = Mp * F * 2;
@@ -1245,7 +1396,7 @@ ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
   if (gnn) {
     S.h_hi = take(fimg);
     S.h_lo = x3 ? take(fimg) : 0;
-    S.part = take(Mp * 16 * tc::HEAD_STRIDE * sizeof(float));  // <= 16 n-tiles
+    S.part = take(Mp * 32 * tc::HEAD_STRIDE * sizeof(float));  // <= 32 n-tiles
   }
   S.total = off + 1024;
   return S;
@@ -1277,9 +1428,10 @@ size_t azg_tc_scratch_bytes(int n, int64_t B, int prec) { return scratch_layout(
 int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int prec, const uint64_t* states, int64_t B,
                       int eval_mask, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn, void* scratch,
                       size_t scratch_bytes, const int32_t* dyn_rows, cudaStream_t st) {
-  const int nn = n * n, F = 64 * nn, A = n + 1, BN = tc::pick_bn(F);
+  const int nn = n * n, F = 64 * nn, A = n + 1, BN = prec_bn(F, prec);
   AZG_REQUIRE(BN != 0, "tcgen05 path: unsupported board size %d", n);
-  const bool x3 = prec == AZG_PREC_BF16X3, gnn = (eval_mask & AZG_EVAL_GNN) != 0;
+  const bool f8 = prec == AZG_PREC_F16F8, x3 = prec == AZG_PREC_BF16X3 || f8, gnn = (eval_mask & AZG_EVAL_GNN) != 0;
+  AZG_REQUIRE(!f8 || azg_trunk_mode() == 0, "tcgen05 path: the fp16+FP8 split needs the fused trunk (unset AZG_TRUNK)");
   const PackLayout L = pack_layout(n, prec, true);
   const ScratchLayout S = scratch_layout(n, B, prec, true);
   AZG_REQUIRE(scratch && scratch_bytes >= S.total, "tcgen05 path: scratch %zu < %zu", scratch_bytes, S.total);
@@ -1296,6 +1448,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     t.states = states; t.w1 = p->conv1_w; t.b1 = p->conv1_b; t.b2 = p->conv2_b;
     t.w_hi = w + L.c2_hi; t.w_lo = x3 ? w + L.c2_lo : nullptr; t.f_hi = f_hi; t.f_lo = f_lo; t.B = B; t.n = n;
     t.dyn_rows = dyn_rows;
+    t.out_f8 = f8 ? 1 : 0;
     if ((rc = x3 ? tc::launch_trunk<true>(t, st) : tc::launch_trunk<false>(t, st))) return rc;
   } else {  // split: im2col image through HBM, conv2 on the generic GEMM kernel (kept for A/B measurements)
     const int grid = (int)(B < 148 * 8 ? B : 148 * 8);
@@ -1313,8 +1466,9 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   }
   azg_phase_end(AZG_PHASE_TRUNK, st);
   // predict's heads ride on GEMM-1 as a side tile when the CTA-pair kernel runs it (AZG_STD_HEADS=split: own launch)
-  const bool std_side = (eval_mask & AZG_EVAL_STD) && azg_trunk_mode() == 0 && tc::gemm_pair_mode() && BN >= 128 &&
-                        azg_std_heads_mode() == 0;
+  const int32_t* scales = (const int32_t*)(w + L.scales);
+  const bool std_side = (eval_mask & AZG_EVAL_STD) && azg_trunk_mode() == 0 &&
+                        (f8 || (tc::gemm_pair_mode() && BN >= 128 && azg_std_heads_mode() == 0));
   if (std_side && !gnn) {  // std only: the same side-tile code with no main n-tiles (bit-identical to the combined call)
     AZG_REQUIRE(pi_std && v_std && A <= 9, "tcgen05 path: bad std outputs");
     azg_phase_begin(AZG_PHASE_HEADS, st);
@@ -1323,6 +1477,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     h.a_hi = f_hi; h.a_lo = f_lo; h.dyn_rows = dyn_rows;
     h.side_hi = w + L.hd_hi; h.side_lo = x3 ? w + L.hd_lo : nullptr;
     h.side_bias = (const float*)(w + L.bias32); h.side_out = (float*)(sc + S.lg32);
+    h.f8 = f8 ? tc::f8_terms() : 0; h.side_exp = scales + 2;
     if ((rc = tc::run_gemm(BN, h, st))) return rc;
     tc::heads32_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const float*)(sc + S.lg32), A, B, dyn_rows, pi_std, v_std);
     AZG_LAUNCH_CHECK();
@@ -1360,7 +1515,8 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   g.pair_ok = 1;
   g.dyn_rows = dyn_rows;
   g.a_hi = f_hi; g.a_lo = f_lo; g.w_hi = w + L.w0_hi; g.w_lo = x3 ? w + L.w0_lo : nullptr; g.bias = p->ot0_b; g.relu = 1;
-  AZG_REQUIRE(g.n_tiles <= 16 && A + 1 <= tc::HEAD_ROWS, "tcgen05 path: head fusion limits exceeded");
+  g.f8 = f8 ? tc::f8_terms() : 0; g.w_exp = scales + 0; g.side_exp = scales + 2;
+  AZG_REQUIRE(g.n_tiles <= 32 && A + 1 <= tc::HEAD_ROWS, "tcgen05 path: head fusion limits exceeded");
   if (std_side) {
     AZG_REQUIRE(pi_std && v_std && A <= 9, "tcgen05 path: bad std outputs");
     g.side_hi = w + L.hd_hi; g.side_lo = x3 ? w + L.hd_lo : nullptr;
@@ -1392,6 +1548,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
   g.side_hi = g.side_lo = nullptr;  // GEMM-2 has no side tile
   g.a_hi = h_hi; g.a_lo = h_lo; g.w_hi = w + L.w2_hi; g.w_lo = x3 ? w + L.w2_lo : nullptr; g.bias = p->ot2_b; g.relu = 0;
+  g.w_exp = scales + 1;
   g.out_mode = tc::OUT_HEADS; g.out_hi = g.out_lo = nullptr; g.out_f32 = nullptr;
   g.head_w = (const float*)(w + L.heads_cat); g.head_rows = A + 1; g.head_part = (float*)(sc + S.part);
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
@@ -1409,26 +1566,33 @@ extern "C" {
 
 size_t azg_c4_packed_bytes(int n, int prec) {
   const int F = 64 * n * n;
-  if (n < 4 || n > 8 || tc::pick_bn(F) == 0 || prec == AZG_PREC_FP32) return 0;
+  if (n < 4 || n > 8 || !prec_is_tc(prec) || prec_bn(F, prec) == 0) return 0;
   return pack_layout(n, prec, true).total + 1024;
 }
 
 int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t packed_bytes, azg_stream stream) {
-  const int nn = n * n, F = 64 * nn, A = n + 1, BN = tc::pick_bn(F);
+  const int nn = n * n, F = 64 * nn, A = n + 1, BN = prec_is_tc(prec) ? prec_bn(F, prec) : 0;
   AZG_REQUIRE(p && packed && p->conv2_w && p->fc_policy_w && p->fc_value_w, "azg_c4_pack: null pointer");
-  AZG_REQUIRE(n >= 4 && n <= 8 && BN != 0 && (prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16), "azg_c4_pack: unsupported n=%d prec=%d", n, prec);
+  AZG_REQUIRE(n >= 4 && n <= 8 && BN != 0, "azg_c4_pack: unsupported n=%d prec=%d", n, prec);
   AZG_REQUIRE(packed_bytes >= azg_c4_packed_bytes(n, prec), "azg_c4_pack: buffer too small");
   AZG_REQUIRE(((uintptr_t)packed & 15) == 0, "azg_c4_pack: buffer must be 16-byte aligned (bulk-copy source)");
   const PackLayout L = pack_layout(n, prec, true);
-  const bool x3 = L.x3;
+  const bool x3 = L.x3, f8 = L.f8;
   uint8_t* w = (uint8_t*)packed;
   cudaStream_t st = (cudaStream_t)stream;
+  int32_t* scales = (int32_t*)(w + L.scales);
+  uint32_t* bits = (uint32_t*)(w + L.scales) + 8;
+  int rc;
   if (p->ot0_w && p->ot2_w) {
+    if (f8) {  // per-tensor power-of-two scales of the FP8 correction rows
+      if ((rc = tc::weight_scale_exp(p->ot0_w, (int64_t)F * F, bits + 0, scales + 0, st))) return rc;
+      if ((rc = tc::weight_scale_exp(p->ot2_w, (int64_t)F * F, bits + 1, scales + 1, st))) return rc;
+    }
     const int64_t cnt = (int64_t)F * (F / 8);
     tc::permuted_weight_image_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(p->ot0_w, F, F, nn, BN, w + L.w0_hi,
-                                                                                   x3 ? w + L.w0_lo : nullptr);
+                                                                                   x3 ? w + L.w0_lo : nullptr, f8 ? scales + 0 : nullptr);
     AZG_LAUNCH_CHECK();
-    int rc = tc::make_image(p->ot2_w, F, F, F, BN, w + L.w2_hi, x3 ? w + L.w2_lo : nullptr, st);
+    rc = tc::make_image(p->ot2_w, F, F, F, BN, w + L.w2_hi, x3 ? w + L.w2_lo : nullptr, st, f8 ? 2 : 0, scales + 1);
     if (rc) return rc;
   }
   tc::conv2_weight_image_kernel<<<(64 * (tc::C2_K / 8) + 127) / 128, 128, 0, st>>>(p->conv2_w, w + L.c2_hi, x3 ? w + L.c2_lo : nullptr);
@@ -1454,8 +1618,10 @@ int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t pa
   }
   {
     const int64_t cnt = (int64_t)32 * (F / 8);
+    if (f8 && (rc = tc::weight_scale_exp((const float*)(w + L.heads_cat), (int64_t)32 * F, bits + 2, scales + 2, st))) return rc;
     tc::permuted_weight_image_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((const float*)(w + L.heads_cat), 32, F, nn, 32,
-                                                                                   w + L.hd_hi, x3 ? w + L.hd_lo : nullptr);
+                                                                                   w + L.hd_hi, x3 ? w + L.hd_lo : nullptr,
+                                                                                   f8 ? scales + 2 : nullptr);
     AZG_LAUNCH_CHECK();
   }
   return AZG_OK;
@@ -1689,13 +1855,13 @@ extern "C" {
 // C[M,F] = act(A[M,F] . W[F,F]^T + bias), fp32 in/out, operands converted on the fly.
 int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int F, int prec, int relu,
                   void* scratch, size_t scratch_bytes, azg_stream stream) {
-  const int BN = tc::pick_bn(F);
+  const int BN = prec_is_tc(prec) ? prec_bn(F, prec) : 0;
   AZG_REQUIRE(A && W && bias && C && scratch, "azg_tc_linear: null pointer");
-  AZG_REQUIRE(BN != 0 && F % 64 == 0 && (prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16), "azg_tc_linear: unsupported F=%d prec=%d", F, prec);
-  const bool x3 = prec == AZG_PREC_BF16X3;
+  AZG_REQUIRE(BN != 0 && F % 64 == 0, "azg_tc_linear: unsupported F=%d prec=%d", F, prec);
+  const bool f8 = prec == AZG_PREC_F16F8, x3 = prec == AZG_PREC_BF16X3 || f8;
   const int64_t m_tiles = azg_ceil_div(M, tc::BM), Mp = azg_ceil_div(M, 2 * tc::BM) * 2 * tc::BM;
   const size_t a_img = (size_t)Mp * F * 2, w_img = (size_t)F * F * 2;
-  const size_t need = (x3 ? 2 : 1) * (a_img + w_img) + 1024;
+  const size_t need = (x3 ? 2 : 1) * (a_img + w_img) + 2048;
   AZG_REQUIRE(scratch_bytes >= need, "azg_tc_linear: scratch %zu < %zu", scratch_bytes, need);
   uint8_t* base = (uint8_t*)(((uintptr_t)scratch + 1023) & ~(uintptr_t)1023);
   uint8_t *a_hi = base, *a_lo = x3 ? base + a_img : nullptr;
@@ -1703,9 +1869,12 @@ int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, i
   uint8_t *w_hi = wbase, *w_lo = x3 ? wbase + w_img : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if ((rc = tc::to_image(A, M, Mp, F, tc::BM, a_hi, a_lo, st))) return rc;
-  if ((rc = tc::to_image(W, F, F, F, BN, w_hi, w_lo, st))) return rc;
+  int32_t* scales = (int32_t*)(wbase + (x3 ? 2 : 1) * w_img);  // [0] weight scale exponent, [1] absmax scratch
+  if (f8 && (rc = tc::weight_scale_exp(W, (int64_t)F * F, (uint32_t*)scales + 1, scales, st))) return rc;
+  if ((rc = tc::to_image(A, M, Mp, F, tc::BM, a_hi, a_lo, st, f8 ? 1 : 0, nullptr))) return rc;
+  if ((rc = tc::to_image(W, F, F, F, BN, w_hi, w_lo, st, f8 ? 2 : 0, scales))) return rc;
   tc::GemmArgs g{};
+  g.f8 = f8 ? tc::f8_terms() : 0; g.w_exp = scales;
   g.M = M; g.m_tiles = (int)m_tiles; g.n_tiles = F / BN; g.KB = F / tc::BK; g.x3 = x3; g.pair_ok = 1;
   g.a_hi = a_hi; g.a_lo = a_lo; g.w_hi = w_hi; g.w_lo = w_lo; g.bias = bias; g.relu = relu;
   g.out_mode = tc::OUT_F32; g.out_f32 = C;

@@ -4,6 +4,8 @@
 #include "azg_common.cuh"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 namespace tc {
 
@@ -213,6 +215,103 @@ __device__ __forceinline__ void split_store(const float* x, uint8_t* hi, uint8_t
   }
   *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
   if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- fp16 + FP8-correction split (AZG_PREC_F16F8) ----------------------------------------------
+// x = fp16(x) + x_lo.  X W^T ~= Xh Wh^T  (kind::f16, K = 16 per instruction)
+//                              + [ e4m3(2^sa X) | e4m3(2^(sa+11) X_lo) ] [ e4m3(2^(sw+11) W_lo) | e4m3(2^sw W) ]^T * 2^-(sa+sw+11)
+// The second product is ONE K-concatenated FP8 contraction (kind::mxf8f6f4, K = 32 per instruction at twice the
+// 16-bit rate) whose power-of-two scale is applied by the tensor core itself: block-scaled MMA with UE8M0 scale
+// factors in TMEM, and because the scale is uniform the scale-factor region is filled with one constant once per
+// kernel.  Both terms accumulate into the SAME fp32 TMEM accumulator: 8 instruction-times per 64-wide k-block
+// instead of the 12 of the three-term bf16 split.  |x_lo| <= 2^-11 |x|, so 2^11 x_lo has the range of x and one
+// scale serves both halves; e4m3 conversion saturates (satfinite), an out-of-range element only loses its correction.
+constexpr int F8_LO_SHIFT = 11;
+constexpr int F8_A_SCALE = 3;  // activations: 2^3 x in e4m3 -> normal precision for |x| in [2^-9, 56]
+
+// instruction descriptor: D = f32, A = B = fp16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// block-scaled instruction descriptor: A = B = E4M3, K-major, scale factors UE8M0 (bit 23), D = f32 (implied)
+__host__ __device__ constexpr uint32_t make_idesc_mxf8(int M, int N) {
+  return ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  umma2_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);  // same kind::f16 instruction, the descriptor names the format
+}
+// D[tmem of both CTAs] += (A * 2^(sfa-127)) (B * 2^(sfb-127))^T, e4m3 operands, K = 32 per instruction
+__device__ __forceinline__ void umma2_mxf8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t sfa_tmem,
+                                           uint32_t sfb_tmem, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+      : "memory");
+}
+__device__ __forceinline__ void umma1_mxf8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t sfa_tmem,
+                                           uint32_t sfb_tmem, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+      : "memory");
+}
+// 16 consecutive TMEM columns of this warp's lane quarter <- one 32-bit value per lane and column
+__device__ __forceinline__ void tmem_st16_const(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ue8m0x4(int exp2) {  // four copies of the UE8M0 byte of 2^exp2
+  const uint32_t b = (uint32_t)(127 + exp2) & 0xffu;
+  return b * 0x01010101u;
+}
+
+// byte offset of byte `kbyte` (0..127) of row r inside one [R x 128 B] tile image
+__host__ __device__ __forceinline__ uint32_t image_offset_bytes(int r, int kbyte) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((kbyte >> 4) ^ (r & 7)) & 7) << 4) + (kbyte & 15));
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_e4m3x2(float a, float b) {  // low byte = e4m3(a)
+  return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+}
+// 8 consecutive elements -> 8 fp16 (hi chunk) + 8 e4m3 of s_main x + 8 e4m3 of s_lo (x - fp16(x))
+__device__ __forceinline__ void split8_f16f8(const float* x, float s_main, float s_lo, uint4& hi, uint2& q_main, uint2& q_lo) {
+  uint32_t h[4], m[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float a = x[2 * e], b = x[2 * e + 1];
+    h[e] = pack_f16x2(a, b);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
+    m[e] = pack_e4m3x2(a * s_main, b * s_main);
+    l[e] = pack_e4m3x2((a - hf.x) * s_lo, (b - hf.y) * s_lo);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  q_main = make_uint2(m[0] | (m[1] << 16), m[2] | (m[3] << 16));
+  q_lo = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+}
+// store 8 consecutive elements (k0 = multiple of 8 inside the k-block) of tile row r in the f16f8 format.
+// `weight` swaps the halves of the correction row: activations [main | lo], weights [lo | main].
+__device__ __forceinline__ void split_store_f16f8(const float* x, uint8_t* hi, uint8_t* lo, size_t tile_off, int r, int k0, float s_main,
+                                                  float s_lo, bool weight) {
+  uint4 h;
+  uint2 qm, ql;
+  split8_f16f8(x, s_main, s_lo, h, qm, ql);
+  *reinterpret_cast<uint4*>(hi + tile_off + image_offset(r, k0)) = h;
+  *reinterpret_cast<uint2*>(lo + tile_off + image_offset_bytes(r, k0)) = weight ? ql : qm;
+  *reinterpret_cast<uint2*>(lo + tile_off + image_offset_bytes(r, 64 + k0)) = weight ? qm : ql;
 }
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

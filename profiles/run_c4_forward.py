@@ -1,4 +1,4 @@
-"""ncu driver: three Connect4 leaf-evaluation steps (65,536 positions, bf16x3)."""
+"""ncu driver: three Connect4 leaf-evaluation steps (65,536 positions; AZG_RUN_PRECISION, default f16f8)."""
 import os
 import sys
 
@@ -11,7 +11,7 @@ from azgnn_b200.games import Connect4Game
 from azgnn_b200.nets import B200Connect4GNNWrapper
 
 a = dict(lr=1e-3, dropout=0.3, epochs=20, batch_size=64, gnn_layers=2, use_gnn=True, numMCTSSims=10, cpuct=1.0, expand_by=5,
-         b200_precision="bf16x3")
+         b200_precision=os.environ.get("AZG_RUN_PRECISION", "f16f8"))
 torch.manual_seed(0)
 net = B200Connect4GNNWrapper(Connect4Game(7), a)
 states = net.states_from_boards(np.random.default_rng(0).integers(-1, 2, size=(65536, 7, 7)).astype(np.int8))
