@@ -14,6 +14,7 @@ Parameters are ordinary torch CUDA tensors inside `modules.*` (so `state_dict`, 
 checkpoints are untouched); kernels read them in place through raw pointers.
 """
 import ctypes as C
+import logging
 import os
 
 import numpy as np
@@ -25,6 +26,9 @@ from .mcts import arg, game_kind, pack_states
 
 _CELL = {torch.int8: _lib.CELL_I8, torch.int64: _lib.CELL_I64, torch.float32: _lib.CELL_F32,
          torch.float64: _lib.CELL_F64}
+
+
+log = logging.getLogger("azgnn_b200")
 
 
 def _device():
@@ -104,10 +108,54 @@ class _Base:
     def weights_changed(self):
         """Call after any in-place parameter update (optimizer step, load): re-tiled copies are stale."""
         self._packed_ok = False
+        self._auto_choice = None
 
 
 class _TwoPlayer(_Base):
     has_gnn = False
+    # `b200_precision: auto` (the default): per weight version, the first of these tensor-core modes whose outputs on a
+    # fixed probe batch stay within AUTO_TOL of the fp32 CUDA-core path (the reference arithmetic); else fp32.
+    AUTO_CANDIDATES = ()
+    AUTO_TOL = 5e-6       # half of the 1e-5 contract on pi and v
+    AUTO_PROBE = 256      # probe positions (seeded iid cells, like the bench workload)
+
+    def _configured_precision(self, args):
+        name = arg(args, "b200_precision", "auto") or "auto"
+        if name not in _lib.PRECISIONS:
+            raise ValueError(f"b200_precision must be one of {sorted(_lib.PRECISIONS)}, got {name!r}")
+        self._auto_choice, self.precision_report = None, {}
+        return _lib.PRECISIONS[name]
+
+    def active_precision(self):
+        """The precision forward_states runs in when none is passed: the configured one, or for `auto` the guarded choice
+        (re-made lazily after weights_changed(); the decision and the probe errors are logged and kept in
+        `precision_report`)."""
+        if self.precision != _lib.PREC_AUTO:
+            return self.precision
+        if self._auto_choice is None:
+            self._auto_choice = _lib.PREC_FP32  # while probing
+            rng = np.random.default_rng(2024)
+            states = self.states_from_boards(rng.integers(-1, 2, size=(self.AUTO_PROBE, self.n, self.n)).astype(np.int8))
+            mask = self._default_mask()
+            ref = self.forward_states(states, mask, precision=_lib.PREC_FP32)
+            choice, report = _lib.PREC_FP32, {}
+            for cand in self.AUTO_CANDIDATES:
+                if not self._precision_supported(cand):
+                    continue
+                out = self.forward_states(states, mask, precision=cand)
+                err = max(float((out[k] - ref[k]).abs().max()) for k in ref)
+                report[_lib.PRECISION_NAMES[cand]] = err
+                if err <= self.AUTO_TOL:
+                    choice = cand
+                    break
+            self.precision_report = report
+            self._auto_choice = choice
+            log.info("b200_precision auto -> %s (probe max |d pi|, |d v| vs fp32: %s)", _lib.PRECISION_NAMES[choice],
+                     ", ".join(f"{k} {v:.2e}" for k, v in report.items()))
+        return self._auto_choice
+
+    def _precision_supported(self, prec):
+        return True
 
     def _outputs(self, B, eval_mask):
         A, dev = self.action_size, self.device
@@ -188,15 +236,20 @@ class _TwoPlayer(_Base):
 class B200Connect4NNetWrapper(_TwoPlayer):
     kind = "connect4"
     supports_dynamic_count = True  # forward_states(count=device scalar): see azg_c4_forward_dyn
+    AUTO_CANDIDATES = (_lib.PREC_F16F8, _lib.PREC_BF16X3)
+
+    def _precision_supported(self, prec):
+        return int(self.lib.azg_c4_packed_bytes(self.n, prec)) > 0
 
     def __init__(self, game, args):
         self._common(game, args)
         dropout = arg(args, "dropout", 0.3)
         self.nnet = modules.Connect4Trunk(self.n, self.action_size, 0.3 if dropout is None else dropout).to(self.device)
         self.gnn = None
-        # default: the tensor-core path in bf16x3 (3-term bf16 split, fp32 accumulation) -- pi and v stay within the fp32
-        # contract (1e-5) at 13x the speed of the CUDA-core fp32 path, so an unchanged config.yaml gets the fast path
-        self.precision = _lib.PRECISIONS[arg(args, "b200_precision", "bf16x3") or "bf16x3"]
+        # default `auto`: the tensor-core path in f16f8 (fp16 product + block-scaled FP8 correction product) or bf16x3
+        # (3-term bf16 split), whichever first keeps a probe batch inside the fp32 contract for the current weights --
+        # an unchanged config.yaml gets the fast path, and a weight version that breaks a split falls back (logged)
+        self.precision = self._configured_precision(args)
         # opt-in: evaluate predict_with_gnn with output_transform.2 folded into the heads (_lib.EVAL_FOLD)
         self.fold_heads = bool(arg(args, "b200_fold_heads", False))
         self._packed, self._packed_ok = {}, False
@@ -232,7 +285,7 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         eval_mask = self._default_mask() if eval_mask is None else eval_mask
         if (eval_mask & _lib.EVAL_GNN) and self.gnn is None:
             raise RuntimeError("predict_with_gnn needs the GNN wrapper")
-        prec = self.precision if precision is None else precision
+        prec = self.active_precision() if precision is None else precision
         if self.fold_heads and prec != _lib.PREC_FP32 and (eval_mask & _lib.EVAL_GNN):
             eval_mask |= _lib.EVAL_FOLD
         B = int(states.shape[0])
@@ -263,12 +316,15 @@ class B200Connect4GNNWrapper(B200Connect4NNetWrapper):
 # ---------------------------------------------------------------------------------------- TicTacToe
 class B200TicTacToeNNetWrapper(_TwoPlayer):
     kind = "tictactoe"
+    AUTO_CANDIDATES = (_lib.PREC_BF16X3,)
 
     def __init__(self, game, args):
         self._common(game, args)
         self.nnet = modules.TicTacToeTrunk(self.n, self.action_size).to(self.device)
         self.gnn = None
-        self.precision = _lib.PRECISIONS[arg(args, "b200_precision", "bf16x3") or "bf16x3"]
+        self.precision = self._configured_precision(args)
+        if self.precision == _lib.PREC_F16F8:
+            raise ValueError("b200_precision f16f8 is a Connect4 mode (tile widths 128..224); TicTacToe runs auto, bf16x3, bf16 or fp32")
         self._packed, self._packed_ok = {}, False
 
     def _ensure_packed(self, prec, params):
@@ -300,7 +356,7 @@ class B200TicTacToeNNetWrapper(_TwoPlayer):
         eval_mask = self._default_mask() if eval_mask is None else eval_mask
         if (eval_mask & _lib.EVAL_GNN) and self.gnn is None:
             raise RuntimeError("predict_with_gnn needs the GNN wrapper")
-        prec = self.precision if precision is None else precision
+        prec = self.active_precision() if precision is None else precision
         B = int(states.shape[0])
         o = self._outputs(B, eval_mask)
         if B == 0:

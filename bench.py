@@ -44,6 +44,22 @@ def reference_args():
                 cpuct=1.0, expand_by=5, tempThreshold=15)
 
 
+def workload_config(batch):
+    """The `config` object of both arms (key-identical: precision, L2 policy and sampling notes are sibling keys)."""
+    return {"workload": "connect4_7x7_gnn_leaf_eval_batch_65536", "positions_per_step_per_gpu": batch,
+            "board": "7x7 (reference geometry; 6x7 is not constructible, SURVEY 8d)", "use_gnn": True,
+            "eval": "predict + predict_with_gnn (shared trunk)", "weights": "random-init seed 0"}
+
+
+DTYPES = {"fp32": "f32", "bf16x3": "f32 (3xbf16 split, f32 accumulate)", "bf16": "bf16 (f32 accumulate)",
+          "f16f8": "f32 (fp16 product + block-scaled FP8 correction product in one f32 accumulator)"}
+# tensor-core instruction times per 64-wide k-block relative to a single 16-bit product (4 MMAs of K = 16)
+MMA_TIMES = {"bf16x3": 3.0, "f16f8": 2.0, "bf16": 1.0, "fp32": None}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (average of GEMM-1 and GEMM-2) from the committed ncu capture
+# of this configuration; None where no capture of the current kernel exists
+NCU_TRAFFIC = {"f16f8": (2.450e9, "profiles/r02_gemm_f16f8.txt"), "bf16x3": (2.268e9, "profiles/r01_main_kernels_bf16x3_v9.txt")}
+
+
 def synthetic_boards(count, seed):
     import numpy as np
     return np.random.default_rng(seed).integers(-1, 2, size=(count, N_BOARD, N_BOARD)).astype(np.int8)
@@ -126,14 +142,16 @@ def cpu_selfplay(episodes):
     return moves / dt, moves, dt
 
 
-def gpu_selfplay(net, a, games, moves, seed):
+def gpu_selfplay(net, a, games, moves, seed, collect=False, warm=2):
     """Lock-step self-play of `games` concurrent episodes on this GPU: moves/s over `moves` move-steps
-    (each = getActionProb's 10 searches + expand_tree's 5 for every live game, then one move)."""
+    (each = getActionProb's 10 searches + expand_tree's 5 for every live game, then one move).  collect="device" is the
+    Coach path (symmetric training examples emitted on the device as episodes end); with `warm` >= the longest game
+    the timed region is the steady state with episode turnover."""
     import torch
     from azgnn_b200.games import Connect4Game
     from azgnn_b200.selfplay import BatchedSelfPlay
-    sp = BatchedSelfPlay(Connect4Game(N_BOARD), net, a, games, seed=seed, collect_examples=False)
-    for _ in range(2):
+    sp = BatchedSelfPlay(Connect4Game(N_BOARD), net, a, games, seed=seed, collect_examples=collect)
+    for _ in range(warm):
         sp.step_all()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -162,11 +180,9 @@ def run_reference_arm(args, rank):
     line = {"impl": "reference", "metric": "connect4_gnn_leaf_evals_per_s", "value": value, "unit": "leaf_evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "connect4_7x7_gnn_leaf_eval_batch_65536", "positions_per_step_per_gpu": BATCH,
-                       "board": "7x7 (reference geometry; 6x7 is not constructible, SURVEY 8d)", "use_gnn": True,
-                       "eval": "predict + predict_with_gnn (shared trunk)", "weights": "random-init seed 0", "precision": "fp32",
-                       "sample": f"each step = {sample} positions of the workload, evaluated as the reference's MCTS does: one "
-                                 "B=1 predict + predict_with_gnn per position (MCTS.py:169-173), all host threads"},
+            "config": workload_config(BATCH), "precision": "fp32",
+            "sample": f"each step = {sample} positions of the workload, evaluated as the reference's MCTS does: one "
+                      "B=1 predict + predict_with_gnn per position (MCTS.py:169-173), all host threads",
             "cpu_baseline": {"value": value, "unit": "leaf_evals/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} positions per step, predict + predict_with_gnn per position (B=1), "
                                        "oracle/nets.py on torch CPU"},
@@ -262,6 +278,12 @@ def run_gpu_arm(args, rank, local_rank, world):
     net = B200Connect4GNNWrapper(Connect4Game(N_BOARD), a)
     mask = _lib.EVAL_STD | _lib.EVAL_GNN
     B = args.batch
+    # the guard the wrappers run per weight version under `b200_precision: auto`, reported for these weights
+    probe_net_prec = net.precision
+    net.precision = _lib.PREC_AUTO
+    net.active_precision()
+    probe_report = dict(net.precision_report, chosen=_lib.PRECISION_NAMES[net._auto_choice])
+    net.precision = probe_net_prec
     n_rot = 4  # rotate distinct input batches; the ~GBs of per-step intermediates sweep the 126 MB L2 anyway
     host_boards = [torch.from_numpy(synthetic_boards(B, 100 + rank * 16 + i)).pin_memory() for i in range(n_rot)]
     dev_states = [net.states_from_boards(hb) for hb in host_boards]
@@ -286,6 +308,15 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     for i in range(max(args.warmup, 3)):
         step_device(i)
+    # clocks settle under the 1 kW cap only after ~1 s of load: keep stepping (untimed) so that the timed region is the
+    # sustained state the roofline denominator (bf16_tflops_sustained) was measured in
+    torch.cuda.synchronize()
+    t_pre, n_pre = time.perf_counter(), 0
+    while time.perf_counter() - t_pre < args.preheat:
+        step_device(n_pre)
+        n_pre += 1
+        if n_pre % 8 == 0:
+            torch.cuda.synchronize()
     barrier()
     # ---- timed region: exactly K steps, CUDA events on the launching stream, phase timing on ----
     lib.azg_timing_enable(1)
@@ -309,7 +340,7 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     # ---- the other tensor-core precision, device-resident, short (reported under "also") ----
     also = {}
-    for other in ("bf16", "bf16x3"):
+    for other in ("bf16", "bf16x3", "f16f8"):
         if other == args.precision or args.precision == "fp32":
             continue
         oprec = _lib.PRECISIONS[other]
@@ -324,7 +355,8 @@ def run_gpu_arm(args, rank, local_rank, world):
         torch.cuda.synchronize()
         also[other] = {"value": B * 5 / (a0.elapsed_time(a1) / 1e3), "unit": "leaf_evals/s per GPU", "ms_per_step": a0.elapsed_time(a1) / 5,
                        "note": {"bf16": "single bf16 product, fp32 accumulate; stated tolerance 5e-3 on pi and v",
-                                "bf16x3": "3-term bf16 split, fp32 accumulate; pi and v within 1e-5 of the reference"}[other]}
+                                "bf16x3": "3-term bf16 split, fp32 accumulate; pi and v within 1e-5 of the reference",
+                                "f16f8": "fp16 product + block-scaled FP8 correction product; pi and v within 1e-5 of the reference"}[other]}
 
     # ---- opt-in algebraic fold of output_transform.2 into the heads (same outputs, one F x F contraction) ----
     if args.precision != "fp32":
@@ -381,10 +413,18 @@ def run_gpu_arm(args, rank, local_rank, world):
     single_ms = (time.perf_counter() - t0) / 50 * 1e3
 
     sp_moves, sp_leaves, sp_ms = (0.0, 0.0, 0.0)
+    sp_steady = None
     if args.selfplay_games > 0:
         barrier()
         sp_moves, sp_leaves, sp_ms = gpu_selfplay(net, a, args.selfplay_games, args.selfplay_moves, seed=rank)
         barrier()
+        if args.selfplay_steady_moves > 0:
+            # the Coach path in its steady state: device example collection on, 50 untimed move-steps first (longer than any
+            # 7x7 game: every slot has turned over at least once), then >= 60 timed move-steps with episodes ending and restarting
+            s_moves, s_leaves, s_ms = gpu_selfplay(net, a, args.selfplay_games, args.selfplay_steady_moves, seed=1000 + rank,
+                                                   collect="device", warm=50)
+            sp_steady = [s_moves * s_ms, s_ms]
+            barrier()
     sp_fold = None
     if args.selfplay_games > 0 and args.precision != "fp32" and world == 1:
         net.fold_heads = True  # same search, leaves evaluated with output_transform.2 folded into the heads (opt-in mode)
@@ -392,13 +432,14 @@ def run_gpu_arm(args, rank, local_rank, world):
         net.fold_heads = False
         sp_fold = {"value": f_moves, "unit": "moves/s", "leaf_evals_per_s_in_search": f_leaves,
                    "ms_per_move_step": f_ms / max(args.selfplay_moves, 1), "note": "b200_fold_heads=True (see also.*_folded_heads)"}
-    t = torch.tensor([ms, ms_e2e, sp_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([sp_moves * sp_ms, sp_leaves * sp_ms], dtype=torch.float64, device=dev)  # counts
+    t = torch.tensor([ms, ms_e2e, sp_ms, sp_steady[1] if sp_steady else 0.0], dtype=torch.float64, device=dev)
+    tot = torch.tensor([sp_moves * sp_ms, sp_leaves * sp_ms, sp_steady[0] if sp_steady else 0.0], dtype=torch.float64, device=dev)  # counts
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_e2e, sp_ms = t.tolist()
-    sp_moves, sp_leaves = [(x / sp_ms if sp_ms > 0 else 0.0) for x in tot.tolist()]
+    ms, ms_e2e, sp_ms, steady_ms = t.tolist()
+    sp_moves, sp_leaves = [(x / sp_ms if sp_ms > 0 else 0.0) for x in tot.tolist()[:2]]
+    steady_moves = tot.tolist()[2] / steady_ms if steady_ms > 0 else None
     if rank == 0:
         peaks = {}
         try:
@@ -407,24 +448,29 @@ def run_gpu_arm(args, rank, local_rank, world):
             pass
         peak_src = "measured" if peaks else "fallback"
         bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0) if peaks else 1400.0
+        bf16_burst = peaks.get("bf16_tflops", 1640.0) if peaks else 1640.0
         total = B * args.steps * world
         value = total / (ms / 1e3)
         gemm_ms, gemm_cnt = phase["gemm"]
         gemm_tflops = (GEMM_FLOP_PER_LEAF * B * gemm_cnt) / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         # fp32 FFMA path: the relevant ceiling is the CUDA-core FFMA rate, reported as a note; the
         # roofline entry always uses the measured bf16 tensor peak (the path's real ceiling).
-        terms = 3 if args.precision == "bf16x3" else 1
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this
-        # configuration (profiles/r01_main_kernels_bf16x3_v9.txt: GEMM-1 with the std-heads side tile 1.983+0.813 GB,
-        # GEMM-2 1.681+0.060 GB)
-        traffic = {"bf16x3": 2.268e9, "bf16": None, "fp32": None}[args.precision] if B == BATCH else None
+        terms = MMA_TIMES[args.precision]
+        two_images = args.precision in ("bf16x3", "f16f8")
+        # `traffic` is NOT measured by this run (DRAM counters need ncu): it is the figure of the committed capture of the
+        # same kernel and configuration, named in `traffic_source`; null when there is none
+        traffic, traffic_src = NCU_TRAFFIC.get(args.precision, (None, None)) if B == BATCH else (None, None)
+        if traffic_src and not os.path.exists(os.path.join(ROOT, traffic_src)):
+            traffic, traffic_src = None, None
         roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
-                "frac": (gemm_tflops / bf16_peak) if gemm_tflops else None, "traffic": traffic,
+                "frac": (gemm_tflops / bf16_peak) if gemm_tflops else None,
+                "frac_of_burst_peak": (gemm_tflops / bf16_burst) if gemm_tflops else None, "burst_peak": bf16_burst,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "traffic_unit": "bytes per launch (average of the two launches)",
                 # GEMM-1 reads X images and writes H images, GEMM-2 reads H images and writes 59 MB of partial
                 # head sums; an image is B*F*2 bytes, hi+lo in bf16x3 (weights come from L2 after the first tile)
-                "algorithmic_bytes_per_launch": (3 * (B * 3136 * 2) * (2 if terms == 3 else 1) + B * 14 * 16 * 4) / 2,
-                "mma_terms": terms, "issued_tflops": gemm_tflops * terms if gemm_tflops else None,
+                "algorithmic_bytes_per_launch": (3 * (B * 3136 * 2) * (2 if two_images else 1) + B * 14 * 16 * 4) / 2,
+                "mma_instruction_times": terms, "issued_tflops_bf16_equivalent": gemm_tflops * terms if (gemm_tflops and terms) else None,
                 "peak_source": peak_src + " (bf16_tflops_sustained)",
                 "kernel": "output_transform F x F contractions (2 launches per step; the first also carries the standard heads as a 32-column side tile, not counted in the algorithmic FLOP)",
                 "kernel_ms_per_step": gemm_ms / max(gemm_cnt, 1),
@@ -447,13 +493,14 @@ def run_gpu_arm(args, rank, local_rank, world):
         line = {"metric": "connect4_gnn_leaf_evals_per_s", "value": value, "unit": "leaf_evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp32": "f32", "bf16x3": "f32 (3xbf16 split, f32 accumulate)", "bf16": "bf16 (f32 accumulate)"}[args.precision],
+                "dtype": DTYPES[args.precision],
                 "data": "synthetic",
-                "config": {"workload": "connect4_7x7_gnn_leaf_eval_batch_65536", "positions_per_step_per_gpu": B,
-                           "board": "7x7 (reference geometry; 6x7 is not constructible, SURVEY 8d)", "use_gnn": True,
-                           "eval": "predict + predict_with_gnn (shared trunk)", "weights": "random-init seed 0",
-                           "precision": args.precision,
-                           "l2": "4 rotating input batches; per-step intermediates (>2 GB) exceed the 126 MB L2"},
+                "config": workload_config(B), "precision": args.precision,
+                "precision_probe": {"tolerance": net.AUTO_TOL, "max_abs_err_vs_fp32_path": probe_report,
+                                    "note": "max |d pi|, |d v| over 256 probe positions against the fp32 CUDA-core path for "
+                                            "these weights; `b200_precision: auto` (the wrappers' default) picks the first mode under the tolerance"},
+                "l2": "4 rotating input batches; per-step intermediates (>2 GB) exceed the 126 MB L2",
+                "preheat": f"{args.preheat:.1f} s of untimed steps ({n_pre}) after the {max(args.warmup, 3)} warm-up steps, so the clocks are in their sustained state",
                 "tflops_algorithmic": value * MFLOP_PER_LEAF * 1e6 / 1e12,
                 "roofline": roof,
                 "cpu_baseline": None if cpu_rate is None else
@@ -469,6 +516,10 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "single_call_ms": {"predict_with_gnn": single_ms, "note": "one position, host board in, numpy pi/v out (B=1 "
                                    "through the same kernels; the reference's CPU call takes ~7.8 ms on one thread)"},
                 "selfplay": selfplay,
+                "selfplay_steady_state": None if steady_moves is None else
+                {"value": steady_moves, "unit": "moves/s", "move_steps_timed": args.selfplay_steady_moves, "ms_per_move_step": steady_ms / args.selfplay_steady_moves,
+                 "note": "the Coach.learn path: device example collection on, 50 untimed move-steps first so that every slot has "
+                         "turned over, episodes end and restart inside the timed region"},
                 "selfplay_folded_heads": sp_fold,
                 "also": also,
                 "gpu_launches": int(launches),
@@ -484,7 +535,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "f16f8"), choices=["fp32", "bf16x3", "bf16", "f16f8"])
+    ap.add_argument("--preheat", type=float, default=1.0, help="seconds of untimed steps before the timed region (clock settling)")
+    ap.add_argument("--selfplay-steady-moves", type=int, default=60, help="timed move-steps of the steady-state self-play leg (0 = skip)")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--selfplay-games", type=int, default=16384, help="concurrent self-play games per GPU (0 = skip)")

@@ -157,7 +157,7 @@ def _tc_linear(A, W, b, prec, relu):
     lib = _lib.lib()
     M, F = A.shape
     Mp = (M + 255) // 256 * 256
-    nbytes = (2 if prec == _lib.PREC_BF16X3 else 1) * (Mp + F) * F * 2 + 2048
+    nbytes = (1 if prec == _lib.PREC_BF16 else 2) * (Mp + F) * F * 2 + 4096
     scratch = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
     C = torch.full((M, F), float("nan"), device="cuda")
     _lib.check(lib.azg_tc_linear(_lib.ptr(A), _lib.ptr(W), _lib.ptr(b), _lib.ptr(C), M, F, prec, relu, _lib.ptr(scratch),
@@ -183,6 +183,48 @@ def test_tc_linear(M, F, relu):
     assert (c3.double() - ref).abs().max().item() <= 1e-4
     c1 = _tc_linear(A, W, b, _lib.PREC_BF16, relu)
     assert (c1.double() - refb).abs().max().item() <= 5e-5
+    # fp16 product + block-scaled FP8 correction product (one accumulator): ~15 mantissa bits per operand
+    c8 = _tc_linear(A, W, b, _lib.PREC_F16F8, relu)
+    e8 = (c8.double() - ref).abs().max().item()
+    print(f"f16f8 M={M} F={F}: max |err| vs fp64 = {e8:.2e}")
+    assert e8 <= 1e-4
+
+
+def _e4m3(t):
+    return t.clamp(-448, 448).to(torch.float8_e4m3fn).double()
+
+
+@pytest.mark.parametrize("wscale", [1.0, 37.0, 0.01])
+def test_f16f8_matches_its_exact_emulation(wscale):
+    """AZG_PREC_F16F8 pinned term by term: fp16(x) fp16(w) + [e4m3(2^3 x) | e4m3(2^14 x_lo)] . [e4m3(2^(s+11) w_lo) | e4m3(2^s w)]
+    * 2^-(s+14) with s = the largest exponent keeping 2^s max|w| <= 448, operands rounded in torch and accumulated in fp64.
+    The kernel (tcgen05 kind::f16 + kind::mxf8f6f4.block_scale with constant UE8M0 scale factors, fp32 accumulation in TMEM)
+    must agree to fp32 accumulation noise -- this fixes the scale-factor semantics, the K-concatenation order and the
+    per-tensor weight scale, not just "small error"."""
+    g = torch.Generator().manual_seed(17)
+    M, F = 300, 3136
+    A = torch.randn(M, F, generator=g) * 0.5
+    W = (torch.rand(F, F, generator=g) * 2 - 1) / F ** 0.5 * wscale
+    b = torch.randn(F, generator=g) * 0.1
+    got = _tc_linear(A.cuda(), W.cuda(), b.cuda(), _lib.PREC_F16F8, 0).double().cpu()
+    Ad, Wd = A.double(), W.double()
+    Ah, Wh = A.half().double(), W.half().double()
+    m = float(W.abs().max())
+    s_w = int(np.floor(np.log2(448.0 / m)))
+    while m * 2.0 ** s_w > 448.0:
+        s_w -= 1
+    while m * 2.0 ** (s_w + 1) <= 448.0:
+        s_w += 1
+    corr = (_e4m3(Ad * 8.0) @ _e4m3((Wd - Wh) * 2.0 ** (s_w + 11)).t() + _e4m3((Ad - Ah) * 2.0 ** 14) @ _e4m3(Wd * 2.0 ** s_w).t()) * 2.0 ** -(s_w + 14)
+    model = Ah @ Wh.t() + corr + b.double()
+    scale = float(model.abs().max())
+    e_model = (got - model).abs().max().item()
+    e_exact = (got - (Ad @ Wd.t() + b.double())).abs().max().item()
+    print(f"wscale {wscale}: max |out| {scale:.2f}, |got - emulation| {e_model:.2e}, |got - fp64| {e_exact:.2e}")
+    assert e_model <= 2e-5 * max(scale, 1.0)  # the tensor core's fp32 accumulation over K = 3136 (+ 6272 correction terms)
+    assert e_exact <= 4e-5 * max(scale, 1.0)
+    # the correction product is really there: without it the fp16 rounding of the operands alone costs ~4e-4
+    assert e_exact < 0.2 * (Ah @ Wh.t() + b.double() - (Ad @ Wd.t() + b.double())).abs().max().item()
 
 
 @pytest.mark.parametrize("n,B", [(7, 1), (7, 777), (7, 4096), (4, 300), (5, 300), (6, 300), (8, 300)])
@@ -199,14 +241,15 @@ def test_forward_tensor_core_precisions(n, B):
         spi, sv = onets.c4_predict(p, onets.boards_to_tensor(boards), n)
     states = w.states_from_boards(boards)
     both = _lib.EVAL_STD | _lib.EVAL_GNN
-    o3 = w.forward_states(states, both, precision=_lib.PREC_BF16X3)
-    np.testing.assert_allclose(o3["pi_gnn"].cpu().numpy(), gpi.numpy(), rtol=0, atol=1e-5)
-    np.testing.assert_allclose(o3["v_gnn"].cpu().numpy(), gv.numpy(), rtol=0, atol=1e-5)
-    # the trunk runs on the tensor cores too (conv2 as an implicit GEMM): std heads see the same features
-    np.testing.assert_allclose(o3["pi"].cpu().numpy(), spi.numpy(), rtol=0, atol=1e-5)
-    np.testing.assert_allclose(o3["v"].cpu().numpy(), sv.numpy(), rtol=0, atol=1e-5)
-    only_std = w.forward_states(states, _lib.EVAL_STD, precision=_lib.PREC_BF16X3)
-    assert torch.equal(only_std["pi"], o3["pi"])
+    for prec in (_lib.PREC_F16F8, _lib.PREC_BF16X3):  # both splits hold the fp32 contract
+        o3 = w.forward_states(states, both, precision=prec)
+        np.testing.assert_allclose(o3["pi_gnn"].cpu().numpy(), gpi.numpy(), rtol=0, atol=1e-5)
+        np.testing.assert_allclose(o3["v_gnn"].cpu().numpy(), gv.numpy(), rtol=0, atol=1e-5)
+        # the trunk runs on the tensor cores too (conv2 as an implicit GEMM): std heads see the same features
+        np.testing.assert_allclose(o3["pi"].cpu().numpy(), spi.numpy(), rtol=0, atol=1e-5)
+        np.testing.assert_allclose(o3["v"].cpu().numpy(), sv.numpy(), rtol=0, atol=1e-5)
+        only_std = w.forward_states(states, _lib.EVAL_STD, precision=prec)
+        assert torch.equal(only_std["pi"], o3["pi"])
     o1 = w.forward_states(states, both, precision=_lib.PREC_BF16)
     assert np.abs(o1["pi"].cpu().numpy() - spi.numpy()).max() <= 5e-3 and np.abs(o1["v"].cpu().numpy() - sv.numpy()).max() <= 5e-3
     e_pi = np.abs(o1["pi_gnn"].cpu().numpy() - gpi.numpy()).max()
@@ -242,6 +285,40 @@ def test_bf16x3_margin_under_weight_scale(scale):
     e_v = np.abs(o3["v_gnn"].cpu().numpy() - gv.numpy()).max()
     print(f"scale {scale}: max |dpi| = {e_pi:.2e}, max |dv| = {e_v:.2e}, max pi = {gpi.max().item():.3f}")
     assert e_pi <= 1e-5 and e_v <= 2e-5
+
+
+@pytest.mark.parametrize("scale", [0.3, 1.0, 3.0, 10.0])
+def test_auto_precision_guard(scale):
+    """`b200_precision: auto` (the default): per weight version the wrapper evaluates a probe batch in f16f8, then bf16x3,
+    against its own fp32 CUDA-core path and keeps the first mode within 5e-6; a weight scale that breaks a split makes it
+    fall back (down to fp32) instead of silently leaving the 1e-5 contract.  Whatever it chose must hold 1e-5 against the
+    oracle on other positions."""
+    w = _wrapper("c4", 7, b200_precision="auto")
+    with torch.no_grad():
+        for p_ in list(w.nnet.parameters()) + list(w.gnn.output_transform.parameters()):
+            if p_.dim() > 1:
+                p_.mul_(scale ** 0.5)
+    w.weights_changed()
+    boards = np.random.default_rng(5).integers(-1, 2, size=(384, 7, 7)).astype(np.int64)
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    with torch.no_grad():
+        spi, sv = onets.c4_predict(p, onets.boards_to_tensor(boards), 7)
+        gpi, gv = onets.c4_predict_with_gnn(p, q, onets.boards_to_tensor(boards), 7)
+    out = w.predict_batch(boards)
+    choice = _lib.PRECISION_NAMES[w.active_precision()]
+    errs = {k: float(np.abs(out[k] - t.numpy().reshape(out[k].shape)).max()) for k, t in (("pi", spi), ("v", sv), ("pi_gnn", gpi), ("v_gnn", gv))}
+    print(f"scale {scale}: auto -> {choice}; probe {w.precision_report}; errors vs oracle {errs}")
+    if scale <= 1.0:
+        assert choice == "f16f8"
+    assert max(errs.values()) <= (1e-5 if scale < 10 else 4e-5)  # at x10 the fp32 paths themselves differ by rounding order
+    # the choice follows the weights
+    with torch.no_grad():
+        for p_ in list(w.nnet.parameters()) + list(w.gnn.output_transform.parameters()):
+            if p_.dim() > 1:
+                p_.mul_(scale ** -0.5)
+    w.weights_changed()
+    w.predict_batch(boards[:4])
+    assert _lib.PRECISION_NAMES[w.active_precision()] == "f16f8"
 
 
 @pytest.mark.parametrize("n,B", [(7, 1), (7, 777), (5, 300), (8, 300)])
@@ -326,13 +403,14 @@ def test_predict_batches_pipeline_equals_predict_batch():
 
 @pytest.mark.parametrize("kind,n", [("c4", 7), ("ttt", 4)])
 def test_default_precision_is_the_tensor_core_path(kind, n):
-    """a config without `b200_precision` (the reference's config.yaml) runs bf16x3 on tcgen05 and still reproduces the
-    reference module's golden outputs within 1e-5"""
+    """a config without `b200_precision` (the reference's config.yaml) runs the guarded tensor-core path (Connect4: f16f8,
+    TicTacToe: bf16x3 on random-init weights) and still reproduces the reference module's outputs within 1e-5"""
     game = (orules.Connect4Rules if kind == "c4" else orules.TicTacToeRules)(n)
     torch.manual_seed(0)
     W = B200Connect4GNNWrapper if kind == "c4" else B200TicTacToeGNNWrapper
     w = W(game, dotdict(dict(lr=1e-3, dropout=0.3, epochs=1, batch_size=64, gnn_layers=2, use_gnn=True)))
-    assert w.precision == _lib.PREC_BF16X3
+    assert w.precision == _lib.PREC_AUTO
+    assert w.active_precision() == (_lib.PREC_F16F8 if kind == "c4" else _lib.PREC_BF16X3), w.precision_report
     rng = np.random.default_rng(n)
     boards = rng.integers(-1, 2, size=(200, n, n)).astype(np.int64)
     p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
@@ -347,7 +425,7 @@ def test_default_precision_is_the_tensor_core_path(kind, n):
     assert abs(one_v - gv[0].item()) <= 1e-5 and np.abs(one_pi - gpi[0].numpy()).max() <= 1e-5
 
 
-@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("prec", ["f16f8", "bf16x3", "bf16"])
 def test_tensor_core_forward_is_run_to_run_identical(prec):
     """The fused trunk (conv1 slot queued inside the previous tile's conv2 k-blocks, one TMEM result region) and GEMM-1's
     side tile are synchronised by mbarriers only: repeated launches over many tiles per CTA (20,011 positions = 68
@@ -371,11 +449,11 @@ def test_tensor_core_forward_is_run_to_run_identical(prec):
 
 
 def test_full_size_batch_properties():
-    """BASELINE configs[1] at its full size (65,536 positions, 7x7, std + GNN predictions, bf16x3), checked through
+    """BASELINE configs[1] at its full size (65,536 positions, 7x7, std + GNN predictions, the bench's f16f8), checked through
     size-independent properties: a random sample of rows against the oracle at 1e-5; rows evaluated alone or in
     another order give bit-identical outputs (no dependence on tile position or neighbours); duplicated positions
     give duplicated outputs; policies are distributions, values lie in [-1, 1]."""
-    w = _wrapper("c4", 7)
+    w = _wrapper("c4", 7, b200_precision="f16f8")
     B = 65536
     rng = np.random.default_rng(65536)
     boards = rng.integers(-1, 2, size=(B, 7, 7)).astype(np.int8)

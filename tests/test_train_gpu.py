@@ -1,6 +1,10 @@
 """K3 parity on the GPU: forward/backward of the training step in libazgnn_b200.so vs the
 reference's autograd (golden gradient summaries) and vs the oracle graph on random batches.
-Tolerances: losses/outputs 1e-5; gradients rtol 1e-3 / atol 2e-6 (fp32, different summation order)."""
+Tolerances (north_star: 1e-5 in fp32): losses/outputs 1e-5; every gradient entry within 1e-5 ABSOLUTE of the reference's
+(asserted and printed per parameter), and additionally within rtol 1e-3 / atol 2e-6 so that small gradients are held
+relatively too.  The one documented exception: a hidden unit whose pre-activation is within rounding of 0 may land on the
+other side of a ReLU than in the reference's summation order, which flips one row of a weight gradient -- at most two such
+rows per parameter are tolerated in the full-tensor comparison, none in the golden samples."""
 import numpy as np
 import pytest
 import torch
@@ -14,6 +18,14 @@ pytestmark = pytest.mark.gpu
 # the comparison graph runs on torch's CUDA ops: keep them in true fp32 (cuDNN convs default to TF32)
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
+GRAD_ATOL = 1e-5
+
+
+def _check_samples(tag, name, got, want):
+    err = float(np.abs(got - want).max())
+    print(f"{tag} {name}: max |d grad| on the golden samples = {err:.2e} (max |grad| {float(np.abs(want).max()):.2e})")
+    assert err <= GRAD_ATOL, (tag, name, err)
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=2e-6)
 
 
 def _wrapper(kind, n, dropout=0.0, **kw):
@@ -42,7 +54,7 @@ def test_gradients_match_reference_golden(kind, n):
     named = dict(w.nnet.named_parameters())
     for name, row, samp in zip(g["std_grad_names"], g["std_grad_rows"], g["std_grad_samples"]):
         gr = named[str(name)].grad.double().flatten().cpu()
-        np.testing.assert_allclose(gr[sample_index(gr.numel(), 64)].numpy(), samp, rtol=1e-3, atol=2e-6)
+        _check_samples(f"{kind}{n} std", str(name), gr[sample_index(gr.numel(), 64)].numpy(), samp)
         assert abs(gr.norm().item() - row[2]) <= 1e-3 * max(1e-3, row[2])
     _zero(w)
     loss = training.gnn_step(training.CudaOps, w, boards, tpi, tv)
@@ -51,7 +63,7 @@ def test_gradients_match_reference_golden(kind, n):
     named = dict(w.gnn.named_parameters())
     for name, row, samp in zip(g["gnn_grad_names"], g["gnn_grad_rows"], g["gnn_grad_samples"]):
         gr = named[str(name)].grad.double().flatten().cpu()
-        np.testing.assert_allclose(gr[sample_index(gr.numel(), 64)].numpy(), samp, rtol=1e-3, atol=2e-6)
+        _check_samples(f"{kind}{n} gnn", str(name), gr[sample_index(gr.numel(), 64)].numpy(), samp)
         assert abs(gr.norm().item() - row[2]) <= 1e-3 * max(1e-3, row[2])
     assert all(p.grad is None for p in w.nnet.parameters())  # the GNN step leaves the trunk alone
 
@@ -76,12 +88,17 @@ def test_gradients_match_oracle_graph(kind, n, B):
         assert abs(l_cuda.item() - l_ref.item()) < 1e-5
         for k, p in params().named_parameters():
             ref = p.grad
-            bad = (got[k] - ref).abs() > 1e-3 * ref.abs().max() + 2e-6
+            diff = (got[k] - ref).abs()
+            bad = (diff > 1e-3 * ref.abs().max() + 2e-6) | (diff > GRAD_ATOL)
             # A hidden unit whose pre-activation is within rounding of 0 can land on either side of the
             # ReLU in the two implementations; that flips one row of the weight gradient (and one bias
             # entry).  Anything beyond two such rows is a real mismatch.
-            rows = bad.reshape(bad.shape[0], -1).any(dim=1).sum().item()
-            assert rows <= 2, (k, rows, (got[k] - ref).abs().max().item(), ref.abs().max().item())
+            row_bad = bad.reshape(bad.shape[0], -1).any(dim=1)
+            rows = row_bad.sum().item()
+            rest = diff.reshape(bad.shape[0], -1)[~row_bad]
+            print(f"{kind}{n} B={B} {step.__name__} {k}: max |d grad| = {float(rest.max()) if rest.numel() else 0.0:.2e} over {int((~row_bad).sum())} rows "
+                  f"({rows} ReLU-boundary rows excluded), max |grad| {float(ref.abs().max()):.2e}")
+            assert rows <= 2, (k, rows, diff.max().item(), ref.abs().max().item())
 
 
 def test_gnn_layers_are_identity_at_batch_one():
@@ -174,7 +191,7 @@ def test_frozenlake_training_step(n, layers):
     named = dict(w.nnet.named_parameters())
     for name, row, samp in zip(g["grad_names"], g["grad_rows"], g["grad_samples"]):
         gr = named[str(name)].grad.double().flatten().cpu()
-        np.testing.assert_allclose(gr[sample_index(gr.numel(), 64)].numpy(), samp, rtol=1e-3, atol=2e-6)
+        _check_samples(f"fl{n} L{layers}", str(name), gr[sample_index(gr.numel(), 64)].numpy(), samp)
         assert abs(gr.norm().item() - row[2]) <= 1e-3 * max(1e-3, row[2])
     got = {k: p.grad.clone() for k, p in w.nnet.named_parameters()}
     for p in w.nnet.parameters():
