@@ -101,6 +101,7 @@ SIGNATURES = {
     "azg_arena_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "azg_arena_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _d, _vp, _sz, C.c_char_p, _vp]),
     "azg_arena_destroy": (_i, [_vp]),
+    "azg_arena_copy_from": (_i, [_vp, _vp, _vp]),
     "azg_arena_action_size": (_i, [_vp]),
     "azg_arena_reset": (_i, [_vp, _vp, _i, _vp]),
     "azg_arena_set_roots": (_i, [_vp, _vp, _vp]),
@@ -137,7 +138,7 @@ def lib():
             raise RuntimeError(f"{LIB_PATH} is not built; run `python alphazero-gnn_b200/build.py` "
                                "(nvcc, sm_100a). There is no CPU fallback.")
         _lib = bind(C.CDLL(LIB_PATH))
-        if _lib.azg_abi_version() != 1:
+        if _lib.azg_abi_version() != 2:
             raise RuntimeError("libazgnn_b200.so ABI version mismatch; rebuild")
     return _lib
 

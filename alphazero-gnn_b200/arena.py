@@ -32,6 +32,7 @@ class DeviceArena:
     def __init__(self, kind, n, n_games, sims_per_move, cpuct, capacity=None, max_depth=None, fl_map=None,
                  device=None):
         self._open(device)
+        self._create_args = dict(kind=kind, n=n, sims_per_move=sims_per_move, cpuct=cpuct, fl_map=fl_map)
         self.kind, self.n, self.G = kind, n, int(n_games)
         self.A = action_size(kind, n)
         self.capacity = int(capacity or default_capacity(kind, n, sims_per_move))
@@ -40,15 +41,10 @@ class DeviceArena:
         game = GAME_KINDS[kind]
         nbytes = self.lib.azg_arena_bytes(game, n, self.G, self.capacity, self.max_depth)
         if nbytes == 0:
-            raise RuntimeError(f"unsupported arena configuration {kind} n={n}")
-        self.mem = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        fl = None
-        if kind == "frozenlake":
-            fl = bytes(fl_map)
-            assert len(fl) == n * n
-        self.handle = C.c_void_p()
-        self._check(self.lib.azg_arena_create(C.byref(self.handle), game, n, self.G, self.capacity, self.max_depth,
-                                             float(cpuct), ptr(self.mem), nbytes, fl, self._stream()))
+            raise RuntimeError(f"unsupported arena configuration {kind} n={n} (Connect4 and FrozenLake: n = 2..8; TicTacToe: "
+                               f"n = 2..5 -- valid-move masks are 32-bit, n >= 6 has {n * n + 1} actions)")
+        self.mem = self._alloc(nbytes)
+        self.handle = self._create_handle(self.mem, nbytes, self.capacity)
         G, A = self.G, self.A
         dev = self.device
         self.leaf_states = torch.zeros(G, 2, dtype=torch.int64, device=dev)
@@ -61,6 +57,41 @@ class DeviceArena:
         self.ended = torch.zeros(G, dtype=torch.float64, device=dev)
         self.ended_tag = torch.zeros(G, dtype=torch.int8, device=dev)
         self._status = torch.zeros(G, dtype=torch.int32, device=dev)
+
+    def _alloc(self, nbytes):
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def _create_handle(self, mem, nbytes, capacity):
+        c = self._create_args
+        fl = None
+        if c["kind"] == "frozenlake":
+            fl = bytes(c["fl_map"])
+            assert len(fl) == c["n"] * c["n"]
+        handle = C.c_void_p()
+        self._check(self.lib.azg_arena_create(C.byref(handle), GAME_KINDS[c["kind"]], c["n"], self.G, int(capacity), self.max_depth,
+                                             float(c["cpuct"]), ptr(mem), nbytes, fl, self._stream()))
+        return handle
+
+    def node_count(self, g=0):
+        """entries in game g's table (synchronises)"""
+        n = C.c_int(0)
+        null = C.c_void_p(None)
+        self._check(self.lib.azg_arena_export(self.handle, int(g), C.byref(n), *([null] * 10), self._stream()))
+        return int(n.value)
+
+    def grow(self, capacity):
+        """Re-home every game's table in a larger arena (azg_arena_copy_from): statistics, roots and node indices are
+        kept, so searches continue exactly as they would have in an unbounded dict."""
+        capacity = int(capacity)
+        assert capacity > self.capacity
+        nbytes = self.lib.azg_arena_bytes(GAME_KINDS[self.kind], self.n, self.G, capacity, self.max_depth)
+        mem = self._alloc(nbytes)
+        handle = self._create_handle(mem, nbytes, capacity)
+        self._check(self.lib.azg_arena_copy_from(handle, self.handle, self._stream()))
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()  # the copy has read the old buffers before they are released
+        self.lib.azg_arena_destroy(self.handle)
+        self.handle, self.mem, self.capacity = handle, mem, capacity
 
     def _open(self, device):
         _lib.require_device()

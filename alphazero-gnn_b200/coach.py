@@ -34,6 +34,7 @@ class Coach:
         self.pnet = None
         self.mcts = self._new_mcts(self.nnet)
         self.trainExamplesHistory = []
+        self.skipFirstSelfPlay = False  # set by loadTrainExamples (Coach.py:25, 91, 202)
         self.curPlayer = 1
 
     def _new_mcts(self, nnet):
@@ -129,12 +130,32 @@ class Coach:
             history = [(DeviceExamples.from_examples(self.game, list(std)), DeviceGnnExamples.from_examples(self.game, list(gnn)))
                        for std, gnn in history]
         self.trainExamplesHistory = history
+        self.skipFirstSelfPlay = True  # examples based on the model were already collected (Coach.py:201-202)
 
     # ------------------------------------------------------------------ multi-GPU plumbing
     @staticmethod
     def _world():
         import torch.distributed as dist
         return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+    def _modules(self, net):
+        return [m for m in (getattr(net, "nnet", None), getattr(net, "gnn", None)) if m is not None]
+
+    def _broadcast_weights(self, net):
+        """Data-parallel training only sums gradients: every rank must start from rank 0's weights."""
+        import torch
+        import torch.distributed as dist
+        with torch.no_grad():
+            for mod in self._modules(net):
+                for t in list(mod.parameters()) + list(mod.buffers()):
+                    dist.broadcast(t, src=0)
+        net.weights_changed()
+
+    def _copy_weights(self, dst, src):
+        """dst <- src, device to device (what reading temp.pth.tar back does, Coach.py:123-124, 150)"""
+        for d, s_ in zip(self._modules(dst), self._modules(src)):
+            d.load_state_dict(s_.state_dict())
+        dst.weights_changed()
 
     # ------------------------------------------------------------------ Coach.py:87-176
     def learn(self):
@@ -149,6 +170,9 @@ class Coach:
         on_device = self._arena_factory is None  # the CPU check arena of the tests keeps host tuples
         assert world == 1 or on_device
         folder = self._folder()
+        two_player = bool(getattr(self.game, "is_two_player", True))
+        if world > 1:
+            self._broadcast_weights(self.nnet)
 
         def sync():
             if on_device:
@@ -157,26 +181,32 @@ class Coach:
         for i in range(1, arg(a, "numIters") + 1):
             log.info(f"Starting Iter #{i} ...")
             t0 = sync()
-            it_std = deque([], maxlen=arg(a, "maxlenOfQueue"))
-            it_gnn = deque([], maxlen=arg(a, "maxlenOfQueue"))
-            n_eps = arg(a, "numEps")
-            my_eps = (n_eps + world - 1) // world  # whole games per rank
-            games = int(arg(a, "n_parallel_games", min(my_eps, 4096)) or min(my_eps, 4096))
-            sp = BatchedSelfPlay(self.game, self.nnet, a, games, seed=i * 1000 + rank,
-                                 collect_examples="device" if on_device else True,
-                                 arena=self._arena_factory(games) if self._arena_factory else None)
-            for std, gnn in sp.play(my_eps):
-                it_std += std
-                it_gnn += gnn
-            self.selfplay_moves = sp.moves_played
-            t1 = sync()
-            if on_device:
-                # whole games were sharded over the ranks with no communication; the data-parallel training step works
-                # on ONE shared minibatch, so every rank now receives every rank's examples (padded all-gather per column)
-                maxlen = arg(a, "maxlenOfQueue")
-                it_std = sp.device_examples.newest(maxlen).all_gathered().newest(maxlen)
-                it_gnn = sp.device_gnn_examples.newest(maxlen).all_gathered().newest(maxlen)
-            self.trainExamplesHistory.append((it_std, it_gnn))
+            t1 = t0
+            if not self.skipFirstSelfPlay or i > 1:  # Coach.py:91
+                it_std = deque([], maxlen=arg(a, "maxlenOfQueue"))
+                it_gnn = deque([], maxlen=arg(a, "maxlenOfQueue"))
+                n_eps = arg(a, "numEps")
+                my_eps = (n_eps + world - 1) // world  # whole games per rank
+                games = int(arg(a, "n_parallel_games", min(my_eps, 4096)) or min(my_eps, 4096))
+                n = self.game.getBoardSize()[0]
+                sp = BatchedSelfPlay(self.game, self.nnet, a, games, seed=i * 1000 + rank,
+                                     collect_examples="device" if on_device else True,
+                                     arena=self._arena_factory(games) if self._arena_factory else None,
+                                     # single-player episodes have no natural end (FrozenLake can wander): the cap of the
+                                     # reference's single-player arena (Arena.py:45), episodes that reach it score 0
+                                     max_episode_steps=None if two_player else 5 * n * n)
+                for std, gnn in sp.play(my_eps):
+                    it_std += std
+                    it_gnn += gnn
+                self.selfplay_moves = sp.moves_played
+                t1 = sync()
+                if on_device:
+                    # whole games were sharded over the ranks with no communication; the data-parallel training step works
+                    # on ONE shared minibatch, so every rank now receives every rank's examples (padded all-gather per column)
+                    maxlen = arg(a, "maxlenOfQueue")
+                    it_std = sp.device_examples.newest(maxlen).all_gathered().newest(maxlen)
+                    it_gnn = sp.device_gnn_examples.newest(maxlen).all_gathered().newest(maxlen)
+                self.trainExamplesHistory.append((it_std, it_gnn))
             if len(self.trainExamplesHistory) > arg(a, "numItersForTrainExamplesHistory"):
                 self.trainExamplesHistory.pop(0)
             if rank == 0 and arg(a, "save_examples", True):
@@ -211,12 +241,8 @@ class Coach:
             if self.pnet is None:
                 self.pnet = self.nnet.__class__(self.game, a)
             if on_device and hasattr(self.pnet, "nnet"):
-                # same weights as reading temp.pth.tar back (Coach.py:123-124), copied device to device; the file stays on
-                # disk for the reject path
-                self.pnet.nnet.load_state_dict(self.nnet.nnet.state_dict())
-                if getattr(self.nnet, "gnn", None) is not None:
-                    self.pnet.gnn.load_state_dict(self.nnet.gnn.state_dict())
-                self.pnet.weights_changed()
+                # same weights as reading temp.pth.tar back (Coach.py:123-124), copied device to device
+                self._copy_weights(self.pnet, self.nnet)
             else:
                 self.pnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
             pmcts = self._new_mcts(self.pnet)
@@ -226,7 +252,9 @@ class Coach:
                 import cProfile
                 prof = cProfile.Profile()
                 prof.enable()
-            if self._use_gnn() and len(gnnExamples) > 0:
+            if not two_player:  # FrozenLakeNet.train(examples) iterates host tuples (FrozenLakeNet.py:76-176)
+                self.nnet.train(trainExamples.to_examples() if hasattr(trainExamples, "to_examples") else trainExamples)
+            elif self._use_gnn() and len(gnnExamples) > 0:
                 self.nnet.train(trainExamples, gnnExamples)
             else:
                 self.nnet.train(trainExamples)
@@ -237,7 +265,12 @@ class Coach:
             t4 = sync()
             nmcts = self._new_mcts(self.nnet)
             n_arena = arg(a, "arenaCompare")
-            if on_device and arg(a, "batched_arena", True):
+            if not two_player:
+                # Arena.playGamesForSinglePlayer (Arena.py:166-247): both models play arenaCompare episodes, pairs are scored
+                from .pit import BatchedSinglePlayerArena
+                factory = (lambda g: self._arena_factory(g)) if self._arena_factory else None
+                pwins, nwins, draws = BatchedSinglePlayerArena(self.game, self.pnet, self.nnet, a, arena_factory=factory).playGames(n_arena)
+            elif on_device and arg(a, "batched_arena", True):
                 # all arenaCompare games in flight at once (pit.BatchedArena; per-game trees instead of the reference's
                 # persistent pair -- set args.batched_arena = False for the sequential reference semantics)
                 from .pit import BatchedArena
@@ -257,7 +290,10 @@ class Coach:
             log.info("NEW/PREV WINS : %d / %d ; DRAWS : %d" % (nwins, pwins, draws))
             accept = i == 1 or ((pwins + nwins > 0) and float(nwins) / (pwins + nwins) >= arg(a, "updateThreshold"))
             if not accept:
-                self.nnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
+                if on_device and hasattr(self.pnet, "nnet"):
+                    self._copy_weights(self.nnet, self.pnet)  # pnet holds temp.pth.tar's weights on every rank
+                else:
+                    self.nnet.load_checkpoint(folder=folder, filename="temp.pth.tar")
             elif rank == 0:
                 best = "best_gnn.pth.tar" if self._use_gnn() else "best.pth.tar"
                 self.nnet.save_checkpoint(folder=folder, filename=self.getCheckpointFile(i))

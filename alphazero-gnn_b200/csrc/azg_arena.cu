@@ -71,6 +71,13 @@ __global__ void arena_reset_kernel(AzgArenaView a, const int32_t* ids, int count
   }
 }
 
+__global__ void arena_copy_kernel(AzgArenaView d, AzgArenaView s) {
+  const int g = blockIdx.x;  // one CTA per game
+  azg_copy_game_nodes(d, s, g, (int)threadIdx.x, (int)blockDim.x);
+  __syncthreads();
+  if (threadIdx.x == 0) azg_copy_game_finish(d, s, g);
+}
+
 __global__ void arena_set_roots_kernel(AzgArenaView a, const AzgState* s) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < a.G) a.root[g] = s[g];
@@ -151,7 +158,7 @@ int azg_arena_create(azg_arena** out, int game, int n, int n_games, int capacity
   memset(a, 0, sizeof(*a));
   if (azg_rules_init(&a->view.rules, game, n, fl_map)) {
     delete a;
-    azg_set_error("azg_arena_create: unsupported game %d / board size %d (2..8)%s", game, n,
+    azg_set_error("azg_arena_create: unsupported game %d / board size %d (Connect4, FrozenLake 2..8; TicTacToe 2..5: at most 32 actions)%s", game, n,
                   game == AZG_GAME_FROZENLAKE && !fl_map ? " / missing map" : "");
     return AZG_ERR_INVALID;
   }
@@ -188,6 +195,16 @@ int azg_arena_reset(azg_arena* a, const int32_t* game_ids, int count, azg_stream
   if (!game_ids) count = a->view.G;
   if (count <= 0) return AZG_OK;
   arena_reset_kernel<<<count, 256, 0, (cudaStream_t)stream>>>(a->view, game_ids, count);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
+int azg_arena_copy_from(azg_arena* dst, const azg_arena* src, azg_stream stream) {
+  AZG_REQUIRE(dst && src && dst != src, "azg_arena_copy_from: bad arenas");
+  const AzgArenaView &d = dst->view, &s = src->view;
+  AZG_REQUIRE(dst->game == src->game && dst->n == src->n && d.G == s.G && d.A == s.A && d.max_depth >= s.max_depth && d.cap >= s.cap,
+              "azg_arena_copy_from: the destination must be the same game with at least the source's capacity (%d < %d?)", d.cap, s.cap);
+  arena_copy_kernel<<<d.G, 256, 0, (cudaStream_t)stream>>>(d, s);
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }

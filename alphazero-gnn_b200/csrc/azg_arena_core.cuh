@@ -426,6 +426,49 @@ AZG_HD void azg_advance_game(const AzgArenaView& a, int g, int action, double* e
   ended_tag[g] = (int8_t)e.tag;
 }
 
+// ---- table growth: copy game g from `s` into the larger `d` (same game, A, max_depth; d.cap >= s.cap) ------------
+// part 1 (any number of lanes): clear d's hash slots and copy the node and edge arrays verbatim (node indices are kept)
+AZG_HD void azg_copy_game_nodes(const AzgArenaView& d, const AzgArenaView& s, int g, int lane, int lanes) {
+  int32_t* hs = d.hslot + (size_t)g * d.hcap;
+  for (int i = lane; i < d.hcap; i += lanes) hs[i] = 0;
+  const int count = s.node_count[g];
+  const size_t sn = (size_t)g * s.cap, dn = (size_t)g * d.cap, A = (size_t)s.A;
+  for (int i = lane; i < count; i += lanes) {
+    d.key[dn + i] = s.key[sn + i];
+    d.es[dn + i] = s.es[sn + i];
+    d.es_tag[dn + i] = s.es_tag[sn + i];
+    d.ns[dn + i] = s.ns[sn + i];
+    d.valids[dn + i] = s.valids[sn + i];
+    d.ptag[dn + i] = s.ptag[sn + i];
+    for (size_t e = 0; e < A; ++e) {
+      d.P[(dn + i) * A + e] = s.P[(sn + i) * A + e];
+      d.Q[(dn + i) * A + e] = s.Q[(sn + i) * A + e];
+      d.qtag[(dn + i) * A + e] = s.qtag[(sn + i) * A + e];
+      d.N[(dn + i) * A + e] = s.N[(sn + i) * A + e];
+    }
+  }
+}
+// part 2 (one lane, after part 1 is complete): per-game scalars, the search path, and the hash rebuilt for d.hcap
+AZG_HD void azg_copy_game_finish(const AzgArenaView& d, const AzgArenaView& s, int g) {
+  d.root[g] = s.root[g];
+  d.sims_left[g] = s.sims_left[g];
+  d.node_count[g] = s.node_count[g];
+  d.pending[g] = s.pending[g];
+  d.path_len[g] = s.path_len[g];
+  d.status[g] = s.status[g];
+  for (int i = 0; i < s.path_len[g] && i < d.max_depth; ++i) {
+    d.path_node[(size_t)g * d.max_depth + i] = s.path_node[(size_t)g * s.max_depth + i];
+    d.path_act[(size_t)g * d.max_depth + i] = s.path_act[(size_t)g * s.max_depth + i];
+  }
+  int32_t* hs = d.hslot + (size_t)g * d.hcap;
+  const AzgState* keys = d.key + (size_t)g * d.cap;
+  for (int i = 0; i < s.node_count[g]; ++i) {
+    uint32_t slot = (uint32_t)azg_hash(keys[i]) & (uint32_t)(d.hcap - 1);
+    while (hs[slot] != 0) slot = (slot + 1) & (uint32_t)(d.hcap - 1);
+    hs[slot] = i + 1;
+  }
+}
+
 // ---- memory carve-up shared by device and host builds -------------------------------------
 static inline size_t azg_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

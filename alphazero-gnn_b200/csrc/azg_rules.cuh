@@ -44,6 +44,9 @@ static inline int azg_rules_init(AzgRules* r, int game, int n, const uint8_t* fl
       }
   } else if (game == AZG_GAME_TICTACTOE) {
     r->A = n * n + 1;  // TicTacToeGame.py:141-143
+    // valid-move masks (azg_valids, AzgArenaView::valids, the exported Vs) are 32-bit: boards whose action count does
+    // not fit (n >= 6: 37+ actions) are refused here, loudly, instead of silently dropping the high cells
+    if (r->A > 32) return 1;
     int k = 0;
     for (int y = 0; y < n; ++y) {  // Board.is_win :66-75: fixed y, all x
       uint64_t m = 0;

@@ -391,7 +391,10 @@ class MCTS:
 
     def __init__(self, game, nnet, args, arena=None, capacity=None, max_depth=None):
         self.game, self.nnet, self.args = game, nnet, args
-        if capacity is None:  # the table persists for as long as the object lives (Coach.py:128-142 reuses it)
+        if capacity is None:
+            # The table persists for as long as the object lives and the reference reuses one object across all
+            # arenaCompare games (Coach.py:128-142): this is only the INITIAL size -- `_ensure_capacity` re-homes the
+            # table in an arena twice as large whenever the next call could fill it (the reference's dicts are unbounded).
             n = game.getBoardSize()[0]
             capacity = max(4096, 4 * (int(arg(args, "numMCTSSims")) + 5) * (n * n + 1))
         self._b = BatchedMCTS(game, nnet, args, n_games=1, arena=arena, capacity=capacity, max_depth=max_depth)
@@ -400,11 +403,20 @@ class MCTS:
     standard_predictions = property(lambda self: self._b.standard_predictions[0])
     gnn_predictions = property(lambda self: self._b.gnn_predictions[0])
 
+    def _ensure_capacity(self, new_nodes):
+        """every search call adds at most one table entry (MCTS.py:154-155, 162-188)"""
+        ar = self._b.arena
+        used = ar.node_count(0)
+        if used + new_nodes + 1 > ar.capacity:
+            ar.grow(max(2 * ar.capacity, used + 4 * (new_nodes + 1)))
+
     def getActionProb(self, canonicalBoard, temp=1):
+        self._ensure_capacity(int(arg(self.args, "numMCTSSims")))
         self._b.set_root_boards([canonicalBoard])
         return self._b.getActionProbs(temp)[0]
 
     def expand_tree(self, canonicalBoard, expand_by=5):
+        self._ensure_capacity(int(arg(self.args, "numMCTSSims")) + int(expand_by))
         self._b.set_root_boards([canonicalBoard])
         self.expanded = True
         res = self._b.expand_tree(expand_by)[0]
@@ -413,6 +425,7 @@ class MCTS:
         return self.expanded_nodes
 
     def search(self, canonicalBoard):
+        self._ensure_capacity(1)
         self._b.set_root_boards([canonicalBoard])
         self._b.search(1)
 

@@ -98,7 +98,7 @@ class BatchedSelfPlay:
         self.max_episode_steps = max_episode_steps
         self.moves_played = 0
         self.episodes_done = 0
-        self._budget = None
+        self._keep_below = None  # play(n): only episodes whose START index is below n contribute (see play)
         if self.device_collect:
             from .replay import DeviceExamples, DeviceGnnExamples
             dev = self.mcts.arena.device if hasattr(self.mcts.arena, "device") else torch.device("cuda", torch.cuda.current_device())
@@ -129,6 +129,9 @@ class BatchedSelfPlay:
         self.step = np.zeros(G, dtype=np.int64)      # episodeStep (Coach.py:32-35)
         self.player = np.ones(G, dtype=np.int64)     # curPlayer
         self.history = [[] for _ in range(G)]        # per game: (canonical board, player, pi, gnn record)
+        self.ep_index = np.arange(G, dtype=np.int64)  # episodes are numbered in the order they START
+        self._next_ep = G
+        self.last_done_index = np.zeros(0, dtype=np.int64)
 
     def _restart(self, ids):
         ids = np.asarray(ids, dtype=np.int32)
@@ -138,6 +141,8 @@ class BatchedSelfPlay:
         self.mcts.arena.set_roots(roots)
         self.step[ids] = 0
         self.player[ids] = 1
+        self.ep_index[ids] = self._next_ep + np.arange(len(ids))
+        self._next_ep += len(ids)
         for g in ids:
             self.history[g] = []
 
@@ -253,12 +258,11 @@ class BatchedSelfPlay:
             for g in done:
                 out.append(self._finish(g, ended[g]) if self.collect else ([], []))
         keep, lens, cur = [], None, None
+        self.last_done_index = self.ep_index[done].copy() if done else np.zeros(0, dtype=np.int64)
         if self.device_collect and done:
-            # `play(n)` keeps exactly n episodes (the reference runs numEps of them): later finishers of the same
-            # move-step are restarted without contributing examples
-            keep = done if self._budget is None else done[:max(self._budget, 0)]
-            if self._budget is not None:
-                self._budget -= len(keep)
+            # `play(n)` keeps the n episodes that STARTED first, however long they take (the reference plays numEps
+            # episodes one after the other; keeping the first n to FINISH would favour short games)
+            keep = done if self._keep_below is None else [g for g in done if self.ep_index[g] < self._keep_below]
             lens, cur = self.step[keep].copy(), self.player[keep].copy()
         if done:
             self.episodes_done += len(done)
@@ -271,7 +275,9 @@ class BatchedSelfPlay:
                 for dst, src in zip(self.g_rec, m.expand_tree_records(readback)):
                     dst[th, gh] = src
             if done:
-                out = (self._finish_device(keep, ended, lens, cur) if keep else []) + [([], []) for _ in done[len(keep):]]
+                if keep:
+                    self._finish_device(keep, ended, lens, cur)
+                out = [([], []) for _ in done]
         return out
 
     def _expand_only(self, check=True):
@@ -282,10 +288,15 @@ class BatchedSelfPlay:
         return None
 
     def play(self, n_episodes):
-        """Run until n_episodes episodes have finished; returns their example lists."""
-        finished = []
-        self._budget = n_episodes if self.device_collect else None
-        while len(finished) < n_episodes:
-            finished.extend(self.step_all())
-        self._budget = None
-        return finished[:n_episodes]
+        """The n_episodes episodes that START first (slots restart as their games end, episodes are numbered in start
+        order), whatever their length: runs until all of them have finished and returns their example lists in the order
+        they finished (the order the device buffers are appended in).  Episodes started later are played to keep the
+        batch full but contribute nothing -- taking the first n to FINISH instead would bias the training set towards
+        short, decisive games (the reference plays numEps episodes sequentially, Coach.py:95-100)."""
+        kept = []
+        self._keep_below = n_episodes
+        while len(kept) < n_episodes:
+            out = self.step_all()
+            kept.extend(ex for idx, ex in zip(self.last_done_index, out) if idx < n_episodes)
+        self._keep_below = None
+        return kept

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AZG_ABI_VERSION 1
+#define AZG_ABI_VERSION 2
 
 #define AZG_OK 0
 #define AZG_ERR_INVALID 1   /* bad argument */
@@ -277,6 +277,11 @@ int azg_arena_create(azg_arena** out, int game, int n, int n_games, int capacity
                      double cpuct, void* device_mem, size_t device_bytes, const uint8_t* fl_map,
                      azg_stream stream);
 int azg_arena_destroy(azg_arena* a);
+/* Table growth: the reference's dicts are unbounded (MCTS.py:15-21) and Coach / Arena reuse one MCTS object across all
+ * arenaCompare games (Coach.py:128-142), so a table can outgrow any fixed capacity.  Copies every game of `src` (nodes,
+ * edges, per-game search state) into `dst`, an arena of the same game / n_games / max_depth created with a larger
+ * capacity_nodes, and rebuilds the hash for the new size; node indices are preserved. */
+int azg_arena_copy_from(azg_arena* dst, const azg_arena* src, azg_stream stream);
 int azg_arena_action_size(const azg_arena* a);
 /* new MCTS object for the listed games (Coach.py:96): clear their tables.  game_ids: device
  * int32 [count], or NULL = all games. */

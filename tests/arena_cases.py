@@ -204,15 +204,25 @@ def case_rules(rules_eval, tag):
 
 
 def case_capacity_overflow(make_arena):
+    """A fixed-capacity table (BatchedMCTS, the self-play path sizes it per episode) reports overflow loudly; the
+    drop-in single-game MCTS object, whose table lives as long as the object, grows instead (azg_arena_copy_from)."""
+    from azgnn_b200.mcts import BatchedMCTS
     name, game, n = _mk_game("c4_7")
-    arena = make_arena(name, n, 1, 10, 1.0, capacity=5)
-    m = MCTS(game, FakeNet(8, salt=9), dotdict(dict(numMCTSSims=20, cpuct=1.0, use_gnn=False)), arena=arena)
+    args = dotdict(dict(numMCTSSims=20, cpuct=1.0, use_gnn=False))
+    b = BatchedMCTS(game, FakeNet(8, salt=9), args, n_games=1, arena=make_arena(name, n, 1, 10, 1.0, capacity=5))
+    b.set_root_boards([game.getInitBoard()])
     try:
-        m.getActionProb(game.getInitBoard(), 1)
+        b.getActionProbs(1)
     except RuntimeError as e:
         assert "table full" in str(e)
     else:
         raise AssertionError("capacity overflow was not reported")
+    arena = make_arena(name, n, 1, 10, 1.0, capacity=5)
+    m = MCTS(game, FakeNet(8, salt=9), args, arena=arena)
+    got = m.getActionProb(game.getInitBoard(), 1)
+    assert arena.capacity > 5 and abs(sum(got) - 1.0) < 1e-12
+    roomy = MCTS(game, FakeNet(8, salt=9), args, arena=make_arena(name, n, 1, 10, 1.0, capacity=4096))
+    assert list(roomy.getActionProb(game.getInitBoard(), 1)) == list(got)  # growth does not change the search
 
 
 def case_compact_lockstep(make_arena, tag="c4_7", G=7, moves=5, sims=14):

@@ -377,8 +377,117 @@ def gen_mcts_fl(n):
     print(f"  frozenlake {n}x{n}: {done} simulations completed before the first cycle")
 
 
+# ------------------------------------------------------------------------------------ example pipeline
+def gen_symmetries():
+    """getSymmetries of every game on seeded boards and policies, all forms in the reference's order (the Connect4
+    mirror with its axis quirk Connect4Game.py:189-215, the TicTacToe 8-fold order TicTacToeGame.py:187-200)."""
+    rng = np.random.default_rng(77)
+    for tag, game in [("c4_5", Connect4Game(5)), ("c4_7", Connect4Game(7)), ("ttt_3", TicTacToeGame(3)), ("ttt_4", TicTacToeGame(4)),
+                      ("fl_4", FrozenLakeGame(4)), ("fl_8", FrozenLakeGame(8))]:
+        n, A = game.getBoardSize()[0], game.getActionSize()
+        boards, pis, fb, fp = [], [], [], []
+        for _ in range(8):
+            if tag.startswith("fl"):
+                b = np.zeros((n, n)); b.reshape(-1)[rng.integers(0, n * n)] = 1
+            else:
+                b = rng.integers(-1, 2, size=(n, n)).astype(np.int64)
+            pi = list(rng.dirichlet(np.ones(A)))
+            forms = game.getSymmetries(b, pi)
+            boards.append(b); pis.append(np.asarray(pi))
+            fb.append(np.stack([np.asarray(x[0]) for x in forms])); fp.append(np.stack([np.asarray(x[1], dtype=np.float64) for x in forms]))
+        save("sym_" + tag, boards=np.stack(boards), pis=np.stack(pis), form_boards=np.stack(fb), form_pis=np.stack(fp))
+
+
+class FakeWrapper:
+    """NeuralNet-shaped holder of the fake net; Coach.__init__ clones it through `nnet.__class__(game, args)` (Coach.py:21)."""
+
+    def __init__(self, game, args):
+        self.net = FakeNet(game.getActionSize(), salt=args.fake_salt, spread=args.fake_spread)
+
+    def predict(self, b):
+        return self.net.predict(b)
+
+    def predict_with_gnn(self, b):
+        return self.net.predict_with_gnn(b)
+
+
+def gen_coach_episode(tag, Game, n, args, seed):
+    """One whole Coach.executeEpisode of the UNMODIFIED reference Coach (Coach.py:27-79) under the fake net: the
+    per-move inputs of getSymmetries (canonical board, pi, player to move) and the returned example tuples -- standard
+    examples (board, pi, signed value) and GNN examples (board, player, initial pi / v, expanded pi / v, signed value),
+    values with their Python / NumPy types."""
+    from Coach import Coach
+    moves = []
+
+    class Recording(Game):
+        def getSymmetries(self, board, pi):
+            moves.append((np.array(board, copy=True), np.asarray(pi, dtype=np.float64), coach.curPlayer,
+                          all(isinstance(x, (int, np.integer)) for x in pi)))
+            return super().getSymmetries(board, pi)
+    game = Recording(n)
+    coach = Coach(game, FakeWrapper(game, args), args)
+    np.random.seed(seed)
+    std, gnn = coach.executeEpisode()
+    out = dict(n=n, seed=seed, final_player=coach.curPlayer,
+               move_boards=np.stack([m[0] for m in moves]), move_pis=np.stack([m[1] for m in moves]),
+               move_players=np.array([m[2] for m in moves]), move_pi_is_int=np.array([m[3] for m in moves]),
+               std_boards=np.stack([np.asarray(e[0]) for e in std]), std_pis=np.stack([np.asarray(e[1], dtype=np.float64) for e in std]),
+               std_pi_is_list=np.array([isinstance(e[1], list) for e in std]),
+               std_v=np.array([float(e[2]) for e in std]), std_v_type=np.array([vtype(e[2]) for e in std]),
+               numMCTSSims=args.numMCTSSims, cpuct=float(args.cpuct), expand_by=args.expand_by, tempThreshold=args.tempThreshold,
+               use_gnn=bool(args.use_gnn), fake_salt=args.fake_salt, fake_spread=float(args.fake_spread))
+    if gnn:
+        out.update(gnn_boards=np.stack([np.asarray(e[0]) for e in gnn]), gnn_players=np.array([e[1] for e in gnn]),
+                   gnn_ip=np.stack([np.asarray(e[2], dtype=np.float64) for e in gnn]), gnn_iv=np.array([float(e[3]) for e in gnn]),
+                   gnn_iv_type=np.array([vtype(e[3]) for e in gnn]),
+                   gnn_ep=np.stack([np.asarray(e[4], dtype=np.float64) for e in gnn]),
+                   gnn_ev=np.array([float(np.asarray(e[5])) for e in gnn]), gnn_ev_type=np.array([vtype(e[5]) for e in gnn]),
+                   gnn_r=np.array([float(e[6]) for e in gnn]), gnn_r_type=np.array([vtype(e[6]) for e in gnn]))
+    save("coach_" + tag, **out)
+    return coach, std, gnn
+
+
+def gen_reference_files():
+    """Files written by the reference's OWN writers, committed as fixtures: a `{'state_dict','gnn'}`
+    checkpoint (TicTacToeGNN.py save_checkpoint, 3x3: 2 MB) with the reference wrapper's predictions for those weights,
+    and the pickled `.examples` history of one episode (Coach.py:178-185)."""
+    import shutil
+    folder = os.path.join(HERE, "ref_files")
+    shutil.rmtree(folder, ignore_errors=True)
+    os.makedirs(folder)
+    args = dotdict(dict(lr=1e-3, dropout=0.3, epochs=1, batch_size=64, gnn_layers=2, use_gnn=True, numMCTSSims=8, cpuct=1.0,
+                        tempThreshold=15, expand_by=3, checkpoint=folder, fake_salt=9, fake_spread=1.0,
+                        numItersForTrainExamplesHistory=20, maxlenOfQueue=200000))
+    game = TicTacToeGame(3)
+    torch.manual_seed(5)
+    w = TicTacToeGNNWrapper(game, args)
+    with torch.no_grad():  # not the seed-0 initialisation every other fixture uses: a loaded file must change the outputs
+        for p_ in list(w.nnet.parameters()) + list(w.gnn.parameters()):
+            p_.add_(0.01 * torch.randn_like(p_))
+    w.save_checkpoint(folder, "best_gnn.pth.tar")
+    rng = np.random.default_rng(3)
+    boards = random_boards(3, 16, rng)
+    pis, vs, gpis, gvs = [], [], [], []
+    for b in boards:
+        pi, v = w.predict(b); gpi, gv = w.predict_with_gnn(b)
+        pis.append(pi); vs.append(v); gpis.append(gpi); gvs.append(gv)
+    names = sorted(w.nnet.state_dict().keys()); gnames = sorted(w.gnn.state_dict().keys())
+    # the .examples file: one reference episode's tuples through the reference's own pickler
+    from collections import deque
+    coach, std, gnn = gen_coach_episode("ttt_3_file", TicTacToeGame, 3, args, seed=31)
+    coach.trainExamplesHistory.append((deque(std, maxlen=args.maxlenOfQueue), deque(gnn, maxlen=args.maxlenOfQueue)))
+    coach.saveTrainExamples(0)
+    save("ref_files_index", boards=boards, pi=np.stack(pis), v=np.array(vs), gnn_pi=np.stack(gpis), gnn_v=np.array(gvs),
+         nnet_names=np.array(names), nnet_shapes=np.array([str(tuple(w.nnet.state_dict()[k].shape)) for k in names]),
+         gnn_names=np.array(gnames), gnn_shapes=np.array([str(tuple(w.gnn.state_dict()[k].shape)) for k in gnames]),
+         checkpoint_file="best_gnn.pth.tar", examples_file=coach.getCheckpointFile(0) + ".examples",
+         n_std=len(std), n_gnn=len(gnn))
+    for f in sorted(os.listdir(folder)):
+        print(f"  ref_files/{f}: {os.path.getsize(os.path.join(folder, f))/1024:.1f} KiB")
+
+
 def main():
-    which = sys.argv[1:] or ["rules", "nets", "mcts"]
+    which = sys.argv[1:] or ["rules", "nets", "mcts", "coach"]
     if "rules" in which:
         gen_rules()
     if "nets" in which:
@@ -402,6 +511,14 @@ def main():
         gen_mcts_known_answer()
         gen_mcts_fl(4)
         gen_mcts_fl(8)
+    if "coach" in which:
+        gen_symmetries()
+        base = dict(cpuct=1.0, tempThreshold=15, expand_by=5, fake_spread=1.0)
+        gen_coach_episode("c4_7_gnn", Connect4Game, 7, dotdict(dict(base, numMCTSSims=10, use_gnn=True, fake_salt=21)), seed=41)
+        gen_coach_episode("c4_5_std", Connect4Game, 5, dotdict(dict(base, numMCTSSims=12, use_gnn=False, fake_salt=22, tempThreshold=4)), seed=42)
+        gen_coach_episode("ttt_3_gnn", TicTacToeGame, 3, dotdict(dict(base, numMCTSSims=20, use_gnn=True, fake_salt=23, tempThreshold=3)), seed=43)
+        gen_coach_episode("ttt_4_gnn", TicTacToeGame, 4, dotdict(dict(base, numMCTSSims=10, use_gnn=True, fake_salt=24)), seed=44)
+        gen_reference_files()
 
 
 if __name__ == "__main__":

@@ -64,6 +64,16 @@ int azgh_arena_create(azgh_arena** out, int game, int n, int n_games, int cap, i
 int azgh_arena_destroy(azgh_arena* a) { delete a; return 0; }
 int azgh_arena_action_size(const azgh_arena* a) { return a->view.A; }
 
+int azgh_arena_copy_from(azgh_arena* dst, const azgh_arena* src, void*) {
+  const AzgArenaView &d = dst->view, &s = src->view;
+  if (d.G != s.G || d.A != s.A || d.max_depth < s.max_depth || d.cap < s.cap) { azg_set_error("copy_from: incompatible arenas"); return AZG_ERR_INVALID; }
+  for (int g = 0; g < d.G; ++g) {
+    azg_copy_game_nodes(d, s, g, 0, 1);
+    azg_copy_game_finish(d, s, g);
+  }
+  return 0;
+}
+
 int azgh_arena_set_roots(azgh_arena* a, const uint64_t* s, void*) {
   memcpy(a->view.root, s, sizeof(AzgState) * a->view.G);
   return 0;

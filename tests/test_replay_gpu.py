@@ -169,3 +169,38 @@ def test_coach_learn_keeps_examples_on_device_and_pickles_the_reference_format(t
     g2 = c2.trainExamplesHistory[0][1]
     for name, _d, _p in DeviceGnnExamples.COLS:
         assert torch.equal(getattr(g2, name), getattr(gnn, name)), name
+
+
+@pytest.mark.parametrize("tag", ["c4_7_gnn", "c4_5_std", "ttt_3_gnn", "ttt_4_gnn"])
+def test_emit_reproduces_the_reference_episode(tag):
+    """azg_emit_examples fed the per-move (canonical board, pi, player) records of one whole episode of the UNMODIFIED
+    reference Coach (tests/golden/coach_*.npz, written by make_golden.py) returns the reference's own standard example
+    tuples: symmetric boards in the reference's order (the Connect4 mirror with its axis quirk, the TicTacToe 8-fold
+    order), policies, signed values and value / policy container types (Coach.py:43-45, 68-79)."""
+    from helpers import golden
+    g = golden("coach_" + tag)
+    kind, n = tag.split("_")[:2]
+    game = _game(kind, int(n))
+    ex = DeviceExamples(game)
+    dev = ex.device
+    E = g["move_boards"].shape[0]
+    final = int(g["final_player"])
+    # the value every stored position gets is r * (-1)^(player != final player); r from the last standard example
+    last_same = int(g["move_players"][-1]) == final
+    r = float(g["std_v"][-1]) * (1.0 if last_same else -1.0)
+    rtag = {1: _lib.TAG_PYFLOAT, 2: _lib.TAG_PYINT, 0: _lib.TAG_F32}[int(g["std_v_type"][-1])]
+    ex.emit(torch.as_tensor(pack_states(ex.kind, g["move_boards"])).to(dev), torch.as_tensor(g["move_pis"]).to(dev),
+            torch.as_tensor(g["move_players"].astype(np.int32)).to(dev), torch.zeros(E, dtype=torch.int32, device=dev),
+            torch.tensor([r], dtype=torch.float64, device=dev), torch.tensor([rtag], dtype=torch.int8, device=dev),
+            torch.tensor([final], dtype=torch.int32, device=dev),
+            pi_int=torch.as_tensor(g["move_pi_is_int"].astype(np.int8)).to(dev))
+    got = ex.to_examples()
+    assert len(got) == g["std_boards"].shape[0]
+    for i, (b, p, v) in enumerate(got):
+        assert np.array_equal(b, g["std_boards"][i]) and b.dtype == g["std_boards"].dtype, i
+        assert np.array_equal(np.asarray(p, dtype=np.float64), g["std_pis"][i]), i
+        assert isinstance(p, list) == bool(g["std_pi_is_list"][i]), i
+        assert float(v) == g["std_v"][i], (i, v, g["std_v"][i])
+        want_t = int(g["std_v_type"][i])
+        assert (isinstance(v, int) and want_t == 2) or (isinstance(v, float) and not isinstance(v, np.floating) and want_t == 1) or \
+            (isinstance(v, np.float32) and want_t == 0), (i, type(v), want_t)
