@@ -90,8 +90,149 @@ struct Smem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
 };
 
+// Epilogue of one accumulator tile for the calling thread's row (TMEM lane): side tile (standard heads) or main tile in
+// any output mode.  `taddr` = this warp's lane quarter at the accumulator's first column; `release()` hands the
+// accumulator back to the MMA issuer as soon as its last TMEM read is done.
+// `grp` of `ngrp` epilogue groups (four warps each) takes every ngrp-th 32-column chunk of the tile; the partial head sums
+// of a group go to slot nt * ngrp + grp of the row (fixed-order reduction in heads_finalize).
+template <int BN, bool TWO, class Release>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr, int mt, int nt, int r_local, int grp, int ngrp,
+                                              Release release) {
+      const int64_t row = (int64_t)mt * BM + r_local;
+      const int NKB = (g.n_tiles * BN) / BK;  // k-blocks of the output image
+      if (TWO && nt == g.n_tiles) {  // side tile: SIDE_N fp32 columns + bias, row-major (one chunk: group 0)
+        if (grp != 0) {
+          release();
+          return;
+        }
+        uint32_t rr[32];
+        tmem_ld32(taddr, rr);
+        tmem_ld_wait();
+        tc_fence_before();
+        release();
+        if (row < g.M) {
+          float4* dst = reinterpret_cast<float4*>(g.side_out + row * SIDE_N);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.side_bias) + j);
+            dst[j] = make_float4(__uint_as_float(rr[4 * j]) + b4.x, __uint_as_float(rr[4 * j + 1]) + b4.y,
+                                 __uint_as_float(rr[4 * j + 2]) + b4.z, __uint_as_float(rr[4 * j + 3]) + b4.w);
+          }
+        }
+        return;
+      }
+      float hacc[HEAD_ROWS];
+#pragma unroll
+      for (int a = 0; a < HEAD_ROWS; ++a) hacc[a] = 0.0f;
+#pragma unroll 1
+      for (int c0 = grp * 32; c0 < BN; c0 += 32 * ngrp) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + (uint32_t)c0, rr);
+        const int n0 = nt * BN + c0;
+        float4 b4[8];  // the chunk's bias (warp-uniform addresses): 8 vector loads in flight under the TMEM load
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j] = __uint_as_float(rr[4 * j]) + b4[j].x;
+          v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + b4[j].y;
+          v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + b4[j].z;
+          v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + b4[j].w;
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (g.out_mode == OUT_HEADS) {
+          // policy/value heads fused into the epilogue (Connect4GNN.py:48-57): this tile's share of
+          // logits[a] = sum_n E[row, n] * Wh[a, n]; the head weights are warp-uniform loads
+          const int N = g.n_tiles * BN;
+#pragma unroll
+          for (int a = 0; a < HEAD_ROWS; ++a) {
+            if (a < g.head_rows) {
+              const float4* wr = reinterpret_cast<const float4*>(g.head_w + (size_t)a * N + n0);
+              float s = hacc[a];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w4 = __ldg(wr + j);
+                s = fmaf(v[4 * j], w4.x, fmaf(v[4 * j + 1], w4.y, fmaf(v[4 * j + 2], w4.z, fmaf(v[4 * j + 3], w4.w, s))));
+              }
+              hacc[a] = s;
+            }
+          }
+        } else if (g.out_mode >= OUT_FEAT) {
+          if (row < g.M) {
+            const int64_t bidx = row / g.feat_nn;
+            const int p = (int)(row - bidx * g.feat_nn);
+            const size_t tile = ((size_t)(bidx >> 7) * g.feat_nn + p) * A_STAGE_BYTES;
+            const int rb = (int)(bidx & 127);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                split_pair(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1], hi[e], lo[e]);
+              }
+              const size_t off = tile + image_offset(rb, c0 + c * 8);
+              *reinterpret_cast<uint4*>(g.out_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              if (g.out_mode == OUT_FEAT_HILO) *reinterpret_cast<uint4*>(g.out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        } else if (g.out_mode == OUT_F32) {
+          if (row < g.M) {
+            float4* dst = reinterpret_cast<float4*>(g.out_f32 + row * (int64_t)(g.n_tiles * BN) + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else {
+          // next GEMM's A operand: columns are its K index; 32 columns = 4 x 16-byte chunks of one image row
+          const int kb = n0 / BK, koff = n0 % BK;
+          const size_t tile = ((size_t)mt * NKB + kb) * A_STAGE_BYTES;
+          if (TWO && g.f8) {  // fp16 image + FP8 correction rows [2^sa h | 2^(sa+11) h_lo], 16 elements per 16-byte chunk
+            const float s_main = (float)(1 << F8_A_SCALE), s_lo = (float)(1 << (F8_A_SCALE + F8_LO_SHIFT));
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint4 h0, h1;
+              uint2 m0, m1, l0, l1;
+              split8_f16f8(v + c * 16, s_main, s_lo, h0, m0, l0);
+              split8_f16f8(v + c * 16 + 8, s_main, s_lo, h1, m1, l1);
+              const int k0 = koff + c * 16;
+              *reinterpret_cast<uint4*>(g.out_hi + tile + image_offset(r_local, k0)) = h0;
+              *reinterpret_cast<uint4*>(g.out_hi + tile + image_offset(r_local, k0 + 8)) = h1;
+              *reinterpret_cast<uint4*>(g.out_lo + tile + image_offset_bytes(r_local, k0)) = make_uint4(m0.x, m0.y, m1.x, m1.y);
+              *reinterpret_cast<uint4*>(g.out_lo + tile + image_offset_bytes(r_local, 64 + k0)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            }
+            continue;
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              split_pair(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1], hi[e], lo[e]);
+            }
+            const size_t off = tile + image_offset(r_local, koff + c * 8);
+            *reinterpret_cast<uint4*>(g.out_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (g.out_mode == OUT_IMG_HILO) *reinterpret_cast<uint4*>(g.out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      release();  // the accumulator is back with the MMA issuer (the partial head sums still go out below)
+      if (g.out_mode == OUT_HEADS && row < g.M) {
+        float* dst = g.head_part + ((size_t)row * (g.n_tiles * ngrp) + nt * ngrp + grp) * HEAD_STRIDE;
+#pragma unroll
+        for (int a = 0; a < HEAD_ROWS; ++a)
+          if (a < g.head_rows) dst[a] = hacc[a];
+      }
+}
+
+constexpr int EPI_GROUPS = 2;                           // epilogue warps 4-7 and 8-11
+constexpr int GEMM_THREADS = 128 + 128 * EPI_GROUPS;     // producer, MMA issuer, TMEM allocator, spare + the epilogue groups
 template <int BN, bool TWO>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B wants 1024-B alignment
   using S = Smem<BN, TWO>;
@@ -123,7 +264,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], TWO ? 256 : 128);
+      mbar_init(&tempty[a], (TWO ? 256 : 128) * EPI_GROUPS);
     }
     fence_barrier_init();
   }
@@ -139,7 +280,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
   if (TWO && g.f8) {
     // uniform block scales: every scale-factor byte the tensor core can read is the same power of two, so the
     // regions are written once (whatever the scale-factor layout) -- A: 2^-(sa+11), W: 2^-sw
-    if (warp >= 4) {
+    if (warp >= 4 && warp < 8) {
       const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
       tmem_st16_const(lane_base + SF_A_COL, ue8m0x4(-(F8_A_SCALE + F8_LO_SHIFT)));
       tmem_st16_const(lane_base + SF_W_COL, ue8m0x4(g.w_exp ? -(*g.w_exp) : 0));
@@ -322,137 +463,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs g
     }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> bias/ReLU -> HBM =================
+    // The epilogue of a 128 x 224 tile takes ~40k cycles with four warps (global loads of bias / head weights and the
+    // scattered image stores), as long as the 8-MMA main loop of the fp16+FP8 split (ncu source view, r02 v1: epilogue
+    // warps busy 68 % of the time, tensor pipe 78 %): two groups of four warps split the tile's 32-column chunks.
     const int q = warp & 3;              // TMEM lane quarter this warp may read
     const int r_local = q * 32 + lane;   // row of the tile == TMEM lane
+    const int grp = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int NKB = (g.n_tiles * BN) / BK;  // k-blocks of the output image
     const uint32_t leader_tempty = TWO ? map_to_cta(&tempty[0], 0) : 0u;
     for (int t = unit; t < total_tiles; t += n_units) {
       const int mt = (t / nt_all) * (TWO ? 2 : 1) + (int)rank, nt = t % nt_all;
-      const int64_t row = (int64_t)mt * BM + r_local;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      if (TWO && nt == g.n_tiles) {  // side tile: SIDE_N fp32 columns + bias, row-major
-        uint32_t rr[32];
-        tmem_ld32(taddr, rr);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive_cluster(leader_tempty + (uint32_t)acc * 8u);
-        if (row < g.M) {
-          float4* dst = reinterpret_cast<float4*>(g.side_out + row * SIDE_N);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.side_bias) + j);
-            dst[j] = make_float4(__uint_as_float(rr[4 * j]) + b4.x, __uint_as_float(rr[4 * j + 1]) + b4.y,
-                                 __uint_as_float(rr[4 * j + 2]) + b4.z, __uint_as_float(rr[4 * j + 3]) + b4.w);
-          }
-        }
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-        continue;
-      }
-      float hacc[HEAD_ROWS];
-#pragma unroll
-      for (int a = 0; a < HEAD_ROWS; ++a) hacc[a] = 0.0f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t rr[32];
-        tmem_ld32(taddr + (uint32_t)c0, rr);
-        tmem_ld_wait();
-        const int n0 = nt * BN + c0;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(rr[j]) + __ldg(g.bias + n0 + j);
-          v[j] = g.relu ? fmaxf(x, 0.0f) : x;
-        }
-        if (g.out_mode == OUT_HEADS) {
-          // policy/value heads fused into the epilogue (Connect4GNN.py:48-57): this tile's share of
-          // logits[a] = sum_n E[row, n] * Wh[a, n]; the head weights are warp-uniform loads
-          const int N = g.n_tiles * BN;
-#pragma unroll
-          for (int a = 0; a < HEAD_ROWS; ++a) {
-            if (a < g.head_rows) {
-              const float4* wr = reinterpret_cast<const float4*>(g.head_w + (size_t)a * N + n0);
-              float s = hacc[a];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 w4 = __ldg(wr + j);
-                s = fmaf(v[4 * j], w4.x, fmaf(v[4 * j + 1], w4.y, fmaf(v[4 * j + 2], w4.z, fmaf(v[4 * j + 3], w4.w, s))));
-              }
-              hacc[a] = s;
-            }
-          }
-        } else if (g.out_mode >= OUT_FEAT) {
-          if (row < g.M) {
-            const int64_t bidx = row / g.feat_nn;
-            const int p = (int)(row - bidx * g.feat_nn);
-            const size_t tile = ((size_t)(bidx >> 7) * g.feat_nn + p) * A_STAGE_BYTES;
-            const int rb = (int)(bidx & 127);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                split_pair(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1], hi[e], lo[e]);
-              }
-              const size_t off = tile + image_offset(rb, c0 + c * 8);
-              *reinterpret_cast<uint4*>(g.out_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              if (g.out_mode == OUT_FEAT_HILO) *reinterpret_cast<uint4*>(g.out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
-        } else if (g.out_mode == OUT_F32) {
-          if (row < g.M) {
-            float4* dst = reinterpret_cast<float4*>(g.out_f32 + row * (int64_t)(g.n_tiles * BN) + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-        } else {
-          // next GEMM's A operand: columns are its K index; 32 columns = 4 x 16-byte chunks of one image row
-          const int kb = n0 / BK, koff = n0 % BK;
-          const size_t tile = ((size_t)mt * NKB + kb) * A_STAGE_BYTES;
-          if (TWO && g.f8) {  // fp16 image + FP8 correction rows [2^sa h | 2^(sa+11) h_lo], 16 elements per 16-byte chunk
-            const float s_main = (float)(1 << F8_A_SCALE), s_lo = (float)(1 << (F8_A_SCALE + F8_LO_SHIFT));
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint4 h0, h1;
-              uint2 m0, m1, l0, l1;
-              split8_f16f8(v + c * 16, s_main, s_lo, h0, m0, l0);
-              split8_f16f8(v + c * 16 + 8, s_main, s_lo, h1, m1, l1);
-              const int k0 = koff + c * 16;
-              *reinterpret_cast<uint4*>(g.out_hi + tile + image_offset(r_local, k0)) = h0;
-              *reinterpret_cast<uint4*>(g.out_hi + tile + image_offset(r_local, k0 + 8)) = h1;
-              *reinterpret_cast<uint4*>(g.out_lo + tile + image_offset_bytes(r_local, k0)) = make_uint4(m0.x, m0.y, m1.x, m1.y);
-              *reinterpret_cast<uint4*>(g.out_lo + tile + image_offset_bytes(r_local, 64 + k0)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-            }
-            continue;
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              split_pair(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1], hi[e], lo[e]);
-            }
-            const size_t off = tile + image_offset(r_local, koff + c * 8);
-            *reinterpret_cast<uint4*>(g.out_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (g.out_mode == OUT_IMG_HILO) *reinterpret_cast<uint4*>(g.out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        }
-      }
-      tc_fence_before();
-      if (TWO) mbar_arrive_cluster(leader_tempty + (uint32_t)acc * 8u);  // 2 x 128 arrivals on the leader's barrier
-      else mbar_arrive(&tempty[acc]);                                    // 128 arrivals release the accumulator
-      if (g.out_mode == OUT_HEADS && row < g.M) {
-        float* dst = g.head_part + ((size_t)row * g.n_tiles + nt) * HEAD_STRIDE;
-#pragma unroll
-        for (int a = 0; a < HEAD_ROWS; ++a)
-          if (a < g.head_rows) dst[a] = hacc[a];
-      }
+      if (TWO) epilogue_tile<BN, TWO>(g, taddr, mt, nt, r_local, grp, EPI_GROUPS, [&] { mbar_arrive_cluster(leader_tempty + (uint32_t)acc * 8u); });
+      else epilogue_tile<BN, TWO>(g, taddr, mt, nt, r_local, grp, EPI_GROUPS, [&] { mbar_arrive(&tempty[acc]); });
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -589,7 +615,7 @@ int launch_gemm_impl(const GemmArgs& g, cudaStream_t st) {
   int grid = TWO ? 2 * (units < sms / 2 ? units : sms / 2) : (units < sms ? units : sms);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -603,6 +629,12 @@ int launch_gemm_impl(const GemmArgs& g, cudaStream_t st) {
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }
+
+
+// Tried and removed (round 2): a variant in which a CTA pair computes two n-tiles per activation stage (256 x 448 super-tile,
+// 44 KB sub-stages, fills 49 instead of 67 B/clk per SM).  Its two 224-column accumulators fill TMEM, so they cannot be
+// double-buffered and the epilogue (tens of thousands of cycles per tile, see the epilogue comment in gemm_bf16_tc_kernel)
+// is exposed: 5.8 ms instead of 4.1 ms for the two contractions.
 
 // the CTA-pair kernel needs BN/2 to be a multiple of 8 rows and an even number of padded m-tiles
 template <int BN>
@@ -619,6 +651,9 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   if (gemm_pair_mode() && g.pair_ok && BN >= 128) return launch_gemm_impl<BN, true>(g, st);
   return launch_gemm_impl<BN, false>(g, st);
 }
+
+// partial head-sum slots per n-tile (one per epilogue group)
+int head_slots_per_tile(const GemmArgs&) { return EPI_GROUPS; }
 
 int run_gemm(int BN, const GemmArgs& g, cudaStream_t st) {
   switch (BN) {
@@ -1396,7 +1431,8 @@ ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
   if (gnn) {
     S.h_hi = take(fimg);
     S.h_lo = x3 ? take(fimg) : 0;
-    S.part = take(Mp * 32 * tc::HEAD_STRIDE * sizeof(float));  // <= 32 n-tiles
+    const int BNp = prec_bn((int)F, prec);
+    S.part = take(Mp * (size_t)(BNp ? 2 * (F / BNp) : 32) * tc::HEAD_STRIDE * sizeof(float));  // two epilogue groups per n-tile
   }
   S.total = off + 1024;
   return S;
@@ -1537,7 +1573,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     azg_phase_end(AZG_PHASE_GEMM, st);
     azg_phase_begin(AZG_PHASE_HEADS, st);
     const float* fb = (const float*)(w + L.fold_b);
-    tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles, A, fb, fb + A, B, dyn_rows,
+    tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles * tc::head_slots_per_tile(g), A, fb, fb + A, B, dyn_rows,
                                                                           pi_gnn, v_gnn);
     AZG_LAUNCH_CHECK();
     if ((rc = finish_std())) return rc;
@@ -1554,7 +1590,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   if ((rc = tc::run_gemm(BN, g, st))) return rc;
   azg_phase_end(AZG_PHASE_GEMM, st);
   azg_phase_begin(AZG_PHASE_HEADS, st);
-  tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles, A, p->fc_policy_b,
+  tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles * tc::head_slots_per_tile(g), A, p->fc_policy_b,
                                                                         p->fc_value_b, B, dyn_rows, pi_gnn, v_gnn);
   AZG_LAUNCH_CHECK();
   if ((rc = finish_std())) return rc;

@@ -47,6 +47,7 @@ class _Columns:
         self.n = game.getBoardSize()[0]
         self.A = game.getActionSize()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._bufs = {}  # name -> storage with spare capacity; the public column is its first len(self) rows
         for name, dtype, per_action in self.COLS:
             shape = (0, 2) if name == "states" else ((0, self.A) if per_action else (0,))
             setattr(self, name, torch.empty(shape, dtype=dtype, device=self.device))
@@ -55,8 +56,34 @@ class _Columns:
         return int(self.states.shape[0])
 
     def _append(self, *cols):
+        """amortised append: storage doubles when full (a `torch.cat` per append re-allocated every column at a new,
+        larger size on every move-step of self-play -- allocator stalls of 50-140 ms once episodes start to end)"""
+        n, k = len(self), int(cols[0].shape[0])
+        if k == 0:
+            return
         for (name, _d, _p), t in zip(self.COLS, cols):
-            setattr(self, name, torch.cat([getattr(self, name), t]))
+            cur = getattr(self, name)
+            buf = self._bufs.get(name)
+            if buf is None or buf.shape[0] < n + k or buf.data_ptr() != cur.data_ptr():
+                cap = max(n + k, 2 * (buf.shape[0] if buf is not None else 0), 4096)
+                buf = torch.empty((cap,) + tuple(cur.shape[1:]), dtype=cur.dtype, device=self.device)
+                buf[:n] = cur
+                self._bufs[name] = buf
+            buf[n:n + k] = t
+            setattr(self, name, buf[:n + k])
+
+    def reserve(self, rows):
+        """storage for `rows` records up front (self-play knows its bound: episodes x plies x symmetries), so that no
+        growth step lands inside a move-step"""
+        n = len(self)
+        for name, _d, _p in self.COLS:
+            cur = getattr(self, name)
+            buf = self._bufs.get(name)
+            if buf is None or buf.shape[0] < rows or buf.data_ptr() != cur.data_ptr():
+                buf = torch.empty((max(int(rows), n),) + tuple(cur.shape[1:]), dtype=cur.dtype, device=self.device)
+                buf[:n] = cur
+                self._bufs[name] = buf
+                setattr(self, name, buf[:n])
 
     def extend(self, other):
         self._append(*[getattr(other, name) for name, _d, _p in self.COLS])
@@ -64,16 +91,31 @@ class _Columns:
     def _like(self, index):
         out = self.__class__.__new__(self.__class__)
         out.__dict__.update(self.__dict__)
+        out._bufs = {}  # never append into storage shared with `self`
         for name, _d, _p in self.COLS:
             setattr(out, name, getattr(self, name)[index])
         return out
 
-    def shuffled(self):
-        """`random.shuffle` of the example list (Coach.py:118): the swaps depend only on the length, so shuffling an
-        index list with the same `random` state gives the permutation the reference's list would get."""
-        idx = list(range(len(self)))
-        random.shuffle(idx)
-        return self._like(torch.as_tensor(idx, dtype=torch.int64, device=self.device))
+    EXACT_SHUFFLE_MAX = 65536
+
+    def shuffled(self, exact=None):
+        """`random.shuffle` of the example list (Coach.py:118).  exact (default for lists of up to EXACT_SHUFFLE_MAX
+        records): the swaps of `random.shuffle` depend only on the length, so shuffling an index list with the same
+        `random` state gives the permutation the reference's list would get.  Longer lists (hundreds of thousands of
+        self-play examples: the Python shuffle of 1.6 M indices took ~1 s per iteration on 8 GPUs) get a device
+        permutation from a generator seeded with 63 bits of the same `random` stream -- still reproducible through
+        `random.seed`, no longer the reference's permutation (minibatches are drawn with replacement from the shuffled
+        list, so only the labelling of the examples changes)."""
+        n = len(self)
+        if exact is None:
+            exact = n <= self.EXACT_SHUFFLE_MAX
+        if exact:
+            idx = list(range(n))
+            random.shuffle(idx)
+            return self._like(torch.as_tensor(idx, dtype=torch.int64, device=self.device))
+        g = torch.Generator(device=self.device)
+        g.manual_seed(random.getrandbits(63))
+        return self._like(torch.randperm(n, generator=g, device=self.device))
 
     def newest(self, maxlen):
         """deque(maxlen) semantics: keep the newest `maxlen` records"""

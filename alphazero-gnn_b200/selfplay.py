@@ -77,7 +77,8 @@ def sample_actions(probs, rng, u=None):
 
 
 class BatchedSelfPlay:
-    def __init__(self, game, nnet, args, n_games, seed=0, collect_examples=True, arena=None, max_episode_steps=None):
+    def __init__(self, game, nnet, args, n_games, seed=0, collect_examples=True, arena=None, max_episode_steps=None,
+                 reserve_episodes=None):
         self.game, self.nnet, self.args = game, nnet, args
         self.G = int(n_games)
         self.use_gnn = bool(arg(args, "use_gnn", False))
@@ -113,6 +114,10 @@ class BatchedSelfPlay:
             self.h_player_host = np.zeros((self.t_cap, self.G), dtype=np.int32)
             self.device_examples = DeviceExamples(game, dev)
             self.device_gnn_examples = DeviceGnnExamples(game, dev)
+            if reserve_episodes:  # an episode stores at most t_cap positions, each in S symmetric forms
+                self.device_examples.reserve(int(reserve_episodes) * self.t_cap * self.device_examples.S)
+                if self.use_gnn:
+                    self.device_gnn_examples.reserve(int(reserve_episodes) * self.t_cap)
             # GNN records (expand_tree, MCTS.py:60-149) per (episode step, game): initial policy, initial value,
             # expanded policy, expanded value payload + type tag -- host arrays, tuples are formed at episode end
             self.g_rec = (np.zeros((self.t_cap, self.G, self.A)), np.zeros((self.t_cap, self.G), dtype=np.float32),

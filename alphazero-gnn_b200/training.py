@@ -296,7 +296,12 @@ def allreduce_grads(params):
             p.grad = torch.zeros_like(p)
     big = [p for p in params if p.grad.numel() >= (1 << 20) and p.grad.is_contiguous()]
     small = [p for p in params if not (p.grad.numel() >= (1 << 20) and p.grad.is_contiguous())]
-    works = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in big]
+    # inside a CUDA-graph capture (the data-parallel step is captured with its collectives) the reductions are enqueued
+    # synchronously with respect to the capturing stream; eager steps overlap them with the small bucket's packing
+    capturing = p.grad.is_cuda and torch.cuda.is_current_stream_capturing()
+    works = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=not capturing) for p in big]
+    if capturing:
+        works = []
     if small:
         flat = torch._utils._flatten_dense_tensors([p.grad for p in small])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
@@ -399,9 +404,21 @@ class _FrozenHeads:
         self.nnet = type("N", (), {k: _L(getattr(n, k)) for k in names})()
 
 
-def _sample(examples, batch_size):
-    """np.random.randint minibatch with replacement (Connect4GNN.py:141,160); rank 0's draw is
-    broadcast so every rank works on the same minibatch."""
+def _shared_rng():
+    """Multi-rank train() call: ONE broadcast of a seed drawn from rank 0's global NumPy RNG; every rank then draws the same
+    minibatch indices locally (a broadcast per minibatch was a host synchronisation per optimizer step)."""
+    seed = torch.tensor([np.random.randint(0, 2 ** 31 - 1)], dtype=torch.int64)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    seed = seed.to(dev)
+    dist.broadcast(seed, src=0)
+    return np.random.RandomState(int(seed.item()))
+
+
+def _sample(examples, batch_size, rng=None):
+    """np.random.randint minibatch with replacement (Connect4GNN.py:141,160); with several ranks every rank draws from
+    the call's shared stream (`_shared_rng`) so that all work on the same minibatch."""
+    if rng is not None:
+        return rng.randint(0, len(examples), min(len(examples), batch_size))
     idx = np.random.randint(0, len(examples), min(len(examples), batch_size))
     rank, world = _world()
     if world > 1:
@@ -418,16 +435,18 @@ class _GraphedStep:
     graph: the ~120 launches of a step are replayed by one `cudaGraphLaunch` instead of being issued from Python
     (the step is launch-bound otherwise: 3.1 ms eager vs 1.9 ms of kernel time per epoch)."""
 
-    def __init__(self, step_fn, w, params, opt, shapes):
+    def __init__(self, step_fn, w, params, opt, shapes, which="std"):
         dev = w.device
         self.static = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
         self.graph = None
-        self.step_fn, self.w, self.params, self.opt = step_fn, w, params, opt
+        self.step_fn, self.w, self.params, self.opt, self.which = step_fn, w, params, opt, which
 
     def _body(self):
         self.opt.zero_grad(set_to_none=True)
         loss = self.step_fn(CudaOps, self.w, *self.static)
-        loss.backward()
+        if loss is not None:
+            loss.backward()
+        exchange_grads(self.w, self.which)  # no-op on one rank; NCCL nodes of the captured graph otherwise
         self.opt.step()
 
     def run(self, tensors, eager):
@@ -440,7 +459,8 @@ class _GraphedStep:
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             self.opt.zero_grad(set_to_none=True)
-            with torch.cuda.graph(self.graph):
+            # thread_local: NCCL's watchdog thread may query events while this thread captures
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self._body()
         self.graph.replay()
 
@@ -451,6 +471,23 @@ def _reset_adam(opt):
         for v in st.values():
             if torch.is_tensor(v):
                 v.zero_()
+
+
+def release_captured_steps(w):
+    """Drop the CUDA graphs (and cached optimizers) of a wrapper.  Multi-rank graphs hold NCCL kernels: NCCL requires
+    them to be destroyed before the communicator is (`destroy_process_group` otherwise blocks forever)."""
+    import gc
+    cache = w.__dict__.pop("_train_cache", None)
+    if cache:
+        for entry in cache.values():
+            if isinstance(entry, dict):
+                for step in entry.get("steps", {}).values():
+                    step.graph = None
+                entry.get("steps", {}).clear()
+        cache.clear()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
 
 
 def _train_cache(w, key, builder):
@@ -469,7 +506,10 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
     gnn_params = list(w.gnn.parameters()) if getattr(w, "gnn", None) is not None else []
     # torch's own Adam, as in the reference; its single-kernel (`fused`) implementation moves each of p, g, m, v once
     # instead of once per foreach pass (1.8 ms -> 0.8 ms for the 120 M GNN parameters)
-    graphed = dev.type == "cuda" and world == 1 and ops is CudaOps and not os.environ.get("AZG_TRAIN_EAGER")
+    # multi-rank steps are captured too, NCCL collectives included (feature all-gather, row-0 gradient and weight-gradient
+    # all-reduces become graph nodes): eager 8-rank epochs were launch-bound, 3.7 ms against 2.2 ms on one GPU
+    graphed = dev.type == "cuda" and ops is CudaOps and not os.environ.get("AZG_TRAIN_EAGER") and \
+        (world == 1 or (dist.get_backend() == "nccl" and not os.environ.get("AZG_TRAIN_DP_EAGER")))
     if graphed:
         # optimizers (state zeroed = re-created) and captured steps persist across train() calls
         def build():
@@ -499,18 +539,22 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
         if key not in cache["steps"]:
             if len(cache["steps"]) >= 6:  # every capture pins its own gradient pool (0.5 GB for the GNN step): odd batch
                 opt.zero_grad()           # shapes beyond a handful run eagerly instead of being captured
-                step_fn(ops, w, *tensors).backward()
+                loss = step_fn(ops, w, *tensors)
+                if loss is not None:
+                    loss.backward()
+                exchange_grads(w, which)
                 opt.step()
                 cache["warm"].add(which)
                 return
-            cache["steps"][key] = _GraphedStep(step_fn, w, params, opt, [t.shape for t in tensors])
+            cache["steps"][key] = _GraphedStep(step_fn, w, params, opt, [t.shape for t in tensors], which)
         eager = which not in cache["warm"]
         cache["steps"][key].run(tensors, eager)
         cache["warm"].add(which)
 
+    shared = _shared_rng() if world > 1 else None
     for _ in range(epochs):
         if examples is not None and len(examples) > 0:
-            idx = _sample(examples, batch_size)
+            idx = _sample(examples, batch_size, shared)
             if hasattr(examples, "sample"):  # replay.DeviceExamples: the minibatch is gathered on the device
                 boards, target_pis, target_vs = examples.sample(batch_size, idx=idx)
             else:
@@ -520,7 +564,7 @@ def train_two_player(w, examples, gnn_examples=None, ops=CudaOps):
                 target_vs = torch.FloatTensor(np.array(vs).astype(np.float64)).to(dev)
             run_step("std", std_step, nnet_params, nnet_opt, (boards, target_pis, target_vs))
         if gnn_opt is not None and gnn_examples is not None and len(gnn_examples) > 0:
-            idx = _sample(gnn_examples, batch_size)
+            idx = _sample(gnn_examples, batch_size, shared)
             if hasattr(gnn_examples, "sample"):  # replay.DeviceGnnExamples
                 boards, expanded_pis, expanded_vs = gnn_examples.sample(batch_size, idx=idx)
             else:

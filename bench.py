@@ -150,7 +150,9 @@ def gpu_selfplay(net, a, games, moves, seed, collect=False, warm=2):
     import torch
     from azgnn_b200.games import Connect4Game
     from azgnn_b200.selfplay import BatchedSelfPlay
-    sp = BatchedSelfPlay(Connect4Game(N_BOARD), net, a, games, seed=seed, collect_examples=collect)
+    # steady-state leg: about one episode ends per slot every ~25 move-steps; room for all of them up front
+    reserve = games * (2 + (warm + moves) // 20) if collect == "device" else None
+    sp = BatchedSelfPlay(Connect4Game(N_BOARD), net, a, games, seed=seed, collect_examples=collect, reserve_episodes=reserve)
     for _ in range(warm):
         sp.step_all()
     torch.cuda.synchronize()
@@ -189,6 +191,45 @@ def run_reference_arm(args, rank):
             "e2e": {"value": value, "unit": "leaf_evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def train_leg(net, epochs, rank, world, dev):
+    """`NeuralNet.train(examples, gnn_examples)` (Connect4GNN.py:122-197) on synthetic examples: ms per epoch (one
+    standard step + one GNN step on B = 64 rows, Adam), through the public call -- minibatch sampling and H2D copies
+    included.  With several ranks the rows are sharded and the step's gradient all-reduce runs on NCCL inside the
+    captured step.  Max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rng = np.random.default_rng(1)
+    A = net.action_size
+    ex = [(rng.integers(-1, 2, size=(N_BOARD, N_BOARD)).astype(np.int64), rng.dirichlet(np.ones(A)), float(rng.uniform(-1, 1)))
+          for _ in range(512)]
+    gex = [(b, None, None, None, p_, v_) for b, p_, v_ in ex]
+    keep = net.args["epochs"]
+    net.args["epochs"] = 20
+    net.train(ex, gex)  # Adam state, graph capture, NCCL warm-up
+    net.args["epochs"] = epochs
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    net.train(ex, gex)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3 / epochs
+    net.args["epochs"] = keep
+    t = torch.tensor([e0.elapsed_time(e1) / epochs, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n_ot = sum(p.numel() for p in net.gnn.output_transform.parameters())
+    n_std = sum(p.numel() for p in net.nnet.parameters())
+    return {"metric": "connect4_gnn_train_epoch_ms", "value": float(t[0]), "wall_ms_per_epoch": float(t[1]), "unit": "ms per epoch (std step + GNN step, B = 64)",
+            "epochs_timed": epochs, "n_gpus": world, "higher_is_better": False,
+            "allreduce_payload_bytes_per_epoch": 4 * (n_ot + n_std) if world > 1 else 0,
+            "note": "NeuralNet.train through the public call; steps replay CUDA graphs (with their NCCL collectives when n_gpus > 1)"}
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -432,6 +473,17 @@ def run_gpu_arm(args, rank, local_rank, world):
         net.fold_heads = False
         sp_fold = {"value": f_moves, "unit": "moves/s", "leaf_evals_per_s_in_search": f_leaves,
                    "ms_per_move_step": f_ms / max(args.selfplay_moves, 1), "note": "b200_fold_heads=True (see also.*_folded_heads)"}
+    # ---- BASELINE configs[3]: the training step (data-parallel, NCCL gradient all-reduce inside the captured step) and one
+    # whole Coach iteration, so that the multi-GPU lines carry the one collective of the path ----
+    train_rec, coach_rec = None, None
+    if args.train_epochs > 0:
+        train_rec = train_leg(net, args.train_epochs, rank, world, dev)
+    if args.coach_eps > 0:
+        barrier()
+        from bench_coach import coach_iteration
+        coach_rec = coach_iteration(args.coach_eps, min(args.coach_eps, 4096), 100, args.precision if args.precision != "fp32" else "fp32",
+                                    rank, world, dev)
+        barrier()
     t = torch.tensor([ms, ms_e2e, sp_ms, sp_steady[1] if sp_steady else 0.0], dtype=torch.float64, device=dev)
     tot = torch.tensor([sp_moves * sp_ms, sp_leaves * sp_ms, sp_steady[0] if sp_steady else 0.0], dtype=torch.float64, device=dev)  # counts
     if world > 1:
@@ -521,12 +573,31 @@ def run_gpu_arm(args, rank, local_rank, world):
                  "note": "the Coach.learn path: device example collection on, 50 untimed move-steps first so that every slot has "
                          "turned over, episodes end and restart inside the timed region"},
                 "selfplay_folded_heads": sp_fold,
+                "train": train_rec,
+                "coach_iteration": coach_rec,
                 "also": also,
                 "gpu_launches": int(launches),
                 "clocks": clocks.summary()}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        shutdown_ranks(net)
+
+
+def shutdown_ranks(*wrappers):
+    """Leave a multi-rank run without hanging: graphs that captured NCCL kernels are destroyed first (NCCL's rule), all
+    ranks meet at a barrier, and the interpreter is left through os._exit so that no late destructor can block a rank that
+    has already reported."""
+    import torch
+    import torch.distributed as dist
+    from azgnn_b200.training import release_captured_steps
+    for w in wrappers:
+        release_captured_steps(w)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)  # the communicators go with the process: destroy_process_group has nothing left to protect here and is
+    # the one call of this script that was ever seen to block (round 2, graphs with captured NCCL kernels still alive)
 
 
 def main():
@@ -543,6 +614,8 @@ def main():
     ap.add_argument("--selfplay-games", type=int, default=16384, help="concurrent self-play games per GPU (0 = skip)")
     ap.add_argument("--selfplay-moves", type=int, default=6)
     ap.add_argument("--cpu-selfplay-episodes", type=int, default=2)
+    ap.add_argument("--train-epochs", type=int, default=60, help="timed epochs (std step + GNN step) of NeuralNet.train; 0 = skip")
+    ap.add_argument("--coach-eps", type=int, default=4096, help="self-play episodes per GPU of the Coach-iteration leg; 0 = skip")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
