@@ -981,7 +981,7 @@ __global__ void heads32_finalize_kernel(const float* __restrict__ lg, int A, int
 //   warps 12-15 epilogue: TMEM -> +bias, ReLU -> feature image (the A operand of GEMM-1)
 // The im2col matrix never exists in HBM (the split version moved 2 x 4.1 GB per 65,536 positions).
 // History of conv1: FFMA with lanes = channels and broadcast LDS of the planes took 42 % of the builders' time
-// (ncu source view, profiles/r01_trunk_fused_v6.txt: 18 LDS per two cells queued behind the tensor core's own
+// (ncu source view of the round-1 v6 capture, since pruned: 18 LDS per two cells queued behind the tensor core's own
 // shared-memory reads); on the tensor core it is 3 MMAs and one tcgen05.ld per thread.
 constexpr int TR_THREADS = 512;
 constexpr int TR_CELL_STRIDE = 64;   // bytes per padded cell: 32 channels x bf16, no pad (see the patch copies)

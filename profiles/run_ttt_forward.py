@@ -1,4 +1,4 @@
-"""ncu driver: TicTacToe 4x4 GNN leaf evaluation, 65,536 positions (fp32 CUDA-core path)."""
+"""ncu driver: TicTacToe 4x4 GNN leaf evaluation, 65,536 positions (default precision: auto -> bf16x3 on tcgen05)."""
 import os
 import sys
 

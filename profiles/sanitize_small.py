@@ -1,5 +1,5 @@
 """compute-sanitizer driver: one small call of every kernel family added in round 1 (grid layer fwd/bwd, weight
-gradients, replay emit/gather, TicTacToe tcgen05 forward, Connect4 tcgen05 forward incl. folded heads, training
+gradients, replay emit/gather, TicTacToe tcgen05 forward, Connect4 tcgen05 forward (bf16x3 and f16f8) incl. folded heads, training
 step pieces).  Sizes are tiny: the tool slows kernels down by 10-100x."""
 import os
 import sys
@@ -24,9 +24,10 @@ for gh, gw, H in ((3, 3, 64), (7, 7, 128), (8, 8, 256)):
     net(x).sum().backward()
 c4 = B200Connect4GNNWrapper(games.Connect4Game(7), a)
 boards = np.random.default_rng(0).integers(-1, 2, size=(300, 7, 7)).astype(np.int8)
-for fold in (False, True):
-    c4.fold_heads = fold
-    c4.forward_states(c4.states_from_boards(boards), _lib.EVAL_STD | _lib.EVAL_GNN)
+for prec in (_lib.PREC_BF16X3, _lib.PREC_F16F8):
+    for fold in (False, True):
+        c4.fold_heads = fold
+        c4.forward_states(c4.states_from_boards(boards), _lib.EVAL_STD | _lib.EVAL_GNN, precision=prec)
 ttt = B200TicTacToeGNNWrapper(games.TicTacToeGame(4), a)
 ttt.forward_states(ttt.states_from_boards(np.random.default_rng(1).integers(-1, 2, size=(300, 4, 4)).astype(np.int8)))
 bt = torch.FloatTensor(boards[:8].astype(np.float64)).cuda()
