@@ -1362,6 +1362,330 @@ int launch_trunk(const TrunkArgs& t, cudaStream_t st) {
   return AZG_OK;
 }
 
+// ---- fused trunk, second generation: conv2 as an implicit GEMM over SHIFTED operand descriptors --------------------------
+// The first fused trunk copies every relu(conv1) cell nine times (once per tap) from the padded plane into SWIZZLE_128B operand
+// stages: 320 KB of shared-memory -> shared-memory traffic per 128-row tile on top of the tensor core's own 280 KB of
+// operand reads, which is what bounds it (data pipe, tensor pipe 28 %).  Here the tensor core reads the padded plane itself:
+//   * the plane is stored as 128-byte cells [32 ch hi (64 B) | 32 ch lo (64 B)], SWIZZLE_128B by the cell index, raster
+//     pitch n+1: the right border of a board row IS the left border of the next row and the bottom border row of a board IS
+//     the top border row of the next board, so board b's cell (x, y) sits at plane cell b (n+1)^2 + (x+1)(n+1) + (y+1);
+//   * GEMM row r = b (n+1)^2 + x (n+1) + y (the position of tap (0,0)); tap (kx, ky) of EVERY row is then plane cell
+//     r + kx (n+1) + ky: the A operand of a tap is the same 128 rows at a different START ADDRESS (any multiple of 128 B:
+//     the tensor core applies the 128-byte swizzle to absolute shared-memory address bits, so a plane written with
+//     chunk ^ (cell & 7) reads back correctly from every start; measured on B200 -- with the descriptor's base-offset
+//     field set to the start's phase the results are WRONG, with the field left 0 they equal the first-generation trunk
+//     bit for bit), K-advance inside the 128-byte cell selects hi / lo and the 16-channel half.
+//     18 K = 16 steps (9 taps x 2), no patch copies, no padded k-block.
+// Rows between boards compute garbage from border / neighbouring cells and are dropped by the epilogue (n = 7: 2 boards per
+// tile, rows 0-54 and 64-118).  conv1 stays on the tensor core as before (operand built from the packed position by the
+// builder warps, result read back from TMEM, bias + ReLU, hi/lo split into the plane); planes, conv1 operand stages and
+// conv1 TMEM regions are double-buffered so that tile i+1's conv1 and plane write-back run under tile i's 36 conv2 MMAs.
+constexpr int T2_PLANE_CELLS = 152;                       // 128 rows + 2 (n+1) + 2 tap reach, n <= 8
+constexpr int T2_PLANE_BYTES = T2_PLANE_CELLS * 128;      // 19 KB, 1024-byte multiple
+
+template <bool X3>
+struct Trunk2Smem {
+  static constexpr int W_OFF = 0;
+  static constexpr int W1_OFF = (X3 ? 2 : 1) * TR_W_BYTES;
+  static constexpr int PLANE_OFF = W1_OFF + TR_W1_BYTES;
+  static constexpr int C1_OFF = PLANE_OFF + 2 * T2_PLANE_BYTES;
+  static constexpr int MISC_OFF = C1_OFF + 2 * A_STAGE_BYTES;
+  static constexpr int TOTAL = MISC_OFF + 1024 + 1024;
+};
+
+constexpr int T2_THREADS = 640;  // 8 builder warps, MMA, TMEM/barrier setup, 2 idle, 2 x 4 epilogue warps
+
+template <bool X3>
+__global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t) {
+  using S = Trunk2Smem<X3>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* w_s = smem + S::W_OFF;
+  uint8_t* w1img = smem + S::W1_OFF;
+  uint8_t* planes = smem + S::PLANE_OFF;
+  uint8_t* c1st = smem + S::C1_OFF;
+  uint64_t* c1_full = (uint64_t*)(smem + S::MISC_OFF);  // [2] conv1 operand written (256 builders)
+  uint64_t* c1_free = c1_full + 2;                       // [2] conv1 MMAs have read the operand stage
+  uint64_t* c1_done = c1_free + 2;                       // [2] conv1 result is in its TMEM region
+  uint64_t* c1_tfree = c1_done + 2;                      // [2] builders have read the conv1 TMEM region (256)
+  uint64_t* pl_full = c1_tfree + 2;                      // [2] plane written (256 builders)
+  uint64_t* pl_free = pl_full + 2;                       // [2] conv2 MMAs have read the plane
+  uint64_t* tfull = pl_free + 2;                         // [2] accumulator complete
+  uint64_t* tempty = tfull + 2;                          // [2] accumulator drained (128 epilogue threads)
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = t.n, nn = n * n, rp = n + 1, bp = rp * rp;  // row pitch and board pitch of the shared-border raster
+  const int G = (127 - (nn + n - 2)) / bp + 1;                // boards per 128-row tile
+  if (t.dyn_rows && *t.dyn_rows < t.B) t.B = *t.dyn_rows;
+  const int64_t tiles = (t.B + G - 1) / G;
+  constexpr int BN = 64;
+  constexpr int ACC_COLS = X3 ? 128 : 64;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t C1_COL = 2 * ACC_COLS;  // two conv1 regions of 32 columns
+
+  for (int i = threadIdx.x; i < 2 * T2_PLANE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(planes)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 2 * A_STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(c1st)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {  // conv1 weights as three bf16 terms along K (Connect4Net.py:32)
+    const int ch = i >> 6, col = i & 63, term = col >> 4, k = col & 15;
+    float v = 0.0f;
+    if (term < 3 && k < 9) {
+      const float w = t.w1[ch * 9 + k];
+      const float hi = __bfloat162float(__float2bfloat16_rn(w));
+      const float mid = __bfloat162float(__float2bfloat16_rn(w - hi));
+      v = term == 0 ? hi : term == 1 ? mid : (w - hi) - mid;
+    }
+    *reinterpret_cast<__nv_bfloat16*>(w1img + image_offset(ch, col)) = __float2bfloat16_rn(v);
+  }
+  if (warp == 9 && lane == 0) {
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&c1_full[k], 256);
+      mbar_init(&c1_free[k], 1);
+      mbar_init(&c1_done[k], 1);
+      mbar_init(&c1_tfree[k], 256);
+      mbar_init(&pl_full[k], 256);
+      mbar_init(&pl_free[k], 1);
+      mbar_init(&tfull[k], 1);
+      mbar_init(&tempty[k], 256);
+    }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    if (lane == 0) {  // conv2 weight images -> smem, once
+      mbar_expect_tx(wbar, (X3 ? 2 : 1) * TR_W_BYTES);
+      if (X3) {
+        for (int kb = 0; kb < C2_KB; ++kb) {
+          bulk_g2s(w_s + kb * 16384, t.w_hi + kb * 8192, 8192, wbar);
+          bulk_g2s(w_s + kb * 16384 + 8192, t.w_lo + kb * 8192, 8192, wbar);
+        }
+      } else {
+        bulk_g2s(w_s, t.w_hi, TR_W_BYTES, wbar);
+      }
+    }
+  } else if (warp < 8) {
+    // ============ builders: two threads per tile row (16 conv1 channels each) ============
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int bl = r / bp, p = r - bl * bp, x = p / rp, y = p - x * rp;
+    const bool row_valid = bl < G && x < n && y < n;
+    const int pc = x * n + y;  // bit of the cell in the packed position
+    uint32_t tap_ok = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int xx = x + k / 3 - 1, yy = y + k % 3 - 1;
+      if (row_valid && xx >= 0 && xx < n && yy >= 0 && yy < n) tap_ok |= 1u << k;
+    }
+    float bias16[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) bias16[j] = __ldg(t.b1 + half * 16 + j);
+    const uint32_t cell = (uint32_t)(r + rp + 1);  // plane cell of this row's own position
+    uint64_t nm = 0, nt = 0;
+    auto fetch = [&](int64_t tile) {
+      nm = nt = 0;
+      const int64_t b = tile * G + bl;
+      if (row_valid && tile < tiles && b < t.B) { nm = t.states[2 * b]; nt = t.states[2 * b + 1]; }
+    };
+    auto c1_operand = [&](int k, uint32_t it) {  // K1 encode + conv1 operand of the tile whose position is in (nm, nt)
+      mbar_wait(&c1_free[k], ((it >> 1) & 1u) ^ 1u);
+      uint8_t* sa = c1st + k * A_STAGE_BYTES;
+      uint32_t pk[5];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        const int sh = (pc + (q / 3 - 1) * n + (q % 3 - 1)) & 63;
+        const uint32_t ok = (tap_ok >> q) & 1u;
+        const uint32_t m = (uint32_t)(nm >> sh) & ok, o = (uint32_t)(nt >> sh) & ok;
+        const uint32_t v = (m ? 0x3F80u : 0u) | (o ? 0xBF80u : 0u);
+        if (q & 1) pk[q >> 1] |= v << 16;
+        else pk[q >> 1] = v;
+      }
+      const uint4 c_even = make_uint4(pk[0], pk[1], pk[2], pk[3]), c_odd = make_uint4(pk[4], 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int c = half * 3 + j;
+        *reinterpret_cast<uint4*>(sa + image_offset(r, c * 8)) = (c & 1) ? c_odd : c_even;
+      }
+      fence_async_smem();
+      mbar_arrive(&c1_full[k]);
+    };
+    fetch(blockIdx.x);
+    if ((int64_t)blockIdx.x < tiles) c1_operand(0, 0);
+    fetch((int64_t)blockIdx.x + gridDim.x);
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int k = (int)(it & 1u);
+      const uint32_t ph = (it >> 1) & 1u;
+      const bool has_next = tile + gridDim.x < tiles;
+      mbar_wait(&c1_done[k], ph);
+      tc_fence_after();
+      uint32_t rr[16];
+      tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C1_COL + (uint32_t)(k * 32 + half * 16), rr);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&c1_tfree[k]);
+      mbar_wait(&pl_free[k], ph ^ 1u);  // the conv2 MMAs of tile it-2 have read this plane
+      if (row_valid && tile * G + bl < t.B) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(rr[j]) + bias16[j], 0.0f);
+        uint8_t* crow = planes + k * T2_PLANE_BYTES + cell * 128u;
+        const uint32_t sw = cell & 7u;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {  // chunks 2 half + c (hi) and 4 + 2 half + c (lo) of the 128-byte cell
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_pair(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1], h[e], l[e]);
+          const uint32_t q = (uint32_t)(half * 2 + c);
+          *reinterpret_cast<uint4*>(crow + (((q ^ sw) & 7u) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (X3) *reinterpret_cast<uint4*>(crow + ((((q + 4u) ^ sw) & 7u) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&pl_full[k]);
+      if (has_next) {
+        c1_operand(k ^ 1, it + 1);
+        fetch(tile + 2 * (int64_t)gridDim.x);
+      }
+    }
+  } else if (warp == 8) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc_c1 = make_idesc(BM, 32);
+      constexpr uint32_t idesc_cat = make_idesc(BM, 2 * BN);
+      mbar_wait(wbar, 0);
+      const uint32_t w_addr = smem_u32(w_s);
+      const uint64_t b_c1 = make_smem_desc(smem_u32(w1img));
+      auto conv1 = [&](int k, uint32_t it) {  // [A | A | A] x [w_hi | w_mid | w_lo]^T -> conv1 region k
+        mbar_wait(&c1_full[k], (it >> 1) & 1u);
+        mbar_wait(&c1_tfree[k], ((it >> 1) & 1u) ^ 1u);  // the builders have read the region's previous content
+        tc_fence_after();
+        const uint64_t a_c1 = make_smem_desc(smem_u32(c1st + k * A_STAGE_BYTES));
+#pragma unroll
+        for (int q = 0; q < 3; ++q) umma_bf16(tmem_base + C1_COL + (uint32_t)(k * 32), a_c1 + 2 * q, b_c1 + 2 * q, idesc_c1, q != 0);
+        umma_commit(&c1_free[k]);
+        umma_commit(&c1_done[k]);
+      };
+      if ((int64_t)blockIdx.x < tiles) conv1(0, 0);
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int k = (int)(it & 1u);
+        const uint32_t ph = (it >> 1) & 1u;
+        if (tile + gridDim.x < tiles) conv1(k ^ 1, it + 1);  // before this tile's conv2: its write-back overlaps the 36 MMAs
+        mbar_wait(&pl_full[k], ph);
+        mbar_wait(&tempty[k], ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(k * ACC_COLS);
+        const uint32_t plane = smem_u32(planes + k * T2_PLANE_BYTES);
+#pragma unroll 1
+        for (int s = 0; s < 18; ++s) {
+          const int tap = s >> 1, kx = tap / 3, ky = tap - kx * 3;
+          const uint32_t a_addr = plane + (uint32_t)(kx * rp + ky) * 128u + (uint32_t)(s & 1) * 32u;
+          const uint64_t a_hi = make_smem_desc(a_addr);  // base-offset field stays 0 (see the header comment)
+          const uint64_t b_w = make_smem_desc(w_addr + (uint32_t)(s >> 2) * (X3 ? 2u : 1u) * (64u * 128u)) + (uint64_t)(2 * (s & 3));
+          if (X3) {
+            umma_bf16(d_tmem, a_hi, b_w, idesc_cat, s != 0);           // hi x [W_hi ; W_lo]: columns 0-63 and 64-127
+            umma_bf16(d_tmem, a_hi + 4, b_w, idesc, 1);                // lo (64 bytes further in the cell) x W_hi
+          } else {
+            umma_bf16(d_tmem, a_hi, b_w, idesc, s != 0);
+          }
+        }
+        umma_commit(&pl_free[k]);
+        umma_commit(&tfull[k]);
+      }
+    }
+  } else if (warp >= 12) {
+    // ======================= epilogue: two groups of four warps, alternate 16-column chunks =======================
+    const int q = warp & 3, r = q * 32 + lane, grp = (warp - 12) >> 2;
+    const int bl = r / bp, p = r - bl * bp, x = p / rp, y = p - x * rp;
+    const bool row_valid = bl < G && x < n && y < n;
+    const int pc = x * n + y;
+    float4 bias4[2][4];  // conv2 bias of this group's two chunks
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bias4[c][j] = __ldg(reinterpret_cast<const float4*>(t.b2 + grp * 16 + c * 32) + j);
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int k = (int)(it & 1u);
+      const int64_t b = tile * G + bl;
+      const bool valid = row_valid && b < t.B;
+      mbar_wait(&tfull[k], (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * ACC_COLS);
+      const size_t tbase = ((size_t)(b >> 7) * nn + pc) * A_STAGE_BYTES;
+      const int rb = (int)(b & 127);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = grp * 16 + c * 32;
+        uint32_t rr[16], r2[16];
+        tmem_ld16(taddr + (uint32_t)c0, rr);
+        if (X3) tmem_ld16(taddr + (uint32_t)(BN + c0), r2);
+        tmem_ld_wait();
+        if (valid) {
+          float x16[16];
+          const float* bb = reinterpret_cast<const float*>(bias4[c]);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float d = __uint_as_float(rr[e]);
+            if (X3) d += __uint_as_float(r2[e]);
+            x16[e] = fmaxf(d + bb[e], 0.0f);
+          }
+          if (X3 && t.out_f8) {
+            const float s_main = (float)(1 << F8_A_SCALE), s_lo = (float)(1 << (F8_A_SCALE + F8_LO_SHIFT));
+            uint4 h0, h1;
+            uint2 m0, m1, l0, l1;
+            split8_f16f8(x16, s_main, s_lo, h0, m0, l0);
+            split8_f16f8(x16 + 8, s_main, s_lo, h1, m1, l1);
+            *reinterpret_cast<uint4*>(t.f_hi + tbase + image_offset(rb, c0)) = h0;
+            *reinterpret_cast<uint4*>(t.f_hi + tbase + image_offset(rb, c0 + 8)) = h1;
+            *reinterpret_cast<uint4*>(t.f_lo + tbase + image_offset_bytes(rb, c0)) = make_uint4(m0.x, m0.y, m1.x, m1.y);
+            *reinterpret_cast<uint4*>(t.f_lo + tbase + image_offset_bytes(rb, 64 + c0)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+          } else {
+            split_store(x16, t.f_hi, X3 ? t.f_lo : nullptr, tbase + image_offset(rb, c0));
+            split_store(x16 + 8, t.f_hi, X3 ? t.f_lo : nullptr, tbase + image_offset(rb, c0 + 8));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[k]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <bool X3>
+int launch_trunk2(const TrunkArgs& t, cudaStream_t st) {
+  static bool configured = false;
+  int dev = 0, sms = 0;
+  AZG_CUDA_CHECK(cudaGetDevice(&dev));
+  AZG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!configured) {
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(c4_trunk2_tc_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Trunk2Smem<X3>::TOTAL));
+    configured = true;
+  }
+  const int n = t.n, bp = (n + 1) * (n + 1);
+  const int G = (127 - (n * n + n - 2)) / bp + 1;
+  const int64_t tiles = (t.B + G - 1) / G;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  c4_trunk2_tc_kernel<X3><<<grid, T2_THREADS, Trunk2Smem<X3>::TOTAL, st>>>(t);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
+
 int make_image(const float* src, int64_t rows, int64_t rows_padded, int K, int R, uint8_t* hi, uint8_t* lo, cudaStream_t st,
                int f8_mode = 0, const int32_t* f8_exp = nullptr) {
   return to_image(src, rows, rows_padded, K, R, hi, lo, st, f8_mode, f8_exp);
@@ -1439,13 +1763,22 @@ ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
 }
 }  // namespace
 
-static int azg_trunk_mode() {
+static int azg_trunk_mode() {  // 0 = fused (either generation), 1 = split (im2col through HBM; A/B measurements)
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("AZG_TRUNK");
     mode = (e && strcmp(e, "split") == 0) ? 1 : 0;
   }
   return mode;
+}
+
+static int azg_trunk_gen() {  // AZG_TRUNK=fused1: the first-generation fused trunk (patch copies), kept for A/B measurements
+  static int gen = -1;
+  if (gen < 0) {
+    const char* e = getenv("AZG_TRUNK");
+    gen = (e && strcmp(e, "fused1") == 0) ? 1 : 2;
+  }
+  return gen;
 }
 
 static int azg_std_heads_mode() {  // AZG_STD_HEADS=split: predict's heads in their own skinny GEMM launch (A/B measurements)
@@ -1485,7 +1818,9 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     t.w_hi = w + L.c2_hi; t.w_lo = x3 ? w + L.c2_lo : nullptr; t.f_hi = f_hi; t.f_lo = f_lo; t.B = B; t.n = n;
     t.dyn_rows = dyn_rows;
     t.out_f8 = f8 ? 1 : 0;
-    if ((rc = x3 ? tc::launch_trunk<true>(t, st) : tc::launch_trunk<false>(t, st))) return rc;
+    if (azg_trunk_gen() == 1) rc = x3 ? tc::launch_trunk<true>(t, st) : tc::launch_trunk<false>(t, st);
+    else rc = x3 ? tc::launch_trunk2<true>(t, st) : tc::launch_trunk2<false>(t, st);
+    if (rc) return rc;
   } else {  // split: im2col image through HBM, conv2 on the generic GEMM kernel (kept for A/B measurements)
     const int grid = (int)(B < 148 * 8 ? B : 148 * 8);
     tc::c4_im2col_kernel<<<grid, 256, 0, st>>>(states, n, B, p->conv1_w, p->conv1_b, a2_hi, a2_lo);
