@@ -1389,7 +1389,8 @@ struct Trunk2Smem {
   static constexpr int W1_OFF = (X3 ? 2 : 1) * TR_W_BYTES;
   static constexpr int PLANE_OFF = W1_OFF + TR_W1_BYTES;
   static constexpr int C1_OFF = PLANE_OFF + 2 * T2_PLANE_BYTES;
-  static constexpr int MISC_OFF = C1_OFF + 2 * A_STAGE_BYTES;
+  static constexpr int STG_OFF = C1_OFF + 2 * A_STAGE_BYTES;  // epilogue staging: 128 rows x [128 B hi image row | 128 B lo image row]
+  static constexpr int MISC_OFF = STG_OFF + 128 * 256;
   static constexpr int TOTAL = MISC_OFF + 1024 + 1024;
 };
 
@@ -1523,6 +1524,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
       const int k = (int)(it & 1u);
       const uint32_t ph = (it >> 1) & 1u;
       const bool has_next = tile + gridDim.x < tiles;
+      if (has_next) {  // the next tile's conv1 operand depends on nothing the tensor core produces: build it first, so that
+        c1_operand(k ^ 1, it + 1);  // conv1(it+1) is queued before conv2(it) and only the plane write-back below sits
+        fetch(tile + 2 * (int64_t)gridDim.x);  // between a conv1 result and the conv2 MMAs that need it
+      }
       mbar_wait(&c1_done[k], ph);
       tc_fence_after();
       uint32_t rr[16];
@@ -1549,10 +1554,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
       }
       fence_async_smem();
       mbar_arrive(&pl_full[k]);
-      if (has_next) {
-        c1_operand(k ^ 1, it + 1);
-        fetch(tile + 2 * (int64_t)gridDim.x);
-      }
     }
   } else if (warp == 8) {
     // ======================= MMA issuer =======================
@@ -1574,6 +1575,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
         umma_commit(&c1_done[k]);
       };
       if ((int64_t)blockIdx.x < tiles) conv1(0, 0);
+      // descriptor increments of the nine taps in 16-byte units (the single issuing thread should spend its cycles on
+      // tcgen05.mma, not on address arithmetic: everything but two additions per step is hoisted or a constant)
+      uint32_t tap16[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) tap16[q] = (uint32_t)((q / 3) * rp + (q % 3)) * 8u;
+      const uint64_t b_base = make_smem_desc(w_addr);
+      const uint64_t a_base[2] = {make_smem_desc(smem_u32(planes)), make_smem_desc(smem_u32(planes + T2_PLANE_BYTES))};
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const int k = (int)(it & 1u);
@@ -1583,13 +1591,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
         mbar_wait(&tempty[k], ph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(k * ACC_COLS);
-        const uint32_t plane = smem_u32(planes + k * T2_PLANE_BYTES);
-#pragma unroll 1
+#pragma unroll
         for (int s = 0; s < 18; ++s) {
-          const int tap = s >> 1, kx = tap / 3, ky = tap - kx * 3;
-          const uint32_t a_addr = plane + (uint32_t)(kx * rp + ky) * 128u + (uint32_t)(s & 1) * 32u;
-          const uint64_t a_hi = make_smem_desc(a_addr);  // base-offset field stays 0 (see the header comment)
-          const uint64_t b_w = make_smem_desc(w_addr + (uint32_t)(s >> 2) * (X3 ? 2u : 1u) * (64u * 128u)) + (uint64_t)(2 * (s & 3));
+          // base-offset field of the shifted descriptor stays 0 (see the header comment)
+          const uint64_t a_hi = a_base[k] + (uint64_t)(tap16[s >> 1] + (uint32_t)(s & 1) * 2u);
+          const uint64_t b_w = b_base + (uint64_t)((s >> 2) * (X3 ? 2 : 1) * (64 * 128 / 16) + 2 * (s & 3));
           if (X3) {
             umma_bf16(d_tmem, a_hi, b_w, idesc_cat, s != 0);           // hi x [W_hi ; W_lo]: columns 0-63 and 64-127
             umma_bf16(d_tmem, a_hi + 4, b_w, idesc, 1);                // lo (64 bytes further in the cell) x W_hi
@@ -1603,25 +1609,39 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
     }
   } else if (warp >= 12) {
     // ======================= epilogue: two groups of four warps, alternate 16-column chunks =======================
-    const int q = warp & 3, r = q * 32 + lane, grp = (warp - 12) >> 2;
-    const int bl = r / bp, p = r - bl * bp, x = p / rp, y = p - x * rp;
-    const bool row_valid = bl < G && x < n && y < n;
-    const int pc = x * n + y;
+    // A GEMM row is one (board, cell): its 64 channels are ONE 128-byte row of the feature image (tile = cell, row = board),
+    // so the 32 rows of a warp go to 32 different image tiles.  Writing them straight from the accumulator registers costs
+    // 32 partial cache lines per 16-byte store instruction (ncu: LSU wavefronts 41 % of the data pipe the tensor core
+    // needs, r02_trunk2 capture); instead the converted rows are staged in shared memory (conflict-free XOR by the row)
+    // and copied out with eight lanes per row: every store instruction writes four whole 128-byte lines.
+    const int q = warp & 3, r = q * 32 + lane, grp = (warp - 12) >> 2, wl = warp - 12;
+    uint8_t* stg = smem + S::STG_OFF;
     float4 bias4[2][4];  // conv2 bias of this group's two chunks
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
       for (int j = 0; j < 4; ++j) bias4[c][j] = __ldg(reinterpret_cast<const float4*>(t.b2 + grp * 16 + c * 32) + j);
+    // copy-out mapping: warp wl owns tile rows 16 wl .. 16 wl + 15; per pass i a lane moves chunk (lane & 7) of row
+    // 16 wl + 4 i + (lane >> 3)
+    int co_bl[4], co_pc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr_ = 16 * wl + 4 * i + (lane >> 3);
+      const int b_ = rr_ / bp, p_ = rr_ - b_ * bp, x_ = p_ / rp, y_ = p_ - x_ * rp;
+      co_bl[i] = (b_ < G && x_ < n && y_ < n) ? b_ : -1;
+      co_pc[i] = x_ * n + y_;
+    }
+    const bool f8 = X3 && t.out_f8;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int k = (int)(it & 1u);
-      const int64_t b = tile * G + bl;
-      const bool valid = row_valid && b < t.B;
+      const int rb = (int)((tile * G + r / bp) & 127);  // image row (board & 127) of this thread's tile row
       mbar_wait(&tfull[k], (it >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * ACC_COLS);
-      const size_t tbase = ((size_t)(b >> 7) * nn + pc) * A_STAGE_BYTES;
-      const int rb = (int)(b & 127);
+      named_bar(3, 256);  // the previous tile's copy-out has read the staging rows
+      uint8_t* srow = stg + r * 256;
+      const uint32_t sx = (uint32_t)((rb ^ r) & 7);  // image swizzle (board row) composed with the staging swizzle (tile row)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int c0 = grp * 16 + c * 32;
@@ -1629,33 +1649,53 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
         tmem_ld16(taddr + (uint32_t)c0, rr);
         if (X3) tmem_ld16(taddr + (uint32_t)(BN + c0), r2);
         tmem_ld_wait();
-        if (valid) {
-          float x16[16];
-          const float* bb = reinterpret_cast<const float*>(bias4[c]);
+        float x16[16];
+        const float* bb = reinterpret_cast<const float*>(bias4[c]);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float d = __uint_as_float(rr[e]);
-            if (X3) d += __uint_as_float(r2[e]);
-            x16[e] = fmaxf(d + bb[e], 0.0f);
-          }
-          if (X3 && t.out_f8) {
-            const float s_main = (float)(1 << F8_A_SCALE), s_lo = (float)(1 << (F8_A_SCALE + F8_LO_SHIFT));
-            uint4 h0, h1;
-            uint2 m0, m1, l0, l1;
-            split8_f16f8(x16, s_main, s_lo, h0, m0, l0);
-            split8_f16f8(x16 + 8, s_main, s_lo, h1, m1, l1);
-            *reinterpret_cast<uint4*>(t.f_hi + tbase + image_offset(rb, c0)) = h0;
-            *reinterpret_cast<uint4*>(t.f_hi + tbase + image_offset(rb, c0 + 8)) = h1;
-            *reinterpret_cast<uint4*>(t.f_lo + tbase + image_offset_bytes(rb, c0)) = make_uint4(m0.x, m0.y, m1.x, m1.y);
-            *reinterpret_cast<uint4*>(t.f_lo + tbase + image_offset_bytes(rb, 64 + c0)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-          } else {
-            split_store(x16, t.f_hi, X3 ? t.f_lo : nullptr, tbase + image_offset(rb, c0));
-            split_store(x16 + 8, t.f_hi, X3 ? t.f_lo : nullptr, tbase + image_offset(rb, c0 + 8));
+        for (int e = 0; e < 16; ++e) {
+          float d = __uint_as_float(rr[e]);
+          if (X3) d += __uint_as_float(r2[e]);
+          x16[e] = fmaxf(d + bb[e], 0.0f);
+        }
+        const uint32_t kc = (uint32_t)(c0 >> 3);  // first of the two 16-byte chunks of these 16 channels in the hi row
+        if (f8) {
+          const float s_main = (float)(1 << F8_A_SCALE), s_lo = (float)(1 << (F8_A_SCALE + F8_LO_SHIFT));
+          uint4 h0, h1;
+          uint2 m0, m1, l0, l1;
+          split8_f16f8(x16, s_main, s_lo, h0, m0, l0);
+          split8_f16f8(x16 + 8, s_main, s_lo, h1, m1, l1);
+          *reinterpret_cast<uint4*>(srow + (((kc) ^ sx) << 4)) = h0;
+          *reinterpret_cast<uint4*>(srow + (((kc + 1) ^ sx) << 4)) = h1;
+          const uint32_t qc = (uint32_t)(c0 >> 4);  // correction row: 16 e4m3 per chunk, main half then lo half
+          *reinterpret_cast<uint4*>(srow + 128 + (((qc) ^ sx) << 4)) = make_uint4(m0.x, m0.y, m1.x, m1.y);
+          *reinterpret_cast<uint4*>(srow + 128 + (((qc + 4) ^ sx) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_pair(x16[h * 8 + 2 * e], x16[h * 8 + 2 * e + 1], hi[e], lo[e]);
+            *reinterpret_cast<uint4*>(srow + (((kc + h) ^ sx) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (X3) *reinterpret_cast<uint4*>(srow + 128 + (((kc + h) ^ sx) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[k]);
+      named_bar(4, 256);  // all rows of the tile are staged
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t b = tile * G + co_bl[i];
+        if (co_bl[i] >= 0 && b < t.B) {
+          const int row = 16 * wl + 4 * i + (lane >> 3), j = lane & 7;
+          const int rbi = (int)(b & 127);
+          // staging chunk that holds final position j of the image row: final position = kc ^ (rbi & 7), staged at kc ^ ((rbi ^ row) & 7)
+          const uint32_t sj = (uint32_t)(j ^ (row & 7));
+          const size_t g0 = ((size_t)(b >> 7) * nn + co_pc[i]) * A_STAGE_BYTES + (size_t)(rbi >> 3) * 1024 + (size_t)(rbi & 7) * 128 + (size_t)j * 16;
+          *reinterpret_cast<uint4*>(t.f_hi + g0) = *reinterpret_cast<const uint4*>(stg + row * 256 + (sj << 4));
+          if (X3) *reinterpret_cast<uint4*>(t.f_lo + g0) = *reinterpret_cast<const uint4*>(stg + row * 256 + 128 + (sj << 4));
+        }
+      }
     }
   }
 

@@ -73,9 +73,15 @@ def test_splits_hold_the_contract_on_a_trained_checkpoint():
     chosen = _lib.PRECISION_NAMES[w.active_precision()]
     print(f"  auto -> {chosen}; probe report {w.precision_report}")
     auto = errors(None)
+    # (1) what the default configuration delivers: the contract, whatever mode the guard had to fall back to
     assert max(auto.values()) <= 1e-5, (chosen, auto)
     assert max(table["fp32"].values()) <= 1e-5
-    # the individual splits on this checkpoint (informative bound: a split the guard would still accept must be inside 1e-5)
+    # (2) the tensor-core splits on a trained network: the tensor core's truncating fp32 accumulation (~1e-5 at K = 3136,
+    # DESIGN.md section 4) puts them AT the 1e-5 line (8e-6 .. 1.3e-5 over several runs), so a fixed mode cannot promise the
+    # fp32 contract here; their stated tolerance on trained weights is 5e-5, and a mode the guard accepts (probe <= 6e-6)
+    # must be inside 1e-5
+    for name in ("bf16x3", "f16f8", "f16f8+fold"):
+        assert max(table[name].values()) <= 5e-5, (name, table[name])
     for name in ("bf16x3", "f16f8"):
         if w.precision_report.get(name, 1.0) <= w.AUTO_TOL:
             assert max(table[name].values()) <= 1e-5, (name, table[name])
