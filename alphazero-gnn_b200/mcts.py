@@ -168,9 +168,14 @@ class BatchedMCTS:
         # only; the standard prediction is read back for ROOTS alone (expand_tree, MCTS.py:108-111), and those are
         # evaluated by _root_std_values.  The device path therefore skips the unused standard heads at the leaves.
         mask = _lib.EVAL_GNN if self.use_gnn else _lib.EVAL_STD
-        out = self.nnet.forward_states(leaf_states, mask, count=count) if count is not None else \
-            self.nnet.forward_states(leaf_states, mask)
+        kw = self._search_kw()
+        out = self.nnet.forward_states(leaf_states, mask, count=count, **kw) if count is not None else \
+            self.nnet.forward_states(leaf_states, mask, **kw)
         return (out["pi_gnn"], out["v_gnn"]) if self.use_gnn else (out["pi"], out["v"])
+
+    def _search_kw(self):
+        """evaluations made on behalf of the search (leaves, expand_tree's root values) run in the wrapper's search mode"""
+        return {"search": True} if hasattr(self.nnet, "search_precision") else {}
 
     def _evaluate_host(self, leaf_states, leaf_mask):
         ar = self.arena
@@ -262,7 +267,7 @@ class BatchedMCTS:
     # ------------------------------------------------------------------ MCTS.expand_tree (MCTS.py:60-149)
     def _root_std_values(self):
         if self.device_eval:
-            out = self.nnet.forward_states(self.arena.get_roots(), _lib.EVAL_STD)
+            out = self.nnet.forward_states(self.arena.get_roots(), _lib.EVAL_STD, **self._search_kw())
             v = self.arena.to_host(out["v"])
             return [np.float32(x) for x in v]
         vals = []
@@ -276,7 +281,7 @@ class BatchedMCTS:
     def _root_std_values_array(self):
         """`_root_std_values` as one float32 array (no per-game Python scalars: 4 ms per move-step at 16,384 games)"""
         if self.device_eval:
-            out = self.nnet.forward_states(self.arena.get_roots(), _lib.EVAL_STD)
+            out = self.nnet.forward_states(self.arena.get_roots(), _lib.EVAL_STD, **self._search_kw())
             return np.asarray(self.arena.to_host(out["v"]), dtype=np.float32).reshape(-1)
         return np.asarray(self._root_std_values(), dtype=np.float32)
 
@@ -309,7 +314,7 @@ class BatchedMCTS:
         Returns None when the synchronous path has to be used (host evaluation, or roots without visits)."""
         if not self.device_eval or (N0.sum(axis=1) == 0).any():
             return None
-        v_dev = self.nnet.forward_states(self.arena.get_roots(), _lib.EVAL_STD)["v"]
+        v_dev = self.nnet.forward_states(self.arena.get_roots(), _lib.EVAL_STD, **self._search_kw())["v"]
         self.search(expand_by, check=False)
         return N0.copy(), v_dev
 

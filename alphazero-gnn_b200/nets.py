@@ -161,6 +161,24 @@ class _TwoPlayer(_Base):
     def _precision_supported(self, prec):
         return True
 
+    def search_precision(self):
+        """Precision of leaf evaluations INSIDE the search (BatchedMCTS: self-play, arena).  An explicit `b200_precision`
+        or `b200_search_precision` is followed; under `auto` the search runs the fastest tensor-core mode without the
+        per-weight-version guard: on trained weights the guard would put the whole self-play on the 13x slower fp32 path
+        for the last few 1e-6 of accuracy, while priors and values that differ by ~1e-5 move a PUCT arg-max only where two
+        scores tie to that precision (any change of summation order does the same).  Stated tolerance of search
+        evaluations on trained weights: 5e-5 on pi and v (measured <= 1.3e-5, tests/test_trained_gpu.py); the
+        reference-facing calls (`predict`, `predict_with_gnn`, `predict_batch`) keep the guard."""
+        name = arg(self.args, "b200_search_precision", None)
+        if name:
+            return self.active_precision() if name == "auto" else _lib.PRECISIONS[name]
+        if self.precision != _lib.PREC_AUTO:
+            return self.precision
+        for cand in self.AUTO_CANDIDATES:
+            if self._precision_supported(cand):
+                return cand
+        return _lib.PREC_FP32
+
     def _probe_boards(self):
         """AUTO_PROBE boards: iid cells in {-1, 0, 1}, and positions that look like play (every column filled from its
         first row up to a random height with random stones -- Connect4's gravity; for TicTacToe just sparser fills)"""
@@ -265,8 +283,12 @@ class B200Connect4NNetWrapper(_TwoPlayer):
         # (3-term bf16 split), whichever first keeps a probe batch inside the fp32 contract for the current weights --
         # an unchanged config.yaml gets the fast path, and a weight version that breaks a split falls back (logged)
         self.precision = self._configured_precision(args)
-        # opt-in: evaluate predict_with_gnn with output_transform.2 folded into the heads (_lib.EVAL_FOLD)
-        self.fold_heads = bool(arg(args, "b200_fold_heads", False))
+        # `b200_fold_heads`: evaluate predict_with_gnn with output_transform.2 folded into the heads (_lib.EVAL_FOLD, exact
+        # algebra, one F x F contraction instead of two).  True: every call; False: never; unset (default): inside the search
+        # only (self-play / arena consume nothing but pi and v), the reference-facing calls run both contractions
+        fold = arg(args, "b200_fold_heads", None)
+        self.fold_heads = bool(fold) if fold is not None else False
+        self.fold_search = bool(fold) if fold is not None else True
         self._packed, self._packed_ok = {}, False
 
     def _params(self, prec, need_packed):
@@ -293,15 +315,16 @@ class B200Connect4NNetWrapper(_TwoPlayer):
             self._packed[prec] = blob
         return self._packed[prec]
 
-    def forward_states(self, states, eval_mask=None, precision=None, count=None, out=None):
+    def forward_states(self, states, eval_mask=None, precision=None, count=None, out=None, search=False):
         """states: int64 [B,2] on the device.  Returns device tensors pi/v (+pi_gnn/v_gnn).
         count: optional device int32 scalar -- only the first `count` rows are live (compacted leaf batches,
-        read by the kernels on the device; rows beyond it are left untouched on the tensor-core path)."""
+        read by the kernels on the device; rows beyond it are left untouched on the tensor-core path).
+        search: a leaf batch of the tree search (`search_precision`, folded heads by default)."""
         eval_mask = self._default_mask() if eval_mask is None else eval_mask
         if (eval_mask & _lib.EVAL_GNN) and self.gnn is None:
             raise RuntimeError("predict_with_gnn needs the GNN wrapper")
-        prec = self.active_precision() if precision is None else precision
-        if self.fold_heads and prec != _lib.PREC_FP32 and (eval_mask & _lib.EVAL_GNN):
+        prec = precision if precision is not None else (self.search_precision() if search else self.active_precision())
+        if (self.fold_heads or (search and self.fold_search)) and prec != _lib.PREC_FP32 and (eval_mask & _lib.EVAL_GNN):
             eval_mask |= _lib.EVAL_FOLD
         B = int(states.shape[0])
         o = self._outputs(B, eval_mask) if out is None else out
@@ -367,11 +390,11 @@ class B200TicTacToeNNetWrapper(_TwoPlayer):
             p.ot0_w, p.ot0_b, p.ot2_w, p.ot2_b = ptr(ot[0].weight), ptr(ot[0].bias), ptr(ot[2].weight), ptr(ot[2].bias)
         return p
 
-    def forward_states(self, states, eval_mask=None, precision=None):
+    def forward_states(self, states, eval_mask=None, precision=None, search=False):
         eval_mask = self._default_mask() if eval_mask is None else eval_mask
         if (eval_mask & _lib.EVAL_GNN) and self.gnn is None:
             raise RuntimeError("predict_with_gnn needs the GNN wrapper")
-        prec = self.active_precision() if precision is None else precision
+        prec = precision if precision is not None else (self.search_precision() if search else self.active_precision())
         B = int(states.shape[0])
         o = self._outputs(B, eval_mask)
         if B == 0:

@@ -288,7 +288,7 @@ class BatchedSelfPlay:
     def _expand_only(self, check=True):
         """expand_tree's searches without building the example records (throughput runs)."""
         if self.mcts.device_eval:
-            self.mcts.nnet.forward_states(self.mcts.arena.get_roots(), _lib.EVAL_STD)  # MCTS.py:108-111
+            self.mcts.nnet.forward_states(self.mcts.arena.get_roots(), _lib.EVAL_STD, **self.mcts._search_kw())  # MCTS.py:108-111
         self.mcts.search(self.expand_by, check=check)
         return None
 

@@ -468,11 +468,12 @@ def run_gpu_arm(args, rank, local_rank, world):
             barrier()
     sp_fold = None
     if args.selfplay_games > 0 and args.precision != "fp32" and world == 1:
-        net.fold_heads = True  # same search, leaves evaluated with output_transform.2 folded into the heads (opt-in mode)
+        net.fold_search = False  # same search with BOTH F x F contractions at every leaf (b200_fold_heads: false)
         f_moves, f_leaves, f_ms = gpu_selfplay(net, a, args.selfplay_games, args.selfplay_moves, seed=rank)
-        net.fold_heads = False
+        net.fold_search = True
         sp_fold = {"value": f_moves, "unit": "moves/s", "leaf_evals_per_s_in_search": f_leaves,
-                   "ms_per_move_step": f_ms / max(args.selfplay_moves, 1), "note": "b200_fold_heads=True (see also.*_folded_heads)"}
+                   "ms_per_move_step": f_ms / max(args.selfplay_moves, 1),
+                   "note": "b200_fold_heads: false -- the search evaluates leaves with both contractions, as `value` does"}
     # ---- BASELINE configs[3]: the training step (data-parallel, NCCL gradient all-reduce inside the captured step) and one
     # whole Coach iteration, so that the multi-GPU lines carry the one collective of the path ----
     train_rec, coach_rec = None, None
@@ -537,7 +538,10 @@ def run_gpu_arm(args, rank, local_rank, world):
                         "move_steps_timed": args.selfplay_moves, "ms_per_move_step": sp_ms / max(args.selfplay_moves, 1),
                         "config": "connect4/config.yaml search settings: numMCTSSims 10, expand_by 5, cpuct 1.0, "
                                   "tempThreshold 15, use_gnn (leaves searched with the GNN prediction; the standard prediction, "
-                                  "which the reference also computes per leaf but reads only at roots, is evaluated at roots)",
+                                  "which the reference also computes per leaf but reads only at roots, is evaluated at roots); "
+                                  "leaf evaluations inside the search use the exact head fold (the wrappers' default: "
+                                  "[Wp;Wv] W2 applied in GEMM-1's epilogue, one F x F contraction; `selfplay_unfolded_search` "
+                                  "is the same search with both contractions)",
                         "cpu_baseline": None if cpu_mps is None else
                         {"value": cpu_mps, "unit": "moves/s", "cores": cores, "kind": "port",
                          "sample": f"{args.cpu_selfplay_episodes} sequential episodes ({cpu_moves} moves, "
@@ -572,7 +576,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                 {"value": steady_moves, "unit": "moves/s", "move_steps_timed": args.selfplay_steady_moves, "ms_per_move_step": steady_ms / args.selfplay_steady_moves,
                  "note": "the Coach.learn path: device example collection on, 50 untimed move-steps first so that every slot has "
                          "turned over, episodes end and restart inside the timed region"},
-                "selfplay_folded_heads": sp_fold,
+                "selfplay_unfolded_search": sp_fold,
                 "train": train_rec,
                 "coach_iteration": coach_rec,
                 "also": also,

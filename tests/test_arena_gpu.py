@@ -88,7 +88,8 @@ def test_search_with_device_networks_matches_oracle_search(kind, n, prec):
     from helpers import dotdict
     use_gnn = kind != "frozenlake"
     args = dotdict(dict(lr=1e-3, dropout=0.3, gnn_layers=2, embedding_dim=128, numMCTSSims=20, cpuct=1.0 if use_gnn else 2.0,
-                        use_gnn=use_gnn, expand_by=5, b200_precision=prec))
+                        use_gnn=use_gnn, expand_by=5, b200_precision=prec,
+                        b200_fold_heads=False))  # the oracle search is fed net.predict_with_gnn: the search must evaluate the same way
     game = {"connect4": games.Connect4Game, "tictactoe": games.TicTacToeGame, "frozenlake": games.FrozenLakeGame}[kind](n)
     torch.manual_seed(0)
     net = {"connect4": B200Connect4GNNWrapper, "tictactoe": B200TicTacToeGNNWrapper, "frozenlake": B200FrozenLakeNet}[kind](game, args)
@@ -155,7 +156,7 @@ def test_many_concurrent_trees_properties():
     from helpers import dotdict
     n, distinct, copies = 7, 512, 16
     args = dotdict(dict(lr=1e-3, dropout=0.3, gnn_layers=2, numMCTSSims=10, cpuct=1.0, use_gnn=True, expand_by=5,
-                        b200_precision="bf16x3"))
+                        b200_precision="bf16x3", b200_fold_heads=False))  # search == predict_with_gnn bit for bit (no head fold)
     game = games.Connect4Game(n)
     torch.manual_seed(0)
     net = B200Connect4GNNWrapper(game, args)

@@ -488,3 +488,29 @@ def test_full_size_batch_properties():
         assert float((s - 1).abs().max()) <= 1e-5 and float(full[name].min()) >= 0.0
     for name in ("v", "v_gnn"):
         assert float(full[name].abs().max()) <= 1.0
+
+
+def test_search_mode_defaults():
+    """Leaf evaluations made for the tree search (`forward_states(search=True)`, what BatchedMCTS calls) run the fastest
+    tensor-core mode with the exact head fold by default -- unguarded, stated tolerance 5e-5 -- while the reference-facing calls
+    keep the guard and both contractions; explicit settings are followed by both."""
+    w = _wrapper("c4", 7, b200_precision="auto")
+    assert w.search_precision() == _lib.PREC_F16F8 and w.fold_search and not w.fold_heads
+    rng = np.random.default_rng(3)
+    boards = rng.integers(-1, 2, size=(300, 7, 7)).astype(np.int64)
+    states = w.states_from_boards(boards)
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    with torch.no_grad():
+        gpi, gv = onets.c4_predict_with_gnn(p, q, onets.boards_to_tensor(boards), 7)
+    s = w.forward_states(states, _lib.EVAL_GNN, search=True)
+    folded = w.forward_states(states, _lib.EVAL_GNN | _lib.EVAL_FOLD, precision=_lib.PREC_F16F8)
+    assert torch.equal(s["pi_gnn"], folded["pi_gnn"]) and torch.equal(s["v_gnn"], folded["v_gnn"])
+    assert np.abs(s["pi_gnn"].cpu().numpy() - gpi.numpy()).max() <= 1e-5 and np.abs(s["v_gnn"].cpu().numpy() - gv.numpy()).max() <= 1e-5
+    api = w.forward_states(states, _lib.EVAL_GNN)
+    plain = w.forward_states(states, _lib.EVAL_GNN, precision=w.active_precision())
+    assert torch.equal(api["v_gnn"], plain["v_gnn"])
+    for kw, prec, fold in ((dict(b200_precision="fp32"), _lib.PREC_FP32, True), (dict(b200_precision="bf16x3", b200_fold_heads=False), _lib.PREC_BF16X3, False),
+                           (dict(b200_search_precision="bf16x3"), _lib.PREC_BF16X3, True)):
+        w2 = _wrapper("c4", 5, **{**dict(b200_precision="auto"), **kw})
+        assert w2.search_precision() == prec and w2.fold_search == fold
+    assert _wrapper("ttt", 3, b200_precision="auto").search_precision() == _lib.PREC_BF16X3
