@@ -50,6 +50,12 @@ class FLParams(C.Structure):
                 ("gnn_b", C.POINTER(_vp)), ("policy_w", _vp), ("policy_b", _vp), ("value_w", _vp), ("value_b", _vp)]
 
 
+class MoveParams(C.Structure):
+    _fields_ = [("G", _i), ("A", _i), ("T", _i)] + [(k, _vp) for k in (
+        "n0", "greedy", "u_tie", "u_sample", "roots", "player", "slot", "n1", "q1", "t1", "v0", "actions", "h_states", "h_pi",
+        "h_player", "h_int", "rec_ip", "rec_iv", "rec_ep", "rec_ev", "rec_evtag", "flags")]
+
+
 # name -> (restype, argtypes); mirrors include/azgnn_b200.h one to one
 SIGNATURES = {
     "azg_last_error": (C.c_char_p, []),
@@ -90,6 +96,7 @@ SIGNATURES = {
     "azg_grid_pack_weights": (_i, [_vp, _i, _i, _vp, _vp]),
     "azg_grid_layer_tc_forward": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "azg_grid_layer_tc_backward_input": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "azg_selfplay_move": (_i, [C.POINTER(MoveParams), _vp]),
     "azg_emit_examples": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "azg_gather_examples": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "azg_grid_dw_scratch_floats": (_sz, [_i]),
@@ -138,7 +145,7 @@ def lib():
             raise RuntimeError(f"{LIB_PATH} is not built; run `python alphazero-gnn_b200/build.py` "
                                "(nvcc, sm_100a). There is no CPU fallback.")
         _lib = bind(C.CDLL(LIB_PATH))
-        if _lib.azg_abi_version() != 2:
+        if _lib.azg_abi_version() != 3:
             raise RuntimeError("libazgnn_b200.so ABI version mismatch; rebuild")
     return _lib
 

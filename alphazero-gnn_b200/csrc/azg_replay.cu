@@ -91,9 +91,139 @@ __global__ void gather_examples_kernel(const State2* __restrict__ states, const 
   }
 }
 
+
+// ---- the host tail of a self-play move, on the device --------------------------------------------------------------------
+// Per game, one thread (Coach.py:36-63 and MCTS.py:36-58, 94-143 between the searches of a move and the move itself):
+//   getActionProb's tail   counts -> policy: temp 1: [(x + 1e-8)] / float(sum(.)) with CPython's left-to-right Neumaier `sum`;
+//                          temp 0: uniform choice among the arg-max counts from the supplied uniform, one-hot policy
+//   np.random.choice       inverse CDF of the policy at the supplied uniform (sequential cumsum, cdf /= cdf[-1])
+//   history                (root state, policy, player, temp-0 flag) -> slot [t, g] of the episode history in HBM
+//   expand_tree record     initial / expanded visit policies and the expanded value sum_a Q N / sum_a N with the NEP-50
+//                          promotion order of the reference's scalar loop (Python number until the first np.float32 term)
+// Every rounding is spelled out (no FMA contraction): the results equal selfplay.probs_from_counts / sample_actions and
+// mcts.expanded_values bit for bit, which tests/test_replay_gpu.py checks through whole self-play runs.
+constexpr int MOVE_MAX_A = 65;  // TicTacToe 8x8 + pass (MOVE_MAX_A of the arena core)
+__global__ void __launch_bounds__(128) selfplay_move_kernel(azg_move_params p) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= p.G) return;
+  const int A = p.A;
+  const int t = p.slot[g];
+  if (t < 0) {
+    p.actions[g] = -1;
+    return;
+  }
+  const int32_t* n0 = p.n0 + (size_t)g * A;
+  double probs[MOVE_MAX_A];
+  int act = 0;
+  if (p.greedy[g]) {
+    int best = n0[0], nbest = 0;
+    for (int a = 1; a < A; ++a) best = n0[a] > best ? n0[a] : best;
+    for (int a = 0; a < A; ++a) nbest += n0[a] == best;
+    const long long k = (long long)__dmul_rn(p.u_tie[g], (double)nbest);
+    int seen = 0, pick = 0;
+    bool found = false;
+    for (int a = 0; a < A; ++a) {
+      seen += n0[a] == best;
+      if (!found && (long long)seen > k) { pick = a; found = true; }
+    }
+    for (int a = 0; a < A; ++a) probs[a] = a == pick ? 1.0 : 0.0;
+  } else {
+    double f = __dadd_rn((double)n0[0], 1e-8), c = 0.0;
+    for (int a = 1; a < A; ++a) {
+      const double v = __dadd_rn((double)n0[a], 1e-8);
+      const double s = __dadd_rn(f, v);
+      c = __dadd_rn(c, fabs(f) >= fabs(v) ? __dadd_rn(__dadd_rn(f, -s), v) : __dadd_rn(__dadd_rn(v, -s), f));
+      f = s;
+    }
+    const double tot = (c != 0.0 && isfinite(c)) ? __dadd_rn(f, c) : f;
+    for (int a = 0; a < A; ++a) probs[a] = __ddiv_rn(__dadd_rn((double)n0[a], 1e-8), tot);
+  }
+  {  // numpy.random.choice(len(p), p=p): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, side='right')
+    double cdf[MOVE_MAX_A];
+    double run = 0.0;
+    for (int a = 0; a < A; ++a) {
+      run = a == 0 ? probs[0] : __dadd_rn(run, probs[a]);
+      cdf[a] = run;
+    }
+    const double last = cdf[A - 1], u = p.u_sample[g];
+    int cnt = 0;
+    for (int a = 0; a < A; ++a) cnt += __ddiv_rn(cdf[a], last) <= u;
+    act = cnt < A - 1 ? cnt : A - 1;
+  }
+  p.actions[g] = act;
+  const size_t slot = (size_t)t * p.G + g;
+  if (p.h_states) {
+    p.h_states[2 * slot] = p.roots[2 * g];
+    p.h_states[2 * slot + 1] = p.roots[2 * g + 1];
+    for (int a = 0; a < A; ++a) p.h_pi[slot * A + a] = probs[a];
+    p.h_player[slot] = p.player[g];
+    p.h_int[slot] = p.greedy[g];
+  }
+  if (p.n1 && p.rec_ip) {
+    // initial / expanded visit policies (MCTS.py:95-103, 125-130): N / sum(N), small integers: exact in any order
+    const int32_t* n1 = p.n1 + (size_t)g * A;
+    long long tot0 = 0, tot1 = 0;
+    for (int a = 0; a < A; ++a) {
+      tot0 += n0[a] > 0 ? n0[a] : 0;
+      tot1 += n1[a] > 0 ? n1[a] : 0;
+    }
+    if (tot0 <= 0) atomicOr(p.flags, 1);  // no root visits: the host path's valid-move fallback is not reproduced here
+    for (int a = 0; a < A; ++a) {
+      const double ip = tot0 > 0 ? __ddiv_rn((double)(n0[a] > 0 ? n0[a] : 0), (double)tot0) : 0.0;
+      p.rec_ip[slot * A + a] = ip;
+      p.rec_ep[slot * A + a] = tot1 > 0 ? __ddiv_rn((double)(n1[a] > 0 ? n1[a] : 0), (double)tot1) : ip;
+    }
+    // expanded value (MCTS.py:132-143), see mcts.expanded_values
+    const double* q1 = p.q1 + (size_t)g * A;
+    const int8_t* t1 = p.t1 + (size_t)g * A;
+    double acc64 = 0.0;
+    float acc32 = 0.0f;
+    bool is32 = false;
+    long long cntv = 0;
+    for (int a = 0; a < A; ++a) {
+      const long long n = n1[a];
+      const bool valid = t1[a] != AZG_TAG_NONE && n > 0;
+      if (!valid) continue;
+      const bool f32 = t1[a] == AZG_TAG_F32;
+      if (!f32) {
+        const double term64 = __dmul_rn(q1[a], (double)n);
+        if (!is32) acc64 = __dadd_rn(acc64, term64);
+        else acc32 = __fadd_rn(acc32, (float)term64);
+      } else {
+        const float term32 = __fmul_rn((float)q1[a], (float)n);
+        acc32 = is32 ? __fadd_rn(acc32, term32) : __fadd_rn((float)acc64, term32);
+        is32 = true;
+      }
+      cntv += n;
+    }
+    double ev;
+    int8_t evtag;
+    if (cntv > 0) {
+      ev = is32 ? (double)__fdiv_rn(acc32, (float)cntv) : __ddiv_rn(acc64, (double)cntv);
+      evtag = is32 ? AZG_TAG_F32 : AZG_TAG_PYFLOAT;
+    } else {
+      ev = (double)p.v0[g];
+      evtag = AZG_TAG_F32;
+    }
+    p.rec_iv[slot] = p.v0[g];
+    p.rec_ev[slot] = ev;
+    p.rec_evtag[slot] = evtag;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int azg_selfplay_move(const azg_move_params* p, azg_stream stream) {
+  AZG_REQUIRE(p && p->G > 0 && p->A >= 1 && p->A <= MOVE_MAX_A, "azg_selfplay_move: bad sizes");
+  AZG_REQUIRE(p->n0 && p->greedy && p->u_tie && p->u_sample && p->slot && p->actions && p->flags, "azg_selfplay_move: null pointer");
+  AZG_REQUIRE(!p->h_states || (p->roots && p->player && p->h_pi && p->h_player && p->h_int && p->T > 0), "azg_selfplay_move: history buffers missing");
+  AZG_REQUIRE(!p->n1 || !p->rec_ip || (p->q1 && p->t1 && p->v0 && p->rec_iv && p->rec_ep && p->rec_ev && p->rec_evtag), "azg_selfplay_move: record buffers missing");
+  selfplay_move_kernel<<<grid_for(p->G, 128), 128, 0, (cudaStream_t)stream>>>(*p);
+  AZG_LAUNCH_CHECK();
+  return AZG_OK;
+}
 
 int azg_emit_examples(int frozenlake, const uint64_t* states, const double* pi, const int32_t* player, const int32_t* game,
                       const double* result, const int8_t* result_tag, const int32_t* cur, int64_t E, int ncells, int A, int S,

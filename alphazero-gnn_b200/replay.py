@@ -262,9 +262,9 @@ class DeviceGnnExamples(_Columns):
         self._init_columns(game, device)
 
     def append_records(self, states, player, ip, iv, ep, ev, evtag, sign, signtag):
-        """device `states` [E,2]; the other columns as host arrays (expand_tree_arrays output, vectorised signs)"""
+        """device `states` [E,2]; the other columns as host arrays or device tensors (expand_tree records, vectorised signs)"""
         d = self.device
-        up = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x)).to(d).to(dt)
+        up = lambda x, dt: (x if torch.is_tensor(x) else torch.as_tensor(np.ascontiguousarray(x))).to(d).to(dt)
         self._append(states, up(player, torch.int32), up(ip, torch.float64), up(iv, torch.float32), up(ep, torch.float64),
                      up(ev, torch.float64), up(evtag, _I8), up(sign, torch.float64), up(signtag, _I8))
 

@@ -11,10 +11,13 @@ move sampling is `numpy.random.choice`'s inverse-CDF rule (Coach.py:63), one uni
 from this object's own Generator (the reference's global-RNG stream is only defined for a
 single sequential game; the compat class `azgnn_b200.mcts.MCTS` keeps that behaviour).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
 from . import _lib
+from ._lib import ptr
 from .mcts import BatchedMCTS, arg, pack_states
 
 EPS = 1e-8
@@ -123,6 +126,21 @@ class BatchedSelfPlay:
             self.g_rec = (np.zeros((self.t_cap, self.G, self.A)), np.zeros((self.t_cap, self.G), dtype=np.float32),
                           np.zeros((self.t_cap, self.G, self.A)), np.zeros((self.t_cap, self.G)),
                           np.zeros((self.t_cap, self.G), dtype=np.int8))
+        # Device tail (azg_selfplay_move): policy from counts, move sampling, history slots and expand_tree records are
+        # computed by ONE kernel from this object's own uniform stream, so per move only the game-ended flags come back to
+        # the host.  Used with device evaluation on the CUDA arena when examples stay on the device or are not collected.
+        self.device_tail = bool(self.mcts.device_eval and (self.device_collect or not self.collect) and
+                                getattr(self.mcts.arena, "device", None) is not None and self.mcts.arena.device.type == "cuda")
+        if self.device_tail:
+            dev = self.mcts.arena.device
+            self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._actions = torch.zeros(self.G, dtype=torch.int32, device=dev)
+            self._init_dev = torch.as_tensor(np.asarray(self.init_state).astype(np.uint64).view(np.int64)).to(dev)
+            if self.device_collect and self.use_gnn:  # expand_tree records per (episode step, game), in HBM
+                tc, G_, A_ = self.t_cap, self.G, self.A
+                self.g_rec_dev = (torch.zeros(tc, G_, A_, dtype=torch.float64, device=dev), torch.zeros(tc, G_, dtype=torch.float32, device=dev),
+                                  torch.zeros(tc, G_, A_, dtype=torch.float64, device=dev), torch.zeros(tc, G_, dtype=torch.float64, device=dev),
+                                  torch.zeros(tc, G_, dtype=torch.int8, device=dev))
         self._start_all()
 
     # ------------------------------------------------------------------ episode bookkeeping
@@ -186,7 +204,10 @@ class BatchedSelfPlay:
                                   torch.as_tensor(cur_players.astype(np.int32)).to(dev), pi_int=self.h_int[t, gi])
         if self.use_gnn:  # Coach.py:72-74: one GNN record per stored position, no symmetries
             players = self.h_player_host[tcol, gcol]  # host mirror of h_player: no read-back behind the queued searches
-            ip, iv, ep, ev, evtag = (x[tcol, gcol] for x in self.g_rec)
+            if self.device_tail:
+                ip, iv, ep, ev, evtag = (x[t, gi] for x in self.g_rec_dev)
+            else:
+                ip, iv, ep, ev, evtag = (x[tcol, gcol] for x in self.g_rec)
             cur_e = np.repeat(cur_players, lens)
             sign = np.repeat(res, lens) * np.where(players != cur_e, -1.0, 1.0)
             self.device_gnn_examples.append_records(self.h_states[t, gi], players, ip, iv, ep, ev, evtag, sign, np.repeat(tag, lens))
@@ -202,6 +223,8 @@ class BatchedSelfPlay:
         pending, `self._inflight`) before this move's records are computed and its finished episodes are emitted.  The
         arena state each search starts from and the order in which `self.rng` is consumed (policy tie-breaks, then the
         sampled moves) are those of the sequential loop."""
+        if self.device_tail:
+            return self._step_all_device()
         m, G = self.mcts, self.G
         n_sims = int(arg(self.args, "numMCTSSims"))
         self.step += 1
@@ -284,6 +307,86 @@ class BatchedSelfPlay:
                     self._finish_device(keep, ended, lens, cur)
                 out = [([], []) for _ in done]
         return out
+
+    def _step_all_device(self):
+        """`step_all` with the host tail on the device: same searches, same uniforms in the same order (tie-break draws
+        of the temp-0 games, then one sampling draw per game), same bookkeeping -- but counts, policies, actions, history
+        and expand_tree records never leave HBM; the one read-back per move is the game-ended flags (+ arena status)."""
+        from .mcts import typed_value
+        m, G, A = self.mcts, self.G, self.A
+        ar = m.arena
+        dev = ar.device
+        n_sims = int(arg(self.args, "numMCTSSims"))
+        self.step += 1
+        greedy = self.step >= self.temp_threshold  # temp == 0 (Coach.py:37)
+        if self._inflight:
+            self._inflight = False  # the searches queued at the end of the previous move; status is read below
+        else:
+            m.search(n_sims, check=False)
+        n0 = ar.root_stats()[0].clone()
+        n1 = q1 = t1 = v0 = None
+        if self.use_gnn:  # expand_tree (MCTS.py:60-149): standard root value, expand_by more searches
+            v0 = m.nnet.forward_states(ar.get_roots(), _lib.EVAL_STD, **m._search_kw())["v"]
+            m.search(self.expand_by, check=False)
+            if self.device_collect:
+                n1, q1, t1 = ar.root_stats()
+        u = np.zeros((2, G))
+        u[0, greedy] = self.rng.random(int(greedy.sum()))  # np.random.choice(bestAs) of the temp-0 games, in game order
+        u[1] = self.rng.random(G)                          # np.random.choice(len(pi), p=pi)
+        th = self.step - 1
+        host = np.stack([th.astype(np.int32), self.player.astype(np.int32), greedy.astype(np.int32)])
+        u_dev = torch.as_tensor(u).to(dev)
+        h_dev = torch.as_tensor(host).to(dev)
+        greedy_dev = h_dev[2].to(torch.int8)
+        roots = ar.get_roots().view(G, 2)
+        p = _lib.MoveParams()
+        p.G, p.A, p.T = G, A, int(getattr(self, "t_cap", 1))
+        p.n0, p.greedy, p.u_tie, p.u_sample = ptr(n0), ptr(greedy_dev), ptr(u_dev[0]), ptr(u_dev[1])
+        p.roots, p.player, p.slot = ptr(roots), ptr(h_dev[1]), ptr(h_dev[0])
+        p.actions, p.flags = ptr(self._actions), ptr(self._flags)
+        if self.device_collect:
+            p.h_states, p.h_pi, p.h_player, p.h_int = ptr(self.h_states), ptr(self.h_pi), ptr(self.h_player), ptr(self.h_int)
+            if n1 is not None:
+                p.n1, p.q1, p.t1, p.v0 = ptr(n1), ptr(q1), ptr(t1), ptr(v0)
+                p.rec_ip, p.rec_iv, p.rec_ep, p.rec_ev, p.rec_evtag = (ptr(x) for x in self.g_rec_dev)
+            self.h_player_host[th, np.arange(G)] = self.player
+        _lib.check(_lib.lib().azg_selfplay_move(C.byref(p), _lib.stream()))
+        e_dev, tag_dev = ar.advance(self._actions)
+        # ---- the one synchronisation of the move ----
+        e_val, e_tag = ar.to_host(e_dev), ar.to_host(tag_dev)
+        ar.check_status()
+        if int(self._flags.item()):
+            raise RuntimeError("self-play: a game had no root visits after its searches")
+        self.moves_played += G
+        if self.two_player:
+            self.player = -self.player
+        over = e_val != 0
+        if self.max_episode_steps is not None:
+            over = over | ((self.step >= self.max_episode_steps) & ~over)
+        done = [int(g) for g in np.flatnonzero(over)]
+        ended = {g: (typed_value(e_val[g], int(e_tag[g])) if e_val[g] != 0 else 0.0) for g in done}
+        self.last_done_index = self.ep_index[done].copy() if done else np.zeros(0, dtype=np.int64)
+        keep, lens, cur = [], None, None
+        if self.device_collect and done:
+            keep = done if self._keep_below is None else [g for g in done if self.ep_index[g] < self._keep_below]
+            lens, cur = self.step[keep].copy(), self.player[keep].copy()
+        if done:
+            self.episodes_done += len(done)
+            ar.reset(np.asarray(done, dtype=np.int32))  # new MCTS per episode, Coach.py:96
+            ids = torch.as_tensor(np.asarray(done, dtype=np.int64)).to(dev)
+            now = ar.get_roots()  # the positions after this move; finished games go back to the initial board
+            now[ids] = self._init_dev
+            ar.set_roots(now)
+            d = np.asarray(done)
+            self.step[d] = 0
+            self.player[d] = 1
+            self.ep_index[d] = self._next_ep + np.arange(len(done))
+            self._next_ep += len(done)
+        m.search(n_sims, check=False)  # next move's searches run while the host emits the finished episodes
+        self._inflight = True
+        if keep:
+            self._finish_device(keep, ended, lens, cur)
+        return [([], []) for _ in done]
 
     def _expand_only(self, check=True):
         """expand_tree's searches without building the example records (throughput runs)."""

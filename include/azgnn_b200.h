@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AZG_ABI_VERSION 2
+#define AZG_ABI_VERSION 3
 
 #define AZG_OK 0
 #define AZG_ERR_INVALID 1   /* bad argument */
@@ -238,6 +238,38 @@ int azg_grid_layer_tc_backward_weights(const float* s, const float* x, int64_t r
  *   entry pi_perm[s][a] (tables built on the host from the reference's own numpy calls).  Outputs: example e*S+s.
  *   out_v may be NULL (positions without a value, e.g. GNN records).  frozenlake != 0: S = 1, states copied.
  * azg_gather_examples: minibatch assembly (Connect4GNN.py:141-148): boards float32 [B,n,n], pi, v float32. */
+/* azg_selfplay_move: what Coach.executeEpisode does between the searches of a move and the move itself (Coach.py:36-63),
+ * for every game of the arena at once: getActionProb's tail (MCTS.py:36-58: counts -> policy with CPython's compensated `sum`,
+ * temp-0 tie-break from u_tie), np.random.choice (inverse CDF at u_sample), the history slot [t, g] (root state, policy, player,
+ * temp-0 flag) and, with n1 / q1 / t1 / v0, expand_tree's record (MCTS.py:94-143: initial / expanded visit policies, expanded
+ * value with the NEP-50 promotion order).  The uniforms come from the caller's NumPy stream, so the results equal the host
+ * path's bit for bit.  slot[g] < 0 skips the game (actions[g] = -1).  flags bit 0: a game had no root visits. */
+typedef struct azg_move_params {
+  int G, A, T;              /* games, actions, history slots per game */
+  const int32_t* n0;        /* [G,A] root visit counts after the numMCTSSims searches */
+  const int8_t* greedy;     /* [G] temp == 0 */
+  const double* u_tie;      /* [G] */
+  const double* u_sample;   /* [G] */
+  const uint64_t* roots;    /* [G,2] packed root states */
+  const int32_t* player;    /* [G] */
+  const int32_t* slot;      /* [G] history slot of this move */
+  const int32_t* n1;        /* [G,A] root counts after expand_by more searches, or NULL */
+  const double* q1;         /* [G,A] */
+  const int8_t* t1;         /* [G,A] Q type tags */
+  const float* v0;          /* [G] standard root value */
+  int32_t* actions;         /* [G] out */
+  uint64_t* h_states;       /* [T,G,2] out, or NULL: no history */
+  double* h_pi;             /* [T,G,A] */
+  int32_t* h_player;        /* [T,G] */
+  int8_t* h_int;            /* [T,G] */
+  double* rec_ip;           /* [T,G,A] out, or NULL: no GNN records */
+  float* rec_iv;            /* [T,G] */
+  double* rec_ep;           /* [T,G,A] */
+  double* rec_ev;           /* [T,G] */
+  int8_t* rec_evtag;        /* [T,G] */
+  int32_t* flags;           /* [1] */
+} azg_move_params;
+int azg_selfplay_move(const azg_move_params* p, azg_stream stream);
 int azg_emit_examples(int frozenlake, const uint64_t* states, const double* pi, const int32_t* player, const int32_t* game,
                       const double* result, const int8_t* result_tag, const int32_t* cur, int64_t E, int ncells, int A, int S,
                       const int32_t* board_perm, const int32_t* pi_perm, uint64_t* out_states, double* out_pi, double* out_v,

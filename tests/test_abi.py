@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 25
     for s in syms:
         assert hasattr(cdll, s), f"{s} declared in include/azgnn_b200.h but not exported"
-    assert cdll.azg_abi_version() == 2
+    assert cdll.azg_abi_version() == 3
 
 
 def test_binding_table_matches_header():
