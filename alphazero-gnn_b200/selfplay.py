@@ -155,6 +155,7 @@ class BatchedSelfPlay:
         self.ep_index = np.arange(G, dtype=np.int64)  # episodes are numbered in the order they START
         self._next_ep = G
         self.last_done_index = np.zeros(0, dtype=np.int64)
+        self.active = np.ones(G, dtype=bool)  # device tail: a slot idles once play(n) needs no further episode from it
 
     def _restart(self, ids):
         ids = np.asarray(ids, dtype=np.int32)
@@ -333,7 +334,7 @@ class BatchedSelfPlay:
         u = np.zeros((2, G))
         u[0, greedy] = self.rng.random(int(greedy.sum()))  # np.random.choice(bestAs) of the temp-0 games, in game order
         u[1] = self.rng.random(G)                          # np.random.choice(len(pi), p=pi)
-        th = self.step - 1
+        th = np.where(self.active, self.step - 1, -1)  # slot -1: the game sits on its final position and is skipped
         host = np.stack([th.astype(np.int32), self.player.astype(np.int32), greedy.astype(np.int32)])
         u_dev = torch.as_tensor(u).to(dev)
         h_dev = torch.as_tensor(host).to(dev)
@@ -349,7 +350,8 @@ class BatchedSelfPlay:
             if n1 is not None:
                 p.n1, p.q1, p.t1, p.v0 = ptr(n1), ptr(q1), ptr(t1), ptr(v0)
                 p.rec_ip, p.rec_iv, p.rec_ep, p.rec_ev, p.rec_evtag = (ptr(x) for x in self.g_rec_dev)
-            self.h_player_host[th, np.arange(G)] = self.player
+            act_g = np.flatnonzero(self.active)
+            self.h_player_host[th[act_g], act_g] = self.player[act_g]
         _lib.check(_lib.lib().azg_selfplay_move(C.byref(p), _lib.stream()))
         e_dev, tag_dev = ar.advance(self._actions)
         # ---- the one synchronisation of the move ----
@@ -357,12 +359,12 @@ class BatchedSelfPlay:
         ar.check_status()
         if int(self._flags.item()):
             raise RuntimeError("self-play: a game had no root visits after its searches")
-        self.moves_played += G
+        self.moves_played += int(self.active.sum())
         if self.two_player:
             self.player = -self.player
-        over = e_val != 0
+        over = (e_val != 0) & self.active
         if self.max_episode_steps is not None:
-            over = over | ((self.step >= self.max_episode_steps) & ~over)
+            over = over | ((self.step >= self.max_episode_steps) & ~over & self.active)
         done = [int(g) for g in np.flatnonzero(over)]
         ended = {g: (typed_value(e_val[g], int(e_tag[g])) if e_val[g] != 0 else 0.0) for g in done}
         self.last_done_index = self.ep_index[done].copy() if done else np.zeros(0, dtype=np.int64)
@@ -372,16 +374,24 @@ class BatchedSelfPlay:
             lens, cur = self.step[keep].copy(), self.player[keep].copy()
         if done:
             self.episodes_done += len(done)
-            ar.reset(np.asarray(done, dtype=np.int32))  # new MCTS per episode, Coach.py:96
-            ids = torch.as_tensor(np.asarray(done, dtype=np.int64)).to(dev)
-            now = ar.get_roots()  # the positions after this move; finished games go back to the initial board
-            now[ids] = self._init_dev
-            ar.set_roots(now)
-            d = np.asarray(done)
-            self.step[d] = 0
-            self.player[d] = 1
-            self.ep_index[d] = self._next_ep + np.arange(len(done))
-            self._next_ep += len(done)
+            # play(n) starts exactly n episodes: once the n-th has started, a slot whose game ends goes idle (its root stays
+            # on the final position: searches return at once, no leaf is evaluated for it) instead of playing an episode
+            # that nobody would keep
+            n_new = len(done) if self._keep_below is None else max(0, min(len(done), self._keep_below - self._next_ep))
+            again, idle = done[:n_new], done[n_new:]
+            if idle:
+                self.active[np.asarray(idle)] = False
+            if again:
+                ar.reset(np.asarray(again, dtype=np.int32))  # new MCTS per episode, Coach.py:96
+                ids = torch.as_tensor(np.asarray(again, dtype=np.int64)).to(dev)
+                now = ar.get_roots()  # the positions after this move; finished games go back to the initial board
+                now[ids] = self._init_dev
+                ar.set_roots(now)
+                d = np.asarray(again)
+                self.step[d] = 0
+                self.player[d] = 1
+                self.ep_index[d] = self._next_ep + np.arange(len(again))
+                self._next_ep += len(again)
         m.search(n_sims, check=False)  # next move's searches run while the host emits the finished episodes
         self._inflight = True
         if keep:
@@ -403,6 +413,11 @@ class BatchedSelfPlay:
         short, decisive games (the reference plays numEps episodes sequentially, Coach.py:95-100)."""
         kept = []
         self._keep_below = n_episodes
+        if self.device_tail:
+            idle = np.flatnonzero(~self.active)
+            if idle.size:  # slots left idle by an earlier play(): back to the initial board with fresh episode numbers
+                self._restart(idle)
+                self.active[:] = True
         while len(kept) < n_episodes:
             out = self.step_all()
             kept.extend(ex for idx, ex in zip(self.last_done_index, out) if idx < n_episodes)
