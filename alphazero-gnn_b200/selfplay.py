@@ -56,12 +56,15 @@ def probs_from_counts(counts, temps, rng):
     x = counts.astype(np.float64) + EPS           # (x + EPS) ** 1.0 == x + EPS
     tot = python_float_sum(x)
     probs = x / tot[:, None]
+    # one tie-break uniform per game and move, used or not: a game's draws then do not depend on what the other slots
+    # of the batch are doing (the device tail lets slots idle; the kept episodes must not change with that)
+    r_all = rng.random(G)
     greedy = np.flatnonzero(np.asarray(temps) == 0)
     if greedy.size:
         c = counts[greedy]
         best = c == c.max(axis=1, keepdims=True)
         # uniform choice among the arg-max actions (np.random.choice(bestAs), MCTS.py:40-41)
-        r = rng.random(greedy.size)
+        r = r_all[greedy]
         k = (r * best.sum(axis=1)).astype(np.int64)
         pick = (np.cumsum(best, axis=1) > k[:, None]).argmax(axis=1)
         probs[greedy] = 0.0
@@ -331,9 +334,9 @@ class BatchedSelfPlay:
             m.search(self.expand_by, check=False)
             if self.device_collect:
                 n1, q1, t1 = ar.root_stats()
-        u = np.zeros((2, G))
-        u[0, greedy] = self.rng.random(int(greedy.sum()))  # np.random.choice(bestAs) of the temp-0 games, in game order
-        u[1] = self.rng.random(G)                          # np.random.choice(len(pi), p=pi)
+        u = np.empty((2, G))
+        u[0] = self.rng.random(G)  # np.random.choice(bestAs) of the temp-0 games (one draw per game, as probs_from_counts)
+        u[1] = self.rng.random(G)  # np.random.choice(len(pi), p=pi)
         th = np.where(self.active, self.step - 1, -1)  # slot -1: the game sits on its final position and is skipped
         host = np.stack([th.astype(np.int32), self.player.astype(np.int32), greedy.astype(np.int32)])
         u_dev = torch.as_tensor(u).to(dev)

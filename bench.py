@@ -142,11 +142,12 @@ def cpu_selfplay(episodes):
     return moves / dt, moves, dt
 
 
-def gpu_selfplay(net, a, games, moves, seed, collect=False, warm=2):
+def gpu_selfplay(net, a, games, moves, seed, collect=False, warm=8):
     """Lock-step self-play of `games` concurrent episodes on this GPU: moves/s over `moves` move-steps
     (each = getActionProb's 10 searches + expand_tree's 5 for every live game, then one move).  collect="device" is the
     Coach path (symmetric training examples emitted on the device as episodes end); with `warm` >= the longest game
-    the timed region is the steady state with episode turnover."""
+    the timed region is the steady state with episode turnover.  The default 8 untimed move-steps let the first games end
+    (7 plies at the earliest) before the clock starts: the first restart pays one-time lazy kernel loads."""
     import torch
     from azgnn_b200.games import Connect4Game
     from azgnn_b200.selfplay import BatchedSelfPlay
