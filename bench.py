@@ -616,7 +616,7 @@ def main():
     ap.add_argument("--selfplay-steady-moves", type=int, default=60, help="timed move-steps of the steady-state self-play leg (0 = skip)")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-sample", type=int, default=4096)
-    ap.add_argument("--selfplay-games", type=int, default=16384, help="concurrent self-play games per GPU (0 = skip)")
+    ap.add_argument("--selfplay-games", type=int, default=32768, help="concurrent self-play games per GPU (0 = skip)")
     ap.add_argument("--selfplay-moves", type=int, default=6)
     ap.add_argument("--cpu-selfplay-episodes", type=int, default=2)
     ap.add_argument("--train-epochs", type=int, default=60, help="timed epochs (std step + GNN step) of NeuralNet.train; 0 = skip")
