@@ -1396,8 +1396,14 @@ struct Trunk2Smem {
 
 constexpr int T2_THREADS = 640;  // 8 builder warps, MMA, TMEM/barrier setup, 2 idle, 2 x 4 epilogue warps
 
-template <bool X3>
+// PAIR (AZG_TRUNK=fused2pair, not the default): a cluster of two CTAs issues every tcgen05.mma ONCE for both CTAs' tiles
+// (cta_group::2, M = 256) and each CTA reads only its half of the weight operand.  Bit-identical to the single-CTA kernel and
+// measured at the same speed (0.655 vs 0.63-0.67 ms, profiles/r02_trunk_fused2.txt): the instruction count was not the bound.  Everything else stays per CTA (builders, planes, conv1 operand stages, epilogue); the peer CTA's MMA warp
+// relays "my operand is ready / my accumulator is drained" to the leader, which owns the issue loop, and every
+// tcgen05.commit is multicast to the same barrier in both CTAs.
+template <bool X3, bool PAIR>
 __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t) {
+  static_assert(X3 || !PAIR, "the CTA-pair trunk exists for the three-term split only");
   using S = Trunk2Smem<X3>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1413,14 +1419,20 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
   uint64_t* pl_free = pl_full + 2;                       // [2] conv2 MMAs have read the plane
   uint64_t* tfull = pl_free + 2;                         // [2] accumulator complete
   uint64_t* tempty = tfull + 2;                          // [2] accumulator drained (128 epilogue threads)
-  uint64_t* wbar = tempty + 2;
+  uint64_t* peer_ready = tempty + 2;                     // [8] PAIR, leader: the peer CTA's c1_full / c1_tfree / pl_full / tempty [2 each]
+  uint64_t* wbar = peer_ready + 8;
   uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int64_t unit = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;   // scheduling unit: CTA or CTA pair
+  const int64_t n_units = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = t.n, nn = n * n, rp = n + 1, bp = rp * rp;  // row pitch and board pitch of the shared-border raster
   const int G = (127 - (nn + n - 2)) / bp + 1;                // boards per 128-row tile
   if (t.dyn_rows && *t.dyn_rows < t.B) t.B = *t.dyn_rows;
   const int64_t tiles = (t.B + G - 1) / G;
+  const int64_t tile_units = PAIR ? (tiles + 1) / 2 : tiles;  // a pair owns two consecutive tiles (the second may not exist)
+  auto tile_of = [&](int64_t tp) { return PAIR ? 2 * tp + (int64_t)rank : tp; };
   constexpr int BN = 64;
   constexpr int ACC_COLS = X3 ? 128 : 64;
   constexpr uint32_t TMEM_COLS = 512;
@@ -1428,8 +1440,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
 
   for (int i = threadIdx.x; i < 2 * T2_PLANE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(planes)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < 2 * A_STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(c1st)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {  // conv1 weights as three bf16 terms along K (Connect4Net.py:32)
-    const int ch = i >> 6, col = i & 63, term = col >> 4, k = col & 15;
+  for (int i = threadIdx.x; i < (PAIR ? 16 : 32) * 64; i += blockDim.x) {  // conv1 weights as three bf16 terms along K (Connect4Net.py:32)
+    const int row = i >> 6, ch = row + (PAIR ? (int)rank * 16 : 0), col = i & 63, term = col >> 4, k = col & 15;  // PAIR: this CTA's 16 of the 32 rows
     float v = 0.0f;
     if (term < 3 && k < 9) {
       const float w = t.w1[ch * 9 + k];
@@ -1437,7 +1449,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
       const float mid = __bfloat162float(__float2bfloat16_rn(w - hi));
       v = term == 0 ? hi : term == 1 ? mid : (w - hi) - mid;
     }
-    *reinterpret_cast<__nv_bfloat16*>(w1img + image_offset(ch, col)) = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(w1img + image_offset(row, col)) = __float2bfloat16_rn(v);
   }
   if (warp == 9 && lane == 0) {
     for (int k = 0; k < 2; ++k) {
@@ -1450,18 +1462,31 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
       mbar_init(&tfull[k], 1);
       mbar_init(&tempty[k], 256);
     }
+    for (int k = 0; k < 8; ++k) mbar_init(&peer_ready[k], 1);
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 9) {
+    if (PAIR) tmem_alloc2(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 9) {
-    if (lane == 0) {  // conv2 weight images -> smem, once
+    if (lane == 0 && PAIR) {
+      // this CTA's halves of the two weight operands: rows of [W_hi ; W_lo] (leader: W_hi, peer: W_lo) for the N = 128 product,
+      // rows 32 rank .. 32 rank + 31 of W_hi for the N = 64 product (row groups of 8: contiguous 4 KB of every k-block image)
+      mbar_expect_tx(wbar, TR_W_BYTES + TR_W_BYTES / 2);
+      for (int kb = 0; kb < C2_KB; ++kb) {
+        bulk_g2s(w_s + kb * 8192, (rank == 0 ? t.w_hi : t.w_lo) + kb * 8192, 8192, wbar);
+        bulk_g2s(w_s + TR_W_BYTES + kb * 4096, t.w_hi + kb * 8192 + rank * 4096, 4096, wbar);
+      }
+    } else if (lane == 0) {  // conv2 weight images -> smem, once
       mbar_expect_tx(wbar, (X3 ? 2 : 1) * TR_W_BYTES);
       if (X3) {
         for (int kb = 0; kb < C2_KB; ++kb) {
@@ -1516,17 +1541,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
       fence_async_smem();
       mbar_arrive(&c1_full[k]);
     };
-    fetch(blockIdx.x);
-    if ((int64_t)blockIdx.x < tiles) c1_operand(0, 0);
-    fetch((int64_t)blockIdx.x + gridDim.x);
+    fetch(tile_of(unit));
+    if (unit < tile_units) c1_operand(0, 0);
+    fetch(tile_of(unit + n_units));
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (int64_t tp = unit; tp < tile_units; tp += n_units, ++it) {
+      const int64_t tile = tile_of(tp);
       const int k = (int)(it & 1u);
       const uint32_t ph = (it >> 1) & 1u;
-      const bool has_next = tile + gridDim.x < tiles;
+      const bool has_next = tp + n_units < tile_units;
       if (has_next) {  // the next tile's conv1 operand depends on nothing the tensor core produces: build it first, so that
         c1_operand(k ^ 1, it + 1);  // conv1(it+1) is queued before conv2(it) and only the plane write-back below sits
-        fetch(tile + 2 * (int64_t)gridDim.x);  // between a conv1 result and the conv2 MMAs that need it
+        fetch(tile_of(tp + 2 * n_units));  // between a conv1 result and the conv2 MMAs that need it
       }
       mbar_wait(&c1_done[k], ph);
       tc_fence_after();
@@ -1557,54 +1583,95 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
     }
   } else if (warp == 8) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
-      constexpr uint32_t idesc_c1 = make_idesc(BM, 32);
-      constexpr uint32_t idesc_cat = make_idesc(BM, 2 * BN);
+    if (lane == 0 && rank != 0) {
+      // peer CTA of a pair: forward this CTA's "ready" events to the leader, in the order the leader waits for them
+      mbar_wait(wbar, 0);  // (keeps the weight copies of this CTA inside the kernel's lifetime before the first relay)
+      const uint32_t leader = map_to_cta(&peer_ready[0], 0);
+      auto relay = [&](uint64_t* local, uint32_t parity, int slot) {
+        mbar_wait(local, parity);
+        mbar_arrive_cluster(leader + (uint32_t)slot * 8u);
+      };
+      if (unit < tile_units) {
+        relay(&c1_full[0], 0u, 0);
+        relay(&c1_tfree[0], 1u, 2);
+      }
+      uint32_t it = 0;
+      for (int64_t tp = unit; tp < tile_units; tp += n_units, ++it) {
+        const int k = (int)(it & 1u);
+        const uint32_t ph = (it >> 1) & 1u, phn = ((it + 1) >> 1) & 1u;
+        if (tp + n_units < tile_units) {
+          relay(&c1_full[k ^ 1], phn, 0 + (k ^ 1));
+          relay(&c1_tfree[k ^ 1], phn ^ 1u, 2 + (k ^ 1));
+        }
+        relay(&pl_full[k], ph, 4 + k);
+        relay(&tempty[k], ph ^ 1u, 6 + k);
+      }
+    } else if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, BN);
+      constexpr uint32_t idesc_c1 = make_idesc(PAIR ? 2 * BM : BM, 32);
+      constexpr uint32_t idesc_cat = make_idesc(PAIR ? 2 * BM : BM, 2 * BN);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (PAIR) umma2_bf16(d, a, b, id, acc);
+        else umma_bf16(d, a, b, id, acc);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (PAIR) umma2_commit(bar);
+        else umma_commit(bar);
+      };
       mbar_wait(wbar, 0);
       const uint32_t w_addr = smem_u32(w_s);
       const uint64_t b_c1 = make_smem_desc(smem_u32(w1img));
       auto conv1 = [&](int k, uint32_t it) {  // [A | A | A] x [w_hi | w_mid | w_lo]^T -> conv1 region k
         mbar_wait(&c1_full[k], (it >> 1) & 1u);
+        if (PAIR) mbar_wait_cluster(&peer_ready[0 + k], (it >> 1) & 1u);
         mbar_wait(&c1_tfree[k], ((it >> 1) & 1u) ^ 1u);  // the builders have read the region's previous content
+        if (PAIR) mbar_wait_cluster(&peer_ready[2 + k], (it >> 1) & 1u);
         tc_fence_after();
         const uint64_t a_c1 = make_smem_desc(smem_u32(c1st + k * A_STAGE_BYTES));
 #pragma unroll
-        for (int q = 0; q < 3; ++q) umma_bf16(tmem_base + C1_COL + (uint32_t)(k * 32), a_c1 + 2 * q, b_c1 + 2 * q, idesc_c1, q != 0);
-        umma_commit(&c1_free[k]);
-        umma_commit(&c1_done[k]);
+        for (int q = 0; q < 3; ++q) mma(tmem_base + C1_COL + (uint32_t)(k * 32), a_c1 + 2 * q, b_c1 + 2 * q, idesc_c1, q != 0);
+        commit(&c1_free[k]);
+        commit(&c1_done[k]);
       };
-      if ((int64_t)blockIdx.x < tiles) conv1(0, 0);
+      if (unit < tile_units) conv1(0, 0);
       // descriptor increments of the nine taps in 16-byte units (the single issuing thread should spend its cycles on
       // tcgen05.mma, not on address arithmetic: everything but two additions per step is hoisted or a constant)
       uint32_t tap16[9];
 #pragma unroll
       for (int q = 0; q < 9; ++q) tap16[q] = (uint32_t)((q / 3) * rp + (q % 3)) * 8u;
       const uint64_t b_base = make_smem_desc(w_addr);
+      const uint64_t b_half = make_smem_desc(w_addr + TR_W_BYTES);  // PAIR: this CTA's 32 rows of W_hi
       const uint64_t a_base[2] = {make_smem_desc(smem_u32(planes)), make_smem_desc(smem_u32(planes + T2_PLANE_BYTES))};
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      for (int64_t tp = unit; tp < tile_units; tp += n_units, ++it) {
         const int k = (int)(it & 1u);
         const uint32_t ph = (it >> 1) & 1u;
-        if (tile + gridDim.x < tiles) conv1(k ^ 1, it + 1);  // before this tile's conv2: its write-back overlaps the 36 MMAs
+        if (tp + n_units < tile_units) conv1(k ^ 1, it + 1);  // before this tile's conv2: its write-back overlaps the 36 MMAs
         mbar_wait(&pl_full[k], ph);
+        if (PAIR) mbar_wait_cluster(&peer_ready[4 + k], ph);
         mbar_wait(&tempty[k], ph ^ 1u);
+        if (PAIR) mbar_wait_cluster(&peer_ready[6 + k], ph);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(k * ACC_COLS);
 #pragma unroll
         for (int s = 0; s < 18; ++s) {
           // base-offset field of the shifted descriptor stays 0 (see the header comment)
           const uint64_t a_hi = a_base[k] + (uint64_t)(tap16[s >> 1] + (uint32_t)(s & 1) * 2u);
+          if (PAIR) {  // each CTA supplies half of the weight rows: 64 of [W_hi ; W_lo], 32 of W_hi
+            mma(d_tmem, a_hi, b_base + (uint64_t)((s >> 2) * (64 * 128 / 16) + 2 * (s & 3)), idesc_cat, s != 0);
+            mma(d_tmem, a_hi + 4, b_half + (uint64_t)((s >> 2) * (32 * 128 / 16) + 2 * (s & 3)), idesc, 1);
+            continue;
+          }
           const uint64_t b_w = b_base + (uint64_t)((s >> 2) * (X3 ? 2 : 1) * (64 * 128 / 16) + 2 * (s & 3));
           if (X3) {
-            umma_bf16(d_tmem, a_hi, b_w, idesc_cat, s != 0);           // hi x [W_hi ; W_lo]: columns 0-63 and 64-127
-            umma_bf16(d_tmem, a_hi + 4, b_w, idesc, 1);                // lo (64 bytes further in the cell) x W_hi
+            mma(d_tmem, a_hi, b_w, idesc_cat, s != 0);           // hi x [W_hi ; W_lo]: columns 0-63 and 64-127
+            mma(d_tmem, a_hi + 4, b_w, idesc, 1);                // lo (64 bytes further in the cell) x W_hi
           } else {
-            umma_bf16(d_tmem, a_hi, b_w, idesc, s != 0);
+            mma(d_tmem, a_hi, b_w, idesc, s != 0);
           }
         }
-        umma_commit(&pl_free[k]);
-        umma_commit(&tfull[k]);
+        commit(&pl_free[k]);
+        commit(&tfull[k]);
       }
     }
   } else if (warp >= 12) {
@@ -1633,7 +1700,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
     }
     const bool f8 = X3 && t.out_f8;
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (int64_t tp = unit; tp < tile_units; tp += n_units, ++it) {
+      const int64_t tile = tile_of(tp);
       const int k = (int)(it & 1u);
       const int rb = (int)((tile * G + r / bp) & 127);  // image row (board & 127) of this thread's tile row
       mbar_wait(&tfull[k], (it >> 1) & 1u);
@@ -1701,27 +1769,42 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: leave together
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <bool X3>
+template <bool X3, bool PAIR>
 int launch_trunk2(const TrunkArgs& t, cudaStream_t st) {
   static bool configured = false;
   int dev = 0, sms = 0;
   AZG_CUDA_CHECK(cudaGetDevice(&dev));
   AZG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (!configured) {
-    AZG_CUDA_CHECK(cudaFuncSetAttribute(c4_trunk2_tc_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Trunk2Smem<X3>::TOTAL));
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(c4_trunk2_tc_kernel<X3, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Trunk2Smem<X3>::TOTAL));
     configured = true;
   }
   const int n = t.n, bp = (n + 1) * (n + 1);
   const int G = (127 - (n * n + n - 2)) / bp + 1;
   const int64_t tiles = (t.B + G - 1) / G;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  c4_trunk2_tc_kernel<X3><<<grid, T2_THREADS, Trunk2Smem<X3>::TOTAL, st>>>(t);
+  const int64_t units = PAIR ? (tiles + 1) / 2 : tiles, max_units = PAIR ? sms / 2 : sms;
+  const int grid = (int)(units < max_units ? units : max_units) * (PAIR ? 2 : 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(T2_THREADS);
+  cfg.dynamicSmemBytes = Trunk2Smem<X3>::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AZG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, c4_trunk2_tc_kernel<X3, PAIR>, t));
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }
@@ -1812,11 +1895,11 @@ static int azg_trunk_mode() {  // 0 = fused (either generation), 1 = split (im2c
   return mode;
 }
 
-static int azg_trunk_gen() {  // AZG_TRUNK=fused1: the first-generation fused trunk (patch copies), kept for A/B measurements
-  static int gen = -1;
+static int azg_trunk_gen() {  // AZG_TRUNK=fused1: the first-generation fused trunk (patch copies); fused2pair: generation 2 on
+  static int gen = -1;        // CTA pairs (cta_group::2) -- both kept for A/B measurements (profiles/r02_trunk_fused2.txt)
   if (gen < 0) {
     const char* e = getenv("AZG_TRUNK");
-    gen = (e && strcmp(e, "fused1") == 0) ? 1 : 2;
+    gen = (e && strcmp(e, "fused1") == 0) ? 1 : (e && strcmp(e, "fused2pair") == 0) ? 3 : 2;
   }
   return gen;
 }
@@ -1859,7 +1942,8 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     t.dyn_rows = dyn_rows;
     t.out_f8 = f8 ? 1 : 0;
     if (azg_trunk_gen() == 1) rc = x3 ? tc::launch_trunk<true>(t, st) : tc::launch_trunk<false>(t, st);
-    else rc = x3 ? tc::launch_trunk2<true>(t, st) : tc::launch_trunk2<false>(t, st);
+    else if (!x3) rc = tc::launch_trunk2<false, false>(t, st);
+    else rc = azg_trunk_gen() == 3 ? tc::launch_trunk2<true, true>(t, st) : tc::launch_trunk2<true, false>(t, st);
     if (rc) return rc;
   } else {  // split: im2col image through HBM, conv2 on the generic GEMM kernel (kept for A/B measurements)
     const int grid = (int)(B < 148 * 8 ? B : 148 * 8);
