@@ -16,16 +16,23 @@
 //                tile in shared memory (pre-scaled by d_row) -> every row sums its <= 5 neighbours -> * d_row
 //                + rowsum*bias, ReLU -> whole 128-byte row segments to HBM
 // so the support matrix X W^T never exists in HBM: algorithmic bytes per layer = 4H read + 4H written per node.
+//
+// MT = 2 (graphs of 129..256 nodes): a tile is 256 rows = two 128-row halves, each with its own TMEM accumulator; the
+// pipeline items run (tile, half, k-block), so producers and MMA issuer only see "one more 128-row operand".  The
+// staging tiles have 256 rows, so a node's neighbours are found across the half boundary: an epilogue thread stages
+// tile rows r and 128 + r (same TMEM lane, the two accumulators) of its group's chunk.  Where only one staging tile
+// fits (H = 256 in bf16x3, weights streamed) the eight warps form ONE group, thread = one of the 256 rows.
 #include "azg_tc.cuh"
 
 namespace gridtc {
 using namespace tc;
 
 constexpr int GT_THREADS = 576;    // 8 producer warps, MMA, TMEM/barrier setup, 2 x 4 epilogue warps
-constexpr int MISC_BYTES = 5120;   // barriers, neighbour table
 
-template <int H, bool X3>
+template <int H, bool X3, int MT>
 struct GridSmem {
+  static constexpr int ROWS = 128 * MT;                      // tile rows
+  static constexpr int MISC_BYTES = MT == 1 ? 5120 : 8192;   // barriers (256 B), neighbour table [ROWS][5], row sums, d
   static constexpr int KB = H / BK;
   static constexpr int A_BYTES = (X3 ? 2 : 1) * A_STAGE_BYTES;
   static constexpr int W_HALF = H * 128;  // one k-block of one weight image
@@ -33,22 +40,27 @@ struct GridSmem {
   static constexpr int W_TOTAL = KB * W_BYTES;  // the whole weight operand (hi and lo images)
   static constexpr int AVAIL = 232448 - 1024 - MISC_BYTES;
   static constexpr int ST32 = 2 * 128 * 36 * 4;  // two staging tiles of 32-column chunks
+  static constexpr int ST_MIN = MT == 1 ? ST32 : ROWS * 20 * 4;  // MT = 2: at least one 16-column tile of 256 rows
   // WRES: the weight images stay resident in shared memory for the life of the CTA (one bulk copy at start) and a
   // pipeline stage holds only the A operand; otherwise (H = 256 in bf16x3: 256 KB of weights) every stage also
   // carries its k-block of the weights, re-streamed from L2 per tile.
-  static constexpr bool WRES = (AVAIL - ST32 - W_TOTAL) / A_BYTES >= 2;
+  static constexpr bool WRES = (AVAIL - ST_MIN - W_TOTAL) / A_BYTES >= 2;
   static constexpr int STAGE_BYTES = A_BYTES + (WRES ? 0 : W_BYTES);
   static constexpr int W_RES_BYTES = WRES ? W_TOTAL : 0;
   // epilogue chunk = columns per tcgen05.ld; two staging tiles (one per epilogue group) of 128 rows x (EC + 4) floats
   // (row stride 144 / 80 B: conflict-free 128-bit accesses).  32 columns unless that leaves fewer than two stages.
-  static constexpr int EC = (AVAIL - W_RES_BYTES - ST32) / STAGE_BYTES >= 2 ? 32 : 16;
+  // MT = 2: two tiles of 32 columns, else two of 16, else (H = 256 in bf16x3) one of 16
+  static constexpr int EC = (AVAIL - W_RES_BYTES - 2 * ROWS * 36 * 4) / STAGE_BYTES >= 2 ? 32 : 16;
   static constexpr int ST_LD = EC + 4;
-  static constexpr int ST_BYTES = 128 * ST_LD * 4;
-  static constexpr int BUDGET = AVAIL - W_RES_BYTES - 2 * ST_BYTES;
+  static constexpr int ST_BYTES = ROWS * ST_LD * 4;
+  static constexpr int NTILE = (AVAIL - W_RES_BYTES - 2 * ST_BYTES) / STAGE_BYTES >= 2 ? 2 : 1;
+  static_assert(MT == 2 || NTILE == 2, "one staging tile per epilogue group");
+  static constexpr int BUDGET = AVAIL - W_RES_BYTES - NTILE * ST_BYTES;
   static constexpr int NST = BUDGET / STAGE_BYTES < 6 ? BUDGET / STAGE_BYTES : 6;
   static constexpr int STAGE_OFF = W_RES_BYTES;
   static constexpr int ST_OFF = STAGE_OFF + NST * STAGE_BYTES;
-  static constexpr int MISC_OFF = ST_OFF + 2 * ST_BYTES;
+  static constexpr int MISC_OFF = ST_OFF + NTILE * ST_BYTES;
+  static constexpr int NACC = MT == 1 ? 2 : (4 * H <= 512 ? 4 : 2);  // TMEM accumulators of H columns (MT = 2: one per half)
   static constexpr int TOTAL = MISC_OFF + MISC_BYTES + 1024;
   static_assert(NST >= 2, "at least two pipeline stages");
 };
@@ -78,33 +90,33 @@ struct GridArgs {
   int relu;
 };
 
-template <int H, bool X3, bool BWD>
+template <int H, bool X3, bool BWD, int MT>
 __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g) {  // 18 warps: 96 registers per thread
-  using S = GridSmem<H, X3>;
-  constexpr int KB = S::KB, NST = S::NST, EC = S::EC, ST_LD = S::ST_LD;
+  using S = GridSmem<H, X3, MT>;
+  constexpr int KB = S::KB, NST = S::NST, EC = S::EC, ST_LD = S::ST_LD, ROWS = S::ROWS, NACC = S::NACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* staging = (float*)(smem + S::ST_OFF);
   uint64_t* full = (uint64_t*)(smem + S::MISC_OFF);
   uint64_t* empty = full + NST;
   uint64_t* tfull = empty + NST;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* wbar = tempty + 2;
+  uint64_t* tempty = tfull + NACC;
+  uint64_t* wbar = tempty + NACC;
   uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
-  float* nb_coef = (float*)(smem + S::MISC_OFF + 256);  // [128][5]
-  float* row_sum = nb_coef + 128 * 5;                   // [128]
-  float* row_d = row_sum + 128;                         // [128] deg^-1/2 (0 for unused tile rows)
+  float* nb_coef = (float*)(smem + S::MISC_OFF + 256);  // [ROWS][5]
+  float* row_sum = nb_coef + ROWS * 5;                  // [ROWS]
+  float* row_d = row_sum + ROWS;                        // [ROWS] deg^-1/2 (0 for unused tile rows)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = g.gh * g.gw;
-  const int G = 128 / n;          // graphs per tile
+  const int G = ROWS / n;         // graphs per tile
   const int R = G * n;            // valid tile rows
   const int64_t tiles = (g.B + G - 1) / G;
   const int64_t total_rows = g.B * n;
-  constexpr uint32_t TMEM_COLS = 2 * H < 32 ? 32 : 2 * H;
+  constexpr uint32_t TMEM_COLS = NACC * H < 32 ? 32 : NACC * H;
 
   // neighbour table of a tile row: (tile row of the neighbour, d_i * d_j); identical for every tile
-  for (int i = threadIdx.x; i < 128 * 5; i += blockDim.x) {
+  for (int i = threadIdx.x; i < ROWS * 5; i += blockDim.x) {
     const int r = i / 5, k = i % 5;
     float coef = 0.0f;
     if (r < R) {
@@ -124,16 +136,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
       mbar_init(&full[s], 256);
       mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NACC; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 256);
+      mbar_init(&tempty[a], S::NTILE == 2 ? 256 : 128);  // both epilogue groups drain an accumulator / one group: four warps
     }
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
   __syncthreads();
-  if (threadIdx.x < 128) {  // rowsum in the same order as the gather below
+  if (threadIdx.x < ROWS) {  // rowsum in the same order as the gather below
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < 5; ++k) s += nb_coef[threadIdx.x * 5 + k];
@@ -160,13 +172,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
     // been converted, so the global loads never wait for the pipeline.
     constexpr int PF = 1;  // 8 float4 (x2 in BWD) per thread = 32 KB (64 KB) of loads in flight per SM
     const int j4 = threadIdx.x & 15, r0 = threadIdx.x >> 4;  // rows r0 + 16 i, float4 j4 (4 channels) of the k-block
-    const int64_t items = ((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * KB;
+    constexpr int IPT = MT * KB;  // items per tile, ordered (half, k-block)
+    const int64_t items = ((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * IPT;
     float4 v[PF][8];
     float4 a[PF][BWD ? 8 : 1];
     auto load = [&](int64_t it, int i, float4& vv, float4& aa) {
-      const int64_t tile = blockIdx.x + (it / KB) * (int64_t)gridDim.x;
+      const int64_t tile = blockIdx.x + (it / IPT) * (int64_t)gridDim.x;
       const int kb = (int)(it % KB);
-      const int r = r0 + 16 * i;
+      const int r = (int)((it % IPT) / KB) * 128 + r0 + 16 * i;  // tile row
       const int64_t row = tile * R + r;
       if (r < R && row < total_rows) {
         vv = __ldcs(reinterpret_cast<const float4*>(g.x + row * H + kb * BK) + j4);
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
       uint32_t phase = 0, acc_phase = 0;
       if (S::WRES) mbar_wait(wbar, 0);
       const uint32_t w_res = smem_u32(smem);
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int64_t item = 0, n_items = ((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * MT; item < n_items; ++item) {  // (tile, half)
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * H);
@@ -250,35 +263,32 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
           }
         }
         umma_commit(&tfull[acc]);
-        if (++acc == 2) {
+        if (++acc == NACC) {
           acc = 0;
           acc_phase ^= 1;
         }
       }
     }
-  } else if (warp >= 10) {
-    // =========================== epilogue: two groups of four warps, alternating column chunks ===========================
-    // Staging: thread = TMEM lane = tile row writes d_row * D[row, EC columns] (d = deg^-1/2).  Gather: a warp covers
-    // RPS rows x EC/4 float4 per step (a row's chunk is contiguous in shared memory and in HBM), so shared-memory
-    // reads and global stores are whole lines; out = d_row * (sum over {self, valid neighbours} of the staged rows)
-    // + rowsum * bias.  Neighbours of row r: r -/+ gw (x -/+ 1), r -/+ 1 (y -/+ 1).
-    constexpr int LPR = EC / 4, RPS = 32 / LPR, STEPS = 32 / RPS;  // lanes per row, rows per step, steps per quarter
-    const int grp = (warp - 10) >> 2;
-    const int q = warp & 3, r = q * 32 + lane;
+  } else if (warp >= 10 && S::NTILE == 1) {
+    // =========================== epilogue, 256-row tiles, one staging tile: one group of eight warps ===========================
+    // warps 10-13 drain the accumulator of rows 0-127, warps 14-17 the one of rows 128-255 (a warp reads the TMEM lane
+    // quarter warp % 4); staging row = tile row, so the gather below crosses the half boundary like any other row.
+    constexpr int LPR = EC / 4, RPS = 32 / LPR, STEPS = 32 / RPS;
+    const int half = (warp - 10) >> 2;
+    const int q = warp & 3, r = half * 128 + q * 32 + lane;
     const int c4 = lane % LPR;
-    float* stg = staging + grp * (S::ST_BYTES / 4);
     const float my_d = row_d[r];
     uint32_t it_mask[STEPS];
 #pragma unroll
     for (int it = 0; it < STEPS; ++it) {
-      const int row = q * 32 + it * RPS + lane / LPR;
+      const int row = half * 128 + q * 32 + it * RPS + lane / LPR;
       uint32_t m = 0;
 #pragma unroll
       for (int k = 0; k < 5; ++k) m |= (nb_coef[row * 5 + k] != 0.0f ? 1u : 0u) << k;
       it_mask[it] = m;
     }
     const int gw = g.gw;
-    int acc = 0;
+    int acc = half;
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int64_t row_base = tile * R;
@@ -286,7 +296,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H);
 #pragma unroll 1
-      for (int c0 = grp * EC; c0 < H; c0 += 2 * EC) {
+      for (int c0 = 0; c0 < H; c0 += EC) {
+        float* stg = staging;
         uint32_t rr[EC];
         if (EC == 32) tmem_ld32(taddr + (uint32_t)c0, rr);
         else tmem_ld16(taddr + (uint32_t)c0, rr);
@@ -298,10 +309,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
                                my_d * __uint_as_float(rr[4 * e + 2]), my_d * __uint_as_float(rr[4 * e + 3]));
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + c4);
-        named_bar(3 + 2 * grp, 128);  // the chunk of every row is staged
+        named_bar(3, 256);  // the chunk of every tile row is staged
 #pragma unroll
         for (int it = 0; it < STEPS; ++it) {
-          const int row = q * 32 + it * RPS + lane / LPR;
+          const int row = half * 128 + q * 32 + it * RPS + lane / LPR;
           const uint32_t m = it_mask[it];
           const float4* src = reinterpret_cast<const float4*>(stg + row * ST_LD) + c4;
           float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -316,11 +327,93 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
           const int64_t grow = row_base + row;
           if (m != 0u && grow < total_rows) __stcs(reinterpret_cast<float4*>(g.out + grow * H + c0) + c4, v);
         }
-        named_bar(4 + 2 * grp, 128);  // every row has gathered: the staging tile may be overwritten
+        named_bar(4, 256);  // every row has gathered: the staging tile may be overwritten
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
-      if (++acc == 2) {
+      acc += 2;
+      if (acc >= NACC) {
+        acc = half;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 10) {
+    // =========================== epilogue: two groups of four warps, alternating column chunks ===========================
+    // Staging: thread = TMEM lane = tile row (MT = 2: rows r and 128 + r, one per accumulator) writes d_row * D[row, EC
+    // columns] (d = deg^-1/2).  Gather: a warp covers RPS rows x EC/4 float4 per step (a row's chunk is contiguous in
+    // shared memory and in HBM), so shared-memory reads and global stores are whole lines; out = d_row * (sum over {self,
+    // valid neighbours} of the staged rows) + rowsum * bias.  Neighbours of row r: r -/+ gw (x -/+ 1), r -/+ 1 (y -/+ 1).
+    constexpr int LPR = EC / 4, RPS = 32 / LPR, STEPS = 32 / RPS;  // lanes per row, rows per step, steps per quarter
+    const int grp = (warp - 10) >> 2;
+    const int q = warp & 3, r = q * 32 + lane;
+    const int c4 = lane % LPR;
+    float* stg = staging + grp * (S::ST_BYTES / 4);
+    float my_d[MT];
+    uint64_t it_mask[MT];  // 5 neighbour-valid bits per gather step
+#pragma unroll
+    for (int h = 0; h < MT; ++h) {
+      my_d[h] = row_d[h * 128 + r];
+      it_mask[h] = 0;
+#pragma unroll
+      for (int it = 0; it < STEPS; ++it) {
+        const int row = h * 128 + q * 32 + it * RPS + lane / LPR;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) it_mask[h] |= (uint64_t)(nb_coef[row * 5 + k] != 0.0f ? 1u : 0u) << (5 * it + k);
+      }
+    }
+    const int gw = g.gw;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t row_base = tile * R;
+#pragma unroll
+      for (int h = 0; h < MT; ++h) mbar_wait(&tfull[acc + h], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H);
+#pragma unroll 1
+      for (int c0 = grp * EC; c0 < H; c0 += 2 * EC) {
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+          uint32_t rr[EC];
+          if (EC == 32) tmem_ld32(taddr + (uint32_t)(h * H + c0), rr);
+          else tmem_ld16(taddr + (uint32_t)(h * H + c0), rr);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(stg + (h * 128 + r) * ST_LD);
+#pragma unroll
+          for (int e = 0; e < EC / 4; ++e)
+            dst[e] = make_float4(my_d[h] * __uint_as_float(rr[4 * e]), my_d[h] * __uint_as_float(rr[4 * e + 1]),
+                                 my_d[h] * __uint_as_float(rr[4 * e + 2]), my_d[h] * __uint_as_float(rr[4 * e + 3]));
+        }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + c4);
+        named_bar(3 + 2 * grp, 128);  // the chunk of every row is staged
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+#pragma unroll
+          for (int it = 0; it < STEPS; ++it) {
+            const int row = h * 128 + q * 32 + it * RPS + lane / LPR;
+            const uint32_t m = (uint32_t)(it_mask[h] >> (5 * it)) & 31u;
+            const float4* src = reinterpret_cast<const float4*>(stg + row * ST_LD) + c4;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m & 1u) s = *src;
+            if (m & 2u) { const float4 t = *(src - gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+            if (m & 4u) { const float4 t = *(src + gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+            if (m & 8u) { const float4 t = *(src - (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+            if (m & 16u) { const float4 t = *(src + (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+            const float d = row_d[row], rs = row_sum[row];
+            float4 v = make_float4(fmaf(d, s.x, rs * b4.x), fmaf(d, s.y, rs * b4.y), fmaf(d, s.z, rs * b4.z), fmaf(d, s.w, rs * b4.w));
+            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            const int64_t grow = row_base + row;
+            if (m != 0u && grow < total_rows) __stcs(reinterpret_cast<float4*>(g.out + grow * H + c0) + c4, v);
+          }
+        }
+        named_bar(4 + 2 * grp, 128);  // every row has gathered: the staging tile may be overwritten
+      }
+      tc_fence_before();
+#pragma unroll
+      for (int h = 0; h < MT; ++h) mbar_arrive(&tempty[acc + h]);
+      acc += MT;
+      if (acc == NACC) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -351,21 +444,21 @@ __global__ void grid_weight_image_kernel(const float* __restrict__ w, int H, int
   split_store(x8, hi, lo, off);
 }
 
-template <int H, bool X3, bool BWD>
+template <int H, bool X3, bool BWD, int MT>
 int launch(const GridArgs& g, cudaStream_t st) {
   static bool configured = false;
-  using S = GridSmem<H, X3>;
+  using S = GridSmem<H, X3, MT>;
   int dev = 0, sms = 0;
   AZG_CUDA_CHECK(cudaGetDevice(&dev));
   AZG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (!configured) {
-    AZG_CUDA_CHECK(cudaFuncSetAttribute(grid_layer_tc_kernel<H, X3, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(grid_layer_tc_kernel<H, X3, BWD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  const int G = 128 / (g.gh * g.gw);
+  const int G = S::ROWS / (g.gh * g.gw);
   const int64_t tiles = (g.B + G - 1) / G;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  grid_layer_tc_kernel<H, X3, BWD><<<grid, GT_THREADS, S::TOTAL, st>>>(g);
+  grid_layer_tc_kernel<H, X3, BWD, MT><<<grid, GT_THREADS, S::TOTAL, st>>>(g);
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }
@@ -601,14 +694,30 @@ int launch_dw(const float* s, const float* x, int64_t rows, float* dw, float* db
   return AZG_OK;
 }
 
+static int wide_tiles(int n) {  // 256-row tiles: needed above 128 nodes; AZG_GRID_TILE=256 forces them for A/B runs
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("AZG_GRID_TILE");
+    forced = (e && strcmp(e, "256") == 0) ? 1 : 0;
+  }
+  return n > 128 || forced;
+}
+
+template <bool BWD, int MT>
+int dispatch_h(const GridArgs& g, int H, bool x3, cudaStream_t st) {
+  switch (H) {
+    case 64: return x3 ? launch<64, true, BWD, MT>(g, st) : launch<64, false, BWD, MT>(g, st);
+    case 128: return x3 ? launch<128, true, BWD, MT>(g, st) : launch<128, false, BWD, MT>(g, st);
+    case 256: return x3 ? launch<256, true, BWD, MT>(g, st) : launch<256, false, BWD, MT>(g, st);
+  }
+  return -1;
+}
+
 template <bool BWD>
 int dispatch(const GridArgs& g, int H, int prec, cudaStream_t st) {
   const bool x3 = prec == AZG_PREC_BF16X3;
-  switch (H) {
-    case 64: return x3 ? launch<64, true, BWD>(g, st) : launch<64, false, BWD>(g, st);
-    case 128: return x3 ? launch<128, true, BWD>(g, st) : launch<128, false, BWD>(g, st);
-    case 256: return x3 ? launch<256, true, BWD>(g, st) : launch<256, false, BWD>(g, st);
-  }
+  const int rc = wide_tiles(g.gh * g.gw) ? dispatch_h<BWD, 2>(g, H, x3, st) : dispatch_h<BWD, 1>(g, H, x3, st);
+  if (rc != -1) return rc;
   azg_set_error("grid layer: hidden size %d not in {64, 128, 256}", H);
   return AZG_ERR_INVALID;
 }
@@ -621,7 +730,7 @@ size_t azg_grid_packed_bytes(int H) { return (size_t)H * H * 2 * 2; }  // hi ima
 
 int azg_grid_tc_supported(int gh, int gw, int H) {
   const int n = gh * gw;
-  return n >= 1 && n <= 128 && (H == 64 || H == 128 || H == 256);
+  return n >= 1 && n <= 256 && (H == 64 || H == 128 || H == 256);
 }
 
 int azg_grid_pack_weights(const float* w, int H, int transpose, void* packed, azg_stream stream) {

@@ -90,7 +90,8 @@ class GridGNNStack(nn.Module):
     """`layers` x GNNLayer(hidden, hidden) over [B, gh*gw, hidden] node features.
 
     precision: "bf16x3" (default; fp32-level accuracy on the tensor cores), "bf16", or "fp32" (CUDA-core SGEMM +
-    separate aggregation kernel -- also the path for graphs of more than 128 nodes or other hidden sizes)."""
+    separate aggregation kernel -- also the path for graphs of more than 256 nodes or other hidden sizes).  Graphs of up to
+    128 nodes share 128-row tiles (128 // n graphs each), 129..256 nodes take one 256-row tile per graph."""
 
     def __init__(self, gh, gw, hidden, layers=2, precision="bf16x3"):
         super().__init__()

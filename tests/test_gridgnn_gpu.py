@@ -38,7 +38,7 @@ def test_grid_gnn_forward_backward(gh, gw, hidden):
         assert bad.float().mean().item() < 1e-3, (a - b).abs().max().item()  # isolated ReLU knife-edge flips only
 
 
-@pytest.mark.parametrize("gh,gw", [(3, 3), (4, 4), (6, 7), (7, 7), (8, 8), (11, 11)])
+@pytest.mark.parametrize("gh,gw", [(3, 3), (4, 4), (6, 7), (7, 7), (8, 8), (11, 11), (9, 15), (12, 13), (15, 16), (16, 16), (1, 200)])
 @pytest.mark.parametrize("hidden", [64, 128, 256])
 def test_fused_tensor_core_layer(gh, gw, hidden):
     """bf16x3 = the fused tcgen05 layer kernel.  Outputs: the fp32 contract (1e-5) against the oracle.  Gradients:
@@ -47,7 +47,7 @@ def test_fused_tensor_core_layer(gh, gw, hidden):
     with a random upstream gradient one such flip moves a whole row of the weight gradient, so comparing gradients
     across different activation patterns says nothing about the backward kernels."""
     torch.manual_seed(gh * 100 + hidden)
-    B = 1531  # the persistent CTAs walk several tiles each
+    B = 1531 if gh * gw <= 128 else 449  # the persistent CTAs walk several tiles each (above 128 nodes: one graph per 256-row tile)
     net = GridGNNStack(gh, gw, hidden, layers=2, precision="bf16x3").cuda()
     assert net.fused
     x = torch.randn(B, gh * gw, hidden, device="cuda", requires_grad=True)
@@ -74,17 +74,33 @@ def test_fused_tensor_core_layer(gh, gw, hidden):
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-6, (a - b).abs().max().item()
 
 
+@pytest.mark.parametrize("gh,gw", [(7, 7), (16, 16), (13, 10)])
 @pytest.mark.parametrize("B", [1, 2, 3, 148 * 2 + 1])
-def test_fused_layer_ragged_batches(B):
+def test_fused_layer_ragged_batches(B, gh, gw):
     """tiles with empty graph slots / a partial last tile, bf16 single-product mode at its stated tolerance (2e-2)"""
     torch.manual_seed(B)
     for precision, tol in (("bf16x3", 1e-5), ("bf16", 2e-2)):
-        net = GridGNNStack(7, 7, 128, layers=2, precision=precision).cuda()
-        x = torch.randn(B, 49, 128, device="cuda")
+        net = GridGNNStack(gh, gw, 128, layers=2, precision=precision).cuda()
+        assert net.fused
+        x = torch.randn(B, gh * gw, 128, device="cuda")
         with torch.no_grad():
             y = net(x)
-            y2 = onets.grid_gnn_forward([l.weight for l in net.gnn_layers], [l.bias for l in net.gnn_layers], x, 7, 7)
+            y2 = onets.grid_gnn_forward([l.weight for l in net.gnn_layers], [l.bias for l in net.gnn_layers], x, gh, gw)
         assert (y - y2).abs().max().item() <= tol * max(1.0, y2.abs().max().item())
+
+
+def test_wide_tiles_on_small_graphs():
+    """AZG_GRID_TILE=256 runs the 256-row tile kernel (two accumulators per tile, one epilogue group) on graphs that fit a
+    128-row tile too: several graphs per tile, some straddling the half boundary.  Read once per process -> subprocess."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, AZG_GRID_TILE="256")
+    sel = "test_fused_tensor_core_layer and (3-3 or 7-7 or 8-8 or 11-11) or test_fused_layer_ragged_batches and 7-7"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", sel],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "no tests ran" not in r.stdout
 
 
 @pytest.mark.parametrize("H", [64, 128, 256])
