@@ -21,7 +21,12 @@
 // pipeline items run (tile, half, k-block), so producers and MMA issuer only see "one more 128-row operand".  The
 // staging tiles have 256 rows, so a node's neighbours are found across the half boundary: an epilogue thread stages
 // tile rows r and 128 + r (same TMEM lane, the two accumulators) of its group's chunk.  Where only one staging tile
-// fits (H = 256 in bf16x3, weights streamed) the eight warps form ONE group, thread = one of the 256 rows.
+// fits (H = 256 in bf16x3) the eight warps form ONE group, thread = one of the 256 rows.
+//
+// PAIR (H = 256 in bf16x3, whose 256 KB of weight images do not fit one SM): a cluster of two CTAs, each with its own
+// tiles, producers, accumulators and epilogue, shares ONE weight operand -- every tcgen05.mma is issued by the leader
+// for both (cta_group::2, M = 256: 128 rows per CTA) and reads weight rows 0-127 from the leader's and 128-255 from
+// the peer's shared memory, where they stay resident (128 KB each) instead of being re-streamed from L2 per tile.
 #include "azg_tc.cuh"
 
 namespace gridtc {
@@ -29,7 +34,7 @@ using namespace tc;
 
 constexpr int GT_THREADS = 576;    // 8 producer warps, MMA, TMEM/barrier setup, 2 x 4 epilogue warps
 
-template <int H, bool X3, int MT>
+template <int H, bool X3, int MT, bool PAIR>
 struct GridSmem {
   static constexpr int ROWS = 128 * MT;                      // tile rows
   static constexpr int MISC_BYTES = MT == 1 ? 5120 : 8192;   // barriers (256 B), neighbour table [ROWS][5], row sums, d
@@ -37,21 +42,25 @@ struct GridSmem {
   static constexpr int A_BYTES = (X3 ? 2 : 1) * A_STAGE_BYTES;
   static constexpr int W_HALF = H * 128;  // one k-block of one weight image
   static constexpr int W_BYTES = (X3 ? 2 : 1) * W_HALF;
-  static constexpr int W_TOTAL = KB * W_BYTES;  // the whole weight operand (hi and lo images)
+  static constexpr int W_ROWS = PAIR ? H / 2 : H;  // weight rows (output features) this CTA holds
+  static constexpr int W_HALF_RES = W_ROWS * 128;  // one k-block of one resident weight image
+  static constexpr int W_TOTAL = KB * W_BYTES / (PAIR ? 2 : 1);  // the resident weight operand (hi and lo images)
   static constexpr int AVAIL = 232448 - 1024 - MISC_BYTES;
   static constexpr int ST32 = 2 * 128 * 36 * 4;  // two staging tiles of 32-column chunks
-  static constexpr int ST_MIN = MT == 1 ? ST32 : ROWS * 20 * 4;  // MT = 2: at least one 16-column tile of 256 rows
+  static constexpr int ST_MIN = MT == 1 ? 2 * 128 * 16 * 4 : ROWS * 16 * 4;  // smallest staging: 16-column tiles (MT = 2: one tile)
   // WRES: the weight images stay resident in shared memory for the life of the CTA (one bulk copy at start) and a
   // pipeline stage holds only the A operand; otherwise (H = 256 in bf16x3: 256 KB of weights) every stage also
   // carries its k-block of the weights, re-streamed from L2 per tile.
   static constexpr bool WRES = (AVAIL - ST_MIN - W_TOTAL) / A_BYTES >= 2;
   static constexpr int STAGE_BYTES = A_BYTES + (WRES ? 0 : W_BYTES);
   static constexpr int W_RES_BYTES = WRES ? W_TOTAL : 0;
-  // epilogue chunk = columns per tcgen05.ld; two staging tiles (one per epilogue group) of 128 rows x (EC + 4) floats
-  // (row stride 144 / 80 B: conflict-free 128-bit accesses).  32 columns unless that leaves fewer than two stages.
+  // epilogue chunk = columns per tcgen05.ld; two staging tiles (one per epilogue group) of 128 rows.  32 columns (row
+  // stride 144 B: a quarter-warp stores 8 rows x 16 B / gathers one row's 128 B without bank conflicts) unless that leaves
+  // fewer than two stages; else 16 columns, rows of 64 B with the 16-byte unit XOR-swizzled by (row >> 1) & 3 (stg_unit):
+  // a quarter-warp stores 8 rows -> 8 distinct units, gathers 2 rows (always of different parity) x 4 units -> 8 distinct.
   // MT = 2: two tiles of 32 columns, else two of 16, else (H = 256 in bf16x3) one of 16
   static constexpr int EC = (AVAIL - W_RES_BYTES - 2 * ROWS * 36 * 4) / STAGE_BYTES >= 2 ? 32 : 16;
-  static constexpr int ST_LD = EC + 4;
+  static constexpr int ST_LD = EC == 32 ? 36 : 16;
   static constexpr int ST_BYTES = ROWS * ST_LD * 4;
   static constexpr int NTILE = (AVAIL - W_RES_BYTES - 2 * ST_BYTES) / STAGE_BYTES >= 2 ? 2 : 1;
   static_assert(MT == 2 || NTILE == 2, "one staging tile per epilogue group");
@@ -63,6 +72,7 @@ struct GridSmem {
   static constexpr int NACC = MT == 1 ? 2 : (4 * H <= 512 ? 4 : 2);  // TMEM accumulators of H columns (MT = 2: one per half)
   static constexpr int TOTAL = MISC_OFF + MISC_BYTES + 1024;
   static_assert(NST >= 2, "at least two pipeline stages");
+  static_assert(!PAIR || WRES, "CTA pairs exist to keep the weights resident");
 };
 
 __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
@@ -78,6 +88,12 @@ __device__ __forceinline__ void split_store4(float4 x, uint8_t* hi, uint8_t* lo,
   if (lo) *reinterpret_cast<uint2*>(lo + off) = make_uint2(l0, l1);
 }
 
+// float4 index of 16-byte unit `c` of staging row `row`
+template <int EC, int ST_LD>
+__device__ __forceinline__ int stg_unit(int row, int c) {
+  return row * (ST_LD / 4) + (EC == 32 ? c : (c ^ ((row >> 1) & 3)));
+}
+
 struct GridArgs {
   const float* x;      // FWD: layer input; BWD: upstream gradient dOut
   const float* act;    // BWD: the layer's output (ReLU gate), else null
@@ -90,9 +106,9 @@ struct GridArgs {
   int relu;
 };
 
-template <int H, bool X3, bool BWD, int MT>
+template <int H, bool X3, bool BWD, int MT, bool PAIR>
 __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g) {  // 18 warps: 96 registers per thread
-  using S = GridSmem<H, X3, MT>;
+  using S = GridSmem<H, X3, MT, PAIR>;
   constexpr int KB = S::KB, NST = S::NST, EC = S::EC, ST_LD = S::ST_LD, ROWS = S::ROWS, NACC = S::NACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -102,7 +118,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
   uint64_t* tfull = empty + NST;
   uint64_t* tempty = tfull + NACC;
   uint64_t* wbar = tempty + NACC;
-  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
+  uint64_t* peer_full = wbar + 1;             // PAIR, leader: the peer CTA's full[] and tempty[] events
+  uint64_t* peer_tempty = peer_full + NST;
+  uint32_t* tmem_slot = (uint32_t*)(peer_tempty + NACC);
+  static_assert((2 * NST + 3 * NACC + 1) * 8 + 4 <= 256, "barrier block");
   float* nb_coef = (float*)(smem + S::MISC_OFF + 256);  // [ROWS][5]
   float* row_sum = nb_coef + ROWS * 5;                  // [ROWS]
   float* row_d = row_sum + ROWS;                        // [ROWS] deg^-1/2 (0 for unused tile rows)
@@ -114,6 +133,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
   const int64_t tiles = (g.B + G - 1) / G;
   const int64_t total_rows = g.B * n;
   constexpr uint32_t TMEM_COLS = NACC * H < 32 ? 32 : NACC * H;
+  // tiles of this CTA: j-th tile = tile_of(j).  A pair walks consecutive tiles (2 u + rank); at the tail the peer's tile
+  // may not exist -- it then runs an all-zero tile through the same pipeline (no loads, no stores).
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int64_t unit = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t n_units = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const int64_t tile_units = PAIR ? (tiles + 1) / 2 : tiles;
+  const int64_t my_tiles = (tile_units - unit + n_units - 1) / n_units;
+  auto tile_of = [&](int64_t j) { const int64_t u = unit + j * n_units; return PAIR ? 2 * u + (int64_t)rank : u; };
 
   // neighbour table of a tile row: (tile row of the neighbour, d_i * d_j); identical for every tile
   for (int i = threadIdx.x; i < ROWS * 5; i += blockDim.x) {
@@ -141,9 +168,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
       mbar_init(&tempty[a], S::NTILE == 2 ? 256 : 128);  // both epilogue groups drain an accumulator / one group: four warps
     }
     mbar_init(wbar, 1);
+    for (int s = 0; s < NST; ++s) mbar_init(&peer_full[s], 1);
+    for (int a = 0; a < NACC; ++a) mbar_init(&peer_tempty[a], 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 9) {
+    if (PAIR) tmem_alloc2(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   __syncthreads();
   if (threadIdx.x < ROWS) {  // rowsum in the same order as the gather below
     float s = 0.0f;
@@ -154,14 +186,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (S::WRES && warp == 9 && lane == 0) {  // weight images -> shared memory, once per CTA
+  if (S::WRES && warp == 9 && lane == 0) {  // weight images -> shared memory, once per CTA (PAIR: this CTA's half of the rows)
     mbar_expect_tx(wbar, S::W_TOTAL);
     for (int kb = 0; kb < KB; ++kb) {
-      bulk_g2s(smem + kb * S::W_HALF, g.w_hi + (size_t)kb * S::W_HALF, S::W_HALF, wbar);
-      if (X3) bulk_g2s(smem + (KB + kb) * S::W_HALF, g.w_lo + (size_t)kb * S::W_HALF, S::W_HALF, wbar);
+      const size_t src = (size_t)kb * S::W_HALF + (size_t)rank * S::W_HALF_RES;  // rows rank * W_ROWS ..: whole 8-row swizzle atoms
+      bulk_g2s(smem + kb * S::W_HALF_RES, g.w_hi + src, S::W_HALF_RES, wbar);
+      if (X3) bulk_g2s(smem + (KB + kb) * S::W_HALF_RES, g.w_lo + src, S::W_HALF_RES, wbar);
     }
   }
   if (warp < 8) {
@@ -173,11 +207,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
     constexpr int PF = 1;  // 8 float4 (x2 in BWD) per thread = 32 KB (64 KB) of loads in flight per SM
     const int j4 = threadIdx.x & 15, r0 = threadIdx.x >> 4;  // rows r0 + 16 i, float4 j4 (4 channels) of the k-block
     constexpr int IPT = MT * KB;  // items per tile, ordered (half, k-block)
-    const int64_t items = ((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * IPT;
+    const int64_t items = my_tiles * IPT;
     float4 v[PF][8];
     float4 a[PF][BWD ? 8 : 1];
     auto load = [&](int64_t it, int i, float4& vv, float4& aa) {
-      const int64_t tile = blockIdx.x + (it / IPT) * (int64_t)gridDim.x;
+      const int64_t tile = tile_of(it / IPT);
       const int kb = (int)(it % KB);
       const int r = (int)((it % IPT) / KB) * 128 + r0 + 16 * i;  // tile row
       const int64_t row = tile * R + r;
@@ -231,38 +265,68 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
     }
   } else if (warp == 8) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, H);
+    if (lane == 0 && rank != 0) {
+      // peer CTA of a pair: forward "accumulator drained" and "stage filled" to the leader, in the leader's wait order
+      mbar_wait(wbar, 0);  // this CTA's weight rows are in place before the leader may issue anything
+      const uint32_t l_full = map_to_cta(peer_full, 0), l_tempty = map_to_cta(peer_tempty, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      if (S::WRES) mbar_wait(wbar, 0);
-      const uint32_t w_res = smem_u32(smem);
-      for (int64_t item = 0, n_items = ((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * MT; item < n_items; ++item) {  // (tile, half)
+      for (int64_t item = 0, n_items = my_tiles * MT; item < n_items; ++item) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * H);
+        mbar_arrive_cluster(l_tempty + (uint32_t)acc * 8u);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + S::STAGE_OFF + stage * S::STAGE_BYTES);
-          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_STAGE_BYTES);
-          const uint64_t b_hi = make_smem_desc(S::WRES ? w_res + kb * S::W_HALF : sa + S::A_BYTES);
-          const uint64_t b_lo = make_smem_desc(S::WRES ? w_res + (KB + kb) * S::W_HALF : sa + S::A_BYTES + S::W_HALF);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
-          if (X3) {
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
-          }
-          umma_commit(&empty[stage]);
+          mbar_arrive_cluster(l_full + (uint32_t)stage * 8u);
           if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if (++acc == NACC) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    } else if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, H);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc_flag) {
+        if (PAIR) umma2_bf16(d, a, b, idesc, acc_flag);
+        else umma_bf16(d, a, b, idesc, acc_flag);
+      };
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      if (S::WRES) mbar_wait(wbar, 0);
+      const uint32_t w_res = smem_u32(smem);
+      for (int64_t item = 0, n_items = my_tiles * MT; item < n_items; ++item) {  // (tile, half)
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        if (PAIR) mbar_wait_cluster(&peer_tempty[acc], (uint32_t)((item / NACC) & 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * H);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (PAIR) mbar_wait_cluster(&peer_full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + S::STAGE_OFF + stage * S::STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_STAGE_BYTES);
+          const uint64_t b_hi = make_smem_desc(S::WRES ? w_res + kb * S::W_HALF_RES : sa + S::A_BYTES);
+          const uint64_t b_lo = make_smem_desc(S::WRES ? w_res + (KB + kb) * S::W_HALF_RES : sa + S::A_BYTES + S::W_HALF);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, b_hi + 2 * k, (kb | k) != 0);
+          if (X3) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_hi + 2 * k, b_lo + 2 * k, 1);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) mma(d_tmem, a_lo + 2 * k, b_hi + 2 * k, 1);
+          }
+          if (PAIR) umma2_commit(&empty[stage]);
+          else umma_commit(&empty[stage]);
+          if (++stage == NST) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (PAIR) umma2_commit(&tfull[acc]);
+        else umma_commit(&tfull[acc]);
         if (++acc == NACC) {
           acc = 0;
           acc_phase ^= 1;
@@ -290,8 +354,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
     const int gw = g.gw;
     int acc = half;
     uint32_t acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int64_t row_base = tile * R;
+    for (int64_t j = 0; j < my_tiles; ++j) {
+      const int64_t row_base = tile_of(j) * R;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H);
@@ -302,11 +366,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
         if (EC == 32) tmem_ld32(taddr + (uint32_t)c0, rr);
         else tmem_ld16(taddr + (uint32_t)c0, rr);
         tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(stg + r * ST_LD);
+        float4* dst = reinterpret_cast<float4*>(stg);
 #pragma unroll
         for (int e = 0; e < EC / 4; ++e)
-          dst[e] = make_float4(my_d * __uint_as_float(rr[4 * e]), my_d * __uint_as_float(rr[4 * e + 1]),
-                               my_d * __uint_as_float(rr[4 * e + 2]), my_d * __uint_as_float(rr[4 * e + 3]));
+          dst[stg_unit<EC, ST_LD>(r, e)] = make_float4(my_d * __uint_as_float(rr[4 * e]), my_d * __uint_as_float(rr[4 * e + 1]),
+                                                       my_d * __uint_as_float(rr[4 * e + 2]), my_d * __uint_as_float(rr[4 * e + 3]));
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + c4);
         named_bar(3, 256);  // the chunk of every tile row is staged
@@ -314,13 +378,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
         for (int it = 0; it < STEPS; ++it) {
           const int row = half * 128 + q * 32 + it * RPS + lane / LPR;
           const uint32_t m = it_mask[it];
-          const float4* src = reinterpret_cast<const float4*>(stg + row * ST_LD) + c4;
+          const float4* src = reinterpret_cast<const float4*>(stg);
           float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m & 1u) s = *src;
-          if (m & 2u) { const float4 t = *(src - gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-          if (m & 4u) { const float4 t = *(src + gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-          if (m & 8u) { const float4 t = *(src - (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-          if (m & 16u) { const float4 t = *(src + (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+          if (m & 1u) s = src[stg_unit<EC, ST_LD>(row, c4)];
+          if (m & 2u) { const float4 t = src[stg_unit<EC, ST_LD>(row - gw, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+          if (m & 4u) { const float4 t = src[stg_unit<EC, ST_LD>(row + gw, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+          if (m & 8u) { const float4 t = src[stg_unit<EC, ST_LD>(row - 1, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+          if (m & 16u) { const float4 t = src[stg_unit<EC, ST_LD>(row + 1, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
           const float d = row_d[row], rs = row_sum[row];
           float4 v = make_float4(fmaf(d, s.x, rs * b4.x), fmaf(d, s.y, rs * b4.y), fmaf(d, s.z, rs * b4.z), fmaf(d, s.w, rs * b4.w));
           if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -364,8 +428,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
     const int gw = g.gw;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int64_t row_base = tile * R;
+    for (int64_t j = 0; j < my_tiles; ++j) {
+      const int64_t row_base = tile_of(j) * R;
 #pragma unroll
       for (int h = 0; h < MT; ++h) mbar_wait(&tfull[acc + h], acc_phase);
       tc_fence_after();
@@ -378,11 +442,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
           if (EC == 32) tmem_ld32(taddr + (uint32_t)(h * H + c0), rr);
           else tmem_ld16(taddr + (uint32_t)(h * H + c0), rr);
           tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(stg + (h * 128 + r) * ST_LD);
+          float4* dst = reinterpret_cast<float4*>(stg);
 #pragma unroll
           for (int e = 0; e < EC / 4; ++e)
-            dst[e] = make_float4(my_d[h] * __uint_as_float(rr[4 * e]), my_d[h] * __uint_as_float(rr[4 * e + 1]),
-                                 my_d[h] * __uint_as_float(rr[4 * e + 2]), my_d[h] * __uint_as_float(rr[4 * e + 3]));
+            dst[stg_unit<EC, ST_LD>(h * 128 + r, e)] =
+                make_float4(my_d[h] * __uint_as_float(rr[4 * e]), my_d[h] * __uint_as_float(rr[4 * e + 1]),
+                            my_d[h] * __uint_as_float(rr[4 * e + 2]), my_d[h] * __uint_as_float(rr[4 * e + 3]));
         }
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + c4);
@@ -393,13 +458,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
           for (int it = 0; it < STEPS; ++it) {
             const int row = h * 128 + q * 32 + it * RPS + lane / LPR;
             const uint32_t m = (uint32_t)(it_mask[h] >> (5 * it)) & 31u;
-            const float4* src = reinterpret_cast<const float4*>(stg + row * ST_LD) + c4;
+            const float4* src = reinterpret_cast<const float4*>(stg);
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m & 1u) s = *src;
-            if (m & 2u) { const float4 t = *(src - gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-            if (m & 4u) { const float4 t = *(src + gw * (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-            if (m & 8u) { const float4 t = *(src - (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-            if (m & 16u) { const float4 t = *(src + (ST_LD / 4)); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+            if (m & 1u) s = src[stg_unit<EC, ST_LD>(row, c4)];
+            if (m & 2u) { const float4 t = src[stg_unit<EC, ST_LD>(row - gw, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+            if (m & 4u) { const float4 t = src[stg_unit<EC, ST_LD>(row + gw, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+            if (m & 8u) { const float4 t = src[stg_unit<EC, ST_LD>(row - 1, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+            if (m & 16u) { const float4 t = src[stg_unit<EC, ST_LD>(row + 1, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
             const float d = row_d[row], rs = row_sum[row];
             float4 v = make_float4(fmaf(d, s.x, rs * b4.x), fmaf(d, s.y, rs * b4.y), fmaf(d, s.z, rs * b4.z), fmaf(d, s.w, rs * b4.w));
             if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -422,9 +487,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: leave together
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -444,21 +511,33 @@ __global__ void grid_weight_image_kernel(const float* __restrict__ w, int H, int
   split_store(x8, hi, lo, off);
 }
 
-template <int H, bool X3, bool BWD, int MT>
+template <int H, bool X3, bool BWD, int MT, bool PAIR>
 int launch(const GridArgs& g, cudaStream_t st) {
   static bool configured = false;
-  using S = GridSmem<H, X3, MT>;
+  using S = GridSmem<H, X3, MT, PAIR>;
   int dev = 0, sms = 0;
   AZG_CUDA_CHECK(cudaGetDevice(&dev));
   AZG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (!configured) {
-    AZG_CUDA_CHECK(cudaFuncSetAttribute(grid_layer_tc_kernel<H, X3, BWD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    AZG_CUDA_CHECK(cudaFuncSetAttribute(grid_layer_tc_kernel<H, X3, BWD, MT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
   const int G = S::ROWS / (g.gh * g.gw);
   const int64_t tiles = (g.B + G - 1) / G;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  grid_layer_tc_kernel<H, X3, BWD, MT><<<grid, GT_THREADS, S::TOTAL, st>>>(g);
+  const int64_t units = PAIR ? (tiles + 1) / 2 : tiles, max_units = PAIR ? sms / 2 : sms;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((units < max_units ? units : max_units) * (PAIR ? 2 : 1)));
+  cfg.blockDim = dim3(GT_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AZG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, grid_layer_tc_kernel<H, X3, BWD, MT, PAIR>, g));
   AZG_LAUNCH_CHECK();
   return AZG_OK;
 }
@@ -694,21 +773,41 @@ int launch_dw(const float* s, const float* x, int64_t rows, float* dw, float* db
   return AZG_OK;
 }
 
-static int wide_tiles(int n) {  // 256-row tiles: needed above 128 nodes; AZG_GRID_TILE=256 forces them for A/B runs
+// 256-row tiles: needed above 128 nodes, and chosen below when they waste fewer tile rows (7x7: 245/256 instead of 98/128
+// rows carry nodes, 9x9: 243/256 instead of 81/128 -- measured 9-15 % faster in bf16x3 for H <= 128; in bf16 mode only the
+// 9x9-like cases gain).  AZG_GRID_TILE=256 / 128 forces the choice for graphs of up to 128 nodes (A/B runs, tests).
+static int wide_tiles(int n, int H, bool x3) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("AZG_GRID_TILE");
-    forced = (e && strcmp(e, "256") == 0) ? 1 : 0;
+    forced = (e && strcmp(e, "256") == 0) ? 2 : (e && strcmp(e, "128") == 0) ? 1 : 0;
   }
-  return n > 128 || forced;
+  if (n > 128) return 1;
+  if (forced) return forced == 2;
+  if (H > 128) return 0;
+  const float u1 = (float)((128 / n) * n) / 128.0f, u2 = (float)((256 / n) * n) / 256.0f;
+  return u2 - u1 > (x3 ? 0.1f : 0.25f);
+}
+
+static int pair_h256() {  // AZG_GRID_PAIR=0: H = 256 in bf16x3 on single CTAs with streamed weights (A/B runs)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("AZG_GRID_PAIR");
+    on = (e && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return on;
 }
 
 template <bool BWD, int MT>
 int dispatch_h(const GridArgs& g, int H, bool x3, cudaStream_t st) {
   switch (H) {
-    case 64: return x3 ? launch<64, true, BWD, MT>(g, st) : launch<64, false, BWD, MT>(g, st);
-    case 128: return x3 ? launch<128, true, BWD, MT>(g, st) : launch<128, false, BWD, MT>(g, st);
-    case 256: return x3 ? launch<256, true, BWD, MT>(g, st) : launch<256, false, BWD, MT>(g, st);
+    case 64: return x3 ? launch<64, true, BWD, MT, false>(g, st) : launch<64, false, BWD, MT, false>(g, st);
+    case 128: return x3 ? launch<128, true, BWD, MT, false>(g, st) : launch<128, false, BWD, MT, false>(g, st);
+    case 256:
+      if (!x3) return launch<256, false, BWD, MT, false>(g, st);
+      // pairs keep the 256 KB of weight images resident (128 KB per CTA); with 256-row tiles there is no room left for the
+      // second staging tile either way and the single CTA measured the same or better
+      return (MT == 1 && pair_h256()) ? launch<256, true, BWD, 1, true>(g, st) : launch<256, true, BWD, MT, false>(g, st);
   }
   return -1;
 }
@@ -716,7 +815,7 @@ int dispatch_h(const GridArgs& g, int H, bool x3, cudaStream_t st) {
 template <bool BWD>
 int dispatch(const GridArgs& g, int H, int prec, cudaStream_t st) {
   const bool x3 = prec == AZG_PREC_BF16X3;
-  const int rc = wide_tiles(g.gh * g.gw) ? dispatch_h<BWD, 2>(g, H, x3, st) : dispatch_h<BWD, 1>(g, H, x3, st);
+  const int rc = wide_tiles(g.gh * g.gw, H, x3) ? dispatch_h<BWD, 2>(g, H, x3, st) : dispatch_h<BWD, 1>(g, H, x3, st);
   if (rc != -1) return rc;
   azg_set_error("grid layer: hidden size %d not in {64, 128, 256}", H);
   return AZG_ERR_INVALID;

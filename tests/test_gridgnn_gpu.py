@@ -89,16 +89,18 @@ def test_fused_layer_ragged_batches(B, gh, gw):
         assert (y - y2).abs().max().item() <= tol * max(1.0, y2.abs().max().item())
 
 
-def test_wide_tiles_on_small_graphs():
-    """AZG_GRID_TILE=256 runs the 256-row tile kernel (two accumulators per tile, one epilogue group) on graphs that fit a
-    128-row tile too: several graphs per tile, some straddling the half boundary.  Read once per process -> subprocess."""
+@pytest.mark.parametrize("env", [{"AZG_GRID_TILE": "256"}, {"AZG_GRID_TILE": "128", "AZG_GRID_PAIR": "0"}])
+def test_forced_tile_shapes_on_small_graphs(env):
+    """The library picks the tile shape per configuration (128-row tiles, 256-row tiles where they waste fewer rows or the graph
+    needs them, CTA pairs for H = 256 in bf16x3).  The switches force the other choice for graphs of up to 128 nodes:
+    AZG_GRID_TILE=256 -> several graphs per 256-row tile, some straddling the half boundary; AZG_GRID_TILE=128 + AZG_GRID_PAIR=0
+    -> 128-row tiles everywhere and single CTAs with streamed weights.  Read once per process -> subprocess."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, AZG_GRID_TILE="256")
     sel = "test_fused_tensor_core_layer and (3-3 or 7-7 or 8-8 or 11-11) or test_fused_layer_ragged_batches and 7-7"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", sel],
-                       env=env, capture_output=True, text=True, timeout=600)
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "no tests ran" not in r.stdout
 
