@@ -88,10 +88,52 @@ __device__ __forceinline__ void split_store4(float4 x, uint8_t* hi, uint8_t* lo,
   if (lo) *reinterpret_cast<uint2*>(lo + off) = make_uint2(l0, l1);
 }
 
-// float4 index of 16-byte unit `c` of staging row `row`
+// float4 index of 16-byte unit `c` of staging row `row`.  32-column chunks: rows of 144 B.  16-column chunks: rows of 64 B
+// placed at slot = row with bits 0 and 2 exchanged, unit XOR-swizzled by (slot >> 1) & 3 -- a quarter-warp that stores 8
+// consecutive rows (one unit each) or gathers rows x and x + 4 (four units each) touches 8 distinct 16-byte bank groups.
 template <int EC, int ST_LD>
 __device__ __forceinline__ int stg_unit(int row, int c) {
-  return row * (ST_LD / 4) + (EC == 32 ? c : (c ^ ((row >> 1) & 3)));
+  if (EC == 32) return row * (ST_LD / 4) + c;
+  const int slot = (row & ~5) | ((row & 1) << 2) | ((row >> 2) & 1);
+  return slot * 4 + (c ^ ((slot >> 1) & 3));
+}
+
+__device__ __forceinline__ void add4(float4& s, const float4& t) {
+  s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+}
+
+// One thread's share of the neighbour gather: RUN = EC / 4 consecutive tile rows (run0 ...) x one 16-byte unit c4, i.e. a
+// quarter-warp (EC = 32) covers whole 128-byte row segments in shared memory and in HBM.  Left / self / right neighbours
+// are consecutive staged rows, so the run is walked with a three-row window: (RUN + 2) + 2 RUN shared loads per RUN
+// outputs instead of 5 RUN (the gather's loads are what fills the shared-memory pipe: profiles/r02_grid_sweep.txt).
+// out = d_row * (self + up + down + left + right, in this order) + rowsum * bias; masks = 5 valid bits per row of the run.
+template <int EC, int ST_LD>
+__device__ __forceinline__ void gather_run(const float4* src, int run0, uint64_t masks, int c4, int gw, const float* row_d,
+                                           const float* row_sum, float4 b4, int relu, float* out_unit, int64_t row_base,
+                                           int64_t total_rows, int H) {
+  constexpr int RUN = EC / 4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 prev = zero, cur = src[stg_unit<EC, ST_LD>(run0, c4)], next;
+  if (masks & 8u) prev = src[stg_unit<EC, ST_LD>(run0 - 1, c4)];
+#pragma unroll
+  for (int k = 0; k < RUN; ++k) {
+    const int row = run0 + k;
+    const uint32_t m = (uint32_t)(masks >> (5 * k)) & 31u;
+    next = zero;
+    if (k + 1 < RUN || (m & 16u)) next = src[stg_unit<EC, ST_LD>(row + 1, c4)];
+    float4 s = (m & 1u) ? cur : zero;
+    if (m & 2u) add4(s, src[stg_unit<EC, ST_LD>(row - gw, c4)]);
+    if (m & 4u) add4(s, src[stg_unit<EC, ST_LD>(row + gw, c4)]);
+    if (m & 8u) add4(s, prev);
+    if (m & 16u) add4(s, next);
+    const float d = row_d[row], rs = row_sum[row];
+    float4 v = make_float4(fmaf(d, s.x, rs * b4.x), fmaf(d, s.y, rs * b4.y), fmaf(d, s.z, rs * b4.z), fmaf(d, s.w, rs * b4.w));
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    const int64_t grow = row_base + row;
+    if (m != 0u && grow < total_rows) __stcs(reinterpret_cast<float4*>(out_unit + grow * H), v);
+    prev = cur;
+    cur = next;
+  }
 }
 
 struct GridArgs {
@@ -337,19 +379,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
     // =========================== epilogue, 256-row tiles, one staging tile: one group of eight warps ===========================
     // warps 10-13 drain the accumulator of rows 0-127, warps 14-17 the one of rows 128-255 (a warp reads the TMEM lane
     // quarter warp % 4); staging row = tile row, so the gather below crosses the half boundary like any other row.
-    constexpr int LPR = EC / 4, RPS = 32 / LPR, STEPS = 32 / RPS;
+    constexpr int LPR = EC / 4, RUN = EC / 4;  // lanes per row = rows per thread
     const int half = (warp - 10) >> 2;
     const int q = warp & 3, r = half * 128 + q * 32 + lane;
-    const int c4 = lane % LPR;
+    const int c4 = lane % LPR, run0 = (r / LPR) * RUN;
     const float my_d = row_d[r];
-    uint32_t it_mask[STEPS];
+    uint64_t run_mask = 0;  // 5 neighbour-valid bits per row of this thread's gather run
 #pragma unroll
-    for (int it = 0; it < STEPS; ++it) {
-      const int row = half * 128 + q * 32 + it * RPS + lane / LPR;
-      uint32_t m = 0;
+    for (int i = 0; i < RUN; ++i) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) m |= (nb_coef[row * 5 + k] != 0.0f ? 1u : 0u) << k;
-      it_mask[it] = m;
+      for (int k = 0; k < 5; ++k) run_mask |= (uint64_t)(nb_coef[(run0 + i) * 5 + k] != 0.0f ? 1u : 0u) << (5 * i + k);
     }
     const int gw = g.gw;
     int acc = half;
@@ -374,23 +413,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + c4);
         named_bar(3, 256);  // the chunk of every tile row is staged
-#pragma unroll
-        for (int it = 0; it < STEPS; ++it) {
-          const int row = half * 128 + q * 32 + it * RPS + lane / LPR;
-          const uint32_t m = it_mask[it];
-          const float4* src = reinterpret_cast<const float4*>(stg);
-          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m & 1u) s = src[stg_unit<EC, ST_LD>(row, c4)];
-          if (m & 2u) { const float4 t = src[stg_unit<EC, ST_LD>(row - gw, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-          if (m & 4u) { const float4 t = src[stg_unit<EC, ST_LD>(row + gw, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-          if (m & 8u) { const float4 t = src[stg_unit<EC, ST_LD>(row - 1, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-          if (m & 16u) { const float4 t = src[stg_unit<EC, ST_LD>(row + 1, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-          const float d = row_d[row], rs = row_sum[row];
-          float4 v = make_float4(fmaf(d, s.x, rs * b4.x), fmaf(d, s.y, rs * b4.y), fmaf(d, s.z, rs * b4.z), fmaf(d, s.w, rs * b4.w));
-          if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          const int64_t grow = row_base + row;
-          if (m != 0u && grow < total_rows) __stcs(reinterpret_cast<float4*>(g.out + grow * H + c0) + c4, v);
-        }
+        gather_run<EC, ST_LD>(reinterpret_cast<const float4*>(stg), run0, run_mask, c4, gw, row_d, row_sum, b4, g.relu,
+                              g.out + c0 + 4 * c4, row_base, total_rows, H);
         named_bar(4, 256);  // every row has gathered: the staging tile may be overwritten
       }
       tc_fence_before();
@@ -404,25 +428,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
   } else if (warp >= 10) {
     // =========================== epilogue: two groups of four warps, alternating column chunks ===========================
     // Staging: thread = TMEM lane = tile row (MT = 2: rows r and 128 + r, one per accumulator) writes d_row * D[row, EC
-    // columns] (d = deg^-1/2).  Gather: a warp covers RPS rows x EC/4 float4 per step (a row's chunk is contiguous in
-    // shared memory and in HBM), so shared-memory reads and global stores are whole lines; out = d_row * (sum over {self,
-    // valid neighbours} of the staged rows) + rowsum * bias.  Neighbours of row r: r -/+ gw (x -/+ 1), r -/+ 1 (y -/+ 1).
-    constexpr int LPR = EC / 4, RPS = 32 / LPR, STEPS = 32 / RPS;  // lanes per row, rows per step, steps per quarter
+    // columns] (d = deg^-1/2).  Gather: gather_run -- EC/4 lanes cover a row's chunk (contiguous in shared memory and in
+    // HBM: whole lines), each walking EC/4 consecutive rows; out = d_row * (sum over {self, valid neighbours} of the staged
+    // rows) + rowsum * bias.  Neighbours of row r: r -/+ gw (x -/+ 1), r -/+ 1 (y -/+ 1).
+    constexpr int LPR = EC / 4, RUN = EC / 4;  // lanes per row = rows per thread in the gather
     const int grp = (warp - 10) >> 2;
     const int q = warp & 3, r = q * 32 + lane;
-    const int c4 = lane % LPR;
+    const int c4 = lane % LPR, run0 = (r / LPR) * RUN;
     float* stg = staging + grp * (S::ST_BYTES / 4);
     float my_d[MT];
-    uint64_t it_mask[MT];  // 5 neighbour-valid bits per gather step
+    uint64_t run_mask[MT];  // 5 neighbour-valid bits per row of this thread's gather run
 #pragma unroll
     for (int h = 0; h < MT; ++h) {
       my_d[h] = row_d[h * 128 + r];
-      it_mask[h] = 0;
+      run_mask[h] = 0;
 #pragma unroll
-      for (int it = 0; it < STEPS; ++it) {
-        const int row = h * 128 + q * 32 + it * RPS + lane / LPR;
+      for (int i = 0; i < RUN; ++i) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) it_mask[h] |= (uint64_t)(nb_coef[row * 5 + k] != 0.0f ? 1u : 0u) << (5 * it + k);
+        for (int k = 0; k < 5; ++k) run_mask[h] |= (uint64_t)(nb_coef[(h * 128 + run0 + i) * 5 + k] != 0.0f ? 1u : 0u) << (5 * i + k);
       }
     }
     const int gw = g.gw;
@@ -453,25 +476,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grid_layer_tc_kernel(GridArgs g
         if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + c4);
         named_bar(3 + 2 * grp, 128);  // the chunk of every row is staged
 #pragma unroll
-        for (int h = 0; h < MT; ++h) {
-#pragma unroll
-          for (int it = 0; it < STEPS; ++it) {
-            const int row = h * 128 + q * 32 + it * RPS + lane / LPR;
-            const uint32_t m = (uint32_t)(it_mask[h] >> (5 * it)) & 31u;
-            const float4* src = reinterpret_cast<const float4*>(stg);
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m & 1u) s = src[stg_unit<EC, ST_LD>(row, c4)];
-            if (m & 2u) { const float4 t = src[stg_unit<EC, ST_LD>(row - gw, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-            if (m & 4u) { const float4 t = src[stg_unit<EC, ST_LD>(row + gw, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-            if (m & 8u) { const float4 t = src[stg_unit<EC, ST_LD>(row - 1, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-            if (m & 16u) { const float4 t = src[stg_unit<EC, ST_LD>(row + 1, c4)]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-            const float d = row_d[row], rs = row_sum[row];
-            float4 v = make_float4(fmaf(d, s.x, rs * b4.x), fmaf(d, s.y, rs * b4.y), fmaf(d, s.z, rs * b4.z), fmaf(d, s.w, rs * b4.w));
-            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            const int64_t grow = row_base + row;
-            if (m != 0u && grow < total_rows) __stcs(reinterpret_cast<float4*>(g.out + grow * H + c0) + c4, v);
-          }
-        }
+        for (int h = 0; h < MT; ++h)
+          gather_run<EC, ST_LD>(reinterpret_cast<const float4*>(stg), h * 128 + run0, run_mask[h], c4, gw, row_d, row_sum, b4, g.relu,
+                                g.out + c0 + 4 * c4, row_base, total_rows, H);
         named_bar(4 + 2 * grp, 128);  // every row has gathered: the staging tile may be overwritten
       }
       tc_fence_before();
