@@ -33,7 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--precisions", default="bf16x3,bf16,fp32")
-    ap.add_argument("--grids", default="3x3,4x4,6x7,7x7,8x8,16x16")
+    ap.add_argument("--grids", default="3x3,4x4,6x7,7x7,8x8,12x12,16x16")
     ap.add_argument("--hiddens", default="64,128,256")
     ap.add_argument("--batches", default="1024,16384,262144")
     args = ap.parse_args()
