@@ -180,6 +180,9 @@ int azg_arena_create(azg_arena** out, int game, int n, int n_games, int capacity
     return AZG_ERR_INVALID;
   }
   *out = a;
+  // roots start as the all-zero state (empty board / FrozenLake start square) until azg_arena_set_roots; the caller's
+  // memory may be recycled
+  AZG_CUDA_CHECK(cudaMemsetAsync(v.root, 0, (size_t)n_games * sizeof(AzgState), (cudaStream_t)stream));
   return azg_arena_reset(a, nullptr, n_games, stream);
 }
 

@@ -149,7 +149,8 @@ class BatchedMCTS:
         self.standard_predictions = [dict() for _ in range(n_games)]
         self.gnn_predictions = [dict() for _ in range(n_games)]
         self.leaf_evals = 0          # positions submitted for evaluation (host path: exact; device paths: see below)
-        self._leaf_total = None      # compact path: exact count accumulated on the device
+        self._leaf_total = None      # compact path: exact count accumulated on the device (int64 [1], updated in place)
+        self._graphs = {}            # n_sims -> "warm" | (CUDAGraph, weights version): captured searches (search(graph=True))
 
     # ------------------------------------------------------------------ roots
     def reset(self, game_ids=None):
@@ -196,24 +197,58 @@ class BatchedMCTS:
             self.leaf_evals += 1
         return ar.to_device(pi, torch.float32), ar.to_device(v, torch.float32), int(mask.sum())
 
-    def search(self, n_sims, check=True):
-        """n_sims MCTS.search calls per game (MCTS.py:33-34), in lock step.  check=False leaves the (synchronising)
-        arena status read-back to the caller, so that host work can overlap the queued rounds (device evaluation only)."""
+    def _search_graphed(self, n_sims):
+        """The compact search has no host round trip (leaf counts stay on the device), so the whole lock-step search --
+        n_sims x (select, network evaluation, expand/backup), ~10 launches each -- replays as ONE CUDA graph.  Small
+        batches (the arena's 50 games per network) are bound by launch overhead, not by the GPU.  First call: eager
+        (loads kernels, packs weights, settles the precision guard); second call: captured, then replayed; a graph is
+        dropped when the network's weights change (it holds the address of the packed weight images)."""
+        version = getattr(self.nnet, "weights_version", 0)
+        st = self._graphs.get(n_sims)
+        if isinstance(st, tuple) and st[1] != version:
+            st = None
+        if st is None:
+            self._graphs[n_sims] = "warm"
+            return False
+        if st == "warm":
+            if self._leaf_total is None:
+                self._leaf_total = torch.zeros(1, dtype=torch.int64, device=self.arena.device)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._search_rounds(n_sims)
+            st = self._graphs[n_sims] = (g, version)
+        st[0].replay()
+        return True
+
+    def _search_rounds(self, n_sims):
         ar = self.arena
         ar.begin(n_sims)
+        for _ in range(n_sims):  # every round retires >= 1 simulation per game that has budget
+            leaf_states, _game, count = ar.select_compact()
+            pi, v = self._evaluate_device(leaf_states, count)
+            ar.expand_backup_compact(pi, v)
+            if self._leaf_total is None:
+                self._leaf_total = torch.zeros(1, dtype=torch.int64, device=ar.device)
+            self._leaf_total.add_(count.reshape(-1)[:1])
+
+    def search(self, n_sims, check=True, graph=False):
+        """n_sims MCTS.search calls per game (MCTS.py:33-34), in lock step.  check=False leaves the (synchronising)
+        arena status read-back to the caller, so that host work can overlap the queued rounds (device evaluation only).
+        graph=True (compact device path only): replay the search as a CUDA graph from the second call on."""
+        ar = self.arena
         if self.compact:
-            for _ in range(n_sims):  # every round retires >= 1 simulation per game that has budget
-                leaf_states, _game, count = ar.select_compact()
-                pi, v = self._evaluate_device(leaf_states, count)
-                ar.expand_backup_compact(pi, v)
-                self._leaf_total = count.to(torch.int64) if self._leaf_total is None else self._leaf_total + count
+            if not (graph and self._search_graphed(n_sims)):
+                self._search_rounds(n_sims)
         elif self.device_eval:
+            ar.begin(n_sims)
             for _ in range(n_sims):
                 leaf_states, _mask = ar.select()
                 pi, v = self._evaluate_device(leaf_states)
                 ar.expand_backup(pi, v)
                 self.leaf_evals += self.G
         else:
+            ar.begin(n_sims)
             while True:
                 leaf_states, leaf_mask = ar.select()
                 pi, v, pending = self._evaluate_host(leaf_states, leaf_mask)

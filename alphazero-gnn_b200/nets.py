@@ -109,6 +109,7 @@ class _Base:
         """Call after any in-place parameter update (optimizer step, load): re-tiled copies are stale."""
         self._packed_ok = False
         self._auto_choice = None
+        self.weights_version = getattr(self, "weights_version", 0) + 1  # captured searches (mcts.py) replay only for the version they saw
 
 
 class _TwoPlayer(_Base):

@@ -29,6 +29,7 @@ class BatchedArena:
         self.game, self.nets = game, (nnet1, nnet2)
         self.args = (args, args if args2 is None else args2)
         self._arena_factory = arena_factory
+        self.graph_search = bool(arg(args, "b200_graph_search", False))  # measured: no gain for one playGames call (capture costs what replay saves)
 
     def _mcts(self, net, n_games):
         arena = self._arena_factory(n_games) if self._arena_factory else None
@@ -63,7 +64,8 @@ class BatchedArena:
                 m.arena.set_roots(states[grp])
                 for d in m.standard_predictions + m.gnn_predictions:
                     d.clear()  # MCTS.py:30-31
-                m.search(int(arg(m.args, "numMCTSSims")))
+                # b200_graph_search: from the second ply on the whole search replays as one CUDA graph (profiles/prof_arena.py)
+                m.search(int(arg(m.args, "numMCTSSims")), graph=self.graph_search and m.arena.device.type == "cuda")
                 N, _, _ = m.root_stats()
                 best = N == N.max(axis=1, keepdims=True)
                 actions = best.argmax(axis=1).astype(np.int32)

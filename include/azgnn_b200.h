@@ -302,7 +302,9 @@ typedef struct azg_arena azg_arena;
 
 /* bytes of device memory the caller must provide to azg_arena_create */
 size_t azg_arena_bytes(int game, int n, int n_games, int capacity_nodes, int max_depth);
-/* fl_map: host pointer to n*n map characters ('S','F','H','G') for AZG_GAME_FROZENLAKE, else NULL.
+/* Every game starts with an empty table and the all-zero root state (empty board / FrozenLake start square) until
+ * azg_arena_set_roots.
+ * fl_map: host pointer to n*n map characters ('S','F','H','G') for AZG_GAME_FROZENLAKE, else NULL.
  * max_depth: a search call entered at depth >= max_depth returns Python-int 0 (cycle policy for
  * single-player games; never reached in two-player games when > n*n+1). */
 int azg_arena_create(azg_arena** out, int game, int n, int n_games, int capacity_nodes, int max_depth,

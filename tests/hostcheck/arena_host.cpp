@@ -58,6 +58,7 @@ int azgh_arena_create(azgh_arena** out, int game, int n, int n_games, int cap, i
   v.p_f32 = (game == AZG_GAME_FROZENLAKE);
   if (azg_arena_carve(&v, (char*)mem) > bytes) { delete a; azg_set_error("arena memory too small"); return AZG_ERR_INVALID; }
   *out = a;
+  memset(v.root, 0, (size_t)n_games * sizeof(AzgState));  // as azg_arena_create: roots start as the all-zero state
   return azgh_arena_reset(a, nullptr, n_games, nullptr);
 }
 

@@ -96,3 +96,40 @@ def test_single_player_arena_frozenlake():
     one, two, draws = BatchedSinglePlayerArena(game, fresh, taught, args).playGames(8)
     assert one + two + draws == 8
     assert two >= one
+
+
+@pytest.mark.parametrize("kind,n,prec", [("c4", 7, "f16f8"), ("c4", 5, "fp32"), ("c4", 6, "bf16x3")])
+def test_graph_replayed_search_equals_eager_search(kind, n, prec):
+    """BatchedMCTS.search(graph=True): the whole lock-step search replayed as one CUDA graph (the arena's launch-bound
+    50-game searches) leaves bit-identical trees: same root statistics ply after ply, same leaf count."""
+    from azgnn_b200.mcts import BatchedMCTS
+    game = games.Connect4Game(n) if kind == "c4" else games.TicTacToeGame(n)
+    args = dotdict(dict(lr=1e-3, dropout=0.3, gnn_layers=2, use_gnn=True, numMCTSSims=9, cpuct=1.0, expand_by=3,
+                        b200_precision=prec))
+    W = B200Connect4GNNWrapper if kind == "c4" else B200TicTacToeGNNWrapper
+    torch.manual_seed(3)
+    net = W(game, args)
+    G = 50
+    eager, graphed = (BatchedMCTS(game, net, args, n_games=G) for _ in range(2))
+    assert eager.compact and graphed.compact
+    for m in (eager, graphed):
+        m.set_root_boards([game.getInitBoard()] * G)
+    rng = np.random.default_rng(0)
+    for ply in range(5):
+        eager.search(9)
+        graphed.search(9, graph=True)
+        (N1, Q1, t1), (N2, Q2, t2) = eager.root_stats(), graphed.root_stats()
+        assert np.array_equal(N1, N2) and np.array_equal(Q1, Q2) and np.array_equal(t1, t2), ply
+        # play a visited move (not always the best one, so that the games diverge from each other)
+        actions = np.array([rng.choice(np.flatnonzero(N1[g] > 0)) for g in range(G)], dtype=np.int32)
+        e1, _ = eager.advance_arrays(actions.copy())
+        e2, _ = graphed.advance_arrays(actions.copy())
+        assert np.array_equal(e1, e2)
+        if (e1 != 0).any():
+            break
+    assert ply >= 2 and isinstance(graphed._graphs[9], tuple), "the third search must have been a graph replay"
+    assert eager.leaf_evaluations() == graphed.leaf_evaluations() > 0
+    # a weight update invalidates the captured graph (it holds the address of the packed weight images)
+    net.weights_changed()
+    graphed.search(9, graph=True)
+    assert graphed._graphs[9] == "warm"
