@@ -57,7 +57,7 @@ DTYPES = {"fp32": "f32", "bf16x3": "f32 (3xbf16 split, f32 accumulate)", "bf16":
 MMA_TIMES = {"bf16x3": 3.0, "f16f8": 2.0, "bf16": 1.0, "fp32": None}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (average of GEMM-1 and GEMM-2) from the committed ncu capture
 # of this configuration; None where no capture of the current kernel exists
-NCU_TRAFFIC = {"f16f8": (2.298e9, "profiles/r02_main_kernels_f16f8.txt"), "bf16x3": (2.268e9, "profiles/r01_main_kernels_bf16x3_v9.txt")}
+NCU_TRAFFIC = {"f16f8": (2.360e9, "profiles/r02_main_kernels_f16f8.txt"), "bf16x3": (2.268e9, "profiles/r01_main_kernels_bf16x3_v9.txt")}
 
 
 def synthetic_boards(count, seed):
