@@ -72,6 +72,16 @@ struct GemmArgs {
   int f8;
   const int32_t* w_exp;
   const int32_t* side_exp;
+  // K-split accumulation (AZG_PREC_F16F8_KS, CTA-pair kernel with fused hi/lo stages only): this launch contracts the
+  // k-blocks [kb0, kb0 + kbn) (kbn = 0: all KB) and its epilogue first adds `acc_in` (row-major fp32 [M, N] partial sums
+  // of the earlier launches, may alias out_f32: every element is read and written by the same thread); `no_bias` leaves
+  // the bias to the last launch; `side_acc` makes the side tile add to side_out instead of writing rr + bias.
+  // The tensor core's fp32 accumulation truncates once per MMA, an error that grows linearly with the number of k-steps
+  // ("the accumulation floor"): C launches of K/C steps, summed here with round-to-nearest adds,
+  // bring it down C times.
+  int kb0, kbn;
+  const float* acc_in;
+  int no_bias, side_acc;
 };
 // TMEM columns of the constant UE8M0 scale-factor regions (f8 mode; accumulators use 2 x BN <= 448 columns)
 constexpr uint32_t SF_A_COL = 448, SF_W_COL = 464, SF_SIDE_COL = 480;
@@ -114,7 +124,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
           float4* dst = reinterpret_cast<float4*>(g.side_out + row * SIDE_N);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.side_bias) + j);
+            const float4 b4 = g.side_acc ? dst[j] : __ldg(reinterpret_cast<const float4*>(g.side_bias) + j);
             dst[j] = make_float4(__uint_as_float(rr[4 * j]) + b4.x, __uint_as_float(rr[4 * j + 1]) + b4.y,
                                  __uint_as_float(rr[4 * j + 2]) + b4.z, __uint_as_float(rr[4 * j + 3]) + b4.w);
           }
@@ -130,16 +140,42 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
         tmem_ld32(taddr + (uint32_t)c0, rr);
         const int n0 = nt * BN + c0;
         float4 b4[8];  // the chunk's bias (warp-uniform addresses): 8 vector loads in flight under the TMEM load
+        if (!g.no_bias) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
-        tmem_ld_wait();
+          for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
+        }
         float v[32];
+        if (g.acc_in) {  // K-split: partial sums of the earlier launches (plain loads: written by the previous kernel)
+          const float4* src = reinterpret_cast<const float4*>(g.acc_in + row * (int64_t)(g.n_tiles * BN) + n0);
+          float4 p4[8];
+          if (row < g.M) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[4 * j] = __uint_as_float(rr[4 * j]) + b4[j].x;
-          v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + b4[j].y;
-          v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + b4[j].z;
-          v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + b4[j].w;
+            for (int j = 0; j < 8; ++j) p4[j] = src[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p4[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] = __fadd_rn(p4[j].x, __uint_as_float(rr[4 * j]));
+            v[4 * j + 1] = __fadd_rn(p4[j].y, __uint_as_float(rr[4 * j + 1]));
+            v[4 * j + 2] = __fadd_rn(p4[j].z, __uint_as_float(rr[4 * j + 2]));
+            v[4 * j + 3] = __fadd_rn(p4[j].w, __uint_as_float(rr[4 * j + 3]));
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+        }
+        if (!g.no_bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] += b4[j].x;
+            v[4 * j + 1] += b4[j].y;
+            v[4 * j + 2] += b4[j].z;
+            v[4 * j + 3] += b4[j].w;
+          }
         }
         if (g.relu) {
 #pragma unroll
@@ -303,7 +339,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs 
   const bool dual = TWO && !g.x3;
   const int NSR = TWO ? 3 : NS;                                            // stages in use
   const uint32_t stage_bytes = TWO ? 2 * S::STAGE_BYTES : S::STAGE_BYTES;
-  const int kb_total = fused3 ? g.KB : dual ? (g.KB + 1) / 2 : (g.x3 ? 3 * g.KB : g.KB);
+  const int kb_total = fused3 ? (g.kbn ? g.kbn : g.KB) : dual ? (g.KB + 1) / 2 : (g.x3 ? 3 * g.KB : g.KB);
+  const int kb_first = fused3 ? g.kb0 : 0;  // K-split launches (fused hi/lo stages only, checked by the launcher)
+  // f8 launches that issue only one of the two products (K-split: main quarters and the correction product go to
+  // different accumulators; AZG_F8_TERMS diagnostics) fill only the half of the stage that product reads
+  const bool need_hi = !(TWO && g.f8) || (g.f8 & 1), need_lo = !(TWO && g.f8) || (g.f8 & 2);
 
   if (warp == 0) {
     // ================= producer: bulk copies of operand tile images =================
@@ -317,9 +357,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           if (side) {  // same stage layout, the weight part is this CTA's 16 rows of the [32 x 64] side tile
-            const int k0 = dual ? 2 * kb : kb, parts = (fused3 || k0 + 1 < g.KB) ? 2 : 1;
-            mbar_expect_tx(&full[stage], parts * (A_STAGE_BYTES + SIDE_STAGE_BYTES));
+            const int k0 = dual ? 2 * kb : kb_first + kb, parts = (fused3 || k0 + 1 < g.KB) ? 2 : 1;
+            mbar_expect_tx(&full[stage], (fused3 ? (int)need_hi + (int)need_lo : parts) * (A_STAGE_BYTES + SIDE_STAGE_BYTES));
             for (int pt = 0; pt < parts; ++pt) {
+              if (fused3 && !(pt ? need_lo : need_hi)) continue;
               const int kk = fused3 ? k0 : k0 + pt;
               const size_t ao = ((size_t)mt * g.KB + kk) * A_STAGE_BYTES;
               const size_t wo = (size_t)kk * (2 * SIDE_STAGE_BYTES) + (size_t)rank * SIDE_STAGE_BYTES;
@@ -348,14 +389,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs 
             }
             continue;
           }
-          mbar_expect_tx(&full[stage], stage_bytes);
+          mbar_expect_tx(&full[stage], fused3 ? ((uint32_t)need_hi + (uint32_t)need_lo) * S::STAGE_BYTES : stage_bytes);
           if (fused3) {  // [A_hi | W_hi half | A_lo | W_lo half]
-            const size_t ao = ((size_t)mt * g.KB + kb) * A_STAGE_BYTES;
-            const size_t wo = ((size_t)nt * g.KB + kb) * S::W_TILE_BYTES + (size_t)rank * S::W_STAGE_BYTES;
-            bulk_g2s(sa, g.a_hi + ao, A_STAGE_BYTES, &full[stage]);
-            bulk_g2s(sa + A_STAGE_BYTES, g.w_hi + wo, S::W_STAGE_BYTES, &full[stage]);
-            bulk_g2s(sa + S::STAGE_BYTES, g.a_lo + ao, A_STAGE_BYTES, &full[stage]);
-            bulk_g2s(sa + S::STAGE_BYTES + A_STAGE_BYTES, g.w_lo + wo, S::W_STAGE_BYTES, &full[stage]);
+            const size_t ao = ((size_t)mt * g.KB + kb_first + kb) * A_STAGE_BYTES;
+            const size_t wo = ((size_t)nt * g.KB + kb_first + kb) * S::W_TILE_BYTES + (size_t)rank * S::W_STAGE_BYTES;
+            if (need_hi) {
+              bulk_g2s(sa, g.a_hi + ao, A_STAGE_BYTES, &full[stage]);
+              bulk_g2s(sa + A_STAGE_BYTES, g.w_hi + wo, S::W_STAGE_BYTES, &full[stage]);
+            }
+            if (need_lo) {
+              bulk_g2s(sa + S::STAGE_BYTES, g.a_lo + ao, A_STAGE_BYTES, &full[stage]);
+              bulk_g2s(sa + S::STAGE_BYTES + A_STAGE_BYTES, g.w_lo + wo, S::W_STAGE_BYTES, &full[stage]);
+            }
           } else {
             // x3: [Xhi|Xhi|Xlo] against [Whi|Wlo|Whi]
             const int seg = g.x3 ? kb / g.KB : 0, kk = g.x3 ? kb % g.KB : kb;
@@ -639,6 +684,8 @@ int launch_gemm_impl(const GemmArgs& g, cudaStream_t st) {
 // the CTA-pair kernel needs BN/2 to be a multiple of 8 rows and an even number of padded m-tiles
 template <int BN>
 int launch_gemm(const GemmArgs& g, cudaStream_t st) {
+  AZG_REQUIRE(!(g.kbn || g.kb0 || g.acc_in || g.no_bias || g.side_acc) || (g.f8 && g.x3 && g.pair_ok && g.kb0 >= 0 && g.kb0 + g.kbn <= g.KB),
+              "tcgen05 GEMM: K-split launches run on the CTA-pair kernel of the fp16+FP8 split only");
   if (g.f8) {
     if constexpr (BN >= 128 && BN <= 224) {
       AZG_REQUIRE(g.pair_ok && g.x3, "tcgen05 GEMM: the fp16+FP8 split runs on the CTA-pair kernel only");
@@ -1659,13 +1706,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) c4_trunk2_tc_kernel(TrunkArgs t
           const uint64_t a_hi = a_base[k] + (uint64_t)(tap16[s >> 1] + (uint32_t)(s & 1) * 2u);
           if (PAIR) {  // each CTA supplies half of the weight rows: 64 of [W_hi ; W_lo], 32 of W_hi
             mma(d_tmem, a_hi, b_base + (uint64_t)((s >> 2) * (64 * 128 / 16) + 2 * (s & 3)), idesc_cat, s != 0);
-            mma(d_tmem, a_hi + 4, b_half + (uint64_t)((s >> 2) * (32 * 128 / 16) + 2 * (s & 3)), idesc, 1);
+            mma(d_tmem + BN, a_hi + 4, b_half + (uint64_t)((s >> 2) * (32 * 128 / 16) + 2 * (s & 3)), idesc, 1);
             continue;
           }
           const uint64_t b_w = b_base + (uint64_t)((s >> 2) * (X3 ? 2 : 1) * (64 * 128 / 16) + 2 * (s & 3));
           if (X3) {
+            // Both correction products go to columns 64-127: the tensor core's fp32 accumulation truncates once per MMA
+            // by up to an ulp OF THE ACCUMULATOR, so small terms added to the large hi x W_hi sum would double its
+            // truncation bias (36 instead of 18 accumulations); among themselves they cost nothing measurable.
             mma(d_tmem, a_hi, b_w, idesc_cat, s != 0);           // hi x [W_hi ; W_lo]: columns 0-63 and 64-127
-            mma(d_tmem, a_hi + 4, b_w, idesc, 1);                // lo (64 bytes further in the cell) x W_hi
+            mma(d_tmem + BN, a_hi + 4, b_w, idesc, 1);           // lo (64 bytes further in the cell) x W_hi: columns 64-127
           } else {
             mma(d_tmem, a_hi, b_w, idesc, s != 0);
           }
@@ -1825,13 +1875,21 @@ struct PackLayout {
   size_t w0_hi, w0_lo, w2_hi, w2_lo, c2_hi, c2_lo, heads, heads_cat, hd_hi, hd_lo, bias32, fold_w, fold_b, scales, total;
   bool x3, gnn, f8;  // x3: hi + lo images (bf16x3 and the fp16+FP8 split); f8: the latter
 };
-inline bool prec_is_tc(int prec) { return prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16 || prec == AZG_PREC_F16F8; }
-inline int prec_bn(int F, int prec) { return prec == AZG_PREC_F16F8 ? tc::pick_bn_f8(F) : tc::pick_bn(F); }
+// AZG_PREC_F16F8_KS runs on the operand images of AZG_PREC_F16F8 (same packed blob, same tile widths); it differs in how
+// the F x F contractions are launched (KSPLIT launches over a quarter of K each, see GemmArgs::kb0)
+constexpr int KSPLIT = 4;
+inline int prec_base(int prec) { return prec == AZG_PREC_F16F8_KS ? AZG_PREC_F16F8 : prec; }
+inline bool prec_is_tc(int prec) {
+  prec = prec_base(prec);
+  return prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16 || prec == AZG_PREC_F16F8;
+}
+inline int prec_bn(int F, int prec) { return prec_base(prec) == AZG_PREC_F16F8 ? tc::pick_bn_f8(F) : tc::pick_bn(F); }
 
 size_t up1k(size_t v) { return (v + 1023) / 1024 * 1024; }
 
 PackLayout pack_layout(int n, int prec, bool gnn) {
   PackLayout L{};
+  prec = prec_base(prec);
   const size_t F = 64 * (size_t)n * n, wimg = F * F * 2, cimg = 64 * (size_t)tc::C2_K * 2;
   L.x3 = prec == AZG_PREC_BF16X3 || prec == AZG_PREC_F16F8;
   L.f8 = prec == AZG_PREC_F16F8;
@@ -1859,11 +1917,13 @@ PackLayout pack_layout(int n, int prec, bool gnn) {
 }
 
 struct ScratchLayout {
-  size_t a2_hi, a2_lo, f_hi, f_lo, h_hi, h_lo, part, lg32, total;
+  size_t a2_hi, a2_lo, f_hi, f_lo, h_hi, h_lo, part, lg32, acc, total;
 };
 
 ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
   ScratchLayout S{};
+  const bool ksplit = prec == AZG_PREC_F16F8_KS;
+  prec = prec_base(prec);
   const bool x3 = prec == AZG_PREC_BF16X3 || prec == AZG_PREC_F16F8;
   const size_t nn = (size_t)n * n, F = 64 * nn;
   const size_t M2p = (size_t)azg_ceil_div(B * (int64_t)nn, tc::BM) * tc::BM, Mp = (size_t)azg_ceil_div(B, 2 * tc::BM) * 2 * tc::BM;  // even number of m-tiles (CTA pairs)
@@ -1880,6 +1940,7 @@ ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
     S.h_lo = x3 ? take(fimg) : 0;
     const int BNp = prec_bn((int)F, prec);
     S.part = take(Mp * (size_t)(BNp ? 2 * (F / BNp) : 32) * tc::HEAD_STRIDE * sizeof(float));  // two epilogue groups per n-tile
+    if (ksplit) S.acc = take(Mp * F * sizeof(float));  // fp32 partial sums of the K-split launches
   }
   S.total = off + 1024;
   return S;
@@ -1922,10 +1983,12 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
                       size_t scratch_bytes, const int32_t* dyn_rows, cudaStream_t st) {
   const int nn = n * n, F = 64 * nn, A = n + 1, BN = prec_bn(F, prec);
   AZG_REQUIRE(BN != 0, "tcgen05 path: unsupported board size %d", n);
+  const int ks = prec == AZG_PREC_F16F8_KS ? KSPLIT : 1;  // launches per F x F contraction (K-split accumulation)
+  const ScratchLayout S = scratch_layout(n, B, prec, true);
+  prec = prec_base(prec);
   const bool f8 = prec == AZG_PREC_F16F8, x3 = prec == AZG_PREC_BF16X3 || f8, gnn = (eval_mask & AZG_EVAL_GNN) != 0;
   AZG_REQUIRE(!f8 || azg_trunk_mode() == 0, "tcgen05 path: the fp16+FP8 split needs the fused trunk (unset AZG_TRUNK)");
   const PackLayout L = pack_layout(n, prec, true);
-  const ScratchLayout S = scratch_layout(n, B, prec, true);
   AZG_REQUIRE(scratch && scratch_bytes >= S.total, "tcgen05 path: scratch %zu < %zu", scratch_bytes, S.total);
   uint8_t* sc = (uint8_t*)(((uintptr_t)scratch + 1023) & ~(uintptr_t)1023);
   const uint8_t* w = (const uint8_t*)packed;
@@ -1933,6 +1996,31 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   uint8_t *f_hi = sc + S.f_hi, *f_lo = x3 ? sc + S.f_lo : nullptr;
   uint8_t *h_hi = sc + S.h_hi, *h_lo = x3 ? sc + S.h_lo : nullptr;
   int rc;
+  // One contraction = one launch, or (AZG_PREC_F16F8_KS) `ks` launches over consecutive quarters of K: all but the last
+  // leave raw fp32 partial sums in S.acc (no bias, no ReLU), the last adds them to its accumulator and runs the normal
+  // fused epilogue; the side tile (standard heads) accumulates in its own [M, 32] output.
+  auto run_contraction = [&](const tc::GemmArgs& full) -> int {
+    if (ks <= 1) return tc::run_gemm(BN, full, st);
+    AZG_REQUIRE(full.KB >= ks && f8, "tcgen05 path: K-split needs the fp16+FP8 split and KB >= %d", ks);
+    float* acc = (float*)(sc + S.acc);
+    // (Tried: the FP8 correction product in a launch of its own over the whole K, so that the main accumulators see half as
+    // many truncating accumulations -- the GEMM's distance from its exact emulation fell from 3.2e-6 to 1.7e-6, pi / v on a
+    // trained checkpoint did not move (what is left there is the 16-17 bit operand representation of the trunk and the
+    // splits), and the step grew from 7.0 to 8.8 ms: not kept.)
+    for (int c = 0; c < ks; ++c) {
+      tc::GemmArgs q = full;
+      q.kb0 = (int)((int64_t)full.KB * c / ks);
+      q.kbn = (int)((int64_t)full.KB * (c + 1) / ks) - q.kb0;
+      q.side_acc = c > 0;
+      q.acc_in = (c > 0 && full.n_tiles > 0) ? acc : nullptr;
+      if (c + 1 < ks) {
+        q.out_mode = tc::OUT_F32; q.out_f32 = acc; q.out_hi = q.out_lo = nullptr; q.no_bias = 1; q.relu = 0;
+      }
+      const int r = tc::run_gemm(BN, q, st);
+      if (r) return r;
+    }
+    return AZG_OK;
+  };
   azg_phase_begin(AZG_PHASE_TRUNK, st);
   tc::GemmArgs g{};
   if (azg_trunk_mode() == 0) {  // fused: encode + conv1 + im2col in smem -> tcgen05 conv2
@@ -1973,7 +2061,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     h.side_hi = w + L.hd_hi; h.side_lo = x3 ? w + L.hd_lo : nullptr;
     h.side_bias = (const float*)(w + L.bias32); h.side_out = (float*)(sc + S.lg32);
     h.f8 = f8 ? tc::f8_terms() : 0; h.side_exp = scales + 2;
-    if ((rc = tc::run_gemm(BN, h, st))) return rc;
+    if ((rc = run_contraction(h))) return rc;
     tc::heads32_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const float*)(sc + S.lg32), A, B, dyn_rows, pi_std, v_std);
     AZG_LAUNCH_CHECK();
     azg_phase_end(AZG_PHASE_HEADS, st);
@@ -2028,7 +2116,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     // applies it to relu(H) tile by tile; H and E never exist in HBM and the second F x F contraction is gone
     g.out_mode = tc::OUT_HEADS; g.out_hi = g.out_lo = nullptr; g.out_f32 = nullptr;
     g.head_w = (const float*)(w + L.fold_w); g.head_rows = A + 1; g.head_part = (float*)(sc + S.part);
-    if ((rc = tc::run_gemm(BN, g, st))) return rc;
+    if ((rc = run_contraction(g))) return rc;
     azg_phase_end(AZG_PHASE_GEMM, st);
     azg_phase_begin(AZG_PHASE_HEADS, st);
     const float* fb = (const float*)(w + L.fold_b);
@@ -2040,13 +2128,13 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     return AZG_OK;
   }
   g.out_mode = x3 ? tc::OUT_IMG_HILO : tc::OUT_IMG; g.out_hi = h_hi; g.out_lo = h_lo;
-  if ((rc = tc::run_gemm(BN, g, st))) return rc;
+  if ((rc = run_contraction(g))) return rc;
   g.side_hi = g.side_lo = nullptr;  // GEMM-2 has no side tile
   g.a_hi = h_hi; g.a_lo = h_lo; g.w_hi = w + L.w2_hi; g.w_lo = x3 ? w + L.w2_lo : nullptr; g.bias = p->ot2_b; g.relu = 0;
   g.w_exp = scales + 1;
   g.out_mode = tc::OUT_HEADS; g.out_hi = g.out_lo = nullptr; g.out_f32 = nullptr;
   g.head_w = (const float*)(w + L.heads_cat); g.head_rows = A + 1; g.head_part = (float*)(sc + S.part);
-  if ((rc = tc::run_gemm(BN, g, st))) return rc;
+  if ((rc = run_contraction(g))) return rc;
   azg_phase_end(AZG_PHASE_GEMM, st);
   azg_phase_begin(AZG_PHASE_HEADS, st);
   tc::heads_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g.head_part, g.n_tiles * tc::head_slots_per_tile(g), A, p->fc_policy_b,
@@ -2353,6 +2441,8 @@ int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, i
   const int BN = prec_is_tc(prec) ? prec_bn(F, prec) : 0;
   AZG_REQUIRE(A && W && bias && C && scratch, "azg_tc_linear: null pointer");
   AZG_REQUIRE(BN != 0 && F % 64 == 0, "azg_tc_linear: unsupported F=%d prec=%d", F, prec);
+  const int ks = prec == AZG_PREC_F16F8_KS ? KSPLIT : 1;  // C doubles as the partial-sum buffer of the K-split launches
+  prec = prec_base(prec);
   const bool f8 = prec == AZG_PREC_F16F8, x3 = prec == AZG_PREC_BF16X3 || f8;
   const int64_t m_tiles = azg_ceil_div(M, tc::BM), Mp = azg_ceil_div(M, 2 * tc::BM) * 2 * tc::BM;
   const size_t a_img = (size_t)Mp * F * 2, w_img = (size_t)F * F * 2;
@@ -2373,7 +2463,18 @@ int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, i
   g.M = M; g.m_tiles = (int)m_tiles; g.n_tiles = F / BN; g.KB = F / tc::BK; g.x3 = x3; g.pair_ok = 1;
   g.a_hi = a_hi; g.a_lo = a_lo; g.w_hi = w_hi; g.w_lo = w_lo; g.bias = bias; g.relu = relu;
   g.out_mode = tc::OUT_F32; g.out_f32 = C;
-  return tc::run_gemm(BN, g, st);
+  for (int c = 0; c < ks; ++c) {
+    tc::GemmArgs q = g;
+    if (ks > 1) {
+      AZG_REQUIRE(g.KB >= ks, "azg_tc_linear: K-split needs K >= %d", ks * tc::BK);
+      q.kb0 = (int)((int64_t)g.KB * c / ks);
+      q.kbn = (int)((int64_t)g.KB * (c + 1) / ks) - q.kb0;
+      q.acc_in = c > 0 ? C : nullptr;
+      if (c + 1 < ks) { q.no_bias = 1; q.relu = 0; }
+    }
+    if ((rc = tc::run_gemm(BN, q, st))) return rc;
+  }
+  return AZG_OK;
 }
 
 }  // extern "C"

@@ -117,10 +117,14 @@ class _TwoPlayer(_Base):
     # `b200_precision: auto` (the default): per weight version, the first of these tensor-core modes whose outputs on a
     # fixed probe batch stay within AUTO_TOL of the fp32 CUDA-core path (the reference arithmetic); else fp32.
     AUTO_CANDIDATES = ()
-    # the 1e-5 contract on pi and v with a margin for positions the probe does not see: on trained checkpoints the maximum
-    # over 4,096 other positions was 1.3-1.75x the maximum over a 256-position probe
-    AUTO_TOL = 6e-6
-    AUTO_PROBE = 1024     # probe positions: half seeded iid cells (the bench workload), half gravity-stacked columns
+    # the 1e-5 contract on pi and v with a margin for positions the probe does not see.  The maximum over N positions of
+    # an error with Gaussian-like tails grows like sqrt(ln N): sqrt(ln 1e6 / ln 8192) = 1.24, so 8e-6 over an 8,192-position
+    # probe keeps 1e-5 for batches of up to ~1e6 positions (tests/test_trained_gpu.py prints the probe maximum beside the
+    # maximum over 4,096 other positions: ratio 1.02 for f16f8ks, 1.08 for f16f8 on a trained checkpoint; with the
+    # earlier 256-position probe it was 1.3-1.75).  The probe costs ~25 ms per weight version (the fp32
+    # CUDA-core path and each candidate on 8,192 positions).
+    AUTO_TOL = 8e-6
+    AUTO_PROBE = 8192     # probe positions: half seeded iid cells (the bench workload), half gravity-stacked columns
 
     def _configured_precision(self, args):
         name = arg(args, "b200_precision", "auto") or "auto"
@@ -270,7 +274,9 @@ class _TwoPlayer(_Base):
 class B200Connect4NNetWrapper(_TwoPlayer):
     kind = "connect4"
     supports_dynamic_count = True  # forward_states(count=device scalar): see azg_c4_forward_dyn
-    AUTO_CANDIDATES = (_lib.PREC_F16F8, _lib.PREC_BF16X3)
+    # f16f8, then the same operands with the K-split accumulation (trained weights: the tensor core's truncating
+    # accumulation, not the operand split, is what breaks 1e-5 -- DESIGN.md section 4), then bf16x3, else fp32
+    AUTO_CANDIDATES = (_lib.PREC_F16F8, _lib.PREC_F16F8_KS, _lib.PREC_BF16X3)
 
     def _precision_supported(self, prec):
         return int(self.lib.azg_c4_packed_bytes(self.n, prec)) > 0
@@ -306,6 +312,7 @@ class B200Connect4NNetWrapper(_TwoPlayer):
     def _ensure_packed(self, prec, params):
         """tcgen05 operand images of the weights (conv2, output_transform, permuted heads), one blob
         per precision, rebuilt lazily after weights_changed()."""
+        prec = _lib.PACKED_AS.get(prec, prec)
         if not self._packed_ok:
             self._packed = {}
             self._packed_ok = True
@@ -362,8 +369,8 @@ class B200TicTacToeNNetWrapper(_TwoPlayer):
         self.nnet = modules.TicTacToeTrunk(self.n, self.action_size).to(self.device)
         self.gnn = None
         self.precision = self._configured_precision(args)
-        if self.precision == _lib.PREC_F16F8:
-            raise ValueError("b200_precision f16f8 is a Connect4 mode (tile widths 128..224); TicTacToe runs auto, bf16x3, bf16 or fp32")
+        if self.precision in (_lib.PREC_F16F8, _lib.PREC_F16F8_KS):
+            raise ValueError("b200_precision f16f8 / f16f8ks is a Connect4 mode (tile widths 128..224); TicTacToe runs auto, bf16x3, bf16 or fp32")
         self._packed, self._packed_ok = {}, False
 
     def _ensure_packed(self, prec, params):

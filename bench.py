@@ -382,7 +382,7 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     # ---- the other tensor-core precision, device-resident, short (reported under "also") ----
     also = {}
-    for other in ("bf16", "bf16x3", "f16f8"):
+    for other in ("bf16", "bf16x3", "f16f8", "f16f8ks"):
         if other == args.precision or args.precision == "fp32":
             continue
         oprec = _lib.PRECISIONS[other]
@@ -398,7 +398,9 @@ def run_gpu_arm(args, rank, local_rank, world):
         also[other] = {"value": B * 5 / (a0.elapsed_time(a1) / 1e3), "unit": "leaf_evals/s per GPU", "ms_per_step": a0.elapsed_time(a1) / 5,
                        "note": {"bf16": "single bf16 product, fp32 accumulate; stated tolerance 5e-3 on pi and v",
                                 "bf16x3": "3-term bf16 split, fp32 accumulate; pi and v within 1e-5 of the reference",
-                                "f16f8": "fp16 product + block-scaled FP8 correction product; pi and v within 1e-5 of the reference"}[other]}
+                                "f16f8": "fp16 product + block-scaled FP8 correction product; pi and v within 1e-5 of the reference",
+                                "f16f8ks": "f16f8 operands, each contraction accumulated in four K-quarters (a quarter of the tensor core's "
+                                           "accumulation error): the mode `auto` falls back to on trained weights before fp32"}[other]}
 
     # ---- opt-in algebraic fold of output_transform.2 into the heads (same outputs, one F x F contraction) ----
     if args.precision != "fp32":
@@ -554,7 +556,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "data": "synthetic",
                 "config": workload_config(B), "precision": args.precision,
                 "precision_probe": {"tolerance": net.AUTO_TOL, "max_abs_err_vs_fp32_path": probe_report,
-                                    "note": "max |d pi|, |d v| over 256 probe positions against the fp32 CUDA-core path for "
+                                    "probe_positions": net.AUTO_PROBE, "note": "max |d pi|, |d v| over the probe positions against the fp32 CUDA-core path for "
                                             "these weights; `b200_precision: auto` (the wrappers' default) picks the first mode under the tolerance"},
                 "l2": "4 rotating input batches; per-step intermediates (>2 GB) exceed the 126 MB L2",
                 "preheat": f"{args.preheat:.1f} s of untimed steps ({n_pre}) after the {max(args.warmup, 3)} warm-up steps, so the clocks are in their sustained state",

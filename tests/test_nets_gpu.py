@@ -225,6 +225,14 @@ def test_f16f8_matches_its_exact_emulation(wscale):
     assert e_exact <= 4e-5 * max(scale, 1.0)
     # the correction product is really there: without it the fp16 rounding of the operands alone costs ~4e-4
     assert e_exact < 0.2 * (Ah @ Wh.t() + b.double() - (Ad @ Wd.t() + b.double())).abs().max().item()
+    # AZG_PREC_F16F8_KS: the same operands, K accumulated in four launches with round-to-nearest fp32 adds in between.
+    # What separates the kernel from its emulation is the tensor core's truncating accumulation, linear in the number of
+    # k-steps: a quarter of K per accumulator must bring it down (measured ~3x; the final adds round too)
+    got_ks = _tc_linear(A.cuda(), W.cuda(), b.cuda(), _lib.PREC_F16F8_KS, 0).double().cpu()
+    e_model_ks = (got_ks - model).abs().max().item()
+    mean_ks, mean_1 = (got_ks - model).abs().mean().item(), (got - model).abs().mean().item()
+    print(f"   K-split: |got - emulation| max {e_model_ks:.2e} (one accumulator {e_model:.2e}), mean {mean_ks:.2e} ({mean_1:.2e})")
+    assert e_model_ks <= 0.6 * e_model and mean_ks <= 0.5 * mean_1
 
 
 @pytest.mark.parametrize("n,B", [(7, 1), (7, 777), (7, 4096), (4, 300), (5, 300), (6, 300), (8, 300)])
@@ -241,7 +249,7 @@ def test_forward_tensor_core_precisions(n, B):
         spi, sv = onets.c4_predict(p, onets.boards_to_tensor(boards), n)
     states = w.states_from_boards(boards)
     both = _lib.EVAL_STD | _lib.EVAL_GNN
-    for prec in (_lib.PREC_F16F8, _lib.PREC_BF16X3):  # both splits hold the fp32 contract
+    for prec in (_lib.PREC_F16F8, _lib.PREC_F16F8_KS, _lib.PREC_BF16X3):  # the splits hold the fp32 contract
         o3 = w.forward_states(states, both, precision=prec)
         np.testing.assert_allclose(o3["pi_gnn"].cpu().numpy(), gpi.numpy(), rtol=0, atol=1e-5)
         np.testing.assert_allclose(o3["v_gnn"].cpu().numpy(), gv.numpy(), rtol=0, atol=1e-5)
@@ -262,6 +270,32 @@ def test_forward_tensor_core_precisions(n, B):
     w.weights_changed()
     o3b = w.forward_states(states, _lib.EVAL_GNN, precision=_lib.PREC_BF16X3)
     assert not np.allclose(o3b["v_gnn"].cpu().numpy(), o3["v_gnn"].cpu().numpy())
+
+
+@pytest.mark.parametrize("prec", ["f16f8", "f16f8ks"])
+@pytest.mark.parametrize("fold", [False, True])
+def test_device_row_count_and_fold_per_precision(prec, fold):
+    """forward_states(count=device scalar), the compacted leaf batches of the search: the first `count` rows equal a plain
+    call on those rows bit for bit (also through the K-split launches, which all read the count on the device), with and
+    without the head fold, and stay within 1e-5 of the oracle."""
+    w = _wrapper("c4", 7)
+    rng = np.random.default_rng(21)
+    boards = rng.integers(-1, 2, size=(700, 7, 7)).astype(np.int64)
+    states = w.states_from_boards(boards)
+    p_, live = _lib.PRECISIONS[prec], 333
+    mask = _lib.EVAL_STD | _lib.EVAL_GNN | (_lib.EVAL_FOLD if fold else 0)
+    count = torch.tensor([live], dtype=torch.int32, device="cuda")
+    out = {k: torch.full_like(v, 7.0) for k, v in w._outputs(700, mask).items()}
+    w.forward_states(states, mask, precision=p_, count=count, out=out)
+    plain = w.forward_states(states[:live].contiguous(), mask, precision=p_)
+    p, q = _cpu_sd(w.nnet), _cpu_sd(w.gnn)
+    with torch.no_grad():
+        gpi, gv = onets.c4_predict_with_gnn(p, q, onets.boards_to_tensor(boards[:live]), 7)
+    for k in plain:
+        assert torch.equal(out[k][:live], plain[k]), k
+        assert bool((out[k][live:] == 7.0).all()), k  # rows beyond the count are left untouched
+    assert np.abs(plain["pi_gnn"].cpu().numpy() - gpi.numpy()).max() <= 1e-5
+    assert np.abs(plain["v_gnn"].cpu().numpy() - gv.numpy()).max() <= 1e-5
 
 
 @pytest.mark.parametrize("scale", [0.3, 3.0])
@@ -289,8 +323,8 @@ def test_bf16x3_margin_under_weight_scale(scale):
 
 @pytest.mark.parametrize("scale", [0.3, 1.0, 3.0, 10.0])
 def test_auto_precision_guard(scale):
-    """`b200_precision: auto` (the default): per weight version the wrapper evaluates a probe batch in f16f8, then bf16x3,
-    against its own fp32 CUDA-core path and keeps the first mode within 6e-6; a weight scale that breaks a split makes it
+    """`b200_precision: auto` (the default): per weight version the wrapper evaluates a probe batch in f16f8, then f16f8ks (the
+    K-split accumulation), then bf16x3, against its own fp32 CUDA-core path and keeps the first mode within AUTO_TOL; a weight scale that breaks a split makes it
     fall back (down to fp32) instead of silently leaving the 1e-5 contract.  Whatever it chose must hold 1e-5 against the
     oracle on other positions."""
     w = _wrapper("c4", 7, b200_precision="auto")
@@ -425,7 +459,7 @@ def test_default_precision_is_the_tensor_core_path(kind, n):
     assert abs(one_v - gv[0].item()) <= 1e-5 and np.abs(one_pi - gpi[0].numpy()).max() <= 1e-5
 
 
-@pytest.mark.parametrize("prec", ["f16f8", "bf16x3", "bf16"])
+@pytest.mark.parametrize("prec", ["f16f8", "f16f8ks", "bf16x3", "bf16"])
 def test_tensor_core_forward_is_run_to_run_identical(prec):
     """The fused trunk (conv1 slot queued inside the previous tile's conv2 k-blocks, one TMEM result region) and GEMM-1's
     side tile are synchronised by mbarriers only: repeated launches over many tiles per CTA (20,011 positions = 68

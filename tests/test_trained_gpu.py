@@ -66,7 +66,8 @@ def test_splits_hold_the_contract_on_a_trained_checkpoint():
           f"max |v| {float(gv.abs().max()):.3f}")
     table = {}
     for name, prec, fold in (("fp32", _lib.PREC_FP32, False), ("bf16x3", _lib.PREC_BF16X3, False), ("f16f8", _lib.PREC_F16F8, False),
-                             ("f16f8+fold", _lib.PREC_F16F8, True), ("bf16", _lib.PREC_BF16, False)):
+                             ("f16f8+fold", _lib.PREC_F16F8, True), ("f16f8ks", _lib.PREC_F16F8_KS, False),
+                             ("f16f8ks+fold", _lib.PREC_F16F8_KS, True), ("bf16", _lib.PREC_BF16, False)):
         table[name] = errors(prec, fold)
         print(f"  {name:11s} max |d pi| {table[name]['pi']:.2e}  |d v| {table[name]['v']:.2e}  |d pi_gnn| {table[name]['pi_gnn']:.2e}  "
               f"|d v_gnn| {table[name]['v_gnn']:.2e}")
@@ -78,10 +79,16 @@ def test_splits_hold_the_contract_on_a_trained_checkpoint():
     assert max(table["fp32"].values()) <= 1e-5
     # (2) the tensor-core splits on a trained network: the tensor core's truncating fp32 accumulation (~1e-5 at K = 3136,
     # DESIGN.md section 4) puts them AT the 1e-5 line (8e-6 .. 1.3e-5 over several runs), so a fixed mode cannot promise the
-    # fp32 contract here; their stated tolerance on trained weights is 5e-5, and a mode the guard accepts (probe <= 6e-6)
+    # fp32 contract here; their stated tolerance on trained weights is 5e-5, and a mode the guard accepts (probe <= AUTO_TOL)
     # must be inside 1e-5
-    for name in ("bf16x3", "f16f8", "f16f8+fold"):
+    for name in ("bf16x3", "f16f8", "f16f8+fold", "f16f8ks", "f16f8ks+fold"):
         assert max(table[name].values()) <= 5e-5, (name, table[name])
-    for name in ("bf16x3", "f16f8"):
+    # (3) the K-split accumulation (four accumulators of K/4 each, summed with round-to-nearest adds) removes most of that
+    # floor: inside the contract with margin on the trained network
+    # (measured over three checkpoints: 6.6e-6 .. 7.3e-6 against 9.1e-6 .. 1.04e-5 in one accumulator; what is left is the
+    # 16-17 bit operand representation of the trunk's bf16 split and of the fp16+FP8 split, not the accumulation)
+    assert max(table["f16f8ks"].values()) <= 0.9 * max(table["f16f8"].values()), (table["f16f8ks"], table["f16f8"])
+    assert max(table["f16f8ks"].values()) <= 1e-5, table["f16f8ks"]
+    for name in ("bf16x3", "f16f8", "f16f8ks"):
         if w.precision_report.get(name, 1.0) <= w.AUTO_TOL:
             assert max(table[name].values()) <= 1e-5, (name, table[name])
