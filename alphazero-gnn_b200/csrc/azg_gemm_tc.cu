@@ -38,6 +38,13 @@ enum { OUT_F32 = 0, OUT_IMG = 1, OUT_IMG_HILO = 2, OUT_FEAT = 3, OUT_FEAT_HILO =
 constexpr int HEAD_ROWS = 10;    // <= 9 policy logits + 1 value (Connect4 n <= 8)
 constexpr int HEAD_STRIDE = 16;  // floats per (row, n-tile) record of partial head sums
 
+// K-split boundaries (k-blocks): equal parts.  (Tried: 40 % of K in the first work item so that the previous tile's real
+// epilogue, ~20k cycles, hides under it -- 3 % faster, but the GEMM's distance from its exact emulation grew from 3.2e-6 to
+// 4.0e-6: not kept.)
+__host__ __device__ inline int ksplit_begin(int KB, int q, int nq) {
+  return q <= 0 ? 0 : q >= nq ? KB : (int)((int64_t)KB * q / nq);
+}
+
 struct GemmArgs {
   const uint8_t* a_hi;  // activation images, tiles [128 x 64], (mt * KB + kb) * 16384
   const uint8_t* a_lo;  // (x3 only)
@@ -82,6 +89,13 @@ struct GemmArgs {
   int kb0, kbn;
   const float* acc_in;
   int no_bias, side_acc;
+  // The same K-split INSIDE one launch (the default of AZG_PREC_F16F8_KS): every tile is contracted as `ksplit` consecutive
+  // work items over a quarter of K each, on alternating TMEM accumulators, and the epilogue warps keep the running fp32
+  // sum of a tile in `kpart` -- a per-CTA [128 x BN] scratch tile (gridDim.x of them, 17 MB in all) that every thread reads
+  // and writes only at its own elements and that therefore never leaves L2.  Same adds in the same order as the
+  // launch-level split: bit-identical results, without its 4.9 GB of partial-sum traffic per contraction.
+  int ksplit;
+  float* kpart;
 };
 // TMEM columns of the constant UE8M0 scale-factor regions (f8 mode; accumulators use 2 x BN <= 448 columns)
 constexpr uint32_t SF_A_COL = 448, SF_W_COL = 464, SF_SIDE_COL = 480;
@@ -107,7 +121,12 @@ struct Smem {
 // of a group go to slot nt * ngrp + grp of the row (fixed-order reduction in heads_finalize).
 template <int BN, bool TWO, class Release>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr, int mt, int nt, int r_local, int grp, int ngrp,
-                                              Release release) {
+                                              Release release, float4* part = nullptr, int q = 0, int nq = 1) {
+      // part / q / nq: in-kernel K-split -- work item q of nq of this tile.  Items before the last only fold their accumulator
+      // into the CTA's partial-sum tile, the last one adds it and runs the tile's real epilogue.  The partial tile is stored
+      // by groups of four columns, rows innermost: `part` points at this thread's row in group 0, group c is part[c * BM] --
+      // a warp's 16-byte accesses are 512 contiguous bytes (row-major rows cost 32 wavefronts per instruction and took 58 %
+      // of the shared-memory / L1 data pipe the tensor core reads its operands through: 6.4 instead of 4.x ms).
       const int64_t row = (int64_t)mt * BM + r_local;
       const int NKB = (g.n_tiles * BN) / BK;  // k-blocks of the output image
       if (TWO && nt == g.n_tiles) {  // side tile: SIDE_N fp32 columns + bias, row-major (one chunk: group 0)
@@ -120,6 +139,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
         tmem_ld_wait();
         tc_fence_before();
         release();
+        if (nq > 1) {  // same order of adds as the launch-level split: ((rr0 + bias) + rr1) + ...
+          float4* pp = part;
+          float4* dst = reinterpret_cast<float4*>(g.side_out + row * SIDE_N);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = q ? pp[j * BM] : __ldg(reinterpret_cast<const float4*>(g.side_bias) + j);
+            const float4 o = make_float4(__uint_as_float(rr[4 * j]) + b4.x, __uint_as_float(rr[4 * j + 1]) + b4.y,
+                                         __uint_as_float(rr[4 * j + 2]) + b4.z, __uint_as_float(rr[4 * j + 3]) + b4.w);
+            if (q + 1 < nq) pp[j * BM] = o;
+            else if (row < g.M) dst[j] = o;
+          }
+          return;
+        }
         if (row < g.M) {
           float4* dst = reinterpret_cast<float4*>(g.side_out + row * SIDE_N);
 #pragma unroll
@@ -129,6 +161,32 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
                                  __uint_as_float(rr[4 * j + 2]) + b4.z, __uint_as_float(rr[4 * j + 3]) + b4.w);
           }
         }
+        return;
+      }
+      if (nq > 1 && q + 1 < nq) {  // fold this quarter's accumulator into the partial sums (no bias, no ReLU)
+#pragma unroll 1
+        for (int c0 = grp * 32; c0 < BN; c0 += 32 * ngrp) {
+          uint32_t rr[32];
+          tmem_ld32(taddr + (uint32_t)c0, rr);
+          float4* pp = part + (c0 >> 2) * BM;
+          float4 p4[8];
+          if (q) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p4[j] = pp[j * BM];
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (q)
+              pp[j * BM] = make_float4(__fadd_rn(p4[j].x, __uint_as_float(rr[4 * j])), __fadd_rn(p4[j].y, __uint_as_float(rr[4 * j + 1])),
+                                  __fadd_rn(p4[j].z, __uint_as_float(rr[4 * j + 2])), __fadd_rn(p4[j].w, __uint_as_float(rr[4 * j + 3])));
+            else
+              pp[j * BM] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]),
+                                       __uint_as_float(rr[4 * j + 3]));
+          }
+        }
+        tc_fence_before();
+        release();
         return;
       }
       float hacc[HEAD_ROWS];
@@ -145,12 +203,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
           for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
         }
         float v[32];
-        if (g.acc_in) {  // K-split: partial sums of the earlier launches (plain loads: written by the previous kernel)
-          const float4* src = reinterpret_cast<const float4*>(g.acc_in + row * (int64_t)(g.n_tiles * BN) + n0);
+        if (g.acc_in || nq > 1) {  // K-split: partial sums of the earlier launches / work items (plain loads)
+          const float4* src = nq > 1 ? part + (c0 >> 2) * BM
+                                     : reinterpret_cast<const float4*>(g.acc_in + row * (int64_t)(g.n_tiles * BN) + n0);
+          const int sstep = nq > 1 ? BM : 1;
           float4 p4[8];
-          if (row < g.M) {
+          if (nq > 1 || row < g.M) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) p4[j] = src[j];
+            for (int j = 0; j < 8; ++j) p4[j] = src[j * sstep];
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) p4[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -265,6 +325,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
       }
 }
 
+constexpr int KPART_MAX_CTAS = 256;                      // in-kernel K-split: per-CTA partial-sum tiles the scratch is sized for
 constexpr int EPI_GROUPS = 2;                           // epilogue warps 4-7 and 8-11
 constexpr int GEMM_THREADS = 128 + 128 * EPI_GROUPS;     // producer, MMA issuer, TMEM allocator, spare + the epilogue groups
 template <int BN, bool TWO>
@@ -341,6 +402,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs 
   const uint32_t stage_bytes = TWO ? 2 * S::STAGE_BYTES : S::STAGE_BYTES;
   const int kb_total = fused3 ? (g.kbn ? g.kbn : g.KB) : dual ? (g.KB + 1) / 2 : (g.x3 ? 3 * g.KB : g.KB);
   const int kb_first = fused3 ? g.kb0 : 0;  // K-split launches (fused hi/lo stages only, checked by the launcher)
+  const int nq = (fused3 && g.ksplit > 1) ? g.ksplit : 1;  // in-kernel K-split: work items per tile
   // f8 launches that issue only one of the two products (K-split: main quarters and the correction product go to
   // different accumulators; AZG_F8_TERMS diagnostics) fill only the half of the stage that product reads
   const bool need_hi = !(TWO && g.f8) || (g.f8 & 1), need_lo = !(TWO && g.f8) || (g.f8 & 2);
@@ -429,7 +491,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = unit; t < total_tiles; t += n_units) {
+      for (int t = unit; t < total_tiles; t += n_units)
+      for (int kq = 0; kq < nq; ++kq) {  // in-kernel K-split: one accumulator per quarter of K
+        const int kq_n = nq > 1 ? ksplit_begin(kb_total, kq + 1, nq) - ksplit_begin(kb_total, kq, nq) : kb_total;
         if (TWO) mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues drained this accumulator
         else mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -438,7 +502,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs 
         const uint32_t idesc = side_tile ? (f8 ? idesc_side_h : idesc_side) : (f8 ? idesc_main_h : idesc_main);
         const uint32_t idesc_q = side_tile ? idesc_side_q : idesc_main_q;
         const uint32_t sfa = tmem_base + SF_A_COL, sfb = tmem_base + (side_tile ? SF_SIDE_COL : SF_W_COL);
-        for (int kb = 0; kb < kb_total; ++kb) {
+        for (int kb = 0; kb < kq_n; ++kb) {
           mbar_wait(&full[stage], phase);  // operands have landed
           if (TWO) mbar_wait_cluster(&pfull[stage], phase);  // ... in the peer CTA as well
           tc_fence_after();
@@ -517,12 +581,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(GemmArgs 
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t leader_tempty = TWO ? map_to_cta(&tempty[0], 0) : 0u;
-    for (int t = unit; t < total_tiles; t += n_units) {
+    float4* part = nq > 1 ? reinterpret_cast<float4*>(g.kpart) + (size_t)blockIdx.x * (BM * (BN / 4)) + r_local : nullptr;  // this thread's row of the CTA's partial tile
+    for (int t = unit; t < total_tiles; t += n_units)
+    for (int kq = 0; kq < nq; ++kq) {
       const int mt = (t / nt_all) * (TWO ? 2 : 1) + (int)rank, nt = t % nt_all;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      if (TWO) epilogue_tile<BN, TWO>(g, taddr, mt, nt, r_local, grp, EPI_GROUPS, [&] { mbar_arrive_cluster(leader_tempty + (uint32_t)acc * 8u); });
+      if (TWO) epilogue_tile<BN, TWO>(g, taddr, mt, nt, r_local, grp, EPI_GROUPS, [&] { mbar_arrive_cluster(leader_tempty + (uint32_t)acc * 8u); }, part, kq, nq);
       else epilogue_tile<BN, TWO>(g, taddr, mt, nt, r_local, grp, EPI_GROUPS, [&] { mbar_arrive(&tempty[acc]); });
       if (++acc == 2) {
         acc = 0;
@@ -670,6 +736,7 @@ int launch_gemm_impl(const GemmArgs& g, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  AZG_REQUIRE(g.ksplit <= 1 || grid <= KPART_MAX_CTAS, "tcgen05 GEMM: %d CTAs exceed the partial-sum scratch of the in-kernel K-split", grid);
   AZG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, TWO>, g));
   AZG_LAUNCH_CHECK();
   return AZG_OK;
@@ -686,6 +753,8 @@ template <int BN>
 int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   AZG_REQUIRE(!(g.kbn || g.kb0 || g.acc_in || g.no_bias || g.side_acc) || (g.f8 && g.x3 && g.pair_ok && g.kb0 >= 0 && g.kb0 + g.kbn <= g.KB),
               "tcgen05 GEMM: K-split launches run on the CTA-pair kernel of the fp16+FP8 split only");
+  AZG_REQUIRE(g.ksplit <= 1 || (g.f8 && g.x3 && g.pair_ok && g.kpart && !g.kbn && !g.acc_in && g.KB >= g.ksplit),
+              "tcgen05 GEMM: the in-kernel K-split runs on the CTA-pair kernel of the fp16+FP8 split only");
   if (g.f8) {
     if constexpr (BN >= 128 && BN <= 224) {
       AZG_REQUIRE(g.pair_ok && g.x3, "tcgen05 GEMM: the fp16+FP8 split runs on the CTA-pair kernel only");
@@ -1878,6 +1947,14 @@ struct PackLayout {
 // AZG_PREC_F16F8_KS runs on the operand images of AZG_PREC_F16F8 (same packed blob, same tile widths); it differs in how
 // the F x F contractions are launched (KSPLIT launches over a quarter of K each, see GemmArgs::kb0)
 constexpr int KSPLIT = 4;
+inline bool ksplit_by_launches() {  // AZG_KSPLIT=launches: four launches per contraction instead of four work items per tile
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("AZG_KSPLIT");
+    mode = (e && strcmp(e, "launches") == 0) ? 1 : 0;
+  }
+  return mode == 1;
+}
 inline int prec_base(int prec) { return prec == AZG_PREC_F16F8_KS ? AZG_PREC_F16F8 : prec; }
 inline bool prec_is_tc(int prec) {
   prec = prec_base(prec);
@@ -1940,7 +2017,9 @@ ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
     S.h_lo = x3 ? take(fimg) : 0;
     const int BNp = prec_bn((int)F, prec);
     S.part = take(Mp * (size_t)(BNp ? 2 * (F / BNp) : 32) * tc::HEAD_STRIDE * sizeof(float));  // two epilogue groups per n-tile
-    if (ksplit) S.acc = take(Mp * F * sizeof(float));  // fp32 partial sums of the K-split launches
+    // K-split partial sums: one [128 x 256] fp32 tile per CTA (in-kernel split), or the whole [Mp, F] matrix when the
+    // split is made of launches (AZG_KSPLIT=launches, the bit-identical reference of the in-kernel form)
+    if (ksplit) S.acc = take(ksplit_by_launches() ? Mp * F * sizeof(float) : (size_t)tc::KPART_MAX_CTAS * tc::BM * 256 * sizeof(float));
   }
   S.total = off + 1024;
   return S;
@@ -2003,14 +2082,20 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
     if (ks <= 1) return tc::run_gemm(BN, full, st);
     AZG_REQUIRE(full.KB >= ks && f8, "tcgen05 path: K-split needs the fp16+FP8 split and KB >= %d", ks);
     float* acc = (float*)(sc + S.acc);
+    if (!ksplit_by_launches()) {  // default: the split happens inside the kernel, partial sums stay in L2
+      tc::GemmArgs q = full;
+      q.ksplit = ks;
+      q.kpart = acc;
+      return tc::run_gemm(BN, q, st);
+    }
     // (Tried: the FP8 correction product in a launch of its own over the whole K, so that the main accumulators see half as
     // many truncating accumulations -- the GEMM's distance from its exact emulation fell from 3.2e-6 to 1.7e-6, pi / v on a
     // trained checkpoint did not move (what is left there is the 16-17 bit operand representation of the trunk and the
     // splits), and the step grew from 7.0 to 8.8 ms: not kept.)
     for (int c = 0; c < ks; ++c) {
       tc::GemmArgs q = full;
-      q.kb0 = (int)((int64_t)full.KB * c / ks);
-      q.kbn = (int)((int64_t)full.KB * (c + 1) / ks) - q.kb0;
+      q.kb0 = tc::ksplit_begin(full.KB, c, ks);
+      q.kbn = tc::ksplit_begin(full.KB, c + 1, ks) - q.kb0;
       q.side_acc = c > 0;
       q.acc_in = (c > 0 && full.n_tiles > 0) ? acc : nullptr;
       if (c + 1 < ks) {
@@ -2463,12 +2548,22 @@ int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, i
   g.M = M; g.m_tiles = (int)m_tiles; g.n_tiles = F / BN; g.KB = F / tc::BK; g.x3 = x3; g.pair_ok = 1;
   g.a_hi = a_hi; g.a_lo = a_lo; g.w_hi = w_hi; g.w_lo = w_lo; g.bias = bias; g.relu = relu;
   g.out_mode = tc::OUT_F32; g.out_f32 = C;
+  if (ks > 1 && !ksplit_by_launches()) {
+    AZG_REQUIRE(g.KB >= ks, "azg_tc_linear: K-split needs K >= %d", ks * tc::BK);
+    float* part = nullptr;
+    AZG_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)tc::KPART_MAX_CTAS * tc::BM * 256 * sizeof(float), st));
+    g.ksplit = ks;
+    g.kpart = part;
+    rc = tc::run_gemm(BN, g, st);
+    AZG_CUDA_CHECK(cudaFreeAsync(part, st));
+    return rc;
+  }
   for (int c = 0; c < ks; ++c) {
     tc::GemmArgs q = g;
     if (ks > 1) {
       AZG_REQUIRE(g.KB >= ks, "azg_tc_linear: K-split needs K >= %d", ks * tc::BK);
-      q.kb0 = (int)((int64_t)g.KB * c / ks);
-      q.kbn = (int)((int64_t)g.KB * (c + 1) / ks) - q.kb0;
+      q.kb0 = tc::ksplit_begin(g.KB, c, ks);
+      q.kbn = tc::ksplit_begin(g.KB, c + 1, ks) - q.kb0;
       q.acc_in = c > 0 ? C : nullptr;
       if (c + 1 < ks) { q.no_bias = 1; q.relu = 0; }
     }

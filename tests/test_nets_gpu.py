@@ -298,6 +298,51 @@ def test_device_row_count_and_fold_per_precision(prec, fold):
     assert np.abs(plain["v_gnn"].cpu().numpy() - gv.numpy()).max() <= 1e-5
 
 
+_KS_DUMP = """
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+import azgnn_b200
+from azgnn_b200 import _lib, games
+from azgnn_b200.nets import B200Connect4GNNWrapper
+out = {{}}
+for n, B in ((7, 2500), (5, 700), (4, 300)):
+    torch.manual_seed(n)
+    w = B200Connect4GNNWrapper(games.Connect4Game(n), dict(lr=1e-3, dropout=0.3, gnn_layers=2, use_gnn=True, b200_precision="f16f8ks"))
+    states = w.states_from_boards(np.random.default_rng(n).integers(-1, 2, size=(B, n, n)).astype(np.int8))
+    for fold in (0, _lib.EVAL_FOLD):
+        o = w.forward_states(states, _lib.EVAL_STD | _lib.EVAL_GNN | fold)
+        for k, v in o.items():
+            out[f"{{n}}_{{fold}}_{{k}}"] = v.cpu().numpy()
+    o = w.forward_states(states, _lib.EVAL_STD)
+    out[f"{{n}}_std_only_v"] = o["v"].cpu().numpy()
+np.savez({path!r}, **out)
+"""
+
+
+def test_in_kernel_k_split_equals_the_split_by_launches(tmp_path):
+    """AZG_PREC_F16F8_KS inside one launch (four work items per tile on alternating TMEM accumulators, partial sums in a per-CTA
+    scratch tile that stays in L2) performs the same fp32 adds in the same order as four launches over a quarter of K each
+    (AZG_KSPLIT=launches, partial sums through an [M, F] matrix in HBM): bit-identical outputs, 7x7 / 5x5 / 4x4, ragged
+    last tiles, with and without the head fold, std-only calls (side tiles only).  Env read once per process -> subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = {}
+    for mode in ("kernel", "launches"):
+        path = str(tmp_path / f"ks_{mode}.npz")
+        env = dict(os.environ)
+        env.pop("AZG_KSPLIT", None)
+        if mode == "launches":
+            env["AZG_KSPLIT"] = "launches"
+        r = subprocess.run([sys.executable, "-c", _KS_DUMP.format(root=root, path=path)], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        got[mode] = dict(np.load(path))
+    assert set(got["kernel"]) == set(got["launches"]) and len(got["kernel"]) >= 27
+    for k in got["kernel"]:
+        assert np.array_equal(got["kernel"][k], got["launches"][k]), k
+
+
 @pytest.mark.parametrize("scale", [0.3, 3.0])
 def test_bf16x3_margin_under_weight_scale(scale):
     """The 3-term split keeps ~16 mantissa bits per operand whatever the weight magnitude; with every
