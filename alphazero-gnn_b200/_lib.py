@@ -15,10 +15,11 @@ EVAL_STD, EVAL_GNN = 1, 2
 EVAL_FOLD = 4  # tensor-core path: output_transform.2 folded into the heads (opt-in, args.b200_fold_heads)
 PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_F16F8 = 0, 1, 2, 3
 PREC_F16F8_KS = 4  # f16f8 operands, each F x F contraction accumulated in four K-quarters (a quarter of the accumulation error)
+PREC_BF16X3_KS = 5  # the same K-split on the bf16x3 operands
 PREC_AUTO = -1  # wrapper-level: the fastest precision whose probe batch stays inside the fp32 contract (nets.py)
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16f8": PREC_F16F8, "f16f8ks": PREC_F16F8_KS,
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16f8": PREC_F16F8, "f16f8ks": PREC_F16F8_KS, "bf16x3ks": PREC_BF16X3_KS,
               "auto": PREC_AUTO}
-PACKED_AS = {PREC_F16F8_KS: PREC_F16F8}  # precisions that read another precision's weight images
+PACKED_AS = {PREC_F16F8_KS: PREC_F16F8, PREC_BF16X3_KS: PREC_BF16X3}  # precisions that read another precision's weight images
 PRECISION_NAMES = {v: k for k, v in PRECISIONS.items()}
 TAG_NONE, TAG_F32, TAG_PYFLOAT, TAG_PYINT = -1, 0, 1, 2
 CELL_I8, CELL_I64, CELL_F32, CELL_F64 = 0, 1, 2, 3

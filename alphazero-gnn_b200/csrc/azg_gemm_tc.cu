@@ -751,10 +751,11 @@ int launch_gemm_impl(const GemmArgs& g, cudaStream_t st) {
 // the CTA-pair kernel needs BN/2 to be a multiple of 8 rows and an even number of padded m-tiles
 template <int BN>
 int launch_gemm(const GemmArgs& g, cudaStream_t st) {
-  AZG_REQUIRE(!(g.kbn || g.kb0 || g.acc_in || g.no_bias || g.side_acc) || (g.f8 && g.x3 && g.pair_ok && g.kb0 >= 0 && g.kb0 + g.kbn <= g.KB),
-              "tcgen05 GEMM: K-split launches run on the CTA-pair kernel of the fp16+FP8 split only");
-  AZG_REQUIRE(g.ksplit <= 1 || (g.f8 && g.x3 && g.pair_ok && g.kpart && !g.kbn && !g.acc_in && g.KB >= g.ksplit),
-              "tcgen05 GEMM: the in-kernel K-split runs on the CTA-pair kernel of the fp16+FP8 split only");
+  const bool pair_kernel = g.pair_ok && BN >= 128 && (g.f8 || gemm_pair_mode());
+  AZG_REQUIRE(!(g.kbn || g.kb0 || g.acc_in || g.no_bias || g.side_acc) || (g.x3 && pair_kernel && g.kb0 >= 0 && g.kb0 + g.kbn <= g.KB),
+              "tcgen05 GEMM: K-split launches run on the CTA-pair kernel of the split precisions only");
+  AZG_REQUIRE(g.ksplit <= 1 || (g.x3 && pair_kernel && g.kpart && !g.kbn && !g.acc_in && g.KB >= g.ksplit),
+              "tcgen05 GEMM: the in-kernel K-split runs on the CTA-pair kernel of the split precisions only");
   if (g.f8) {
     if constexpr (BN >= 128 && BN <= 224) {
       AZG_REQUIRE(g.pair_ok && g.x3, "tcgen05 GEMM: the fp16+FP8 split runs on the CTA-pair kernel only");
@@ -1955,7 +1956,8 @@ inline bool ksplit_by_launches() {  // AZG_KSPLIT=launches: four launches per co
   }
   return mode == 1;
 }
-inline int prec_base(int prec) { return prec == AZG_PREC_F16F8_KS ? AZG_PREC_F16F8 : prec; }
+inline int prec_base(int prec) { return prec == AZG_PREC_F16F8_KS ? AZG_PREC_F16F8 : prec == AZG_PREC_BF16X3_KS ? AZG_PREC_BF16X3 : prec; }
+inline bool prec_ksplit(int prec) { return prec == AZG_PREC_F16F8_KS || prec == AZG_PREC_BF16X3_KS; }
 inline bool prec_is_tc(int prec) {
   prec = prec_base(prec);
   return prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16 || prec == AZG_PREC_F16F8;
@@ -1999,7 +2001,7 @@ struct ScratchLayout {
 
 ScratchLayout scratch_layout(int n, int64_t B, int prec, bool gnn) {
   ScratchLayout S{};
-  const bool ksplit = prec == AZG_PREC_F16F8_KS;
+  const bool ksplit = prec_ksplit(prec);
   prec = prec_base(prec);
   const bool x3 = prec == AZG_PREC_BF16X3 || prec == AZG_PREC_F16F8;
   const size_t nn = (size_t)n * n, F = 64 * nn;
@@ -2062,7 +2064,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
                       size_t scratch_bytes, const int32_t* dyn_rows, cudaStream_t st) {
   const int nn = n * n, F = 64 * nn, A = n + 1, BN = prec_bn(F, prec);
   AZG_REQUIRE(BN != 0, "tcgen05 path: unsupported board size %d", n);
-  const int ks = prec == AZG_PREC_F16F8_KS ? KSPLIT : 1;  // launches per F x F contraction (K-split accumulation)
+  const int ks = prec_ksplit(prec) ? KSPLIT : 1;  // work items (or launches) per F x F contraction (K-split accumulation)
   const ScratchLayout S = scratch_layout(n, B, prec, true);
   prec = prec_base(prec);
   const bool f8 = prec == AZG_PREC_F16F8, x3 = prec == AZG_PREC_BF16X3 || f8, gnn = (eval_mask & AZG_EVAL_GNN) != 0;
@@ -2080,7 +2082,7 @@ int azg_tc_c4_forward(const void* packed, const azg_c4_params* p, int n, int pre
   // fused epilogue; the side tile (standard heads) accumulates in its own [M, 32] output.
   auto run_contraction = [&](const tc::GemmArgs& full) -> int {
     if (ks <= 1) return tc::run_gemm(BN, full, st);
-    AZG_REQUIRE(full.KB >= ks && f8, "tcgen05 path: K-split needs the fp16+FP8 split and KB >= %d", ks);
+    AZG_REQUIRE(full.KB >= ks && x3, "tcgen05 path: K-split needs one of the split precisions and KB >= %d", ks);
     float* acc = (float*)(sc + S.acc);
     if (!ksplit_by_launches()) {  // default: the split happens inside the kernel, partial sums stay in L2
       tc::GemmArgs q = full;
@@ -2526,7 +2528,7 @@ int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, i
   const int BN = prec_is_tc(prec) ? prec_bn(F, prec) : 0;
   AZG_REQUIRE(A && W && bias && C && scratch, "azg_tc_linear: null pointer");
   AZG_REQUIRE(BN != 0 && F % 64 == 0, "azg_tc_linear: unsupported F=%d prec=%d", F, prec);
-  const int ks = prec == AZG_PREC_F16F8_KS ? KSPLIT : 1;  // C doubles as the partial-sum buffer of the K-split launches
+  const int ks = prec_ksplit(prec) ? KSPLIT : 1;  // C doubles as the partial-sum buffer of the K-split launches
   prec = prec_base(prec);
   const bool f8 = prec == AZG_PREC_F16F8, x3 = prec == AZG_PREC_BF16X3 || f8;
   const int64_t m_tiles = azg_ceil_div(M, tc::BM), Mp = azg_ceil_div(M, 2 * tc::BM) * 2 * tc::BM;

@@ -561,7 +561,8 @@ int azg_c4_forward_dyn(const azg_c4_params* p, int n, const uint64_t* states, in
   AZG_REQUIRE(p && states && workspace, "azg_c4_forward: null pointer");
   AZG_REQUIRE(n >= 4 && n <= 8, "azg_c4_forward: board size %d unsupported (4..8)", n);
   AZG_REQUIRE((eval_mask & ~7) == 0 && (eval_mask & 3) != 0, "azg_c4_forward: bad eval_mask %d", eval_mask);
-  AZG_REQUIRE(prec == AZG_PREC_FP32 || prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16 || prec == AZG_PREC_F16F8 || prec == AZG_PREC_F16F8_KS,
+  AZG_REQUIRE(prec == AZG_PREC_FP32 || prec == AZG_PREC_BF16X3 || prec == AZG_PREC_BF16 || prec == AZG_PREC_F16F8 || prec == AZG_PREC_F16F8_KS ||
+                  prec == AZG_PREC_BF16X3_KS,
               "azg_c4_forward: bad prec %d", prec);
   if (B <= 0) return AZG_OK;
   cudaStream_t st = (cudaStream_t)stream;

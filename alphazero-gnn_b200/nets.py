@@ -276,7 +276,7 @@ class B200Connect4NNetWrapper(_TwoPlayer):
     supports_dynamic_count = True  # forward_states(count=device scalar): see azg_c4_forward_dyn
     # f16f8, then the same operands with the K-split accumulation (trained weights: the tensor core's truncating
     # accumulation, not the operand split, is what breaks 1e-5 -- DESIGN.md section 4), then bf16x3, else fp32
-    AUTO_CANDIDATES = (_lib.PREC_F16F8, _lib.PREC_F16F8_KS, _lib.PREC_BF16X3)
+    AUTO_CANDIDATES = (_lib.PREC_F16F8, _lib.PREC_F16F8_KS, _lib.PREC_BF16X3_KS)
 
     def _precision_supported(self, prec):
         return int(self.lib.azg_c4_packed_bytes(self.n, prec)) > 0
@@ -369,7 +369,7 @@ class B200TicTacToeNNetWrapper(_TwoPlayer):
         self.nnet = modules.TicTacToeTrunk(self.n, self.action_size).to(self.device)
         self.gnn = None
         self.precision = self._configured_precision(args)
-        if self.precision in (_lib.PREC_F16F8, _lib.PREC_F16F8_KS):
+        if self.precision in (_lib.PREC_F16F8, _lib.PREC_F16F8_KS, _lib.PREC_BF16X3_KS):
             raise ValueError("b200_precision f16f8 / f16f8ks is a Connect4 mode (tile widths 128..224); TicTacToe runs auto, bf16x3, bf16 or fp32")
         self._packed, self._packed_ok = {}, False
 

@@ -57,6 +57,8 @@ extern "C" {
                              launches over a quarter of K with round-to-nearest fp32 adds of the partial sums in between:
                              the tensor core's truncating accumulation error, linear in the number of k-steps (~1e-5 at
                              K = 3136 on trained weights), is divided by four.  Connect4 path (azg_c4_forward*)        */
+#define AZG_PREC_BF16X3_KS 5 /* the same K-split on the AZG_PREC_BF16X3 operands (three bf16 terms: the finer operand
+                             representation, 12 instead of 8 MMA times per k-block)                                     */
 
 /* value type tags (NumPy>=2 / NEP 50 semantics of MCTS.py:228-233) */
 #define AZG_TAG_NONE (-1) /* edge not in Qsa            */
@@ -125,7 +127,7 @@ int azg_c4_forward_dyn(const azg_c4_params* p, int n, const uint64_t* states, in
                        int eval_mask, int prec, float* pi_std, float* v_std, float* pi_gnn, float* v_gnn,
                        void* workspace, size_t workspace_bytes, azg_stream stream);
 /* Build the tcgen05 operand images of the weights (conv2, output_transform, permuted heads) for
- * AZG_PREC_BF16X3 / AZG_PREC_BF16 / AZG_PREC_F16F8 (AZG_PREC_F16F8_KS reads the AZG_PREC_F16F8 images and may be passed
+ * AZG_PREC_BF16X3 / AZG_PREC_BF16 / AZG_PREC_F16F8 (AZG_PREC_F16F8_KS / AZG_PREC_BF16X3_KS read the AZG_PREC_F16F8 / AZG_PREC_BF16X3 images and may be passed
  * instead: same bytes); the result goes into azg_c4_params.ot_packed.  Call again after
  * every optimizer step / load_checkpoint.  packed: device memory, 16-byte aligned. */
 size_t azg_c4_packed_bytes(int n, int prec);
@@ -133,7 +135,7 @@ int azg_c4_pack(const azg_c4_params* p, int n, int prec, void* packed, size_t pa
 
 /* One dense layer on the tcgen05 path, for parity tests of the GEMM in isolation:
  * C[M,F] = act(A[M,F] . W[F,F]^T + bias), fp32 in/out, prec = AZG_PREC_BF16X3 | AZG_PREC_BF16 | AZG_PREC_F16F8 |
- * AZG_PREC_F16F8_KS.
+ * AZG_PREC_F16F8_KS | AZG_PREC_BF16X3_KS.
  * scratch: >= 2*(ceil(M/256)*256 + F)*F*2 + 1024 bytes (x3) or half of that (bf16). */
 int azg_tc_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int F, int prec,
                   int relu, void* scratch, size_t scratch_bytes, azg_stream stream);

@@ -249,7 +249,7 @@ def test_forward_tensor_core_precisions(n, B):
         spi, sv = onets.c4_predict(p, onets.boards_to_tensor(boards), n)
     states = w.states_from_boards(boards)
     both = _lib.EVAL_STD | _lib.EVAL_GNN
-    for prec in (_lib.PREC_F16F8, _lib.PREC_F16F8_KS, _lib.PREC_BF16X3):  # the splits hold the fp32 contract
+    for prec in (_lib.PREC_F16F8, _lib.PREC_F16F8_KS, _lib.PREC_BF16X3, _lib.PREC_BF16X3_KS):  # the splits hold the fp32 contract
         o3 = w.forward_states(states, both, precision=prec)
         np.testing.assert_allclose(o3["pi_gnn"].cpu().numpy(), gpi.numpy(), rtol=0, atol=1e-5)
         np.testing.assert_allclose(o3["v_gnn"].cpu().numpy(), gv.numpy(), rtol=0, atol=1e-5)
@@ -272,7 +272,7 @@ def test_forward_tensor_core_precisions(n, B):
     assert not np.allclose(o3b["v_gnn"].cpu().numpy(), o3["v_gnn"].cpu().numpy())
 
 
-@pytest.mark.parametrize("prec", ["f16f8", "f16f8ks"])
+@pytest.mark.parametrize("prec", ["f16f8", "f16f8ks", "bf16x3ks"])
 @pytest.mark.parametrize("fold", [False, True])
 def test_device_row_count_and_fold_per_precision(prec, fold):
     """forward_states(count=device scalar), the compacted leaf batches of the search: the first `count` rows equal a plain
@@ -504,7 +504,7 @@ def test_default_precision_is_the_tensor_core_path(kind, n):
     assert abs(one_v - gv[0].item()) <= 1e-5 and np.abs(one_pi - gpi[0].numpy()).max() <= 1e-5
 
 
-@pytest.mark.parametrize("prec", ["f16f8", "f16f8ks", "bf16x3", "bf16"])
+@pytest.mark.parametrize("prec", ["f16f8", "f16f8ks", "bf16x3", "bf16x3ks", "bf16"])
 def test_tensor_core_forward_is_run_to_run_identical(prec):
     """The fused trunk (conv1 slot queued inside the previous tile's conv2 k-blocks, one TMEM result region) and GEMM-1's
     side tile are synchronised by mbarriers only: repeated launches over many tiles per CTA (20,011 positions = 68

@@ -67,7 +67,8 @@ def test_splits_hold_the_contract_on_a_trained_checkpoint():
     table = {}
     for name, prec, fold in (("fp32", _lib.PREC_FP32, False), ("bf16x3", _lib.PREC_BF16X3, False), ("f16f8", _lib.PREC_F16F8, False),
                              ("f16f8+fold", _lib.PREC_F16F8, True), ("f16f8ks", _lib.PREC_F16F8_KS, False),
-                             ("f16f8ks+fold", _lib.PREC_F16F8_KS, True), ("bf16", _lib.PREC_BF16, False)):
+                             ("f16f8ks+fold", _lib.PREC_F16F8_KS, True), ("bf16x3ks", _lib.PREC_BF16X3_KS, False),
+                             ("bf16", _lib.PREC_BF16, False)):
         table[name] = errors(prec, fold)
         print(f"  {name:11s} max |d pi| {table[name]['pi']:.2e}  |d v| {table[name]['v']:.2e}  |d pi_gnn| {table[name]['pi_gnn']:.2e}  "
               f"|d v_gnn| {table[name]['v_gnn']:.2e}")
@@ -89,6 +90,6 @@ def test_splits_hold_the_contract_on_a_trained_checkpoint():
     # 16-17 bit operand representation of the trunk's bf16 split and of the fp16+FP8 split, not the accumulation)
     assert max(table["f16f8ks"].values()) <= 0.9 * max(table["f16f8"].values()), (table["f16f8ks"], table["f16f8"])
     assert max(table["f16f8ks"].values()) <= 1e-5, table["f16f8ks"]
-    for name in ("bf16x3", "f16f8", "f16f8ks"):
+    for name in ("bf16x3", "f16f8", "f16f8ks", "bf16x3ks"):
         if w.precision_report.get(name, 1.0) <= w.AUTO_TOL:
             assert max(table[name].values()) <= 1e-5, (name, table[name])
