@@ -382,7 +382,7 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     # ---- the other tensor-core precision, device-resident, short (reported under "also") ----
     also = {}
-    for other in ("bf16", "bf16x3", "f16f8", "f16f8ks"):
+    for other in ("bf16", "bf16x3", "f16f8", "f16f8ks", "bf16x3ks"):
         if other == args.precision or args.precision == "fp32":
             continue
         oprec = _lib.PRECISIONS[other]
@@ -400,7 +400,8 @@ def run_gpu_arm(args, rank, local_rank, world):
                                 "bf16x3": "3-term bf16 split, fp32 accumulate; pi and v within 1e-5 of the reference",
                                 "f16f8": "fp16 product + block-scaled FP8 correction product; pi and v within 1e-5 of the reference",
                                 "f16f8ks": "f16f8 operands, each contraction accumulated in four K-quarters (a quarter of the tensor core's "
-                                           "accumulation error): the mode `auto` falls back to on trained weights before fp32"}[other]}
+                                           "accumulation error): the mode `auto` falls back to on trained weights",
+                                "bf16x3ks": "the same K-split on the bf16x3 operands: `auto`'s last tensor-core candidate before fp32"}[other]}
 
     # ---- opt-in algebraic fold of output_transform.2 into the heads (same outputs, one F x F contraction) ----
     if args.precision != "fp32":
