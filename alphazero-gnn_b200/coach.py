@@ -15,6 +15,7 @@ Coach.py:16-176) on top of the arena.
 """
 import logging
 import os
+import shutil
 from collections import deque
 from pickle import Pickler, Unpickler
 from random import shuffle
@@ -50,8 +51,12 @@ class _CheckpointWriter:
                 if item is not None:
                     payload, paths, done = item
                     done.synchronize()  # the non-blocking copies into the pinned snapshot have landed
-                    for path in paths:
-                        torch.save(payload, path)
+                    # one serialisation per file set; further names (checkpoint_i + best, Coach.py:163-176) are byte copies --
+                    # copyfile runs in the kernel without the GIL, torch.save's pickling and CRC pass compete with the
+                    # self-play loop of the next iteration for it
+                    torch.save(payload, paths[0])
+                    for path in paths[1:]:
+                        shutil.copyfile(paths[0], path)
             except Exception as e:  # surfaced by flush()
                 self.err = e
             finally:
