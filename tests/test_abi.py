@@ -51,3 +51,22 @@ def test_no_cpu_fallback():
         B200Connect4GNNWrapper(G(), dict(lr=1e-3))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         DeviceArena("connect4", 7, 4, 10, 1.0)
+
+
+def test_header_constants_match_the_python_binding():
+    """#define AZG_PREC_* / AZG_EVAL_* in include/azgnn_b200.h == the integers `_lib.py` passes through ctypes; every precision
+    name a config may use (`b200_precision`) maps to one of them; precisions that share another precision's packed weight
+    images (`PACKED_AS`) point at a real precision."""
+    import os
+    import re
+    from azgnn_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "azgnn_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(AZG_(?:PREC|EVAL)_\w+)\s+(-?\d+)", text)}
+    want = {"AZG_PREC_FP32": _lib.PREC_FP32, "AZG_PREC_BF16X3": _lib.PREC_BF16X3, "AZG_PREC_BF16": _lib.PREC_BF16,
+            "AZG_PREC_F16F8": _lib.PREC_F16F8, "AZG_PREC_F16F8_KS": _lib.PREC_F16F8_KS, "AZG_PREC_BF16X3_KS": _lib.PREC_BF16X3_KS,
+            "AZG_EVAL_STD": _lib.EVAL_STD, "AZG_EVAL_GNN": _lib.EVAL_GNN, "AZG_EVAL_FOLD": _lib.EVAL_FOLD}
+    assert {k: defs.get(k) for k in want} == want
+    assert {k for k in defs if k.startswith("AZG_PREC_")} == {k for k in want if k.startswith("AZG_PREC_")}
+    assert set(_lib.PRECISIONS.values()) == {v for k, v in want.items() if k.startswith("AZG_PREC_")} | {_lib.PREC_AUTO}
+    assert all(src in _lib.PRECISION_NAMES and dst in _lib.PRECISION_NAMES for src, dst in _lib.PACKED_AS.items())
