@@ -52,9 +52,11 @@ def workload_config(batch):
 
 
 DTYPES = {"fp32": "f32", "bf16x3": "f32 (3xbf16 split, f32 accumulate)", "bf16": "bf16 (f32 accumulate)",
-          "f16f8": "f32 (fp16 product + block-scaled FP8 correction product in one f32 accumulator)"}
+          "f16f8": "f32 (fp16 product + block-scaled FP8 correction product in one f32 accumulator)",
+          "f16f8ks": "f32 (fp16 product + block-scaled FP8 correction product, four f32 accumulators of K/4 summed with round-to-nearest adds)",
+          "bf16x3ks": "f32 (3xbf16 split, four f32 accumulators of K/4 summed with round-to-nearest adds)"}
 # tensor-core instruction times per 64-wide k-block relative to a single 16-bit product (4 MMAs of K = 16)
-MMA_TIMES = {"bf16x3": 3.0, "f16f8": 2.0, "bf16": 1.0, "fp32": None}
+MMA_TIMES = {"bf16x3": 3.0, "f16f8": 2.0, "bf16": 1.0, "fp32": None, "f16f8ks": 2.0, "bf16x3ks": 3.0}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (average of GEMM-1 and GEMM-2) from the committed ncu capture
 # of this configuration; None where no capture of the current kernel exists
 NCU_TRAFFIC = {"f16f8": (2.360e9, "profiles/r02_main_kernels_f16f8.txt"), "bf16x3": (2.268e9, "profiles/r01_main_kernels_bf16x3_v9.txt")}
@@ -513,7 +515,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         # fp32 FFMA path: the relevant ceiling is the CUDA-core FFMA rate, reported as a note; the
         # roofline entry always uses the measured bf16 tensor peak (the path's real ceiling).
         terms = MMA_TIMES[args.precision]
-        two_images = args.precision in ("bf16x3", "f16f8")
+        two_images = args.precision in ("bf16x3", "f16f8", "f16f8ks", "bf16x3ks")
         # `traffic` is NOT measured by this run (DRAM counters need ncu): it is the figure of the committed capture of the
         # same kernel and configuration, named in `traffic_source`; null when there is none
         traffic, traffic_src = NCU_TRAFFIC.get(args.precision, (None, None)) if B == BATCH else (None, None)
@@ -614,7 +616,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "f16f8"), choices=["fp32", "bf16x3", "bf16", "f16f8"])
+    ap.add_argument("--precision", default=os.environ.get("AZG_BENCH_PRECISION", "f16f8"), choices=["fp32", "bf16x3", "bf16", "f16f8", "f16f8ks", "bf16x3ks"])
     ap.add_argument("--preheat", type=float, default=1.0, help="seconds of untimed steps before the timed region (clock settling)")
     ap.add_argument("--selfplay-steady-moves", type=int, default=60, help="timed move-steps of the steady-state self-play leg (0 = skip)")
     ap.add_argument("--batch", type=int, default=BATCH)
